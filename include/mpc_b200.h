@@ -1,0 +1,133 @@
+/*
+ * mpc_b200.h -- C ABI of libmpc_b200.so: batched finite-horizon MPC solves on NVIDIA B200 (sm_100a).
+ *
+ * The reference (konnpaku-youmu/Model_Predictive_Control) is pure Python and has no FFI; its
+ * "plugin interface" for this path is the Python call surface of
+ *   session_1/FHC.py            ricatti_recursion (:51-61), AutoCruising (:20-29)
+ *   session_1/LinearSystem.py   LinearSystem.f/simulate/prediction (:16-35)
+ *   session_1/session1_sol.py   riccati_recursion (:44-65), simulate (:68-91)
+ *   session_2|3/problem.py      Problem (:4-32 / :8-36), session_2/log.py ControllerLog (:8-12)
+ *   session_4/session4_sol.py   MPCController (:113-230), integrators (:22-56)
+ * Each entry point below names the reference interface it replaces.  INTEGRATION.md shows the
+ * ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch); the library never keeps
+ *     memory between calls.  Kernels are asynchronous on `stream` (a cudaStream_t passed as void*);
+ *     no call synchronises the device.
+ *   - return value: 0 = ok, < 0 = mpc_error (invalid argument), > 0 = cudaError_t.  Never aborts.
+ *     mpc_last_error() returns a thread-local message for the last non-zero return.
+ *   - per-scenario solver outcomes (status, iterations) are DATA, not errors.
+ *   - dtype: MPC_F64 (reference arithmetic, numpy default) or MPC_F32.
+ *   - "batch stride" arguments (s*) are in ELEMENTS between consecutive scenarios; 0 = the array
+ *     is shared by every scenario.
+ *   - matrices are row-major.
+ */
+#ifndef MPC_B200_H
+#define MPC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPC_B200_VERSION 100 /* 0.1.0 */
+
+typedef void* mpc_stream_t; /* cudaStream_t */
+
+enum mpc_dtype { MPC_F64 = 0, MPC_F32 = 1 };
+
+enum mpc_error {
+  MPC_OK = 0,
+  MPC_ERR_NULL = -1,        /* required pointer is NULL */
+  MPC_ERR_SHAPE = -2,       /* dimension out of the supported range */
+  MPC_ERR_DTYPE = -3,       /* unknown dtype enum */
+  MPC_ERR_ALIGN = -4,       /* pointer / stride not aligned to the element size */
+  MPC_ERR_UNSUPPORTED = -5, /* valid request that this build has no kernel for */
+  MPC_ERR_WORKSPACE = -6    /* workspace missing or too small */
+};
+
+/* per-scenario status codes written by the constrained solvers (ControllerLog.solver_success,
+ * reference session_2/log.py:10, is `status == MPC_SOLVED`) */
+enum mpc_solve_status {
+  MPC_SOLVED = 1,
+  MPC_MAX_ITER = 2,
+  MPC_INFEASIBLE = 3,
+  MPC_UNSOLVED = 0
+};
+
+int mpc_version(void);
+const char* mpc_last_error(void);
+
+/* Largest (n, m) the generic (CTA-per-scenario) kernels accept. */
+#define MPC_MAX_NX 32
+#define MPC_MAX_NU 16
+
+/* ---------------------------------------------------------------------------------------------
+ * K1  batched backward Riccati recursion.
+ * Replaces FHC.ricatti_recursion (session_1/FHC.py:51-61) and session1_sol.riccati_recursion
+ * (session_1/session1_sol.py:44-65):  P_N = Pf;  K_k = -(R + B'PB)^-1 B'PA;  P_k = Q + A'PA + A'PB K_k.
+ * Sign convention u = +K x.  P is NOT symmetrised between stages (as the reference).
+ *   A [*,n,n]  B [*,n,m]  Q [*,n,n]  R [*,m,m]  Pf [*,n,n]   (batch stride s?, 0 = shared)
+ *   K  out [N][batch][m][n]    K[0] = first-stage gain (the reference returns the list reversed)
+ *   P  out, optional: all_P != 0 -> [N+1][batch][n][n] (P[0] = cost-to-go at stage 0, P[N] = Pf)
+ *                     all_P == 0 -> [batch][n][n] = P[0] only.  NULL = not written.
+ */
+int mpc_riccati(const void* A, int64_t sA, const void* B, int64_t sB, const void* Q, int64_t sQ,
+                const void* R, int64_t sR, const void* Pf, int64_t sPf, void* K, void* P, int all_P,
+                int64_t batch, int n, int m, int N, int dtype, mpc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2  batched linear rollout under time-varying state feedback, batch-contiguous layout.
+ * Replaces LinearSystem.simulate / prediction (session_1/LinearSystem.py:20-35) driven by
+ * AutoCruising.control_law / pred (session_1/FHC.py:25-29) and session1_sol.simulate (:68-91).
+ *   x0 [n][batch]  ->  X [T][n][batch] (X[0] = x0), U [T-1][m][batch] (optional)
+ *   transition i (0-based) applies gain index g = gain_offset + gain_step * i:
+ *       (0,0) gains[0] every step          AutoCruising.control_law  (FHC.py:25-26)
+ *       (1,1) gains[t], t = 1..T-1         AutoCruising.pred through LinearSystem.prediction
+ *                                          (FHC.py:28-29, LinearSystem.py:30-31 -- skips gains[0])
+ *       (0,1) gains[t], t = 0..T-2         session1_sol.py:121-126
+ *   K [ng][*][m][n] with stage stride sK_stage and batch stride sK (0 = shared gains)
+ *   A, B shared (sA = sB = 0) or per scenario.
+ *   cost   optional [batch]: sum_i x_i'Q x_i + u_i'R u_i  +  x_{T-1}' Pf x_{T-1}  (Q, R, Pf shared;
+ *          all three required when cost != NULL)
+ *   unstable optional [batch] uint8: 1 when any |x_t|_2 > norm_limit (session1_sol.py:86-89 uses 100)
+ */
+int mpc_lq_rollout(const void* A, int64_t sA, const void* B, int64_t sB, const void* K,
+                   int64_t sK_stage, int64_t sK, int gain_offset, int gain_step, const void* x0,
+                   void* X, void* U, const void* Q, const void* R, const void* Pf, void* cost,
+                   uint8_t* unstable, double norm_limit, int64_t batch, int n, int m, int T,
+                   int dtype, mpc_stream_t stream);
+
+/* One plant step x+ = A x + B u with a caller-supplied input: LinearSystem.f
+ * (session_1/LinearSystem.py:16-18) for policies that are arbitrary Python callables.
+ *   A [n][n], B [n][m] shared;  x [n][batch], u [m][batch] -> xn [n][batch] (xn != x). */
+int mpc_linear_step(const void* A, const void* B, const void* x, const void* u, void* xn,
+                    int64_t batch, int n, int m, int dtype, mpc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1+K2 fused  per-scenario finite-horizon LQ solve (one thread per scenario):
+ * backward recursion of FHC.ricatti_recursion (FHC.py:51-61) followed by the optimal open-loop
+ * plan u_k = K_k x_k, x_{k+1} = A x_k + B u_k (LinearSystem.f, LinearSystem.py:16-18) and the cost
+ * V = sum x'Qx + u'Ru + x_N' Pf x_N  (= x0' P_0 x0, FHC.py:123-124).
+ *   x0 [batch][n];  outputs stage-major:  X [N+1][batch][n], U [N][batch][m], V [batch];
+ *   optional K [N][batch][m][n], P0 [batch][n][n].
+ * Supported (n, m): n <= 4, m <= 2 (register-resident); others -> MPC_ERR_UNSUPPORTED.
+ */
+int mpc_lq_solve(const void* A, int64_t sA, const void* B, int64_t sB, const void* Q, int64_t sQ,
+                 const void* R, int64_t sR, const void* Pf, int64_t sPf, const void* x0, void* X,
+                 void* U, void* V, void* K, void* P0, int64_t batch, int n, int m, int N, int dtype,
+                 mpc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Device FP pipe probe: runs a register-resident FMA chain kernel and reports achieved
+ * FLOP/s (2 flops per FMA).  Used by bench.py as the measured FP64 / FP32 vector-pipe roofline
+ * denominator (MEASURED_PEAKS.json only carries HBM and bf16 tensor peaks).  Synchronises.
+ */
+int mpc_fma_peak_probe(int dtype, double* flops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPC_B200_H */

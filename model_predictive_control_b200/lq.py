@@ -1,0 +1,171 @@
+"""Device-level LQ operators on torch CUDA tensors (thin wrappers over the C ABI).
+
+These are the building blocks under the reference-shaped API in ``FHC.py``,
+``LinearSystem.py`` and ``session1_sol.py``.  Layouts are the library's (see
+include/mpc_b200.h): models ``[batch, n, n]`` (or shared ``[n, n]``), rollouts batch-contiguous
+``[T, n, batch]``, fused solves stage-major ``[N+1, batch, n]``.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+def _model(t, rows, cols, name):
+    """Return (contiguous tensor, batch or None, stride in elements)."""
+    if t.dim() == 2:
+        if tuple(t.shape) != (rows, cols):
+            raise ValueError(f"{name} must be ({rows},{cols}), got {tuple(t.shape)}")
+        return t.contiguous(), None, 0
+    if t.dim() == 3 and tuple(t.shape[1:]) == (rows, cols):
+        return t.contiguous(), t.shape[0], rows * cols
+    raise ValueError(f"{name} must be ({rows},{cols}) or (batch,{rows},{cols}), got {tuple(t.shape)}")
+
+
+def _common_batch(bs, extra=None):
+    vals = {b for b in bs if b is not None}
+    if extra is not None:
+        vals.add(extra)
+    if len(vals) > 1:
+        raise ValueError(f"inconsistent batch sizes {sorted(vals)}")
+    return vals.pop() if vals else None
+
+
+def riccati(A, B, Q, R, Pf, N, all_P=True):
+    """Backward Riccati recursion (K1).  Returns K [N, batch, m, n], P [N+1, batch, n, n]
+    (or [batch, n, n] = P_0 when ``all_P`` is false).  batch = 1 when every matrix is shared.
+    Replaces reference session_1/FHC.py:51-61."""
+    _lib.require_cuda(A, B, Q, R, Pf)
+    n, m = A.shape[-1], B.shape[-1]
+    A, bA, sA = _model(A, n, n, "A")
+    B, bB, sB = _model(B, n, m, "B")
+    Q, bQ, sQ = _model(Q, n, n, "Q")
+    R, bR, sR = _model(R, m, m, "R")
+    Pf, bP, sP = _model(Pf, n, n, "P_f")
+    batch = _common_batch([bA, bB, bQ, bR, bP]) or 1
+    N = int(N)
+    if N < 0:
+        raise ValueError("horizon must be non-negative")
+    K = torch.empty((N, batch, m, n), dtype=A.dtype, device=A.device)
+    P = torch.empty((N + 1, batch, n, n) if all_P else (batch, n, n), dtype=A.dtype, device=A.device)
+    with torch.cuda.device(A.device):
+        _lib.check(_lib.lib().mpc_riccati(
+            _lib.ptr(A), sA, _lib.ptr(B), sB, _lib.ptr(Q), sQ, _lib.ptr(R), sR, _lib.ptr(Pf), sP,
+            _lib.ptr(K), _lib.ptr(P), 1 if all_P else 0, batch, n, m, N, _lib.dtype_enum(A),
+            _lib.stream(A.device)))
+    return K, P
+
+
+def lq_rollout(A, B, K, x0, T, gain_offset=0, gain_step=0, Q=None, R=None, Pf=None,
+               want_U=False, want_cost=False, want_unstable=False, norm_limit=100.0):
+    """Batched linear rollout under state feedback (K2).
+
+    x0 [n, batch]; K [ng, m, n] (shared) or [ng, batch, m, n]; A, B shared or [batch, ., .].
+    Returns dict with X [T, n, batch] and optionally U [T-1, m, batch], cost [batch],
+    unstable [batch] (uint8).  Transition i uses gain ``gain_offset + gain_step * i``.
+    Replaces reference session_1/LinearSystem.py:20-35 + FHC.py:25-29."""
+    _lib.require_cuda(A, B, K, x0)
+    n, m = A.shape[-1], B.shape[-1]
+    if x0.dim() != 2 or x0.shape[0] != n:
+        raise ValueError(f"x0 must be (n={n}, batch), got {tuple(x0.shape)}")
+    batch = x0.shape[1]
+    x0 = x0.contiguous()
+    A, bA, sA = _model(A, n, n, "A")
+    B, bB, sB = _model(B, n, m, "B")
+    T = int(T)
+    if T < 1:
+        raise ValueError("need at least one state")
+    ng_needed = gain_offset + gain_step * (T - 2) + 1 if T >= 2 else 0
+    if K.dim() == 3:
+        K = K.contiguous()
+        sKs, sK, bK = m * n, 0, None
+    elif K.dim() == 4:
+        K = K.contiguous()
+        bK = K.shape[1]
+        sKs, sK = bK * m * n, m * n
+    else:
+        raise ValueError("gains must be [ng, m, n] or [ng, batch, m, n]")
+    if tuple(K.shape[-2:]) != (m, n):
+        raise ValueError(f"gain blocks must be ({m},{n})")
+    if K.shape[0] < ng_needed:
+        raise IndexError(f"policy needs gains[{ng_needed - 1}] but only {K.shape[0]} gains were set")
+    _common_batch([bA, bB, bK], batch)
+    X = torch.empty((T, n, batch), dtype=x0.dtype, device=x0.device)
+    U = torch.empty((max(T - 1, 0), m, batch), dtype=x0.dtype, device=x0.device) if want_U else None
+    cost = torch.empty((batch,), dtype=x0.dtype, device=x0.device) if want_cost else None
+    unstable = torch.empty((batch,), dtype=torch.uint8, device=x0.device) if want_unstable else None
+    if want_cost:
+        if Q is None or R is None or Pf is None:
+            raise ValueError("cost needs Q, R and Pf")
+        Q, R, Pf = Q.contiguous(), R.contiguous(), Pf.contiguous()
+    with torch.cuda.device(x0.device):
+        _lib.check(_lib.lib().mpc_lq_rollout(
+            _lib.ptr(A), sA, _lib.ptr(B), sB, _lib.ptr(K), sKs, sK, int(gain_offset), int(gain_step),
+            _lib.ptr(x0), _lib.ptr(X), _lib.ptr(U), _lib.ptr(Q) if want_cost else None,
+            _lib.ptr(R) if want_cost else None, _lib.ptr(Pf) if want_cost else None, _lib.ptr(cost),
+            _lib.ptr(unstable), float(norm_limit), batch, n, m, T, _lib.dtype_enum(x0),
+            _lib.stream(x0.device)))
+    return {"X": X, "U": U, "cost": cost, "unstable": unstable}
+
+
+def linear_step(A, B, x, u):
+    """x+ = A x + B u for x [n, batch], u [m, batch] (reference LinearSystem.py:16-18)."""
+    _lib.require_cuda(A, B, x, u)
+    n, m = A.shape[-1], B.shape[-1]
+    x, u = x.contiguous(), u.contiguous()
+    if x.shape[0] != n or u.shape[0] != m or x.shape[1] != u.shape[1]:
+        raise ValueError(f"shape mismatch: x {tuple(x.shape)}, u {tuple(u.shape)} for n={n}, m={m}")
+    xn = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().mpc_linear_step(_lib.ptr(A.contiguous()), _lib.ptr(B.contiguous()), _lib.ptr(x),
+                                              _lib.ptr(u), _lib.ptr(xn), x.shape[1], n, m,
+                                              _lib.dtype_enum(x), _lib.stream(x.device)))
+    return xn
+
+
+class LqSolveBuffers:
+    """Pre-allocated outputs of :func:`lq_solve` so that a timed loop allocates nothing."""
+
+    def __init__(self, batch, n, m, N, dtype, device, want_K=False, want_P0=False):
+        self.X = torch.empty((N + 1, batch, n), dtype=dtype, device=device)
+        self.U = torch.empty((N, batch, m), dtype=dtype, device=device)
+        self.V = torch.empty((batch,), dtype=dtype, device=device)
+        self.K = torch.empty((N, batch, m, n), dtype=dtype, device=device) if want_K else None
+        self.P0 = torch.empty((batch, n, n), dtype=dtype, device=device) if want_P0 else None
+
+
+def lq_solve(A, B, Q, R, Pf, x0, N, want_K=False, want_P0=False, out=None):
+    """Fused per-scenario finite-horizon LQ solve (K1+K2): x0 [batch, n] ->
+    X [N+1, batch, n], U [N, batch, m], V [batch] (+ K [N, batch, m, n], P0 [batch, n, n]).
+    Models shared ([n,n]) or per scenario ([batch,n,n])."""
+    _lib.require_cuda(A, B, Q, R, Pf, x0)
+    n, m = A.shape[-1], B.shape[-1]
+    if x0.dim() != 2 or x0.shape[1] != n:
+        raise ValueError(f"x0 must be (batch, n={n}), got {tuple(x0.shape)}")
+    batch = x0.shape[0]
+    x0 = x0.contiguous()
+    A, bA, sA = _model(A, n, n, "A")
+    B, bB, sB = _model(B, n, m, "B")
+    Q, bQ, sQ = _model(Q, n, n, "Q")
+    R, bR, sR = _model(R, m, m, "R")
+    Pf, bP, sP = _model(Pf, n, n, "P_f")
+    _common_batch([bA, bB, bQ, bR, bP], batch)
+    N = int(N)
+    if out is None:
+        out = LqSolveBuffers(batch, n, m, N, x0.dtype, x0.device, want_K, want_P0)
+    with torch.cuda.device(x0.device):
+        _lib.check(_lib.lib().mpc_lq_solve(
+            _lib.ptr(A), sA, _lib.ptr(B), sB, _lib.ptr(Q), sQ, _lib.ptr(R), sR, _lib.ptr(Pf), sP,
+            _lib.ptr(x0), _lib.ptr(out.X), _lib.ptr(out.U), _lib.ptr(out.V), _lib.ptr(out.K),
+            _lib.ptr(out.P0), batch, n, m, N, _lib.dtype_enum(x0), _lib.stream(x0.device)))
+    return out
+
+
+def fma_peak(dtype=torch.float64):
+    """Measured FMA-pipe FLOP/s of the current device (roofline denominator for fp kernels)."""
+    import ctypes
+    out = ctypes.c_double(0.0)
+    _lib.check(_lib.lib().mpc_fma_peak_probe(_lib.MPC_F64 if dtype == torch.float64 else _lib.MPC_F32,
+                                             ctypes.byref(out)))
+    return out.value

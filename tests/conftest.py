@@ -7,6 +7,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+if os.path.join(ROOT, "tests") not in sys.path:
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
 def pytest_configure(config):
@@ -17,3 +19,30 @@ def pytest_configure(config):
 def golden():
     with open(os.path.join(ROOT, "tests", "golden", "session1.json")) as fh:
         return json.load(fh)
+
+
+@pytest.fixture(scope="session")
+def hh():
+    """CPU loops over the kernels' __host__ __device__ bodies (tests/harness)."""
+    import harness
+    lib = harness.load()
+    if lib is None:
+        pytest.skip("nvcc not available to build the host harness")
+    return lib
+
+
+def gpu_available():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    if gpu_available():
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)

@@ -1,0 +1,87 @@
+// TEST INFRASTRUCTURE -- not part of the product library.
+// Runs the __host__ __device__ per-scenario bodies of model_predictive_control_b200/csrc/*_core.cuh
+// in plain CPU loops, so that `pytest -m "not gpu"` can check their algebra and indexing against
+// the oracle on a machine without a GPU.  Nothing in the package links or loads this file.
+#include <vector>
+
+#include "../../model_predictive_control_b200/csrc/lq_core.cuh"
+
+using namespace mpc;
+
+namespace mpc {
+void set_error(const char*, ...) {}
+int fail(int code, const char*, ...) { return code; }
+int check_launch(const char*) { return 0; }
+}  // namespace mpc
+
+template <int NX, int NU>
+static void riccati_loop(const RiccatiArgs<double>& a) {
+  for (int64_t b = 0; b < a.batch; ++b) riccati_body<double, NX, NU, false>(a, b);
+}
+
+extern "C" int hh_riccati(const double* A, int64_t sA, const double* B, int64_t sB, const double* Q,
+                          int64_t sQ, const double* R, int64_t sR, const double* Pf, int64_t sPf,
+                          double* K, double* P, int all_P, int64_t batch, int n, int m, int N) {
+  RiccatiArgs<double> a{A, B, Q, R, Pf, sA, sB, sQ, sR, sPf, K, P, all_P, batch, N};
+  if (n == 2 && m == 1) riccati_loop<2, 1>(a);
+  else if (n == 4 && m == 1) riccati_loop<4, 1>(a);
+  else if (n == 4 && m == 2) riccati_loop<4, 2>(a);
+  else return -5;
+  return 0;
+}
+
+template <int NX, int NU>
+static void rollout_loop(const RolloutArgs<double>& a, int vec) {
+  using L = RolloutSmem<double, NX, NU>;
+  const bool shared = a.sA == 0 && a.sB == 0 && a.sK == 0;
+  if (!shared) {
+    for (int64_t b = 0; b < a.batch; ++b) rollout_perscn_body<double, NX, NU>(a, b);
+    return;
+  }
+  std::vector<double> sm(L::total(a.ng), 0.0);
+  for (int i = 0; i < NX * NX; ++i) {
+    sm[L::oA + i] = a.A[i];
+    sm[L::oQ + i] = a.Q ? a.Q[i] : 0.0;
+    sm[L::oPf + i] = a.Pf ? a.Pf[i] : 0.0;
+  }
+  for (int i = 0; i < NX * NU; ++i) sm[L::oB + i] = a.B[i];
+  for (int i = 0; i < NU * NU; ++i) sm[L::oR + i] = a.R ? a.R[i] : 0.0;
+  for (int i = 0; i < a.ng * NU * NX; ++i) sm[L::oK + i] = a.K[(int64_t)(i / (NU * NX)) * a.sK_stage + i % (NU * NX)];
+  if (vec == 2)
+    for (int64_t b = 0; b < a.batch; b += 2) rollout_shared_body<double, NX, NU, 2>(a, sm.data(), b);
+  else
+    for (int64_t b = 0; b < a.batch; ++b) rollout_shared_body<double, NX, NU, 1>(a, sm.data(), b);
+}
+
+extern "C" int hh_lq_rollout(const double* A, int64_t sA, const double* B, int64_t sB, const double* K,
+                             int64_t sK_stage, int64_t sK, int gain_offset, int gain_step,
+                             const double* x0, double* X, double* U, const double* Q, const double* R,
+                             const double* Pf, double* cost, uint8_t* unstable, double norm_limit,
+                             int64_t batch, int n, int m, int T, int vec) {
+  const int ng = (T >= 2) ? gain_offset + gain_step * (T - 2) + 1 : 0;
+  RolloutArgs<double> a{A, B, sA, sB, K, sK_stage, sK, ng, gain_offset, gain_step, x0, X, U, Q, R, Pf,
+                        cost, unstable, norm_limit * norm_limit, batch, T};
+  if (n == 2 && m == 1) rollout_loop<2, 1>(a, vec);
+  else if (n == 4 && m == 1) rollout_loop<4, 1>(a, vec);
+  else if (n == 4 && m == 2) rollout_loop<4, 2>(a, vec);
+  else return -5;
+  return 0;
+}
+
+template <int NX, int NU>
+static void lq_solve_loop(const LqSolveArgs<double>& a) {
+  std::vector<double> Ks((size_t)a.N * NU * NX);
+  for (int64_t b = 0; b < a.batch; ++b) lq_solve_body<double, NX, NU, false>(a, b, Ks.data(), 1);
+}
+
+extern "C" int hh_lq_solve(const double* A, int64_t sA, const double* B, int64_t sB, const double* Q,
+                           int64_t sQ, const double* R, int64_t sR, const double* Pf, int64_t sPf,
+                           const double* x0, double* X, double* U, double* V, double* K, double* P0,
+                           int64_t batch, int n, int m, int N) {
+  LqSolveArgs<double> a{A, B, Q, R, Pf, sA, sB, sQ, sR, sPf, x0, X, U, V, K, P0, batch, N};
+  if (n == 2 && m == 1) lq_solve_loop<2, 1>(a);
+  else if (n == 4 && m == 1) lq_solve_loop<4, 1>(a);
+  else if (n == 4 && m == 2) lq_solve_loop<4, 2>(a);
+  else return -5;
+  return 0;
+}

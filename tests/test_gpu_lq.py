@@ -1,0 +1,264 @@
+"""GPU parity of the LQ path (K1, K2, fused solve) through the reference-shaped API and the
+device-level operators, against the numpy oracle and the golden vectors generated from the
+reference's own session-1 code.  Tolerances: 1e-6 relative fp64 / 1e-4 fp32 (north star); the
+fp64 kernels are in fact held to 1e-9."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import lq as olq  # noqa: E402
+
+RTOL64, RTOL32 = 1e-9, 1e-4
+
+
+def arr(x):
+    return np.asarray(x, dtype=np.float64)
+
+
+@pytest.fixture(scope="module")
+def mods():
+    import torch
+    from model_predictive_control_b200 import FHC, LinearSystem, lq, session1_sol
+    assert torch.cuda.is_available()
+    return FHC, LinearSystem, session1_sol, lq, torch
+
+
+def models(rng, batch, n, m):
+    A = np.eye(n) + 0.5 * np.diag(np.ones(n - 1), 1) + 0.05 * rng.standard_normal((batch, n, n))
+    B = np.zeros((n, m)); B[-1, 0] = -0.5
+    if m > 1:
+        B[-2, 1] = 0.3
+    B = B + 0.05 * rng.standard_normal((batch, n, m))
+    Q = np.eye(n) * (1 + 0.2 * rng.random((batch, 1, 1)))
+    R = 0.1 * np.eye(m) * (1 + rng.random((batch, 1, 1)))
+    return A, B, Q, R
+
+
+def test_cfg1_golden_recursion(mods, golden):
+    FHC, *_ = mods
+    g = golden["cfg1"]
+    A, B, Q, R = arr(g["A"]), arr(g["B"]), arr(g["Q"]), arr(g["R"])  # R is 1-D (FHC.py:141)
+    for N, rec in g["recursion"].items():
+        P, K = FHC.ricatti_recursion(A, B, Q, R, Q, int(N))
+        assert isinstance(P, list) and len(P) == int(N) + 1 and len(K) == int(N)
+        assert P[0].shape == (2, 2) and K[0].shape == (1, 2) and isinstance(K[0], np.ndarray)
+        np.testing.assert_allclose(np.array(K), arr(rec["K"]), rtol=RTOL64, atol=1e-12)
+        np.testing.assert_allclose(np.array(P), arr(rec["P"]), rtol=RTOL64, atol=1e-12)
+        np.testing.assert_array_equal(P[-1], Q)
+
+
+def test_cfg1_cost_sweep(mods, golden):
+    FHC, *_ = mods
+    g = golden["cfg1"]
+    V, V_inf = FHC.terminal_cost_sweep(arr(g["A"]), arr(g["B"]), arr(g["Q"]), arr(g["R"]), arr(g["Q"]), arr(g["x0"]))
+    np.testing.assert_allclose(V, g["V_N_1to9"], rtol=RTOL64)
+    np.testing.assert_allclose(V_inf, g["V_inf"], rtol=1e-9)
+
+
+def test_cfg1_closed_loop_and_prediction(mods, golden):
+    FHC, LinearSystem, sol, _, _ = mods
+    g = golden["cfg1"]
+    A, B, Q, R, x0 = arr(g["A"]), arr(g["B"]), arr(g["Q"]), arr(g["R"]), arr(g["x0"])
+    for N, cl in g["closed_loop"].items():
+        N = int(N)
+        _, gains = FHC.ricatti_recursion(A, B, Q, R, Q, N)
+        sys = FHC.AutoCruising(A, B)
+        sys.set_opti_gain(gains)
+        assert sys.simulate(x0, sys.control_law, 30) is None
+        assert sys.x.shape == (2, 1, 30)
+        np.testing.assert_allclose(sys.x, arr(cl["X"]), rtol=1e-8, atol=1e-12)
+        for t, pr in zip((0, 1, 7), cl["pred_t0_t1_t7"]):
+            xp = sys.prediction(sys.x[:, :, t], sys.pred, N)
+            assert xp.shape == (2, 1, N)
+            np.testing.assert_allclose(xp, arr(pr), rtol=1e-8, atol=1e-12)
+        # instructor-solution loop (session1_sol.py:68-91)
+        f = sol.linear_dynamics(A, B)
+        xs, flag = sol.simulate(10 * np.ones(2), f, sol.feedback_policy(gains, receding=True), 30)
+        assert xs.shape == (31, 2)
+        np.testing.assert_allclose(xs, arr(cl["sol_X"]), rtol=1e-8, atol=1e-12)
+        assert flag == cl["sol_flag"]
+        xp, _ = sol.simulate(10 * np.ones(2), f, sol.feedback_policy(gains, receding=False), N)
+        np.testing.assert_allclose(xp, arr(cl["sol_pred"]), rtol=1e-8, atol=1e-12)
+
+
+def test_prediction_skips_gain0(mods, golden):
+    """Reference quirk: LinearSystem.prediction never applies gains[0] (LinearSystem.py:30-31)."""
+    FHC, *_ = mods
+    g = golden["cfg1"]
+    A, B, Q, R, x0 = arr(g["A"]), arr(g["B"]), arr(g["Q"]), arr(g["R"]), arr(g["x0"])
+    _, K = FHC.ricatti_recursion(A, B, Q, R, Q, 10)
+    sys = FHC.AutoCruising(A, B)
+    sys.set_opti_gain(K)
+    xp = sys.prediction(x0, sys.pred, 10)
+    np.testing.assert_allclose(xp[:, 0, 1], [15.0, -7.941782569134741], rtol=1e-9)
+
+
+def test_sol_argument_order(mods, golden):
+    _, _, sol, _, _ = mods
+    g = golden["cfg1"]
+    A, B, Q, R = arr(g["A"]), arr(g["B"]), arr(g["Q"]), arr(g["R"]).reshape(1, 1)
+    rec = g["recursion"]["20"]
+    P, K = sol.riccati_recursion(A, B, R, Q, Q, 20)
+    np.testing.assert_allclose(np.array(K), arr(rec["K_sol"]), rtol=RTOL64, atol=1e-12)
+    np.testing.assert_allclose(np.array(P), arr(rec["P_sol"]), rtol=RTOL64, atol=1e-12)
+    A2, B2, Q2, R2 = sol.setup()
+    np.testing.assert_allclose(R2, [[0.1]])
+
+
+def test_generic_callables_take_the_step_path(mods, golden):
+    """Arbitrary Python policies still work (one device step per call), as in the reference."""
+    FHC, LinearSystem, *_ = mods
+    g = golden["cfg1"]
+    A, B, Q, R, x0 = arr(g["A"]), arr(g["B"]), arr(g["Q"]), arr(g["R"]), arr(g["x0"])
+    _, K = FHC.ricatti_recursion(A, B, Q, R, Q, 6)
+    sys = LinearSystem.LinearSystem(A, B)
+    sys.simulate(x0, lambda x, t: K[0] @ x, 30)
+    np.testing.assert_allclose(sys.x, arr(g["closed_loop"]["6"]["X"]), rtol=1e-8, atol=1e-12)
+    np.testing.assert_allclose(sys.f(x0, K[0] @ x0), A @ x0 + B @ (K[0] @ x0), rtol=1e-12)
+
+
+def test_cfg2a_golden_batched_shared_model(mods, golden):
+    FHC, *_ = mods
+    g = golden["cfg2a"]
+    A, B, Q, R, x0 = arr(g["A"]), arr(g["B"]), arr(g["Q"]), arr(g["R"]), arr(g["x0"])
+    P, K = FHC.ricatti_recursion(A, B, Q, R, Q, g["N"])
+    np.testing.assert_allclose(np.array(K), arr(g["K"]), rtol=RTOL64, atol=1e-12)
+    np.testing.assert_allclose(np.array(P), arr(g["P"]), rtol=RTOL64, atol=1e-12)
+    sys = FHC.AutoCruising(A, B)
+    sys.set_opti_gain(K)
+    sys.simulate(x0, sys.control_law, 30)
+    np.testing.assert_allclose(sys.x, arr(g["simulate_30"]), rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(sys.prediction(x0, sys.pred, 20), arr(g["prediction_20"]), rtol=1e-8, atol=1e-10)
+
+
+def test_cfg2b_golden_per_scenario_models(mods, golden):
+    FHC, _, _, lq, torch = mods
+    g = golden["cfg2b"]
+    A, B, Q, R = arr(g["A"]), arr(g["B"]), arr(g["Q"]), arr(g["R"])
+    P, K = FHC.ricatti_recursion(A, B, Q, R, Q, g["N"])  # batched leading dim
+    assert K[0].shape == (A.shape[0], 1, 4)
+    np.testing.assert_allclose(np.array(K), arr(g["K"]), rtol=RTOL64, atol=1e-12)
+    np.testing.assert_allclose(np.array(P), arr(g["P"]), rtol=RTOL64, atol=1e-12)
+
+
+def test_n12_m4_generic_kernel(mods, golden):
+    FHC, *_ = mods
+    g = golden["n12m4"]
+    A, B, Q, R = arr(g["A"]), arr(g["B"]), arr(g["Q"]), arr(g["R"])
+    P, K = FHC.ricatti_recursion(A, B, Q, R, Q, g["N"])
+    np.testing.assert_allclose(P[0], arr(g["P0_fhc"]), rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(K[0], arr(g["K0_fhc"]), rtol=1e-8, atol=1e-10)
+    Po, Ko = olq.ricatti_recursion(A, B, Q, R, Q, g["N"])
+    np.testing.assert_allclose(np.array(K), np.array(Ko), rtol=1e-8, atol=1e-10)
+
+
+@pytest.mark.parametrize("n,m", [(2, 1), (4, 1), (4, 2), (3, 2), (12, 4)])
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_riccati_random_batched(mods, n, m, dtype):
+    _, _, _, lq, torch = mods
+    rng = np.random.default_rng(10 + n + m)
+    batch, N = (1000, 20) if n <= 4 else (37, 10)
+    A, B, Q, R = models(rng, batch, n, m)
+    dt = torch.float64 if dtype == "f64" else torch.float32
+    dev = lambda a: torch.tensor(a, dtype=dt, device="cuda")
+    K, P = lq.riccati(dev(A), dev(B), dev(Q), dev(R), dev(Q), N)
+    Po, Ko = olq.ricatti_recursion(A, B, Q, R, Q, N)
+    rtol = RTOL64 if dtype == "f64" else RTOL32
+    scaleK, scaleP = np.abs(np.array(Ko)).max(), np.abs(np.array(Po)).max()
+    assert np.abs(K.cpu().numpy() - np.array(Ko)).max() <= rtol * scaleK * 10
+    assert np.abs(P.cpu().numpy() - np.array(Po)).max() <= rtol * scaleP * 10
+    K0, P0 = lq.riccati(dev(A), dev(B), dev(Q), dev(R), dev(Q), N, all_P=False)
+    assert torch.equal(K0, K) and torch.equal(P0, P[0])
+
+
+@pytest.mark.parametrize("batch", [1, 2, 31, 33, 255, 1000, 4097])
+def test_rollout_ragged_batches(mods, batch):
+    """Odd batch sizes take the scalar path, even ones the vectorised path; both match the oracle."""
+    _, _, _, lq, torch = mods
+    rng = np.random.default_rng(batch)
+    A, B, Q, R = (M[0] for M in models(rng, 1, 4, 1))
+    N, T = 20, 21
+    Po, Ko = olq.ricatti_recursion(A, B, Q, R, Q, N)
+    x0 = rng.uniform(-10, 10, (4, batch))
+    dev = lambda a: torch.tensor(np.asarray(a), dtype=torch.float64, device="cuda")
+    res = lq.lq_rollout(dev(A), dev(B), dev(np.array(Ko)), dev(x0), T, gain_offset=0, gain_step=1,
+                        Q=dev(Q), R=dev(R), Pf=dev(Q), want_U=True, want_cost=True, want_unstable=True)
+    Xo = olq.simulate(A, B, x0, [None] + list(Ko), T, mode="pred")  # gains[t-1] at step t
+    np.testing.assert_allclose(res["X"].permute(1, 2, 0).cpu().numpy(), Xo, rtol=1e-9, atol=1e-10)
+    V = olq.cost_to_go(Po[0], x0)
+    np.testing.assert_allclose(res["cost"].cpu().numpy(), V, rtol=1e-9)  # optimal plan: cost = x0'P0 x0
+    assert res["U"].shape == (T - 1, 1, batch)
+
+
+@pytest.mark.parametrize("n,m", [(2, 1), (4, 1), (4, 2)])
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("shared", [False, True])
+def test_lq_solve_fused(mods, n, m, dtype, shared):
+    _, _, _, lq, torch = mods
+    rng = np.random.default_rng(100 + n + m)
+    batch, N = 777, 20
+    A, B, Q, R = models(rng, 1 if shared else batch, n, m)
+    x0 = rng.uniform(-10, 10, (batch, n))
+    dt = torch.float64 if dtype == "f64" else torch.float32
+    dev = lambda a: torch.tensor(a, dtype=dt, device="cuda")
+    sq = (lambda a: a[0]) if shared else (lambda a: a)
+    out = lq.lq_solve(dev(sq(A)), dev(sq(B)), dev(sq(Q)), dev(sq(R)), dev(sq(Q)), dev(x0), N, want_K=True, want_P0=True)
+    rtol = 1e-8 if dtype == "f64" else RTOL32
+    X, U, V = out.X.cpu().numpy(), out.U.cpu().numpy(), out.V.cpu().numpy()
+    for b in range(0, batch, 97):
+        i = 0 if shared else b
+        Xb, Ub, Vb, Pb, Kb = olq.lq_open_loop(A[i], B[i], Q[i], R[i], Q[i], x0[b], N)
+        sx, su = np.abs(Xb).max(), max(np.abs(Ub).max(), 1e-30)
+        assert np.abs(X[:, b] - Xb).max() <= rtol * sx * 10
+        assert np.abs(U[:, b] - Ub).max() <= rtol * su * 10
+        assert abs(V[b] - Vb) <= rtol * abs(Vb) * 10
+        assert np.abs(out.K[:, b].cpu().numpy() - np.array(Kb)).max() <= rtol * np.abs(np.array(Kb)).max() * 10
+        assert np.abs(out.P0[b].cpu().numpy() - Pb[0]).max() <= rtol * np.abs(Pb[0]).max() * 10
+
+
+def test_full_size_properties_cfg2(mods):
+    """1M scenarios (BASELINE config 2): size-independent properties of the fused solve:
+    V == x0' P0 x0, X satisfies the dynamics, U = K X, linearity in x0, and agreement with the
+    unfused K1 -> K2 pipeline."""
+    _, _, _, lq, torch = mods
+    torch.manual_seed(0)
+    B_, n, m, N = 1 << 20, 4, 1, 20
+    dd = dict(dtype=torch.float64, device="cuda")
+    A0 = torch.eye(n, **dd) + 0.5 * torch.diag(torch.ones(n - 1, **dd), 1)
+    B0 = torch.zeros(n, m, **dd); B0[-1, 0] = -0.5
+    A = A0 + 0.05 * torch.randn(B_, n, n, **dd)
+    Bm = B0 + 0.05 * torch.randn(B_, n, m, **dd)
+    Q = torch.eye(n, **dd) * (1 + 0.2 * torch.rand(B_, 1, 1, **dd))
+    R = 0.1 * torch.eye(m, **dd) * (1 + torch.rand(B_, 1, 1, **dd))
+    x0 = torch.rand(B_, n, **dd) * 20 - 10
+    out = lq.lq_solve(A, Bm, Q, R, Q, x0, N, want_K=True, want_P0=True)
+    V_quad = torch.einsum("bi,bij,bj->b", x0, out.P0, x0)
+    assert torch.allclose(out.V, V_quad, rtol=1e-9, atol=1e-9)
+    Xn = torch.einsum("bij,kbj->kbi", A, out.X[:-1]) + torch.einsum("bij,kbj->kbi", Bm, out.U)
+    assert torch.allclose(out.X[1:], Xn, rtol=1e-10, atol=1e-9)
+    assert torch.allclose(out.U, torch.einsum("kbij,kbj->kbi", out.K, out.X[:-1]), rtol=1e-10, atol=1e-9)
+    out2 = lq.lq_solve(A, Bm, Q, R, Q, 2.0 * x0, N)
+    assert torch.allclose(out2.U, 2.0 * out.U, rtol=1e-12, atol=1e-12)
+    assert torch.allclose(out2.V, 4.0 * out.V, rtol=1e-12)
+    K, P = lq.riccati(A, Bm, Q, R, Q, N, all_P=False)
+    assert torch.allclose(K, out.K, rtol=1e-12, atol=1e-14) and torch.allclose(P, out.P0, rtol=1e-12)
+    res = lq.lq_rollout(A, Bm, K, x0.t().contiguous(), N + 1, gain_offset=0, gain_step=1)
+    assert torch.allclose(res["X"].permute(0, 2, 1), out.X, rtol=1e-12, atol=1e-12)
+
+
+def test_torch_in_torch_out_and_errors(mods, golden):
+    FHC, _, _, lq, torch = mods
+    g = golden["cfg1"]
+    dev = lambda a: torch.tensor(arr(a), device="cuda")
+    P, K = FHC.ricatti_recursion(dev(g["A"]), dev(g["B"]), dev(g["Q"]), dev(g["R"]), dev(g["Q"]), 5)
+    assert isinstance(K[0], torch.Tensor) and K[0].is_cuda and K[0].shape == (1, 2)
+    with pytest.raises(ValueError):
+        lq.riccati(dev(g["A"]), dev(g["B"]), dev(np.eye(3)), dev([[0.1]]), dev(g["Q"]), 5)
+    with pytest.raises(ValueError):
+        lq.riccati(dev(g["A"]).cpu(), dev(g["B"]), dev(g["Q"]), dev([[0.1]]), dev(g["Q"]), 5)
+    with pytest.raises(IndexError):  # prediction beyond the available gains, as gains[t] would raise
+        lq.lq_rollout(dev(g["A"]), dev(g["B"]), torch.stack(K), dev(g["x0"]), 10, gain_offset=1, gain_step=1)
+    # N = 0: P = [P_f], K = []
+    P0, K0 = FHC.ricatti_recursion(arr(g["A"]), arr(g["B"]), arr(g["Q"]), arr(g["R"]), arr(g["Q"]), 0)
+    assert len(P0) == 1 and len(K0) == 0
