@@ -135,11 +135,19 @@ def test_cfg2a_golden_batched_shared_model(mods, golden):
 def test_cfg2b_golden_per_scenario_models(mods, golden):
     FHC, _, _, lq, torch = mods
     g = golden["cfg2b"]
-    A, B, Q, R = arr(g["A"]), arr(g["B"]), arr(g["Q"]), arr(g["R"])
-    P, K = FHC.ricatti_recursion(A, B, Q, R, Q, g["N"])  # batched leading dim
-    assert K[0].shape == (A.shape[0], 1, 4)
-    np.testing.assert_allclose(np.array(K), arr(g["K"]), rtol=RTOL64, atol=1e-12)
-    np.testing.assert_allclose(np.array(P), arr(g["P"]), rtol=RTOL64, atol=1e-12)
+    A, B, Q, R, x0 = arr(g["A"]), arr(g["B"]), arr(g["Q"]), arr(g["R"]), arr(g["x0"])
+    nb = A.shape[0]
+    P, K = FHC.ricatti_recursion(A, B, Q, R.reshape(-1, 1, 1), Q, g["N"])  # batched leading dim
+    assert K[0].shape == (nb, 1, 4)
+    Kg = arr(g["K"]).transpose(1, 0, 2, 3)  # golden is [scenario][stage]
+    Pg = arr(g["P"]).transpose(1, 0, 2, 3)
+    np.testing.assert_allclose(np.array(K), Kg, rtol=RTOL64, atol=1e-12)
+    np.testing.assert_allclose(np.array(P), Pg, rtol=RTOL64, atol=1e-12)
+    # per-scenario closed loop with gains[0] (reference: one AutoCruising.simulate per scenario)
+    dev = lambda a: torch.tensor(a, dtype=torch.float64, device="cuda")
+    res = lq.lq_rollout(dev(A), dev(B), dev(np.array(K)), dev(x0.T.copy()), 21, gain_offset=0, gain_step=0)
+    Xg = arr(g["simulate_21"])[:, :, 0, :]  # [scenario][n][T]
+    np.testing.assert_allclose(res["X"].permute(2, 1, 0).cpu().numpy(), Xg, rtol=1e-8, atol=1e-10)
 
 
 def test_n12_m4_generic_kernel(mods, golden):
