@@ -1,6 +1,8 @@
 // LQ path kernels and their C ABI: mpc_riccati (K1), mpc_lq_rollout (K2), mpc_lq_solve (K1+K2).
 // sm_100a only.  See include/mpc_b200.h for the contract and the reference lines each entry
 // point replaces.
+#include <stdlib.h>
+
 #include "lq_core.cuh"
 
 namespace mpc {
@@ -317,7 +319,13 @@ static int launch_lq_solve(const LqSolveArgs<T>& a, cudaStream_t st) {
                   stride_ok(a.sR, NU * NU) && stride_ok(a.sPf, NX * NX);
   int threads = kLqThreads;
   size_t per_thread = sizeof(T) * (size_t)a.N * NU * NX;
-  while (threads > 32 && per_thread * threads > 100 * 1024) threads >>= 1;
+  // the on-chip gains bound the resident warps: keep each CTA's slice <= ~44 KB so that >= 5 CTAs
+  // share the 227 KB of an SM
+  while (threads > 32 && per_thread * threads > 44 * 1024) threads >>= 1;
+  if (const char* env = getenv("MPC_LQ_THREADS")) {
+    const int t = atoi(env);
+    if (t >= 32 && t <= kLqThreads && t % 32 == 0) threads = t;
+  }
   const size_t smem = per_thread * threads;
   MPC_REQUIRE(smem <= 220 * 1024, MPC_ERR_SHAPE, "mpc_lq_solve: horizon %d too long for on-chip gains", a.N);
   const unsigned grid = (unsigned)((a.batch + threads - 1) / threads);

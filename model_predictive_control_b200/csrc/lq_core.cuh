@@ -255,44 +255,39 @@ MPC_HD void lq_solve_body(const LqSolveArgs<T>& a, int64_t b, T* Ks, int kstride
   constexpr int AMM = AL ? RowAlign<T, NU * NU>::value : ES;
   constexpr int AN = AL ? RowAlign<T, NX>::value : ES;
   constexpr int AM = AL ? RowAlign<T, NU>::value : ES;
-  T A[NX * NX], B[NX * NU], Q[NX * NX], R[NU * NU];
+  T A[NX * NX], B[NX * NU];
   load_row<T, NX * NX, ANN>(a.A + b * a.sA, A);
   load_row<T, NX * NU, ANM>(a.B + b * a.sB, B);
-  load_row<T, NX * NX, ANN>(a.Q + b * a.sQ, Q);
-  load_row<T, NU * NU, AMM>(a.R + b * a.sR, R);
+  T x[NX], xn[NX], u[NU];
+  load_row<T, NX, AN>(a.x0 + b * NX, x);
+  store_row<T, NX, AN>(a.X + b * NX, x);
   {
-    T P[NX * NX], K[NU * NX];
+    T Q[NX * NX], R[NU * NU], P[NX * NX], K[NU * NX];
+    load_row<T, NX * NX, ANN>(a.Q + b * a.sQ, Q);
+    load_row<T, NU * NU, AMM>(a.R + b * a.sR, R);
     load_row<T, NX * NX, ANN>(a.Pf + b * a.sPf, P);
     for (int k = a.N - 1; k >= 0; --k) {
-      riccati_stage<T, NX, NU>(A, B, Q, R, P, K);
+      riccati_stage<T, NX, NU, true>(A, B, Q, R, P, K);
 #pragma unroll
       for (int e = 0; e < NU * NX; ++e) Ks[(k * (NU * NX) + e) * kstride] = K[e];
       if (a.K) store_row<T, NU * NX, ANM>(a.K + ((int64_t)k * a.batch + b) * (NU * NX), K);
     }
     if (a.P0) store_row<T, NX * NX, ANN>(a.P0 + b * (NX * NX), P);
+    // optimal cost exactly as the reference evaluates it: V_N(x0) = x0' P_0 x0 (FHC.py:123-124)
+    a.V[b] = quad<T, NX>(P, x);
   }
-  T x[NX], xn[NX], u[NU], V = T(0);
-  load_row<T, NX, AN>(a.x0 + b * NX, x);
-  store_row<T, NX, AN>(a.X + b * NX, x);
   for (int k = 0; k < a.N; ++k) {
     T K[NU * NX];
 #pragma unroll
     for (int e = 0; e < NU * NX; ++e) K[e] = Ks[(k * (NU * NX) + e) * kstride];
     mv<T, NU, NX, false>(K, x, u);
     store_row<T, NU, AM>(a.U + ((int64_t)k * a.batch + b) * NU, u);
-    V += quad<T, NX>(Q, x) + quad<T, NU>(R, u);
     mv<T, NX, NX, false>(A, x, xn);
     mv<T, NX, NU, true>(B, u, xn);
 #pragma unroll
     for (int i = 0; i < NX; ++i) x[i] = xn[i];
     store_row<T, NX, AN>(a.X + ((int64_t)(k + 1) * a.batch + b) * NX, x);
   }
-  {
-    T Pf[NX * NX];
-    load_row<T, NX * NX, ANN>(a.Pf + b * a.sPf, Pf);
-    V += quad<T, NX>(Pf, x);
-  }
-  a.V[b] = V;
 }
 
 }  // namespace mpc

@@ -89,7 +89,7 @@ MPC_HD void neg_solve(T* S, T* G) {
 //   W = P A;  G = B'W;  PB = P B;  S = R + B'PB;  K = -S^-1 G;  W += PB K;  P = Q + A'W
 // which is algebraically  K = -(R+B'PB)^-1 B'PA,  P = Q + A'PA + A'PB K  and costs
 // 4n^3 + 6n^2 m + 4 n m^2 + O(m^3) flops (F_ric).
-template <typename T, int NX, int NU>
+template <typename T, int NX, int NU, bool SYM = false>
 MPC_HD void riccati_stage(const T* A, const T* B, const T* Q, const T* R, T* P,
                                               T* K) {
   T W[NX * NX];
@@ -103,9 +103,24 @@ MPC_HD void riccati_stage(const T* A, const T* B, const T* Q, const T* R, T* P,
   mtm<T, NU, NX, NU, true>(B, PB, S);
   neg_solve<T, NU, NX>(S, K);
   mm<T, NX, NU, NX, true>(PB, K, W);
+  if constexpr (SYM) {
+    // P is symmetric in exact arithmetic: form the upper triangle of Q + A'W and mirror it.
+    // (The reference does not symmetrise; the difference is rounding-level, ~1e-16 relative.)
 #pragma unroll
-  for (int i = 0; i < NX * NX; ++i) P[i] = Q[i];
-  mtm<T, NX, NX, NX, true>(A, W, P);
+    for (int i = 0; i < NX; ++i)
+#pragma unroll
+      for (int j = i; j < NX; ++j) {
+        T acc = Q[i * NX + j];
+#pragma unroll
+        for (int k = 0; k < NX; ++k) acc = fma_<T>(A[k * NX + i], W[k * NX + j], acc);
+        P[i * NX + j] = acc;
+        P[j * NX + i] = acc;
+      }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NX * NX; ++i) P[i] = Q[i];
+    mtm<T, NX, NX, NX, true>(A, W, P);
+  }
 }
 
 }  // namespace mpc
