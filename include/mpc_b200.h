@@ -121,6 +121,34 @@ int mpc_lq_solve(const void* A, int64_t sA, const void* B, int64_t sB, const voi
                  mpc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * K4  batched box-constrained linear MPC QP
+ *     min  sum_{k<N} x_k'Q x_k + u_k'R u_k + x_N'Pf x_N
+ *     s.t. x_{k+1} = A_k x_k + B_k u_k + c_k,  u_lo <= u_k <= u_hi (k<N),  x_lo <= x_k <= x_hi (1<=k<=N)
+ * i.e. the QP posed by the reference's Problem data (session_2/problem.py:8-24,
+ * session_3/problem.py:12-28; the reference has no solver for it) and, with ltv = 1, the linearised
+ * QP of session 4's closed loop (session_4/session4_sol.py:158-217 cost/bounds).  Outputs follow the
+ * reference's per-solve log schema ControllerLog (session_2/log.py:8-12): status (solver_success =
+ * status == MPC_SOLVED), X (state_prediction), U (input_prediction).
+ *   ltv = 0: A [n][n], B [n][m] shared by all scenarios and stages, c ignored
+ *   ltv = 1: A [N][n*n][batch], B [N][n*m][batch], c [N][n][batch]
+ *   Q, R, Pf, u_lo [m], u_hi [m], x_lo [n], x_hi [n] shared; |bound| >= 1e19 = unbounded
+ *   x0 [n][batch]; warm_U optional [N][m][batch] (start point; clamped into the box)
+ *   U [N][m][batch], X [N+1][n][batch], cost [batch], status [batch], iters [batch],
+ *   sat_u [N][m][batch] / sat_x [N][n][batch] optional int8: -1 at lower bound, +1 at upper, 0 free.
+ *   Inputs at an active bound are returned exactly equal to the bound.
+ *   ws: caller-owned workspace of mpc_boxqp_workspace_bytes(...) bytes.
+ * Method: Mehrotra predictor-corrector interior point, Newton systems solved by Riccati sweeps;
+ * float64 only (MPC_F32 -> MPC_ERR_UNSUPPORTED).  Supported (n, m): (2,1), (4,1), (4,2).
+ */
+int64_t mpc_boxqp_workspace_bytes(int64_t batch, int n, int m, int N, int dtype);
+int mpc_boxqp_solve(const void* A, const void* B, const void* c, int ltv, const void* Q, const void* R,
+                    const void* Pf, const void* u_lo, const void* u_hi, const void* x_lo,
+                    const void* x_hi, const void* x0, const void* warm_U, void* U, void* X, void* cost,
+                    int32_t* status, int32_t* iters, int8_t* sat_u, int8_t* sat_x, void* ws,
+                    int64_t ws_bytes, int64_t batch, int n, int m, int N, int max_iter, double eps,
+                    int dtype, mpc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Device FP pipe probe: runs a register-resident FMA chain kernel and reports achieved
  * FLOP/s (2 flops per FMA).  Used by bench.py as the measured FP64 / FP32 vector-pipe roofline
  * denominator (MEASURED_PEAKS.json only carries HBM and bf16 tensor peaks).  Synchronises.

@@ -1,0 +1,131 @@
+"""Device-level box-constrained linear MPC QP solver (K4) on torch CUDA tensors.
+
+    min  sum_{k<N} x_k'Q x_k + u_k'R u_k + x_N'Pf x_N
+    s.t. x_{k+1} = A_k x_k + B_k u_k + c_k,  u_lo <= u_k <= u_hi,  x_lo <= x_k <= x_hi (k >= 1)
+
+The QP is the one posed by the reference's ``Problem`` data (session_2/problem.py:8-24,
+session_3/problem.py:12-28); results carry the fields of the reference's per-solve log
+(session_2/log.py:8-12).  Library layout is batch-contiguous: x0 [n, batch], U [N, m, batch],
+X [N+1, n, batch].
+"""
+from __future__ import annotations
+
+from ctypes import POINTER, c_double, c_int, c_int8, c_int32, c_int64, c_void_p
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+
+_lib.register("mpc_boxqp_workspace_bytes", c_int64, [c_int64, c_int, c_int, c_int, c_int])
+_lib.register("mpc_boxqp_solve", c_int,
+              [c_void_p] * 3 + [c_int] + [c_void_p] * 16 + [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int,
+                                                           c_double, c_int, c_void_p])
+
+BIG = 1e20  # "no bound"
+
+
+@dataclass
+class BoxQpResult:
+    """Batched counterpart of the reference's ControllerLog entry (session_2/log.py:10-12)."""
+    U: torch.Tensor        # input_prediction  [N, m, batch]
+    X: torch.Tensor        # state_prediction  [N+1, n, batch]
+    cost: torch.Tensor     # [batch]
+    status: torch.Tensor   # int32 [batch]: 1 solved, 2 max_iter, 3 infeasible
+    iters: torch.Tensor    # int32 [batch]
+    sat_u: torch.Tensor    # int8 [N, m, batch]: -1 lower, +1 upper, 0 free
+    sat_x: torch.Tensor    # int8 [N, n, batch]
+
+    @property
+    def solver_success(self):
+        return self.status == _lib.MPC_SOLVED
+
+    @property
+    def input_prediction(self):   # [batch, N, m] view
+        return self.U.permute(2, 0, 1)
+
+    @property
+    def state_prediction(self):   # [batch, N+1, n] view
+        return self.X.permute(2, 0, 1)
+
+
+class BoxQpWorkspace:
+    """Caller-owned scratch + outputs, reusable across solves of the same shape."""
+
+    def __init__(self, batch, n, m, N, device, sat=True):
+        dd = dict(dtype=torch.float64, device=device)
+        nbytes = _lib.lib().mpc_boxqp_workspace_bytes(batch, n, m, N, _lib.MPC_F64)
+        self.ws = torch.empty(max(nbytes // 8, 1), **dd)
+        self.nbytes = nbytes
+        self.U = torch.empty((N, m, batch), **dd)
+        self.X = torch.empty((N + 1, n, batch), **dd)
+        self.cost = torch.empty(batch, **dd)
+        self.status = torch.empty(batch, dtype=torch.int32, device=device)
+        self.iters = torch.empty(batch, dtype=torch.int32, device=device)
+        self.sat_u = torch.empty((N, m, batch), dtype=torch.int8, device=device) if sat else None
+        self.sat_x = torch.empty((N, n, batch), dtype=torch.int8, device=device) if sat else None
+        self.shape = (batch, n, m, N)
+
+
+def _vec(v, k, device, name):
+    t = torch.as_tensor(v, dtype=torch.float64, device=device).reshape(-1)
+    if t.numel() == 1 and k > 1:
+        t = t.expand(k)
+    if t.numel() != k:
+        raise ValueError(f"{name} must have {k} entries, got {t.numel()}")
+    t = torch.nan_to_num(t, posinf=BIG, neginf=-BIG)
+    return t.contiguous()
+
+
+def solve(A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi, c=None, warm_U=None, max_iter=60, eps=1e-9,
+          workspace=None):
+    """Solve ``batch`` QPs.  x0 [n, batch] (CUDA, float64).
+
+    LTI: A [n,n], B [n,m] shared (c must be None).
+    LTV: A [N, n*n, batch], B [N, n*m, batch], c [N, n, batch] per scenario and stage.
+    Bounds are per coordinate, shared by all stages and scenarios; +-inf = unbounded.
+    """
+    _lib.require_cuda(A, B, Q, R, Pf, x0)
+    if x0.dtype != torch.float64:
+        raise ValueError("the box-QP solver computes in float64 (the reference's arithmetic)")
+    dev = x0.device
+    N = int(N)
+    ltv = A.dim() == 3
+    if ltv:
+        n = x0.shape[0]
+        m = B.shape[1] // n
+        batch = x0.shape[1]
+        if tuple(A.shape) != (N, n * n, batch) or tuple(B.shape) != (N, n * m, batch) or c is None or \
+                tuple(c.shape) != (N, n, batch):
+            raise ValueError("LTV model must be A [N,n*n,batch], B [N,n*m,batch], c [N,n,batch]")
+        c = c.contiguous()
+    else:
+        n, m = B.shape
+        if c is not None:
+            raise ValueError("affine term c is only supported with per-scenario stage matrices")
+        if x0.dim() != 2 or x0.shape[0] != n:
+            raise ValueError(f"x0 must be (n={n}, batch), got {tuple(x0.shape)}")
+        batch = x0.shape[1]
+    A, B, x0 = A.contiguous(), B.contiguous(), x0.contiguous()
+    Q, R, Pf = (torch.as_tensor(M, dtype=torch.float64, device=dev).contiguous() for M in (Q, R, Pf))
+    if tuple(Q.shape) != (n, n) or tuple(R.shape) != (m, m) or tuple(Pf.shape) != (n, n):
+        raise ValueError("Q, Pf must be (n,n) and R (m,m)")
+    ulo, uhi = _vec(u_lo, m, dev, "u_lo"), _vec(u_hi, m, dev, "u_hi")
+    xlo, xhi = _vec(x_lo, n, dev, "x_lo"), _vec(x_hi, n, dev, "x_hi")
+    if bool((ulo > uhi).any()) or bool((xlo > xhi).any()):
+        raise ValueError("lower bound above upper bound")
+    if warm_U is not None:
+        if tuple(warm_U.shape) != (N, m, batch):
+            raise ValueError(f"warm_U must be (N, m, batch) = {(N, m, batch)}")
+        warm_U = warm_U.contiguous()
+    w = workspace if workspace is not None else BoxQpWorkspace(batch, n, m, N, dev)
+    if w.shape != (batch, n, m, N):
+        raise ValueError(f"workspace was built for {w.shape}, need {(batch, n, m, N)}")
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().mpc_boxqp_solve(
+            _lib.ptr(A), _lib.ptr(B), _lib.ptr(c), 1 if ltv else 0, _lib.ptr(Q), _lib.ptr(R), _lib.ptr(Pf),
+            _lib.ptr(ulo), _lib.ptr(uhi), _lib.ptr(xlo), _lib.ptr(xhi), _lib.ptr(x0), _lib.ptr(warm_U),
+            _lib.ptr(w.U), _lib.ptr(w.X), _lib.ptr(w.cost), _lib.ptr(w.status), _lib.ptr(w.iters),
+            _lib.ptr(w.sat_u), _lib.ptr(w.sat_x), _lib.ptr(w.ws), w.nbytes, batch, n, m, N, int(max_iter),
+            float(eps), _lib.MPC_F64, _lib.stream(dev)))
+    return BoxQpResult(w.U, w.X, w.cost, w.status, w.iters, w.sat_u, w.sat_x)

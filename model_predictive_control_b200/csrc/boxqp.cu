@@ -1,0 +1,81 @@
+// K4 kernel + C ABI: batched box-constrained LQ-MPC QP (interior point with Riccati Newton solves).
+#include "boxqp_core.cuh"
+
+namespace mpc {
+
+constexpr int kQpThreads = 128;
+
+template <typename T, int NX, int NU>
+__global__ void __launch_bounds__(kQpThreads) boxqp_ipm_kernel(BoxQpArgs<T> a) {
+  using SH = BoxQpShared<NX, NU>;
+  __shared__ T sh[SH::total];
+  for (int i = threadIdx.x; i < SH::total; i += blockDim.x) {
+    T v;
+    if (i < SH::oB) v = a.ltv ? T(0) : a.A[i - SH::oA];
+    else if (i < SH::oQ) v = a.ltv ? T(0) : a.B[i - SH::oB];
+    else if (i < SH::oR) v = a.Q[i - SH::oQ];
+    else if (i < SH::oPf) v = a.R[i - SH::oR];
+    else if (i < SH::oLo) v = a.Pf[i - SH::oPf];
+    else if (i < SH::oLo + NU) v = a.u_lo[i - SH::oLo];
+    else if (i < SH::oHi) v = a.x_lo[i - SH::oLo - NU];
+    else if (i < SH::oHi + NU) v = a.u_hi[i - SH::oHi];
+    else v = a.x_hi[i - SH::oHi - NU];
+    sh[i] = v;
+  }
+  __syncthreads();
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.batch) return;
+  BoxQpIpm<T, NX, NU> ipm(a, sh, b);
+  ipm.solve();
+}
+
+template <typename T, int NX, int NU>
+static int launch_boxqp(const BoxQpArgs<T>& a, cudaStream_t st) {
+  const unsigned grid = (unsigned)((a.batch + kQpThreads - 1) / kQpThreads);
+  boxqp_ipm_kernel<T, NX, NU><<<grid, kQpThreads, 0, st>>>(a);
+  return check_launch("boxqp_ipm_kernel");
+}
+
+}  // namespace mpc
+
+using namespace mpc;
+
+extern "C" int64_t mpc_boxqp_workspace_bytes(int64_t batch, int n, int m, int N, int dtype) {
+  if (batch < 0 || n < 1 || m < 1 || N < 1) return 0;
+  const int64_t es = dtype == MPC_F32 ? 4 : 8;
+  return boxqp_ws_elems(n, m, N) * batch * es;
+}
+
+extern "C" int mpc_boxqp_solve(const void* A, const void* B, const void* c, int ltv, const void* Q,
+                               const void* R, const void* Pf, const void* u_lo, const void* u_hi,
+                               const void* x_lo, const void* x_hi, const void* x0, const void* warm_U,
+                               void* U, void* X, void* cost, int32_t* status, int32_t* iters,
+                               int8_t* sat_u, int8_t* sat_x, void* ws, int64_t ws_bytes, int64_t batch,
+                               int n, int m, int N, int max_iter, double eps, int dtype,
+                               mpc_stream_t stream) {
+  MPC_REQUIRE(dtype == MPC_F64 || dtype == MPC_F32, MPC_ERR_DTYPE, "mpc_boxqp_solve: unknown dtype %d", dtype);
+  MPC_REQUIRE(dtype == MPC_F64, MPC_ERR_UNSUPPORTED,
+              "mpc_boxqp_solve: the interior-point iteration runs in float64 only (barrier weights span > 1e10)");
+  MPC_REQUIRE(n >= 1 && n <= MPC_MAX_NX && m >= 1 && m <= MPC_MAX_NU, MPC_ERR_SHAPE, "mpc_boxqp_solve: bad (n=%d, m=%d)", n, m);
+  MPC_REQUIRE(N >= 1 && batch >= 0 && max_iter >= 1, MPC_ERR_SHAPE, "mpc_boxqp_solve: bad N / batch / max_iter");
+  MPC_REQUIRE(A && B && Q && R && Pf && u_lo && u_hi && x_lo && x_hi && x0 && U && X && cost && status && iters,
+              MPC_ERR_NULL, "mpc_boxqp_solve: null pointer");
+  MPC_REQUIRE(!ltv || c, MPC_ERR_NULL, "mpc_boxqp_solve: ltv model needs c");
+  if (batch == 0) return MPC_OK;
+  MPC_REQUIRE(ws && ws_bytes >= mpc_boxqp_workspace_bytes(batch, n, m, N, dtype), MPC_ERR_WORKSPACE,
+              "mpc_boxqp_solve: workspace too small (%lld < %lld bytes)", (long long)ws_bytes,
+              (long long)mpc_boxqp_workspace_bytes(batch, n, m, N, dtype));
+  for (const void* p : {A, B, c, Q, R, Pf, u_lo, u_hi, x_lo, x_hi, x0, warm_U, (const void*)U, (const void*)X,
+                        (const void*)cost, (const void*)ws})
+    MPC_REQUIRE(!p || aligned(p, 8), MPC_ERR_ALIGN, "mpc_boxqp_solve: misaligned pointer");
+  BoxQpArgs<double> a{(const double*)A, (const double*)B, (const double*)c, ltv ? 1 : 0, (const double*)Q,
+                      (const double*)R, (const double*)Pf, (const double*)u_lo, (const double*)u_hi,
+                      (const double*)x_lo, (const double*)x_hi, (const double*)x0, (const double*)warm_U,
+                      (double*)U, (double*)X, (double*)cost, status, iters, sat_u, sat_x, (double*)ws, batch, N,
+                      max_iter, eps};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 2 && m == 1) return launch_boxqp<double, 2, 1>(a, st);
+  if (n == 4 && m == 1) return launch_boxqp<double, 4, 1>(a, st);
+  if (n == 4 && m == 2) return launch_boxqp<double, 4, 2>(a, st);
+  return fail(MPC_ERR_UNSUPPORTED, "mpc_boxqp_solve: no kernel instantiated for n=%d m=%d", n, m);
+}

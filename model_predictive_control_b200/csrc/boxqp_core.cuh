@@ -1,0 +1,550 @@
+// K4: per-scenario body of the box-constrained LQ-MPC QP solver.
+//
+//   min  sum_{k<N} x_k'Q x_k + u_k'R u_k + x_N'Pf x_N
+//   s.t. x_{k+1} = A_k x_k + B_k u_k + c_k,  u_lo <= u_k <= u_hi,  x_lo <= x_{k+1} <= x_hi
+//
+// (the QP posed by the reference's session_2/problem.py:8-24 and session_3/problem.py:12-28, and --
+// with per-scenario stage matrices A_k, B_k, c_k -- the linearised QP of session 4's closed loop,
+// session_4/session4_sol.py:158-217).  The reference ships no solver for it.
+//
+// Method: Mehrotra predictor-corrector interior point.  With z_k = (u_k, x_{k+1}), slacks s and
+// multipliers lam for every finite bound, each Newton system (residual form, unknown dz)
+//     dz = argmin 1/2 dz'(H + Sigma) dz - rhs'dz   s.t. dx_{k+1} = A_k dx_k + B_k du_k, dx_0 = 0
+//     Sigma = lam_l/s_l + lam_u/s_u,   rhs = -H z + (sig mu - cc_l)/s_l - Sigma_l r_l - (sig mu - cc_u)/s_u + Sigma_u r_u
+// is an unconstrained LQ problem with stage-varying diagonal weight updates, solved by one
+// backward Riccati sweep (factorisation + feed-forward) and one forward rollout; the corrector
+// reuses the stored gains.  The iterate z always satisfies the dynamics exactly (it starts from a
+// rollout and moves along dynamics-consistent directions).  In residual form every term of rhs
+// stays O(lam), so the rounding error of the huge barrier weights (Sigma ~ 1e12) scales with |dz|
+// and vanishes at the solution.  A first-order (projected-gradient / ADMM) iteration was evaluated in
+// oracle/boxqp.py (admm_riccati): 600-2000+ iterations for 1e-6 parity on the session-2 data versus
+// ~15 here, so the interior-point iteration is the one that ships.
+//
+// One thread per scenario.  All per-scenario state lives in a caller-provided workspace laid out
+// [stage][element][batch] (batch-contiguous), so every access of a warp is one coalesced row.
+// The body is __host__ __device__: tests/harness runs it on the CPU against oracle/boxqp.py.
+#pragma once
+
+#include "smallmat.cuh"
+
+namespace mpc {
+
+constexpr double kBigBound = 1e19;  // |bound| >= kBigBound means "no bound"
+
+template <typename T>
+struct BoxQpArgs {
+  const T *A, *B, *c;  // ltv == 0: shared A [n][n], B [n][m], c null
+                       // ltv == 1: A [N][n*n][batch], B [N][n*m][batch], c [N][n][batch]
+  int ltv;
+  const T *Q, *R, *Pf;                  // shared
+  const T *u_lo, *u_hi, *x_lo, *x_hi;   // shared [m], [m], [n], [n]
+  const T* x0;                          // [n][batch]
+  const T* warm_U;                      // optional [N][m][batch]
+  T* U;                                 // [N][m][batch]
+  T* X;                                 // [N+1][n][batch]
+  T* cost;                              // [batch]
+  int32_t* status;                      // [batch]
+  int32_t* iters;                       // [batch]
+  int8_t* sat_u;                        // optional [N][m][batch]: -1 lower, +1 upper, 0 free
+  int8_t* sat_x;                        // optional [N][n][batch]
+  T* ws;                                // workspace, boxqp_ws_elems(n, m, N) * batch elements
+  int64_t batch;
+  int N;
+  int max_iter;
+  T eps;
+};
+
+// workspace elements per scenario
+inline int64_t boxqp_ws_elems(int n, int m, int N) {
+  const int d = n + m;
+  return (int64_t)N * (8 * d + m * n + m * m + m);
+}
+
+// shared-parameter block (shared memory on the device)
+template <int NX, int NU>
+struct BoxQpShared {
+  static constexpr int D = NX + NU;
+  static constexpr int oA = 0;
+  static constexpr int oB = oA + NX * NX;
+  static constexpr int oQ = oB + NX * NU;
+  static constexpr int oR = oQ + NX * NX;
+  static constexpr int oPf = oR + NU * NU;
+  static constexpr int oLo = oPf + NX * NX;  // [u_lo | x_lo]
+  static constexpr int oHi = oLo + D;        // [u_hi | x_hi]
+  static constexpr int total = oHi + D;
+};
+
+template <typename T, int NX, int NU>
+struct BoxQpIpm {
+  static constexpr int D = NX + NU;
+  using SH = BoxQpShared<NX, NU>;
+
+  const BoxQpArgs<T>& a;
+  const T* sh;
+  int64_t b, bs;
+  T mu0;  // initial barrier parameter = max(1, max|Q|, max|R|)
+  // workspace sections
+  T *z, *sl, *su, *ll, *lu, *zh, *ccl, *ccu, *Kw, *Sw, *dw;  // zh holds the Newton direction dz
+
+  MPC_HD BoxQpIpm(const BoxQpArgs<T>& args, const T* shared, int64_t scenario)
+      : a(args), sh(shared), b(scenario), bs(args.batch) {
+    const int64_t sec = (int64_t)a.N * D * bs;
+    z = a.ws;
+    sl = z + sec;
+    su = sl + sec;
+    ll = su + sec;
+    lu = ll + sec;
+    zh = lu + sec;
+    ccl = zh + sec;
+    ccu = ccl + sec;
+    Kw = ccu + sec;
+    Sw = Kw + (int64_t)a.N * NU * NX * bs;
+    dw = Sw + (int64_t)a.N * NU * NU * bs;
+    mu0 = T(1);
+    for (int i = 0; i < NX * NX; ++i) {
+      const T v = sh[SH::oQ + i] < T(0) ? -sh[SH::oQ + i] : sh[SH::oQ + i];
+      mu0 = v > mu0 ? v : mu0;
+    }
+    for (int i = 0; i < NU * NU; ++i) {
+      const T v = sh[SH::oR + i] < T(0) ? -sh[SH::oR + i] : sh[SH::oR + i];
+      mu0 = v > mu0 ? v : mu0;
+    }
+  }
+
+  MPC_HD int64_t ix(int k, int i, int per) const { return ((int64_t)k * per + i) * bs + b; }
+  MPC_HD bool hasl(int i) const { return sh[SH::oLo + i] > T(-kBigBound); }
+  MPC_HD bool hasu(int i) const { return sh[SH::oHi + i] < T(kBigBound); }
+  MPC_HD T lo(int i) const { return sh[SH::oLo + i]; }
+  MPC_HD T hi(int i) const { return sh[SH::oHi + i]; }
+
+  MPC_HD void load_stage(int k, T* A, T* B, T* c) const {
+    if (a.ltv) {
+#pragma unroll
+      for (int i = 0; i < NX * NX; ++i) A[i] = a.A[ix(k, i, NX * NX)];
+#pragma unroll
+      for (int i = 0; i < NX * NU; ++i) B[i] = a.B[ix(k, i, NX * NU)];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) c[i] = a.c[ix(k, i, NX)];
+    } else {
+#pragma unroll
+      for (int i = 0; i < NX * NX; ++i) A[i] = sh[SH::oA + i];
+#pragma unroll
+      for (int i = 0; i < NX * NU; ++i) B[i] = sh[SH::oB + i];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) c[i] = T(0);
+    }
+  }
+
+  // x+ = A x + B u + c
+  MPC_HD static void step(const T* A, const T* B, const T* c, const T* x, const T* u, T* xn) {
+#pragma unroll
+    for (int i = 0; i < NX; ++i) xn[i] = c[i];
+    mv<T, NX, NX, true>(A, x, xn);
+    mv<T, NX, NU, true>(B, u, xn);
+  }
+
+  // ---- start point: inputs clamped into their box, states by rollout, slacks >= 1, lam = mu0/s
+  MPC_HD void init() {
+    T x[NX], xn[NX], u[NU], A[NX * NX], B[NX * NU], c[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) x[i] = a.x0[i * bs + b];
+    for (int k = 0; k < a.N; ++k) {
+      load_stage(k, A, B, c);
+#pragma unroll
+      for (int j = 0; j < NU; ++j) {
+        T v = a.warm_U ? a.warm_U[ix(k, j, NU)] : T(0);
+        v = v < lo(j) ? lo(j) : v;
+        v = v > hi(j) ? hi(j) : v;
+        u[j] = v;
+      }
+      step(A, B, c, x, u, xn);
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        const T zi = i < NU ? u[i] : xn[i - NU];
+        T s_l = T(1), s_u = T(1), l_l = T(0), l_u = T(0);
+        if (hasl(i)) {
+          s_l = zi - lo(i);
+          s_l = s_l > T(1) ? s_l : T(1);
+          l_l = mu0 / s_l;
+        }
+        if (hasu(i)) {
+          s_u = hi(i) - zi;
+          s_u = s_u > T(1) ? s_u : T(1);
+          l_u = mu0 / s_u;
+        }
+        const int64_t o = ix(k, i, D);
+        z[o] = zi;
+        sl[o] = s_l;
+        su[o] = s_u;
+        ll[o] = l_l;
+        lu[o] = l_u;
+        ccl[o] = T(0);
+        ccu[o] = T(0);
+      }
+#pragma unroll
+      for (int i = 0; i < NX; ++i) x[i] = xn[i];
+    }
+  }
+
+  // ---- backward sweep: (factorisation and) feed-forward terms of the Newton step.
+  // rhs_i = -(H z)_i + (sig_mu - cc_l)/s_l - Sigma_l r_l - (sig_mu - cc_u)/s_u + Sigma_u r_u
+  template <bool FACTOR>
+  MPC_HD void backward(T sig_mu) {
+    T Pacc[NX * NX], pacc[NX];
+#pragma unroll
+    for (int i = 0; i < NX * NX; ++i) Pacc[i] = sh[SH::oPf + i];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) pacc[i] = T(0);
+    for (int k = a.N - 1; k >= 0; --k) {
+      T sig[D], rhs[D], zk[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) zk[i] = z[ix(k, i, D)];
+      // -(H z): inputs weighted by R, state x_{k+1} by Q (Pf for the last stage)
+      {
+        const T* Qx = sh + (k == a.N - 1 ? SH::oPf : SH::oQ);
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+          T acc = T(0);
+#pragma unroll
+          for (int j = 0; j < NU; ++j) acc = fma_<T>(-sh[SH::oR + i * NU + j], zk[j], acc);
+          rhs[i] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+          T acc = T(0);
+#pragma unroll
+          for (int j = 0; j < NX; ++j) acc = fma_<T>(-Qx[i * NX + j], zk[NU + j], acc);
+          rhs[NU + i] = acc;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        const int64_t o = ix(k, i, D);
+        T sg = T(0), r = rhs[i];
+        if (hasl(i)) {
+          const T s = sl[o], l = ll[o];
+          const T inv = T(1) / s;
+          const T cc = FACTOR ? T(0) : ccl[o];
+          const T rl = zk[i] - lo(i) - s;
+          sg += l * inv;
+          r += (sig_mu - cc) * inv - l * inv * rl;
+        }
+        if (hasu(i)) {
+          const T s = su[o], l = lu[o];
+          const T inv = T(1) / s;
+          const T cc = FACTOR ? T(0) : ccu[o];
+          const T ru = hi(i) - zk[i] - s;
+          sg += l * inv;
+          r -= (sig_mu - cc) * inv - l * inv * ru;
+        }
+        sig[i] = sg;
+        rhs[i] = r;
+      }
+      T A[NX * NX], B[NX * NU], c[NX], K[NU * NX], Sinv[NU * NU];
+      load_stage(k, A, B, c);
+      if constexpr (FACTOR) {
+        // P = Pacc + diag(Sigma_x);  S = R + diag(Sigma_u) + B'PB;  K = -S^-1 B'PA;
+        // Pacc <- Q + A'(PA + PB K)
+#pragma unroll
+        for (int i = 0; i < NX; ++i) Pacc[i * NX + i] += sig[NU + i];
+        T PA[NX * NX], PB[NX * NU], S[NU * NU];
+        mm<T, NX, NX, NX, false>(Pacc, A, PA);
+        mm<T, NX, NX, NU, false>(Pacc, B, PB);
+#pragma unroll
+        for (int i = 0; i < NU * NU; ++i) S[i] = sh[SH::oR + i];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) S[i * NU + i] += sig[i];
+        mtm<T, NU, NX, NU, true>(B, PB, S);
+        sym_inverse(S, Sinv);
+        T G[NU * NX];
+        mtm<T, NU, NX, NX, false>(B, PA, G);
+#pragma unroll
+        for (int i = 0; i < NU; ++i)
+#pragma unroll
+          for (int j = 0; j < NX; ++j) {
+            T acc = T(0);
+#pragma unroll
+            for (int l = 0; l < NU; ++l) acc = fma_<T>(Sinv[i * NU + l], G[l * NX + j], acc);
+            K[i * NX + j] = -acc;
+          }
+        mm<T, NX, NU, NX, true>(PB, K, PA);  // PA <- PA + PB K
+#pragma unroll
+        for (int i = 0; i < NX; ++i)
+#pragma unroll
+          for (int j = i; j < NX; ++j) {
+            T acc = sh[SH::oQ + i * NX + j];
+#pragma unroll
+            for (int l = 0; l < NX; ++l) acc = fma_<T>(A[l * NX + i], PA[l * NX + j], acc);
+            Pacc[i * NX + j] = acc;
+            Pacc[j * NX + i] = acc;
+          }
+#pragma unroll
+        for (int i = 0; i < NU * NX; ++i) Kw[ix(k, i, NU * NX)] = K[i];
+#pragma unroll
+        for (int i = 0; i < NU * NU; ++i) Sw[ix(k, i, NU * NU)] = Sinv[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < NU * NX; ++i) K[i] = Kw[ix(k, i, NU * NX)];
+#pragma unroll
+        for (int i = 0; i < NU * NU; ++i) Sinv[i] = Sw[ix(k, i, NU * NU)];
+      }
+      // h = -(rhs_x + pacc);  gu = rhs_u - B'h;  dff = Sinv gu;  pacc <- -A'h + K'gu
+      T h[NX], gu[NU], dff[NU];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) h[i] = -(rhs[NU + i] + pacc[i]);
+#pragma unroll
+      for (int j = 0; j < NU; ++j) {
+        T acc = rhs[j];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) acc = fma_<T>(-B[i * NU + j], h[i], acc);
+        gu[j] = acc;
+      }
+      mv<T, NU, NU, false>(Sinv, gu, dff);
+#pragma unroll
+      for (int j = 0; j < NU; ++j) dw[ix(k, j, NU)] = dff[j];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        T acc = T(0);
+#pragma unroll
+        for (int l = 0; l < NX; ++l) acc = fma_<T>(-A[l * NX + i], h[l], acc);
+#pragma unroll
+        for (int j = 0; j < NU; ++j) acc = fma_<T>(K[j * NX + i], gu[j], acc);
+        pacc[i] = acc;
+      }
+    }
+  }
+
+  // inverse of a small symmetric positive definite matrix
+  MPC_HD static void sym_inverse(const T* S, T* Si) {
+    if constexpr (NU == 1) {
+      Si[0] = T(1) / S[0];
+    } else if constexpr (NU == 2) {
+      const T det = S[0] * S[3] - S[1] * S[2];
+      const T id = T(1) / det;
+      Si[0] = S[3] * id;
+      Si[1] = -S[1] * id;
+      Si[2] = -S[2] * id;
+      Si[3] = S[0] * id;
+    } else {
+      // Gauss-Jordan without pivoting (SPD)
+      T M[NU * NU];
+#pragma unroll
+      for (int i = 0; i < NU * NU; ++i) {
+        M[i] = S[i];
+        Si[i] = (i / NU == i % NU) ? T(1) : T(0);
+      }
+#pragma unroll
+      for (int p = 0; p < NU; ++p) {
+        const T inv = T(1) / M[p * NU + p];
+#pragma unroll
+        for (int j = 0; j < NU; ++j) {
+          M[p * NU + j] *= inv;
+          Si[p * NU + j] *= inv;
+        }
+#pragma unroll
+        for (int r = 0; r < NU; ++r) {
+          if (r == p) continue;
+          const T f = M[r * NU + p];
+#pragma unroll
+          for (int j = 0; j < NU; ++j) {
+            M[r * NU + j] = fma_<T>(-f, M[p * NU + j], M[r * NU + j]);
+            Si[r * NU + j] = fma_<T>(-f, Si[p * NU + j], Si[r * NU + j]);
+          }
+        }
+      }
+    }
+  }
+
+  struct Acc {
+    T amin, s0, s1, s2, dzmax, rp;
+  };
+
+  // ---- forward sweep: dz by rollout with the stored gains; per element the slack / multiplier
+  // directions.  AFFINE: stores cc = ds*dlam (second-order term) and accumulates the sums that give
+  // mu_aff for any step length.  Otherwise stores dz and accumulates the step ratios / norms.
+  template <bool AFFINE>
+  MPC_HD void forward(T sig_mu, Acc& acc) {
+    T x[NX], xn[NX], u[NU], A[NX * NX], B[NX * NU], c[NX];
+    acc.amin = T(1e30);
+    acc.s0 = acc.s1 = acc.s2 = acc.dzmax = acc.rp = T(0);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) x[i] = T(0);  // dx_0 = 0
+    for (int k = 0; k < a.N; ++k) {
+      load_stage(k, A, B, c);
+      T K[NU * NX];
+#pragma unroll
+      for (int i = 0; i < NU * NX; ++i) K[i] = Kw[ix(k, i, NU * NX)];
+#pragma unroll
+      for (int j = 0; j < NU; ++j) u[j] = dw[ix(k, j, NU)];
+      mv<T, NU, NX, true>(K, x, u);
+      mv<T, NX, NX, false>(A, x, xn);
+      mv<T, NX, NU, true>(B, u, xn);
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        const int64_t o = ix(k, i, D);
+        const T dz = i < NU ? u[i] : xn[i - NU];
+        const T zi = z[o];
+        if (!AFFINE) {
+          zh[o] = dz;
+          const T ad = dz < T(0) ? -dz : dz;
+          acc.dzmax = ad > acc.dzmax ? ad : acc.dzmax;
+        }
+        if (hasl(i)) {
+          const T s = sl[o], l = ll[o];
+          const T r = zi - lo(i) - s;
+          const T ds = dz + r;
+          const T cc = AFFINE ? T(0) : ccl[o];
+          const T dl = (sig_mu - cc) / s - l - l / s * ds;
+          if (ds < T(0)) { const T q = -s / ds; acc.amin = q < acc.amin ? q : acc.amin; }
+          if (dl < T(0)) { const T q = -l / dl; acc.amin = q < acc.amin ? q : acc.amin; }
+          acc.s0 += s * l;
+          acc.s1 += s * dl + l * ds;
+          acc.s2 += ds * dl;
+          if (AFFINE) ccl[o] = ds * dl;
+          const T ar = r < T(0) ? -r : r;
+          acc.rp = ar > acc.rp ? ar : acc.rp;
+        }
+        if (hasu(i)) {
+          const T s = su[o], l = lu[o];
+          const T r = hi(i) - zi - s;
+          const T ds = -dz + r;
+          const T cc = AFFINE ? T(0) : ccu[o];
+          const T dl = (sig_mu - cc) / s - l - l / s * ds;
+          if (ds < T(0)) { const T q = -s / ds; acc.amin = q < acc.amin ? q : acc.amin; }
+          if (dl < T(0)) { const T q = -l / dl; acc.amin = q < acc.amin ? q : acc.amin; }
+          acc.s0 += s * l;
+          acc.s1 += s * dl + l * ds;
+          acc.s2 += ds * dl;
+          if (AFFINE) ccu[o] = ds * dl;
+          const T ar = r < T(0) ? -r : r;
+          acc.rp = ar > acc.rp ? ar : acc.rp;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NX; ++i) x[i] = xn[i];
+    }
+  }
+
+  // ---- step: (z, s, lam) += alpha * direction; returns max |z|
+  MPC_HD T update(T sig_mu, T alpha) {
+    T zn = T(1);
+    for (int k = 0; k < a.N; ++k) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        const int64_t o = ix(k, i, D);
+        const T zi = z[o];
+        const T dz = zh[o];
+        if (hasl(i)) {
+          const T s = sl[o], l = ll[o];
+          const T ds = dz + (zi - lo(i) - s);
+          const T dl = (sig_mu - ccl[o]) / s - l - l / s * ds;
+          sl[o] = s + alpha * ds;
+          ll[o] = l + alpha * dl;
+        }
+        if (hasu(i)) {
+          const T s = su[o], l = lu[o];
+          const T ds = -dz + (hi(i) - zi - s);
+          const T dl = (sig_mu - ccu[o]) / s - l - l / s * ds;
+          su[o] = s + alpha * ds;
+          lu[o] = l + alpha * dl;
+        }
+        const T zn_i = zi + alpha * dz;
+        z[o] = zn_i;
+        const T az = zn_i < T(0) ? -zn_i : zn_i;
+        zn = az > zn ? az : zn;
+      }
+    }
+    return zn;
+  }
+
+  // ---- output: active set from the complementarity pairs, variables snapped onto active bounds,
+  // states by rollout of the snapped inputs, cost as the reference defines it.
+  MPC_HD void output(int status, int iters) {
+    T x[NX], xn[NX], u[NU], A[NX * NX], B[NX * NU], c[NX];
+    T cost = T(0);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      x[i] = a.x0[i * bs + b];
+      a.X[i * bs + b] = x[i];
+    }
+    for (int k = 0; k < a.N; ++k) {
+      load_stage(k, A, B, c);
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        const int64_t o = ix(k, i, D);
+        int sat = 0;
+        if (hasl(i) && ll[o] > sl[o]) sat = -1;
+        if (hasu(i) && lu[o] > su[o]) sat = 1;
+        if (i < NU) {
+          u[i] = sat < 0 ? lo(i) : (sat > 0 ? hi(i) : z[o]);
+          a.U[ix(k, i, NU)] = u[i];
+          if (a.sat_u) a.sat_u[ix(k, i, NU)] = (int8_t)sat;
+        } else if (a.sat_x) {
+          a.sat_x[ix(k, i - NU, NX)] = (int8_t)sat;
+        }
+      }
+      cost += quad<T, NX>(sh + SH::oQ, x) + quad<T, NU>(sh + SH::oR, u);
+      step(A, B, c, x, u, xn);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        x[i] = xn[i];
+        a.X[ix(k + 1, i, NX)] = x[i];
+      }
+    }
+    cost += quad<T, NX>(sh + SH::oPf, x);
+    a.cost[b] = cost;
+    a.status[b] = status;
+    a.iters[b] = iters;
+  }
+
+  MPC_HD void solve() {
+    int ncons = 0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) ncons += (hasl(i) ? 1 : 0) + (hasu(i) ? 1 : 0);
+    ncons *= a.N;
+    init();
+    int status = MPC_UNSOLVED, it = 0;
+    T rp = T(0), zn = T(1);
+    if (ncons == 0) {  // no finite bound: one Newton step is the LQ optimum
+      Acc acc;
+      backward<true>(T(0));
+      forward<false>(T(0), acc);
+      update(T(0), T(1));
+      status = MPC_SOLVED;
+      it = 1;
+    }
+    const T inv_nc = ncons ? T(1) / T(ncons) : T(0);
+    while (status == MPC_UNSOLVED && it < a.max_iter) {
+      ++it;
+      Acc acc;
+      backward<true>(T(0));
+      forward<true>(T(0), acc);
+      const T mu = acc.s0 * inv_nc;
+      const T a_aff = acc.amin < T(1) ? acc.amin : T(1);
+      const T mu_aff = (acc.s0 + a_aff * (acc.s1 + a_aff * acc.s2)) * inv_nc;
+      T ratio = mu_aff / (mu > T(1e-300) ? mu : T(1e-300));
+      T sigma = ratio * ratio * ratio;
+      sigma = sigma < T(1) ? sigma : T(1);
+      const T sig_mu = sigma * mu;
+      backward<false>(sig_mu);
+      forward<false>(sig_mu, acc);
+      T alpha = T(0.995) * acc.amin;
+      alpha = alpha < T(1) ? alpha : T(1);
+      zn = update(sig_mu, alpha);
+      const T mu_new = (acc.s0 + alpha * (acc.s1 + alpha * acc.s2)) * inv_nc;
+      rp = (T(1) - alpha) * acc.rp;
+      const bool done = (mu_new <= a.eps * mu0) && (rp <= a.eps * zn) && (alpha * acc.dzmax <= T(1e-6) * zn);
+      if (done) {
+        status = MPC_SOLVED;
+      } else if (!(alpha >= T(1e-6)) || !(mu_new <= T(1e15) * mu0)) {
+        // stalled: step length collapsed / barrier parameter exploded.  With a bound residual that
+        // cannot be closed the box and the dynamics do not meet: infeasible.
+        status = (rp <= T(1e-6) * zn) ? MPC_MAX_ITER : MPC_INFEASIBLE;
+      }
+    }
+    if (status == MPC_UNSOLVED) status = (rp <= T(1e-6) * zn) ? MPC_MAX_ITER : MPC_INFEASIBLE;
+    output(status, it);
+  }
+};
+
+}  // namespace mpc

@@ -1,0 +1,187 @@
+"""GPU parity of the box-constrained linear MPC QP (K4) against the exact CPU oracle
+(HiGHS active set + dense KKT refinement) and the numpy restatement of the GPU algorithm.
+Tolerance 1e-6 relative on U and X (north star, fp64); saturation patterns must be identical and
+saturated inputs exactly equal to their bound."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import boxqp as bq  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def mods():
+    import torch
+    from model_predictive_control_b200 import boxqp, problem, log
+    assert torch.cuda.is_available()
+    return boxqp, problem, log, torch
+
+
+def session_x0(rng, batch):
+    return np.stack([rng.uniform(-100, 0, batch), rng.uniform(-10, 15, batch)], 1)
+
+
+def check_against_exact(res_U, res_X, res_cost, status, sat_u, sat_x, ex_list, ulo, uhi):
+    n_checked = 0
+    for b, ex in enumerate(ex_list):
+        if ex["status"] == bq.MAX_ITER:  # oracle could not certify (degenerate active set)
+            continue
+        if ex["status"] == bq.INFEASIBLE:
+            assert status[b] == bq.INFEASIBLE
+            continue
+        assert status[b] == bq.SOLVED
+        su, sx = max(1.0, np.abs(ex["U"]).max()), max(1.0, np.abs(ex["X"]).max())
+        assert np.abs(res_U[b] - ex["U"]).max() <= 1e-6 * su
+        assert np.abs(res_X[b] - ex["X"]).max() <= 1e-6 * sx
+        assert abs(res_cost[b] - ex["cost"]) <= 1e-9 * abs(ex["cost"])
+        np.testing.assert_array_equal(sat_u[b], ex["sat_u"])
+        np.testing.assert_array_equal(sat_x[b], ex["sat_x"])
+        for j in range(len(ulo)):
+            assert np.all(res_U[b][:, j][ex["sat_u"][:, j] > 0] == uhi[j])
+            assert np.all(res_U[b][:, j][ex["sat_u"][:, j] < 0] == ulo[j])
+        n_checked += 1
+    return n_checked
+
+
+@pytest.mark.parametrize("which,N", [("Problem", 5), ("Problem", 30), ("Problem3", 30)])
+def test_session23_problem(mods, which, N):
+    boxqp, problem, log, torch = mods
+    prob = getattr(problem, which)(N=N)
+    oprob = (bq.Problem if which == "Problem" else bq.session3_problem)(N=N)
+    rng = np.random.default_rng(100 + N)
+    batch = 200
+    x0 = session_x0(rng, batch)
+    x0[0] = [-100.0, 0.0]
+    x0[1] = [-1.0, 14.0]
+    mpc = problem.LinearMPC(prob)
+    res = mpc.solve(x0)
+    assert res.input_prediction.shape == (batch, N, 1) and res.state_prediction.shape == (batch, N + 1, 2)
+    U = res.input_prediction.cpu().numpy(); X = res.state_prediction.cpu().numpy()
+    status = res.status.cpu().numpy()
+    ulo, uhi, xlo, xhi = bq.problem_bounds(oprob)
+    ex = [bq.solve_exact(oprob.A, oprob.B, oprob.Q, oprob.R, oprob.Q, N, x0[b], ulo, uhi, xlo, xhi) for b in range(batch)]
+    n = check_against_exact(U, X, res.cost.cpu().numpy(), status, res.sat_u.permute(2, 0, 1).cpu().numpy(),
+                            res.sat_x.permute(2, 0, 1).cpu().numpy(), ex, ulo, uhi)
+    assert n >= batch * 0.9
+    assert status[1] == bq.INFEASIBLE and not bool(res.solver_success[1])
+    if N == 5:
+        np.testing.assert_array_equal(U[0, :, 0], [10, 10, 10, 10, -20])
+    # numpy restatement of the same algorithm: same statuses and iteration counts
+    port = bq.ipm_riccati(oprob.A, oprob.B, oprob.Q, oprob.R, oprob.Q, N, x0, ulo, uhi, xlo, xhi)
+    np.testing.assert_array_equal(status, port["status"])
+    assert np.abs(res.iters.cpu().numpy() - port["iters"]).max() <= 1
+
+
+def test_policy_call_and_log(mods):
+    boxqp, problem, log, torch = mods
+    prob = problem.Problem(N=10)
+    mpc = problem.LinearMPC(prob)
+    lg = log.ControllerLog()
+    u = mpc(np.array([-50.0, 5.0]), lg)
+    assert u.shape == (1,) and isinstance(u, np.ndarray)
+    assert len(lg.solver_success) == 1 and bool(lg.solver_success[0])
+    assert lg.state_prediction[0].shape == (11, 2) and lg.input_prediction[0].shape == (10, 1)
+    np.testing.assert_allclose(lg.input_prediction[0][0], u)
+    X, U = problem.closed_loop(prob, np.array([[-50.0, 5.0], [-20.0, 0.0]]), 15, mpc, lg)
+    assert X.shape == (2, 16, 2) and U.shape == (2, 15, 1) and len(lg.solver_success) == 16
+    # closed loop obeys the plant and the bounds
+    np.testing.assert_allclose(X[:, 1:], X[:, :-1] @ prob.A.T + U @ prob.B.T, rtol=1e-12, atol=1e-12)
+    assert U.max() <= prob.u_max and U.min() >= prob.u_min and X[:, :, 0].max() <= prob.p_max + 1e-9
+
+
+@pytest.mark.parametrize("n,m", [(2, 1), (4, 1), (4, 2)])
+def test_ltv_per_scenario(mods, n, m):
+    boxqp, problem, log, torch = mods
+    rng = np.random.default_rng(n * 10 + m)
+    batch, N = 40, 15
+    A0 = np.eye(n) + 0.1 * np.diag(np.ones(n - 1), 1)
+    B0 = np.zeros((n, m)); B0[-1, 0] = 0.1
+    if m > 1:
+        B0[-2, 1] = 0.1
+    A = A0 + 0.02 * rng.standard_normal((N, batch, n, n))
+    B = B0 + 0.02 * rng.standard_normal((N, batch, n, m))
+    c = 0.01 * rng.standard_normal((N, batch, n))
+    Q = np.diag(rng.uniform(0.5, 2.0, n)); R = np.diag(rng.uniform(0.05, 0.2, m)); Pf = 5 * Q
+    ulo, uhi = -np.ones(m), 0.5 * np.ones(m)
+    xlo, xhi = -2.0 * np.ones(n), 2.0 * np.ones(n)
+    xlo[0] = -np.inf
+    x0 = rng.uniform(-1.5, 1.5, (batch, n))
+    warm = rng.uniform(-2, 2, (N, batch, m))
+    dev = lambda a: torch.tensor(np.ascontiguousarray(a), dtype=torch.float64, device="cuda")
+    res = boxqp.solve(dev(A.reshape(N, batch, n * n).transpose(0, 2, 1)), dev(B.reshape(N, batch, n * m).transpose(0, 2, 1)),
+                      dev(Q), dev(R), dev(Pf), N, dev(x0.T), ulo, uhi, xlo, xhi, c=dev(c.transpose(0, 2, 1)),
+                      warm_U=dev(warm.transpose(0, 2, 1)))
+    ex = [bq.solve_exact(A[:, b], B[:, b], Q, R, Pf, N, x0[b], ulo, uhi, xlo, xhi, c=c[:, b]) for b in range(batch)]
+    nchk = check_against_exact(res.input_prediction.cpu().numpy(), res.state_prediction.cpu().numpy(), res.cost.cpu().numpy(),
+                               res.status.cpu().numpy(), res.sat_u.permute(2, 0, 1).cpu().numpy(),
+                               res.sat_x.permute(2, 0, 1).cpu().numpy(), ex, ulo, uhi)
+    assert nchk >= batch // 2
+
+
+def test_unconstrained_equals_session1_lq(mods):
+    """With every bound at infinity the QP is the finite-horizon LQ problem of session 1."""
+    boxqp, problem, log, torch = mods
+    from model_predictive_control_b200 import lq
+    prob = problem.Problem(N=12)
+    rng = np.random.default_rng(3)
+    x0 = rng.uniform(-5, 5, (64, 2))
+    dev = lambda a: torch.tensor(np.asarray(a, dtype=np.float64), device="cuda")
+    res = boxqp.solve(dev(prob.A), dev(prob.B), dev(prob.Q), dev(prob.R), dev(prob.Q), 12, dev(x0.T.copy()),
+                      [-np.inf], [np.inf], [-np.inf] * 2, [np.inf] * 2)
+    out = lq.lq_solve(dev(prob.A), dev(prob.B), dev(prob.Q), dev(prob.R), dev(prob.Q), dev(x0), 12)
+    assert torch.allclose(res.input_prediction, out.U.permute(1, 0, 2), rtol=1e-9, atol=1e-10)
+    assert torch.allclose(res.cost, out.V, rtol=1e-10)
+    assert int(res.iters.max()) == 1 and bool(res.solver_success.all())
+
+
+def test_full_size_properties_cfg3(mods):
+    """256k scenarios, N = 30 (BASELINE config 3): size-independent properties -- predictions obey
+    the dynamics and the bounds, saturated inputs sit exactly on the bound, the cost equals the
+    re-evaluated objective, infeasible starts are flagged, and a subsample matches the exact oracle."""
+    boxqp, problem, log, torch = mods
+    prob = problem.Problem(N=30)
+    batch = 1 << 18
+    g = torch.Generator(device="cuda"); g.manual_seed(7)
+    x0 = torch.stack([torch.rand(batch, generator=g, device="cuda", dtype=torch.float64) * 100 - 100,
+                      torch.rand(batch, generator=g, device="cuda", dtype=torch.float64) * 25 - 10], dim=1)
+    res = problem.LinearMPC(prob).solve(x0)
+    ok = res.solver_success
+    frac_inf = float((res.status == 3).double().mean())
+    assert 0.0 < frac_inf < 0.1 and int((res.status == 2).sum()) == 0
+    U, X = res.input_prediction[ok], res.state_prediction[ok]
+    A = torch.tensor(prob.A, device="cuda"); B = torch.tensor(prob.B, device="cuda")
+    assert torch.allclose(X[:, 1:], X[:, :-1] @ A.t() + U @ B.t(), rtol=1e-12, atol=1e-10)
+    assert float(U.max()) <= prob.u_max and float(U.min()) >= prob.u_min
+    tol = 1e-7
+    assert float(X[:, 1:, 0].max()) <= prob.p_max + tol and float(X[:, 1:, 1].max()) <= prob.v_max + tol
+    assert float(X[:, 1:, 0].min()) >= prob.p_min - tol and float(X[:, 1:, 1].min()) >= prob.v_min - tol
+    sat = res.sat_u.permute(2, 0, 1)[ok]
+    assert bool((U[sat > 0] == prob.u_max).all()) and bool((U[sat < 0] == prob.u_min).all())
+    Q = torch.tensor(np.asarray(prob.Q, float), device="cuda"); R = torch.tensor(np.asarray(prob.R, float), device="cuda")
+    J = torch.einsum("bki,ij,bkj->b", X[:, :-1], Q, X[:, :-1]) + torch.einsum("bki,ij,bkj->b", U, R, U) \
+        + torch.einsum("bi,ij,bj->b", X[:, -1], Q, X[:, -1])
+    assert torch.allclose(res.cost[ok], J, rtol=1e-11)
+    idx = torch.arange(0, batch, batch // 64)[:64]
+    oprob = bq.Problem(N=30)
+    ulo, uhi, xlo, xhi = bq.problem_bounds(oprob)
+    x0h = x0[idx].cpu().numpy()
+    ex = [bq.solve_exact(oprob.A, oprob.B, oprob.Q, oprob.R, oprob.Q, 30, x0h[i], ulo, uhi, xlo, xhi) for i in range(64)]
+    check_against_exact(res.input_prediction[idx].cpu().numpy(), res.state_prediction[idx].cpu().numpy(),
+                        res.cost[idx].cpu().numpy(), res.status[idx].cpu().numpy(),
+                        res.sat_u.permute(2, 0, 1)[idx].cpu().numpy(), res.sat_x.permute(2, 0, 1)[idx].cpu().numpy(), ex, ulo, uhi)
+
+
+def test_errors(mods):
+    boxqp, problem, log, torch = mods
+    prob = problem.Problem(N=5)
+    dev = lambda a: torch.tensor(np.asarray(a, dtype=np.float64), device="cuda")
+    x0 = dev(np.zeros((2, 4)))
+    with pytest.raises(ValueError):
+        boxqp.solve(dev(prob.A), dev(prob.B), dev(prob.Q), dev(prob.R), dev(prob.Q), 5, x0, [1.0], [-1.0], [-1, -1], [1, 1])
+    with pytest.raises(ValueError):
+        boxqp.solve(dev(prob.A), dev(prob.B), dev(prob.Q), dev(prob.R), dev(prob.Q), 5, x0.float(), [-1.0], [1.0], [-1, -1], [1, 1])
+    from model_predictive_control_b200 import _lib
+    with pytest.raises(_lib.MpcError):  # (n, m) without an instantiated kernel
+        boxqp.solve(dev(np.eye(3)), dev(np.ones((3, 1))), dev(np.eye(3)), dev([[1.0]]), dev(np.eye(3)), 5, dev(np.zeros((3, 4))),
+                    [-1.0], [1.0], [-1] * 3, [1] * 3)
