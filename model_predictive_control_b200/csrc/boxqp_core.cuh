@@ -82,7 +82,8 @@ struct BoxQpIpm {
   const BoxQpArgs<T>& a;
   const T* sh;
   int64_t b, bs;
-  T mu0;  // initial barrier parameter = max(1, max|Q|, max|R|)
+  T mu_scale;  // max(1, max|Q|, max|R|): scale of the complementarity tolerance
+  T mu0;       // start value of the barrier parameter, per scenario: max(mu_scale, |H z0|_inf)
   // workspace sections
   T *z, *sl, *su, *ll, *lu, *zh, *ccl, *ccu, *Kw, *Sw, *dw;  // zh holds the Newton direction dz
 
@@ -100,15 +101,16 @@ struct BoxQpIpm {
     Kw = ccu + sec;
     Sw = Kw + (int64_t)a.N * NU * NX * bs;
     dw = Sw + (int64_t)a.N * NU * NU * bs;
-    mu0 = T(1);
+    mu_scale = T(1);
     for (int i = 0; i < NX * NX; ++i) {
       const T v = sh[SH::oQ + i] < T(0) ? -sh[SH::oQ + i] : sh[SH::oQ + i];
-      mu0 = v > mu0 ? v : mu0;
+      mu_scale = v > mu_scale ? v : mu_scale;
     }
     for (int i = 0; i < NU * NU; ++i) {
       const T v = sh[SH::oR + i] < T(0) ? -sh[SH::oR + i] : sh[SH::oR + i];
-      mu0 = v > mu0 ? v : mu0;
+      mu_scale = v > mu_scale ? v : mu_scale;
     }
+    mu0 = mu_scale;
   }
 
   MPC_HD int64_t ix(int k, int i, int per) const { return ((int64_t)k * per + i) * bs + b; }
@@ -144,45 +146,71 @@ struct BoxQpIpm {
   }
 
   // ---- start point: inputs clamped into their box, states by rollout, slacks >= 1, lam = mu0/s
+  // with mu0 = max(mu_scale, |H z0|_inf): multipliers start at the size of the cost gradient.
+  // Pass 0 only measures |H z0|_inf, pass 1 writes the start point.
   MPC_HD void init() {
-    T x[NX], xn[NX], u[NU], A[NX * NX], B[NX * NU], c[NX];
+    T g0 = T(0);
+    for (int pass = 0; pass < 2; ++pass) {
+      T x[NX], xn[NX], u[NU], A[NX * NX], B[NX * NU], c[NX];
 #pragma unroll
-    for (int i = 0; i < NX; ++i) x[i] = a.x0[i * bs + b];
-    for (int k = 0; k < a.N; ++k) {
-      load_stage(k, A, B, c);
+      for (int i = 0; i < NX; ++i) x[i] = a.x0[i * bs + b];
+      for (int k = 0; k < a.N; ++k) {
+        load_stage(k, A, B, c);
 #pragma unroll
-      for (int j = 0; j < NU; ++j) {
-        T v = a.warm_U ? a.warm_U[ix(k, j, NU)] : T(0);
-        v = v < lo(j) ? lo(j) : v;
-        v = v > hi(j) ? hi(j) : v;
-        u[j] = v;
-      }
-      step(A, B, c, x, u, xn);
-#pragma unroll
-      for (int i = 0; i < D; ++i) {
-        const T zi = i < NU ? u[i] : xn[i - NU];
-        T s_l = T(1), s_u = T(1), l_l = T(0), l_u = T(0);
-        if (hasl(i)) {
-          s_l = zi - lo(i);
-          s_l = s_l > T(1) ? s_l : T(1);
-          l_l = mu0 / s_l;
+        for (int j = 0; j < NU; ++j) {
+          T v = a.warm_U ? a.warm_U[ix(k, j, NU)] : T(0);
+          v = v < lo(j) ? lo(j) : v;
+          v = v > hi(j) ? hi(j) : v;
+          u[j] = v;
         }
-        if (hasu(i)) {
-          s_u = hi(i) - zi;
-          s_u = s_u > T(1) ? s_u : T(1);
-          l_u = mu0 / s_u;
-        }
-        const int64_t o = ix(k, i, D);
-        z[o] = zi;
-        sl[o] = s_l;
-        su[o] = s_u;
-        ll[o] = l_l;
-        lu[o] = l_u;
-        ccl[o] = T(0);
-        ccu[o] = T(0);
-      }
+        step(A, B, c, x, u, xn);
+        if (pass == 0) {
+          const T* Qx = sh + (k == a.N - 1 ? SH::oPf : SH::oQ);
 #pragma unroll
-      for (int i = 0; i < NX; ++i) x[i] = xn[i];
+          for (int i = 0; i < NU; ++i) {
+            T acc = T(0);
+#pragma unroll
+            for (int j = 0; j < NU; ++j) acc = fma_<T>(sh[SH::oR + i * NU + j], u[j], acc);
+            acc = acc < T(0) ? -acc : acc;
+            g0 = acc > g0 ? acc : g0;
+          }
+#pragma unroll
+          for (int i = 0; i < NX; ++i) {
+            T acc = T(0);
+#pragma unroll
+            for (int j = 0; j < NX; ++j) acc = fma_<T>(Qx[i * NX + j], xn[j], acc);
+            acc = acc < T(0) ? -acc : acc;
+            g0 = acc > g0 ? acc : g0;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < D; ++i) {
+            const T zi = i < NU ? u[i] : xn[i - NU];
+            T s_l = T(1), s_u = T(1), l_l = T(0), l_u = T(0);
+            if (hasl(i)) {
+              s_l = zi - lo(i);
+              s_l = s_l > T(1) ? s_l : T(1);
+              l_l = mu0 / s_l;
+            }
+            if (hasu(i)) {
+              s_u = hi(i) - zi;
+              s_u = s_u > T(1) ? s_u : T(1);
+              l_u = mu0 / s_u;
+            }
+            const int64_t o = ix(k, i, D);
+            z[o] = zi;
+            sl[o] = s_l;
+            su[o] = s_u;
+            ll[o] = l_l;
+            lu[o] = l_u;
+            ccl[o] = T(0);
+            ccu[o] = T(0);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) x[i] = xn[i];
+      }
+      if (pass == 0) mu0 = g0 > mu_scale ? g0 : mu_scale;
     }
   }
 
@@ -533,7 +561,7 @@ struct BoxQpIpm {
       zn = update(sig_mu, alpha);
       const T mu_new = (acc.s0 + alpha * (acc.s1 + alpha * acc.s2)) * inv_nc;
       rp = (T(1) - alpha) * acc.rp;
-      const bool done = (mu_new <= a.eps * mu0) && (rp <= a.eps * zn) && (alpha * acc.dzmax <= T(1e-6) * zn);
+      const bool done = (mu_new <= a.eps * mu_scale) && (rp <= a.eps * zn) && (alpha * acc.dzmax <= T(1e-6) * zn);
       if (done) {
         status = MPC_SOLVED;
       } else if (!(alpha >= T(1e-6)) || !(mu_new <= T(1e15) * mu0)) {

@@ -429,11 +429,19 @@ def ipm_riccati(A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi, c=None, warm_U=No
     for k in range(N):
         x = mv(Ab[k], x) + mv(Bb[k], U0[k]) + cb[k]
         z[k, :, :m] = U0[k]; z[k, :, m:] = x
-    mu0 = max(1.0, float(np.abs(Q).max()), float(np.abs(R).max()))
+    # barrier parameter: tolerance scale from the weights; start value per scenario from the size of
+    # the cost gradient at the start point (a centred start: lam ~ |H z0| / s)
+    mu_scale = max(1.0, float(np.abs(Q).max()), float(np.abs(R).max()))
+    g0 = np.zeros(batch)
+    for k in range(N):
+        g0 = np.maximum(g0, np.abs(z[k][:, :m] @ R.T).max(axis=1))
+        g0 = np.maximum(g0, np.abs(z[k][:, m:] @ (Pf if k == N - 1 else Q).T).max(axis=1))
+    mu0 = np.maximum(mu_scale, g0)[None, :, None]
     sl = np.where(has_l, np.maximum(z - lo_f, 1.0), 1.0)
     su = np.where(has_u, np.maximum(hi_f - z, 1.0), 1.0)
     ll = np.where(has_l, mu0 / sl, 0.0)
     lu = np.where(has_u, mu0 / su, 0.0)
+    mu0 = mu0[0, :, 0]
 
     status = np.zeros(batch, dtype=np.int32)
     iters = np.zeros(batch, dtype=np.int32)
@@ -514,7 +522,7 @@ def ipm_riccati(A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi, c=None, warm_U=No
         step = alpha * np.abs(dz).max(axis=(0, 2))
         if verbose:
             print(it, "mu", mu_new.max(), "rp", rp.max(), "alpha", alpha.min(), "step", step.max())
-        done = active & (mu_new <= eps * mu0) & (rp <= eps * zn) & (step <= 1e-6 * zn)
+        done = active & (mu_new <= eps * mu_scale) & (rp <= eps * zn) & (step <= 1e-6 * zn)
         status[done] = SOLVED
         active &= ~done
         # stalled: the step length collapses / the barrier parameter explodes.  With a bound
