@@ -64,7 +64,8 @@ class LinearMPC:
 
     ``solve(x0)`` with x0 (n,) or (batch, n) returns a :class:`boxqp.BoxQpResult` (fields
     ``solver_success``, ``state_prediction`` (batch, N+1, n), ``input_prediction`` (batch, N, m) as
-    in the reference's ControllerLog).  ``__call__(y, log=None)`` is the policy the course's
+    in the reference's ControllerLog; the tensors alias a workspace that the next ``solve`` reuses).
+    ``__call__(y, log=None)`` is the policy the course's
     simulator calls every step: returns u_0 and appends the three log entries.
     """
 
@@ -101,12 +102,14 @@ class LinearMPC:
         as_np = not io.is_tensor(y)
         single = (np.ndim(y) if as_np else y.dim()) == 1
         res = self.solve(y)
+        # the result aliases the reusable workspace: what leaves this call is copied
+        keep = (lambda t: io.back(t, True)) if as_np else (lambda t: t.clone())
         if log is not None:
-            log.solver_success.append(io.back(res.solver_success[0] if single else res.solver_success, as_np))
-            log.state_prediction.append(io.back(res.state_prediction[0] if single else res.state_prediction, as_np))
-            log.input_prediction.append(io.back(res.input_prediction[0] if single else res.input_prediction, as_np))
+            log.solver_success.append(keep(res.solver_success[0] if single else res.solver_success))
+            log.state_prediction.append(keep(res.state_prediction[0] if single else res.state_prediction))
+            log.input_prediction.append(keep(res.input_prediction[0] if single else res.input_prediction))
         u0 = res.U[0].t()  # (batch, m)
-        return io.back(u0[0] if single else u0, as_np)
+        return keep(u0[0] if single else u0)
 
 
 def closed_loop(problem: Problem, x0, n_steps: int, controller: LinearMPC = None, log: ControllerLog = None):
