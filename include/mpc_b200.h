@@ -149,6 +149,43 @@ int mpc_boxqp_solve(const void* A, const void* B, const void* c, int ltv, const 
                     int dtype, mpc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * K5  session-4 kinematic bicycle, real-time-iteration (RTI) MPC.
+ * Replaces, for a batch of scenarios, the per-step work of MPCController.__call__/solve
+ * (session_4/session4_sol.py:113-230: OCP cost/bounds :166-181, Euler model :191-192; RK4 variant
+ * template.py:141) and of the closed-loop driver exercise5 (:443-465).  The reference solves the
+ * nonlinear OCP with CasADi + IPOPT; here ONE linearised QP (K4, ltv = 1) is solved per control
+ * step.  The bicycle ODE is our definition (rcracers is not vendored), see csrc/bicycle_core.cuh:
+ *   state [p_x, p_y, psi, v], input [a, delta], parameters lr = axis_rear, lf = axis_front,
+ *   friction, accel = acceleration (session_4/parameters.py:7-8,47-48).  float64 only.
+ *
+ * mpc_bicycle_rti_prepare: shift the previous plan (first == 0) or keep it (first != 0), roll the
+ *   model out from y [4][batch] and linearise:  U_prev [N][2][batch] -> warm_U [N][2][batch],
+ *   A [N][16][batch], B [N][8][batch], c [N][4][batch]  (inputs of mpc_boxqp_solve with ltv = 1).
+ * mpc_bicycle_plant_step: x [4][batch], u [2][batch] -> xn;  substeps = 0: forward Euler over ts
+ *   (session4_sol.py:22-25), substeps > 0: RK4 sub-steps (stands in for odeint, :37-56);
+ *   friction [batch] (s_friction = 1) or one shared value (s_friction = 0).
+ * mpc_rti_closed_loop: `steps` control steps of prepare -> QP -> apply u_0 -> plant in ONE kernel.
+ *   U_plan [N][2][batch] in/out (initial plan; zeros = cold start), X_pred [N+1][4][batch] (last
+ *   prediction), X_cl [steps+1][4][batch], U_cl [steps][2][batch], cost_cl [batch] (sum of
+ *   x'Qx + u'Ru along the closed loop), viol_cl [batch] (max state-bound violation), n_sat (applied
+ *   inputs on a bound), n_fail (steps whose QP did not reach MPC_SOLVED), iters_total, last_status.
+ */
+int mpc_bicycle_rti_prepare(double lr, double lf, double accel, double friction, double ts, int rk4,
+                            const void* y, const void* U_prev, int first, void* warm_U, void* A, void* B,
+                            void* c, int64_t batch, int N, int dtype, mpc_stream_t stream);
+int mpc_bicycle_plant_step(double lr, double lf, double accel, double ts, const void* friction,
+                           int64_t s_friction, int substeps, const void* x, const void* u, void* xn,
+                           int64_t batch, int dtype, mpc_stream_t stream);
+int64_t mpc_rti_workspace_bytes(int64_t batch, int N, int dtype);
+int mpc_rti_closed_loop(double lr, double lf, double accel, double friction_model, double ts, int rk4,
+                        const void* friction_plant, int plant_substeps, int steps, const void* Q,
+                        const void* R, const void* Pf, const void* u_lo, const void* u_hi, const void* x_lo,
+                        const void* x_hi, const void* x0, void* U_plan, void* X_pred, void* X_cl, void* U_cl,
+                        void* cost_cl, void* viol_cl, int32_t* n_sat, int32_t* n_fail, int32_t* iters_total,
+                        int32_t* last_status, void* ws, int64_t ws_bytes, int64_t batch, int N, int max_iter,
+                        double eps, int dtype, mpc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Device FP pipe probe: runs a register-resident FMA chain kernel and reports achieved
  * FLOP/s (2 flops per FMA).  Used by bench.py as the measured FP64 / FP32 vector-pipe roofline
  * denominator (MEASURED_PEAKS.json only carries HBM and bf16 tensor peaks).  Synchronises.

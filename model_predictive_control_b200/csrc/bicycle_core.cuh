@@ -1,0 +1,262 @@
+// K5: kinematic bicycle (session 4) -- model, exact Jacobians, Euler / RK4 discretisation with
+// chain-rule sensitivities, plant step, and the RTI preparation step (shift, roll out, linearise).
+//
+// The reference takes the model from rcracers.simulator.dynamics.KinematicBicycle (not vendored;
+// call sites /root/reference/session_4/session4_sol.py:11,74,191,452) and the integrators from
+// session4_sol.py:22-34.  OUR DEFINITION of the ODE (state [p_x, p_y, psi, v], input [a, delta]):
+//     beta = atan(l_r tan(delta) / (l_r + l_f))
+//     p_x' = v cos(psi + beta)   p_y' = v sin(psi + beta)   psi' = v sin(beta) / l_r
+//     v'   = acceleration * a - friction * v
+#pragma once
+
+#include <math.h>
+
+#include "boxqp_core.cuh"
+
+namespace mpc {
+
+template <typename T>
+struct BicycleModel {
+  T lr, lf, accel, ts;
+  int rk4;  // OCP discretisation: 0 forward Euler (session4_sol.py:192), 1 RK4 (template.py:141)
+};
+
+template <typename T>
+MPC_HD void bicycle_f(const BicycleModel<T>& p, T friction, const T* x, const T* u, T* f) {
+  const T beta = atan(p.lr * tan(u[1]) / (p.lr + p.lf));
+  T s, c;
+  sincos(x[2] + beta, &s, &c);
+  f[0] = x[3] * c;
+  f[1] = x[3] * s;
+  f[2] = x[3] * sin(beta) / p.lr;
+  f[3] = p.accel * u[0] - friction * x[3];
+}
+
+// f, Jx = df/dx [4x4], Ju = df/du [4x2]
+template <typename T>
+MPC_HD void bicycle_jac(const BicycleModel<T>& p, T friction, const T* x, const T* u, T* f, T* Jx, T* Ju) {
+  const T kap = p.lr / (p.lr + p.lf);
+  const T td = tan(u[1]);
+  const T beta = atan(kap * td);
+  const T dbeta = kap * (T(1) + td * td) / (T(1) + kap * kap * td * td);
+  T s, c, sb, cb;
+  sincos(x[2] + beta, &s, &c);
+  sincos(beta, &sb, &cb);
+  const T v = x[3];
+  f[0] = v * c;
+  f[1] = v * s;
+  f[2] = v * sb / p.lr;
+  f[3] = p.accel * u[0] - friction * v;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) Jx[i] = T(0);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) Ju[i] = T(0);
+  Jx[0 * 4 + 2] = -v * s;
+  Jx[0 * 4 + 3] = c;
+  Jx[1 * 4 + 2] = v * c;
+  Jx[1 * 4 + 3] = s;
+  Jx[2 * 4 + 3] = sb / p.lr;
+  Jx[3 * 4 + 3] = -friction;
+  Ju[0 * 2 + 1] = -v * s * dbeta;
+  Ju[1 * 2 + 1] = v * c * dbeta;
+  Ju[2 * 2 + 1] = v * cb * dbeta / p.lr;
+  Ju[3 * 2 + 0] = p.accel;
+}
+
+// One RK4 stage's total derivatives: Dx = Jx (I + h Dpx), Du = Jx (h Dpu) + Ju
+template <typename T>
+MPC_HD void rk4_chain(const T* Jx, const T* Ju, T h, const T* Dpx, const T* Dpu, T* Dx, T* Du) {
+  T M[16], Mu[8];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) M[i] = h * Dpx[i] + ((i / 4 == i % 4) ? T(1) : T(0));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) Mu[i] = h * Dpu[i];
+  mm<T, 4, 4, 4, false>(Jx, M, Dx);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) Du[i] = Ju[i];
+  mm<T, 4, 4, 2, true>(Jx, Mu, Du);
+}
+
+// x+ = f_d(x, u), A = d f_d / dx, B = d f_d / du
+template <typename T>
+MPC_HD void bicycle_discretize(const BicycleModel<T>& p, T friction, const T* x, const T* u, T* xn, T* A, T* B) {
+  const T ts = p.ts;
+  if (!p.rk4) {
+    T f[4];
+    bicycle_jac(p, friction, x, u, f, A, B);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xn[i] = fma_<T>(ts, f[i], x[i]);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) A[i] = ts * A[i] + ((i / 4 == i % 4) ? T(1) : T(0));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) B[i] = ts * B[i];
+    return;
+  }
+  T k1[4], k2[4], k3[4], k4[4], xs[4], Jx[16], Ju[8];
+  T D1x[16], D1u[8], D2x[16], D2u[8], D3x[16], D3u[8], D4x[16], D4u[8];
+  bicycle_jac(p, friction, x, u, k1, D1x, D1u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) xs[i] = x[i] + T(0.5) * ts * k1[i];
+  bicycle_jac(p, friction, xs, u, k2, Jx, Ju);
+  rk4_chain(Jx, Ju, T(0.5) * ts, D1x, D1u, D2x, D2u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) xs[i] = x[i] + T(0.5) * ts * k2[i];
+  bicycle_jac(p, friction, xs, u, k3, Jx, Ju);
+  rk4_chain(Jx, Ju, T(0.5) * ts, D2x, D2u, D3x, D3u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) xs[i] = x[i] + ts * k3[i];
+  bicycle_jac(p, friction, xs, u, k4, Jx, Ju);
+  rk4_chain(Jx, Ju, ts, D3x, D3u, D4x, D4u);
+  const T w = ts / T(6);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) xn[i] = x[i] + w * (k1[i] + T(2) * k2[i] + T(2) * k3[i] + k4[i]);
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    A[i] = w * (D1x[i] + T(2) * D2x[i] + T(2) * D3x[i] + D4x[i]) + ((i / 4 == i % 4) ? T(1) : T(0));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) B[i] = w * (D1u[i] + T(2) * D2u[i] + T(2) * D3u[i] + D4u[i]);
+}
+
+// Plant: forward Euler over ts (substeps == 0; the nominal model of session4_sol.py:453) or classic
+// RK4 with `substeps` equal sub-steps (stands in for the reference's odeint plant,
+// session4_sol.py:37-56: a documented deviation).
+template <typename T>
+MPC_HD void bicycle_plant(const BicycleModel<T>& p, T friction, int substeps, T* x, const T* u) {
+  if (substeps <= 0) {
+    T f[4];
+    bicycle_f(p, friction, x, u, f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = fma_<T>(p.ts, f[i], x[i]);
+    return;
+  }
+  const T h = p.ts / T(substeps);
+  for (int s = 0; s < substeps; ++s) {
+    T k1[4], k2[4], k3[4], k4[4], xs[4];
+    bicycle_f(p, friction, x, u, k1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xs[i] = x[i] + T(0.5) * h * k1[i];
+    bicycle_f(p, friction, xs, u, k2);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xs[i] = x[i] + T(0.5) * h * k2[i];
+    bicycle_f(p, friction, xs, u, k3);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xs[i] = x[i] + h * k3[i];
+    bicycle_f(p, friction, xs, u, k4);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = x[i] + h / T(6) * (k1[i] + T(2) * k2[i] + T(2) * k3[i] + k4[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// RTI preparation for one scenario: shift the previous plan (first == 0), roll the nonlinear model
+// out from the measured state y, linearise along the trajectory:
+//   warm[k] = first ? Uprev[k] : Uprev[min(k+1, N-1)]
+//   xbar_{k+1} = f_d(xbar_k, warm[k]);  A_k, B_k its Jacobians;  c_k = xbar_{k+1} - A_k xbar_k - B_k warm[k]
+// Layouts: y [4][batch], Uprev / warm [N][2][batch], A [N][16][batch], B [N][8][batch], c [N][4][batch].
+template <typename T>
+MPC_HD void rti_prepare_body(const BicycleModel<T>& p, T friction, const T* y, const T* Uprev, int first, T* warm,
+                             T* A, T* B, T* c, int N, int64_t bs, int64_t b) {
+  T x[4], xn[4], u[2], Ak[16], Bk[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) x[i] = y[i * bs + b];
+  for (int k = 0; k < N; ++k) {
+    const int ks = first ? k : (k + 1 < N ? k + 1 : N - 1);
+    u[0] = Uprev[((int64_t)ks * 2 + 0) * bs + b];
+    u[1] = Uprev[((int64_t)ks * 2 + 1) * bs + b];
+    warm[((int64_t)k * 2 + 0) * bs + b] = u[0];
+    warm[((int64_t)k * 2 + 1) * bs + b] = u[1];
+    bicycle_discretize(p, friction, x, u, xn, Ak, Bk);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) A[((int64_t)k * 16 + i) * bs + b] = Ak[i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) B[((int64_t)k * 8 + i) * bs + b] = Bk[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      T acc = xn[i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc = fma_<T>(-Ak[i * 4 + j], x[j], acc);
+      acc = fma_<T>(-Bk[i * 2 + 0], u[0], acc);
+      acc = fma_<T>(-Bk[i * 2 + 1], u[1], acc);
+      c[((int64_t)k * 4 + i) * bs + b] = acc;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = xn[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Closed loop (session4_sol.py:443-465 with the RTI controller): per control step
+//   prepare -> LTV box QP (K4) -> apply u_0 -> plant step, with running summaries.
+template <typename T>
+struct RtiLoopArgs {
+  BicycleModel<T> model;    // prediction model (friction_model below)
+  T friction_model;
+  const T* friction_plant;  // [batch] per-scenario plant friction
+  int plant_substeps;       // 0: Euler plant; > 0: RK4 sub-steps
+  int steps;
+  const T* x0;              // [4][batch]
+  T* xcur;                  // [4][batch] scratch: measured state of the current step
+  T* Acur;                  // [N][16][batch] scratch
+  T* Bcur;                  // [N][8][batch]
+  T* ccur;                  // [N][4][batch]
+  T* warm;                  // [N][2][batch]
+  T* X_cl;                  // [steps+1][4][batch]
+  T* U_cl;                  // [steps][2][batch]
+  T* cost_cl;               // [batch] sum_t x_t'Q x_t + u_t'R u_t
+  T* viol_cl;               // [batch] max state-bound violation of the closed-loop trajectory
+  int32_t* n_sat;           // [batch] number of applied inputs on a bound
+  int32_t* n_fail;          // [batch] number of steps whose QP did not reach MPC_SOLVED
+  int32_t* iters_total;     // [batch]
+  BoxQpArgs<T> qp;          // ltv = 1; A/B/c = Acur/Bcur/ccur; x0 = xcur; warm_U = warm;
+                            // U = plan buffer: initial plan on entry (zeros = cold start), last plan on exit
+};
+
+template <typename T>
+MPC_HD void rti_closed_loop_body(const RtiLoopArgs<T>& a, const T* sh, int64_t b) {
+  using SH = BoxQpShared<4, 2>;
+  const int64_t bs = a.qp.batch;
+  const int N = a.qp.N;
+  T x[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    x[i] = a.x0[i * bs + b];
+    a.X_cl[i * bs + b] = x[i];
+  }
+  const T fr_plant = a.friction_plant[b];
+  T cost = T(0), viol = T(0);
+  int nsat = 0, nfail = 0, itsum = 0;
+  for (int t = 0; t < a.steps; ++t) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a.xcur[i * bs + b] = x[i];
+    rti_prepare_body<T>(a.model, a.friction_model, a.xcur, a.qp.U, t == 0 ? 1 : 0, a.warm, a.Acur, a.Bcur, a.ccur, N,
+                        bs, b);
+    BoxQpIpm<T, 4, 2> ipm(a.qp, sh, b);
+    ipm.solve();
+    T u[2];
+    u[0] = a.qp.U[(int64_t)0 * bs + b];
+    u[1] = a.qp.U[(int64_t)1 * bs + b];
+    if (a.qp.status[b] != MPC_SOLVED) ++nfail;
+    itsum += a.qp.iters[b];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (u[j] == sh[SH::oLo + j] || u[j] == sh[SH::oHi + j]) ++nsat;
+      a.U_cl[((int64_t)t * 2 + j) * bs + b] = u[j];
+    }
+    cost += quad<T, 4>(sh + SH::oQ, x) + quad<T, 2>(sh + SH::oR, u);
+    bicycle_plant<T>(a.model, fr_plant, a.plant_substeps, x, u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      a.X_cl[((int64_t)(t + 1) * 4 + i) * bs + b] = x[i];
+      const T lo = sh[SH::oLo + 2 + i], hi = sh[SH::oHi + 2 + i];
+      const T v = (lo - x[i]) > (x[i] - hi) ? (lo - x[i]) : (x[i] - hi);
+      viol = v > viol ? v : viol;
+    }
+  }
+  a.cost_cl[b] = cost;
+  a.viol_cl[b] = viol;
+  a.n_sat[b] = nsat;
+  a.n_fail[b] = nfail;
+  a.iters_total[b] = itsum;
+}
+
+}  // namespace mpc

@@ -1,0 +1,202 @@
+"""CPU oracle for the session-4 path (TEST INFRASTRUCTURE): kinematic bicycle, integrators, the
+real-time-iteration (RTI) step and the closed-loop driver.
+
+PARITY UNPINNED BY THE REFERENCE.  The reference solves the nonlinear OCP with CasADi + IPOPT
+(/root/reference/session_4/session4_sol.py:113-230) and takes the vehicle model from ``rcracers``
+(``KinematicBicycle``, call sites session4_sol.py:11,74,191,452); neither dependency is vendored,
+pinned or installed, so nothing here can be checked against reference outputs.  What follows the
+reference: state order [p_x, p_y, psi, v] and input order [a, delta] (session4_sol.py:176-181),
+weights Q = diag(1, 3, .1, .01), Q_T = 10 Q, R = diag(1, .01) (:166-169), bounds from
+VehicleParameters (:176-181, parameters.py:17-29), N = 50, ts = 0.05, x0 = [.6, -.25, 0, 0]
+(:445-447), Euler / RK4 integrators (:22-34), plant mismatch friction *= 0.8 (:461-463).
+
+OUR DEFINITION of the bicycle ODE (an assumption, the rcracers source is not available):
+    beta = atan(l_r tan(delta) / (l_r + l_f))
+    p_x' = v cos(psi + beta),  p_y' = v sin(psi + beta),  psi' = v sin(beta) / l_r,
+    v'   = acceleration * a - friction * v
+with l_r = axis_rear, l_f = axis_front, friction, acceleration from VehicleParameters
+(parameters.py:7-8,47-48).
+
+The north star replaces the converged IPOPT solve by ONE linearised QP per control step (RTI):
+shift the previous input plan, roll the nonlinear model out from the measured state, linearise
+along that trajectory, solve the LTV box QP, apply u_0.  The restatement here is that algorithm;
+the QP is solved by oracle.boxqp (exact active-set solver or the numpy port of the GPU method).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import boxqp as bq
+
+
+@dataclass
+class VehicleParameters:
+    """Subset of /root/reference/session_4/parameters.py:4-54 that the kinematic model uses."""
+    axis_front: float = 0.047
+    axis_rear: float = 0.05
+    max_steer: float = 0.384
+    max_drive: float = 1.0
+    min_drive: float = -1.0
+    min_pos_x: float = -3.0
+    max_pos_x: float = 3.0
+    min_pos_y: float = -2.0
+    max_pos_y: float = 2.0
+    min_vel: float = -0.5
+    max_vel: float = 0.5
+    max_heading: float = 2 * np.pi
+    min_heading: float = -2 * np.pi
+    friction: float = 1
+    acceleration: float = 2
+
+
+def weights(variant="sol"):
+    """(Q, Q_T, R): session4_sol.py:166-169; template.py:135-137 (Q_N = 5 Q)."""
+    Q = np.diag([1.0, 3.0, 0.1, 0.01])
+    R = np.diag([1.0, 1e-2])
+    return Q, (10.0 if variant == "sol" else 5.0) * Q, R
+
+
+def bounds(p: VehicleParameters):
+    """Input and state boxes (session4_sol.py:176-181)."""
+    return (np.array([p.min_drive, -p.max_steer]), np.array([p.max_drive, p.max_steer]),
+            np.array([p.min_pos_x, p.min_pos_y, p.min_heading, p.min_vel]),
+            np.array([p.max_pos_x, p.max_pos_y, p.max_heading, p.max_vel]))
+
+
+# ------------------------------------------------------------------------------------------------
+# model (batched over the leading axis: x [batch, 4], u [batch, 2], friction scalar or [batch])
+# ------------------------------------------------------------------------------------------------
+def bicycle_f(x, u, lr, lf, friction, accel):
+    psi, v = x[..., 2], x[..., 3]
+    a, delta = u[..., 0], u[..., 1]
+    beta = np.arctan(lr * np.tan(delta) / (lr + lf))
+    return np.stack([v * np.cos(psi + beta), v * np.sin(psi + beta), v * np.sin(beta) / lr,
+                     accel * a - friction * v], axis=-1)
+
+
+def bicycle_jac(x, u, lr, lf, friction, accel):
+    """(f, df/dx [...,4,4], df/du [...,4,2])."""
+    psi, v = x[..., 2], x[..., 3]
+    delta = u[..., 1]
+    kap = lr / (lr + lf)
+    td = np.tan(delta)
+    beta = np.arctan(kap * td)
+    dbeta = kap * (1 + td * td) / (1 + kap * kap * td * td)
+    c, s = np.cos(psi + beta), np.sin(psi + beta)
+    Jx = np.zeros(x.shape[:-1] + (4, 4)); Ju = np.zeros(x.shape[:-1] + (4, 2))
+    Jx[..., 0, 2] = -v * s; Jx[..., 0, 3] = c
+    Jx[..., 1, 2] = v * c; Jx[..., 1, 3] = s
+    Jx[..., 2, 3] = np.sin(beta) / lr
+    Jx[..., 3, 3] = -friction
+    Ju[..., 0, 1] = -v * s * dbeta
+    Ju[..., 1, 1] = v * c * dbeta
+    Ju[..., 2, 1] = v * np.cos(beta) * dbeta / lr
+    Ju[..., 3, 0] = accel
+    return bicycle_f(x, u, lr, lf, friction, accel), Jx, Ju
+
+
+def forward_euler(f, ts):
+    """session4_sol.py:22-25."""
+    return lambda x, u: x + f(x, u) * ts
+
+
+def runge_kutta4(f, ts):
+    """session4_sol.py:27-34."""
+    def rk4(x, u):
+        s1 = f(x, u)
+        s2 = f(x + 0.5 * ts * s1, u)
+        s3 = f(x + 0.5 * ts * s2, u)
+        s4 = f(x + ts * s3, u)
+        return x + ts / 6.0 * (s1 + 2 * s2 + 2 * s3 + s4)
+    return rk4
+
+
+def discretize(x, u, ts, par, friction, method="euler"):
+    """One step x+ = f_d(x, u) with its Jacobians A = d f_d/dx, B = d f_d/du (exact chain rule)."""
+    lr, lf, acc = par.axis_rear, par.axis_front, par.acceleration
+    I = np.eye(4)
+    if method == "euler":
+        f, Jx, Ju = bicycle_jac(x, u, lr, lf, friction, acc)
+        return x + ts * f, I + ts * Jx, ts * Ju
+    k1, J1x, J1u = bicycle_jac(x, u, lr, lf, friction, acc)
+    k2, J2x, J2u = bicycle_jac(x + 0.5 * ts * k1, u, lr, lf, friction, acc)
+    D2x = J2x @ (I + 0.5 * ts * J1x); D2u = J2x @ (0.5 * ts * J1u) + J2u
+    k3, J3x, J3u = bicycle_jac(x + 0.5 * ts * k2, u, lr, lf, friction, acc)
+    D3x = J3x @ (I + 0.5 * ts * D2x); D3u = J3x @ (0.5 * ts * D2u) + J3u
+    k4, J4x, J4u = bicycle_jac(x + ts * k3, u, lr, lf, friction, acc)
+    D4x = J4x @ (I + ts * D3x); D4u = J4x @ (ts * D3u) + J4u
+    xn = x + ts / 6.0 * (k1 + 2 * k2 + 2 * k3 + k4)
+    return xn, I + ts / 6.0 * (J1x + 2 * D2x + 2 * D3x + D4x), ts / 6.0 * (J1u + 2 * D2u + 2 * D3u + D4u)
+
+
+def plant_step(x, u, ts, par, friction, method="rk4", substeps=4):
+    """Plant x+ : Euler (nominal model, session4_sol.py:453) or RK4 with fixed sub-steps (stands in for
+    the reference's odeint plant, session4_sol.py:37-56 -- documented deviation)."""
+    return _plant(x, u, ts, par, friction, method, substeps)
+
+
+# ------------------------------------------------------------------------------------------------
+# RTI
+# ------------------------------------------------------------------------------------------------
+def rti_prepare(y, U_prev, ts, par, friction, method="euler", first=False):
+    """Shift the previous plan, roll out, linearise.  y [batch,4], U_prev [N,batch,2].
+    Returns Ubar [N,batch,2], A [N,batch,4,4], B [N,batch,4,2], c [N,batch,4], Xbar [N+1,batch,4]."""
+    N = U_prev.shape[0]
+    Ubar = U_prev.copy() if first else np.concatenate([U_prev[1:], U_prev[-1:]], axis=0)
+    A, B, c, X = [], [], [], [y]
+    x = y
+    for k in range(N):
+        xn, Ak, Bk = discretize(x, Ubar[k], ts, par, friction, method)
+        A.append(Ak); B.append(Bk)
+        c.append(xn - np.einsum("bij,bj->bi", Ak, x) - np.einsum("bij,bj->bi", Bk, Ubar[k]))
+        X.append(xn)
+        x = xn
+    return Ubar, np.array(A), np.array(B), np.array(c), np.array(X)
+
+
+def closed_loop(x0, n_steps, N=50, ts=0.05, par=None, friction_model=None, friction_plant=None, ocp_method="euler",
+                plant_method="rk4", substeps=4, variant="sol", qp="port", max_iter=60):
+    """Batched RTI closed loop.  x0 [batch,4].  qp = "port" (numpy restatement of the GPU interior
+    point method, batched) or "exact" (HiGHS active set + KKT refinement, one scenario at a time).
+    Returns dict(X [steps+1,batch,4], U [steps,batch,2], status [steps,batch], cost [batch], viol [batch])."""
+    par = par or VehicleParameters()
+    x = np.atleast_2d(np.asarray(x0, float))
+    batch = x.shape[0]
+    fm = par.friction if friction_model is None else friction_model
+    fp = np.full(batch, par.friction, float) if friction_plant is None else np.broadcast_to(np.asarray(friction_plant, float), (batch,))
+    Q, QT, R = weights(variant)
+    ulo, uhi, xlo, xhi = bounds(par)
+    U_prev = np.zeros((N, batch, 2))
+    Xs, Us, Ss = [x], [], []
+    cost = np.zeros(batch); viol = np.zeros(batch)
+    for t in range(n_steps):
+        Ubar, A, B, c, _ = rti_prepare(x, U_prev, ts, par, fm, ocp_method, first=(t == 0))
+        if qp == "port":
+            r = bq.ipm_riccati(list(A), list(B), Q, R, QT, N, x, ulo, uhi, xlo, xhi, c=list(c), warm_U=Ubar, max_iter=max_iter)
+            U, status = r["U"], r["status"]
+        else:
+            U = np.zeros((N, batch, 2)); status = np.zeros(batch, dtype=np.int32)
+            for b in range(batch):
+                e = bq.solve_exact(A[:, b], B[:, b], Q, R, QT, N, x[b], ulo, uhi, xlo, xhi, c=c[:, b])
+                U[:, b], status[b] = e["U"], e["status"]
+        u0 = U[0]
+        cost += np.einsum("bi,ij,bj->b", x, Q, x) + np.einsum("bi,ij,bj->b", u0, R, u0)
+        x = _plant(x, u0, ts, par, fp, plant_method, substeps)
+        viol = np.maximum(viol, np.maximum(xlo - x, x - xhi).max(axis=1).clip(min=0))
+        U_prev = U
+        Xs.append(x); Us.append(u0); Ss.append(status)
+    return {"X": np.array(Xs), "U": np.array(Us), "status": np.array(Ss), "cost": cost, "viol": viol}
+
+
+def _plant(x, u, ts, par, friction, method, substeps):
+    lr, lf, acc = par.axis_rear, par.axis_front, par.acceleration
+    f = lambda xx, uu: bicycle_f(xx, uu, lr, lf, friction, acc)
+    if method == "euler":
+        return x + ts * f(x, u)
+    h = ts / substeps
+    for _ in range(substeps):
+        s1 = f(x, u); s2 = f(x + 0.5 * h * s1, u); s3 = f(x + 0.5 * h * s2, u); s4 = f(x + h * s3, u)
+        x = x + h / 6.0 * (s1 + 2 * s2 + 2 * s3 + s4)
+    return x

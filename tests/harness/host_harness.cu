@@ -6,6 +6,7 @@
 
 #include "../../model_predictive_control_b200/csrc/lq_core.cuh"
 #include "../../model_predictive_control_b200/csrc/boxqp_core.cuh"
+#include "../../model_predictive_control_b200/csrc/bicycle_core.cuh"
 
 using namespace mpc;
 
@@ -118,5 +119,60 @@ extern "C" int hh_boxqp_solve(const double* A, const double* B, const double* c,
   else if (n == 4 && m == 1) boxqp_loop<4, 1>(a);
   else if (n == 4 && m == 2) boxqp_loop<4, 2>(a);
   else return -5;
+  return 0;
+}
+
+extern "C" int hh_rti_prepare(double lr, double lf, double accel, double friction, double ts, int rk4, const double* y,
+                              const double* Uprev, int first, double* warm, double* A, double* B, double* c,
+                              int64_t batch, int N) {
+  BicycleModel<double> m{lr, lf, accel, ts, rk4};
+  for (int64_t b = 0; b < batch; ++b) rti_prepare_body<double>(m, friction, y, Uprev, first, warm, A, B, c, N, batch, b);
+  return 0;
+}
+
+extern "C" int hh_plant_step(double lr, double lf, double accel, double ts, const double* friction, int substeps,
+                             const double* x, const double* u, double* xn, int64_t batch) {
+  BicycleModel<double> m{lr, lf, accel, ts, 0};
+  for (int64_t b = 0; b < batch; ++b) {
+    double xv[4], uv[2] = {u[b], u[batch + b]};
+    for (int i = 0; i < 4; ++i) xv[i] = x[i * batch + b];
+    bicycle_plant<double>(m, friction[b], substeps, xv, uv);
+    for (int i = 0; i < 4; ++i) xn[i * batch + b] = xv[i];
+  }
+  return 0;
+}
+
+extern "C" int hh_rti_closed_loop(double lr, double lf, double accel, double friction_model, double ts, int rk4,
+                                  const double* friction_plant, int plant_substeps, int steps, const double* Q,
+                                  const double* R, const double* Pf, const double* u_lo, const double* u_hi,
+                                  const double* x_lo, const double* x_hi, const double* x0, double* U_plan,
+                                  double* X_pred, double* X_cl, double* U_cl, double* cost_cl, double* viol_cl,
+                                  int32_t* n_sat, int32_t* n_fail, int32_t* iters_total, int32_t* last_status,
+                                  int64_t batch, int N, int max_iter, double eps) {
+  using SH = BoxQpShared<4, 2>;
+  std::vector<double> sh(SH::total, 0.0);
+  for (int i = 0; i < 16; ++i) { sh[SH::oQ + i] = Q[i]; sh[SH::oPf + i] = Pf[i]; }
+  for (int i = 0; i < 4; ++i) sh[SH::oR + i] = R[i];
+  for (int i = 0; i < 2; ++i) { sh[SH::oLo + i] = u_lo[i]; sh[SH::oHi + i] = u_hi[i]; }
+  for (int i = 0; i < 4; ++i) { sh[SH::oLo + 2 + i] = x_lo[i]; sh[SH::oHi + 2 + i] = x_hi[i]; }
+  std::vector<double> ws((size_t)((boxqp_ws_elems(4, 2, N) + 6 + (int64_t)N * 30) * batch));
+  double* w = ws.data();
+  double* qp_ws = w; w += boxqp_ws_elems(4, 2, N) * batch;
+  double* xcur = w; w += 4 * batch;
+  double* Acur = w; w += (int64_t)N * 16 * batch;
+  double* Bcur = w; w += (int64_t)N * 8 * batch;
+  double* ccur = w; w += (int64_t)N * 4 * batch;
+  double* warm = w; w += (int64_t)N * 2 * batch;
+  double* qp_cost = w; w += batch;
+  int32_t* qp_iters = (int32_t*)w;
+  RtiLoopArgs<double> a;
+  a.model = BicycleModel<double>{lr, lf, accel, ts, rk4};
+  a.friction_model = friction_model; a.friction_plant = friction_plant; a.plant_substeps = plant_substeps;
+  a.steps = steps; a.x0 = x0; a.xcur = xcur; a.Acur = Acur; a.Bcur = Bcur; a.ccur = ccur; a.warm = warm;
+  a.X_cl = X_cl; a.U_cl = U_cl; a.cost_cl = cost_cl; a.viol_cl = viol_cl; a.n_sat = n_sat; a.n_fail = n_fail;
+  a.iters_total = iters_total;
+  a.qp = BoxQpArgs<double>{Acur, Bcur, ccur, 1, Q, R, Pf, u_lo, u_hi, x_lo, x_hi, xcur, warm, U_plan, X_pred, qp_cost,
+                           last_status, qp_iters, nullptr, nullptr, qp_ws, batch, N, max_iter, eps};
+  for (int64_t b = 0; b < batch; ++b) rti_closed_loop_body<double>(a, sh.data(), b);
   return 0;
 }
