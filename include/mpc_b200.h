@@ -121,6 +121,23 @@ int mpc_lq_solve(const void* A, int64_t sA, const void* B, int64_t sB, const voi
                  mpc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * K3  condensed prediction matrices of the LTI MPC problem ("condensed form" of the QP posed by the
+ * reference's Problem data, session_2/problem.py:8-24):  X = Phi x0 + Gamma U,
+ *   Phi = [A; ..; A^N] [N n][n],  Gamma_{ij} = A^(i-j) B [N n][N m],  H = Gamma'Qbar Gamma + Rbar
+ *   [N m][N m],  F = Gamma'Qbar Phi [N m][n],  Qbar = blkdiag(Q,..,Q,Pf);  J(U) = U'HU + 2 x0'F'U + c.
+ * One CTA per model (batch stride s?, 0 = shared); outputs [batch][rows][cols] row-major, any NULL.
+ */
+int mpc_condense(const void* A, int64_t sA, const void* B, int64_t sB, const void* Q, int64_t sQ, const void* R,
+                 int64_t sR, const void* Pf, int64_t sPf, void* Phi, void* Gamma, void* H, void* F, int64_t batch,
+                 int n, int m, int N, int dtype, mpc_stream_t stream);
+
+/* K6  per-rank summary of a batch of solves / closed loops (the payload of the final NCCL gather):
+ *   out8 = {scenarios, sum cost, max violation, sum saturated inputs, #infeasible, #max_iter,
+ *           sum iterations, #solved};  every input array is optional (NULL). */
+int mpc_summary(const void* cost, const void* viol, const int32_t* n_sat, const int32_t* status,
+                const int32_t* iters, int64_t batch, double* out8, int dtype, mpc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * K4  batched box-constrained linear MPC QP
  *     min  sum_{k<N} x_k'Q x_k + u_k'R u_k + x_N'Pf x_N
  *     s.t. x_{k+1} = A_k x_k + B_k u_k + c_k,  u_lo <= u_k <= u_hi (k<N),  x_lo <= x_k <= x_hi (1<=k<=N)

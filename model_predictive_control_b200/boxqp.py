@@ -129,3 +129,35 @@ def solve(A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi, c=None, warm_U=None, ma
             _lib.ptr(w.sat_u), _lib.ptr(w.sat_x), _lib.ptr(w.ws), w.nbytes, batch, n, m, N, int(max_iter),
             float(eps), _lib.MPC_F64, _lib.stream(dev)))
     return BoxQpResult(w.U, w.X, w.cost, w.status, w.iters, w.sat_u, w.sat_x)
+
+
+_lib.register("mpc_condense", c_int, [c_void_p, c_int64] * 5 + [c_void_p] * 4 + [c_int64, c_int, c_int, c_int, c_int, c_void_p])
+
+
+def condense(A, B, Q, R, Pf, N):
+    """Condensed prediction matrices (K3).  Models shared ([n,n], ...) or batched ([batch,n,n], ...).
+    Returns Phi [.., N n, n], Gamma [.., N n, N m], H [.., N m, N m], F [.., N m, n] with
+    H = Gamma' Qbar Gamma + Rbar, F = Gamma' Qbar Phi, so J(U) = U'HU + 2 x0'F'U + const."""
+    from .lq import _common_batch, _model
+    _lib.require_cuda(A, B, Q, R, Pf)
+    n, m = A.shape[-1], B.shape[-1]
+    A, bA, sA = _model(A, n, n, "A")
+    B, bB, sB = _model(B, n, m, "B")
+    Q, bQ, sQ = _model(Q, n, n, "Q")
+    R, bR, sR = _model(R, m, m, "R")
+    Pf, bP, sP = _model(Pf, n, n, "Pf")
+    b = _common_batch([bA, bB, bQ, bR, bP])
+    batch = b or 1
+    N = int(N)
+    dd = dict(dtype=A.dtype, device=A.device)
+    Phi = torch.empty((batch, N * n, n), **dd)
+    Gam = torch.empty((batch, N * n, N * m), **dd)
+    H = torch.empty((batch, N * m, N * m), **dd)
+    F = torch.empty((batch, N * m, n), **dd)
+    with torch.cuda.device(A.device):
+        _lib.check(_lib.lib().mpc_condense(_lib.ptr(A), sA, _lib.ptr(B), sB, _lib.ptr(Q), sQ, _lib.ptr(R), sR,
+                                           _lib.ptr(Pf), sP, _lib.ptr(Phi), _lib.ptr(Gam), _lib.ptr(H), _lib.ptr(F),
+                                           batch, n, m, N, _lib.dtype_enum(A), _lib.stream(A.device)))
+    if b is None:
+        return Phi[0], Gam[0], H[0], F[0]
+    return Phi, Gam, H, F

@@ -185,3 +185,63 @@ def test_errors(mods):
     with pytest.raises(_lib.MpcError):  # (n, m) without an instantiated kernel
         boxqp.solve(dev(np.eye(3)), dev(np.ones((3, 1))), dev(np.eye(3)), dev([[1.0]]), dev(np.eye(3)), 5, dev(np.zeros((3, 4))),
                     [-1.0], [1.0], [-1] * 3, [1] * 3)
+
+
+@pytest.mark.parametrize("n,m,N", [(2, 1, 5), (2, 1, 30), (4, 2, 20), (12, 4, 50)])
+def test_condense_matches_oracle(mods, n, m, N):
+    boxqp, problem, log, torch = mods
+    rng = np.random.default_rng(n + m + N)
+    if n == 2:
+        p = bq.Problem(N=N)
+        A, B, Q, R, Pf = p.A, p.B, np.asarray(p.Q, float), np.asarray(p.R, float), 3.0 * np.asarray(p.Q, float)
+    else:
+        A = np.eye(n) + 0.1 * rng.standard_normal((n, n)); B = rng.standard_normal((n, m))
+        Q = np.diag(rng.uniform(0.5, 2, n)); R = np.diag(rng.uniform(0.05, 0.5, m)); Pf = 2.0 * Q
+    dev = lambda a: torch.tensor(np.asarray(a, dtype=np.float64), device="cuda")
+    Phi, Gam, H, F = boxqp.condense(dev(A), dev(B), dev(Q), dev(R), dev(Pf), N)
+    Po, Go, Ho, Fo = bq.condense(A, B, Q, R, Pf, N)
+    for got, ref in ((Phi, Po), (Gam, Go), (H, Ho), (F, Fo)):
+        assert got.shape == ref.shape
+        assert np.abs(got.cpu().numpy() - ref).max() <= 1e-9 * max(1.0, np.abs(ref).max())
+    # batched models: one CTA per model
+    As = np.stack([A, A + 0.01]); Bs = np.stack([B, 2 * B])
+    Phi2, Gam2, H2, F2 = boxqp.condense(dev(As), dev(Bs), dev(Q), dev(R), dev(Pf), N)
+    Ho2 = bq.condense(As[1], Bs[1], Q, R, Pf, N)[2]
+    assert np.abs(H2[1].cpu().numpy() - Ho2).max() <= 1e-9 * max(1.0, np.abs(Ho2).max())
+    assert torch.equal(H2[0], H)
+
+
+def test_condensed_qp_agrees_with_solver(mods):
+    """The condensed matrices and the structure-exploiting solver describe the same QP: at the solver's
+    optimum the projected-gradient residual of the condensed problem vanishes on the free inputs."""
+    boxqp, problem, log, torch = mods
+    prob = problem.Problem(N=30)
+    dev = lambda a: torch.tensor(np.asarray(a, dtype=np.float64), device="cuda")
+    Phi, Gam, H, F = boxqp.condense(dev(prob.A), dev(prob.B), dev(prob.Q), dev(prob.R), dev(prob.Q), 30)
+    rng = np.random.default_rng(0)
+    x0 = np.stack([rng.uniform(-100, 0, 64), rng.uniform(-10, 15, 64)], 1)
+    res = problem.LinearMPC(prob).solve(x0)
+    ok = res.solver_success & (res.sat_x.abs().sum(dim=(0, 1)) == 0)   # no active state bound
+    U = res.input_prediction[ok][:, :, 0]
+    g = 2 * (U @ H + dev(x0)[ok] @ F.t())            # gradient of U'HU + 2 x0'F'U
+    free = res.sat_u.permute(2, 0, 1)[ok][:, :, 0] == 0
+    assert float(g[free].abs().max()) <= 1e-6 * float(g.abs().max())
+    X = res.state_prediction[ok][:, 1:].reshape(U.shape[0], -1)
+    assert torch.allclose(X, dev(x0)[ok] @ Phi.t() + U @ Gam.t(), rtol=1e-10, atol=1e-9)
+
+
+def test_summary_kernel(mods):
+    boxqp, problem, log, torch = mods
+    from model_predictive_control_b200 import distributed as D
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    b = 100003
+    cost = torch.rand(b, generator=g, device="cuda", dtype=torch.float64)
+    viol = torch.rand(b, generator=g, device="cuda", dtype=torch.float64)
+    nsat = torch.randint(0, 50, (b,), generator=g, device="cuda", dtype=torch.int32)
+    status = torch.randint(1, 4, (b,), generator=g, device="cuda", dtype=torch.int32)
+    iters = torch.randint(1, 60, (b,), generator=g, device="cuda", dtype=torch.int32)
+    s = D.merge_summaries(D.local_summary(cost, viol, nsat, status, iters)[None].cpu())
+    assert s["scenarios"] == b and abs(s["sum_cost"] - float(cost.sum())) <= 1e-9 * b
+    assert s["max_violation"] == float(viol.max()) and s["sum_saturated"] == int(nsat.sum())
+    assert s["n_infeasible"] == int((status == 3).sum()) and s["n_max_iter"] == int((status == 2).sum())
+    assert s["n_solved"] == int((status == 1).sum()) and s["sum_iters"] == int(iters.sum())
