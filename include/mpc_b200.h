@@ -155,7 +155,8 @@ int mpc_summary(const void* cost, const void* viol, const int32_t* n_sat, const 
  *   Inputs at an active bound are returned exactly equal to the bound.
  *   ws: caller-owned workspace of mpc_boxqp_workspace_bytes(...) bytes.
  * Method: Mehrotra predictor-corrector interior point, Newton systems solved by Riccati sweeps;
- * float64 only (MPC_F32 -> MPC_ERR_UNSUPPORTED).  Supported (n, m): (2,1), (4,1), (4,2).
+ * float64 only (MPC_F32 -> MPC_ERR_UNSUPPORTED).  Supported (n, m): (2,1), (4,1), (4,2) register-resident;
+ * (12,4) runs from thread-local memory (functional, not yet tuned).
  */
 int64_t mpc_boxqp_workspace_bytes(int64_t batch, int n, int m, int N, int dtype);
 int mpc_boxqp_solve(const void* A, const void* B, const void* c, int ltv, const void* Q, const void* R,

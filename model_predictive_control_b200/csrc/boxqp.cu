@@ -77,5 +77,6 @@ extern "C" int mpc_boxqp_solve(const void* A, const void* B, const void* c, int 
   if (n == 2 && m == 1) return launch_boxqp<double, 2, 1>(a, st);
   if (n == 4 && m == 1) return launch_boxqp<double, 4, 1>(a, st);
   if (n == 4 && m == 2) return launch_boxqp<double, 4, 2>(a, st);
+  if (n == 12 && m == 4) return launch_boxqp<double, 12, 4>(a, st);
   return fail(MPC_ERR_UNSUPPORTED, "mpc_boxqp_solve: no kernel instantiated for n=%d m=%d", n, m);
 }

@@ -245,3 +245,36 @@ def test_summary_kernel(mods):
     assert s["max_violation"] == float(viol.max()) and s["sum_saturated"] == int(nsat.sum())
     assert s["n_infeasible"] == int((status == 3).sum()) and s["n_max_iter"] == int((status == 2).sum())
     assert s["n_solved"] == int((status == 1).sum()) and s["sum_iters"] == int(iters.sum())
+
+
+def cfg5_model(seed=1234 + 5):
+    """BASELINE config 5: four triple-integrator chains at Ts = 0.1 with weak
+    seeded coupling, Q = I, R = 0.1 I, |u| <= 1, |x_i| <= 5."""
+    rng = np.random.default_rng(seed)
+    Ts = 0.1
+    Ac = np.array([[1, Ts, Ts * Ts / 2], [0, 1, Ts], [0, 0, 1.0]])
+    Bc = np.array([[Ts**3 / 6], [Ts * Ts / 2], [Ts]])
+    A = np.kron(np.eye(4), Ac) + 0.01 * rng.standard_normal((12, 12))
+    B = np.kron(np.eye(4), Bc)
+    return A, B, np.eye(12), 0.1 * np.eye(4)
+
+
+def test_cfg5_shape_n12_m4_N50(mods):
+    boxqp, problem, log, torch = mods
+    A, B, Q, R = cfg5_model()
+    N, batch = 50, 48
+    rng = np.random.default_rng(9)
+    x0 = rng.uniform(-2, 2, (batch, 12))
+    ulo, uhi, xlo, xhi = -np.ones(4), np.ones(4), -5 * np.ones(12), 5 * np.ones(12)
+    dev = lambda a: torch.tensor(np.asarray(a, dtype=np.float64), device="cuda")
+    res = boxqp.solve(dev(A), dev(B), dev(Q), dev(R), dev(Q), N, dev(x0.T.copy()), ulo, uhi, xlo, xhi)
+    ex = [bq.solve_exact(A, B, Q, R, Q, N, x0[b], ulo, uhi, xlo, xhi) for b in range(12)]
+    nchk = check_against_exact(res.input_prediction[:12].cpu().numpy(), res.state_prediction[:12].cpu().numpy(),
+                               res.cost[:12].cpu().numpy(), res.status[:12].cpu().numpy(),
+                               res.sat_u.permute(2, 0, 1)[:12].cpu().numpy(), res.sat_x.permute(2, 0, 1)[:12].cpu().numpy(),
+                               ex, ulo, uhi)
+    assert nchk >= 4   # the rest of the first dozen starts outside the feasible set and is flagged infeasible
+    port = bq.ipm_riccati(A, B, Q, R, Q, N, x0, ulo, uhi, xlo, xhi)
+    np.testing.assert_array_equal(res.status.cpu().numpy(), port["status"])
+    ok = port["status"] == 1
+    assert np.abs(res.input_prediction.cpu().numpy()[ok] - port["U"].transpose(1, 0, 2)[ok]).max() <= 1e-6
