@@ -1,12 +1,16 @@
 // K4 kernel + C ABI: batched box-constrained LQ-MPC QP (interior point with Riccati Newton solves).
+#include <stdlib.h>
+
 #include "boxqp_core.cuh"
 
 namespace mpc {
 
 constexpr int kQpThreads = 128;
 
-template <typename T, int NX, int NU>
-__global__ void __launch_bounds__(kQpThreads) boxqp_ipm_kernel(BoxQpArgs<T> a) {
+// MINB = resident CTAs per SM the register allocation must allow (latency hiding for the streamed
+// workspace matters more than a few spills).
+template <typename T, int NX, int NU, int MINB>
+__global__ void __launch_bounds__(kQpThreads, MINB) boxqp_ipm_kernel(BoxQpArgs<T> a) {
   using SH = BoxQpShared<NX, NU>;
   __shared__ T sh[SH::total];
   for (int i = threadIdx.x; i < SH::total; i += blockDim.x) {
@@ -32,7 +36,16 @@ __global__ void __launch_bounds__(kQpThreads) boxqp_ipm_kernel(BoxQpArgs<T> a) {
 template <typename T, int NX, int NU>
 static int launch_boxqp(const BoxQpArgs<T>& a, cudaStream_t st) {
   const unsigned grid = (unsigned)((a.batch + kQpThreads - 1) / kQpThreads);
-  boxqp_ipm_kernel<T, NX, NU><<<grid, kQpThreads, 0, st>>>(a);
+  int minb = (NX + NU <= 3) ? 3 : 2;  // measured on B200: (2,1) best at 3 CTAs/SM (168 regs), (4,x) at 2 (255 regs)
+  if (const char* env = getenv("MPC_QP_MINB")) minb = atoi(env);
+  if constexpr (NX + NU > 8) {
+    boxqp_ipm_kernel<T, NX, NU, 1><<<grid, kQpThreads, 0, st>>>(a);
+  } else {
+    if (minb >= 6) boxqp_ipm_kernel<T, NX, NU, 6><<<grid, kQpThreads, 0, st>>>(a);
+    else if (minb >= 4) boxqp_ipm_kernel<T, NX, NU, 4><<<grid, kQpThreads, 0, st>>>(a);
+    else if (minb >= 3) boxqp_ipm_kernel<T, NX, NU, 3><<<grid, kQpThreads, 0, st>>>(a);
+    else boxqp_ipm_kernel<T, NX, NU, 2><<<grid, kQpThreads, 0, st>>>(a);
+  }
   return check_launch("boxqp_ipm_kernel");
 }
 

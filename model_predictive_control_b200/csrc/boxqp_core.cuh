@@ -57,7 +57,7 @@ struct BoxQpArgs {
 // workspace elements per scenario
 inline int64_t boxqp_ws_elems(int n, int m, int N) {
   const int d = n + m;
-  return (int64_t)N * (8 * d + m * n + m * m + m);
+  return (int64_t)N * (7 * d + m * n + m * m + m);
 }
 
 // shared-parameter block (shared memory on the device)
@@ -77,6 +77,9 @@ struct BoxQpShared {
 template <typename T, int NX, int NU>
 struct BoxQpIpm {
   static constexpr int D = NX + NU;
+  // small stages are double-buffered in registers (the next stage's operands are requested while
+  // the current one is being computed); larger ones rely on occupancy to hide the loads
+  static constexpr bool kPrefetch = (D <= 3);
   using SH = BoxQpShared<NX, NU>;
 
   const BoxQpArgs<T>& a;
@@ -84,8 +87,8 @@ struct BoxQpIpm {
   int64_t b, bs;
   T mu_scale;  // max(1, max|Q|, max|R|): scale of the complementarity tolerance
   T mu0;       // start value of the barrier parameter, per scenario: max(mu_scale, |H z0|_inf)
-  // workspace sections
-  T *z, *sl, *su, *ll, *lu, *zh, *ccl, *ccu, *Kw, *Sw, *dw;  // zh holds the Newton direction dz
+  // workspace sections, each [N][per][batch]
+  T *z, *sl, *su, *ll, *lu, *dza, *dzw, *Kw, *Sw, *dw;
 
   MPC_HD BoxQpIpm(const BoxQpArgs<T>& args, const T* shared, int64_t scenario)
       : a(args), sh(shared), b(scenario), bs(args.batch) {
@@ -95,10 +98,9 @@ struct BoxQpIpm {
     su = sl + sec;
     ll = su + sec;
     lu = ll + sec;
-    zh = lu + sec;
-    ccl = zh + sec;
-    ccu = ccl + sec;
-    Kw = ccu + sec;
+    dza = lu + sec;   // affine (predictor) direction dz_aff
+    dzw = dza + sec;  // corrector direction dz
+    Kw = dzw + sec;
     Sw = Kw + (int64_t)a.N * NU * NX * bs;
     dw = Sw + (int64_t)a.N * NU * NU * bs;
     mu_scale = T(1);
@@ -119,14 +121,41 @@ struct BoxQpIpm {
   MPC_HD T lo(int i) const { return sh[SH::oLo + i]; }
   MPC_HD T hi(int i) const { return sh[SH::oHi + i]; }
 
-  MPC_HD void load_stage(int k, T* A, T* B, T* c) const {
+  // ---- one stage's iterate.  All loads are unconditional and issued together (entries without a
+  // bound hold s = 1, lam = 0), so a stage visit costs one memory round trip instead of a chain.
+  struct Stage {
+    T z[D], sl[D], su[D], ll[D], lu[D];
+  };
+  MPC_HD void load(int k, Stage& s) const {
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      const int64_t o = ix(k, i, D);
+      s.z[i] = z[o];
+      s.sl[i] = sl[o];
+      s.su[i] = su[o];
+      s.ll[i] = ll[o];
+      s.lu[i] = lu[o];
+    }
+  }
+  MPC_HD void load_vec(const T* base, int k, int per, T* v) const {
+    for (int i = 0; i < per; ++i) v[i] = base[ix(k, i, per)];
+  }
+  template <int PER>
+  MPC_HD void loadn(const T* base, int k, T* v) const {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) v[i] = base[ix(k, i, PER)];
+  }
+  template <int PER>
+  MPC_HD void storen(T* base, int k, const T* v) const {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) base[ix(k, i, PER)] = v[i];
+  }
+
+  MPC_HD void load_model(int k, T* A, T* B, T* c) const {
     if (a.ltv) {
-#pragma unroll
-      for (int i = 0; i < NX * NX; ++i) A[i] = a.A[ix(k, i, NX * NX)];
-#pragma unroll
-      for (int i = 0; i < NX * NU; ++i) B[i] = a.B[ix(k, i, NX * NU)];
-#pragma unroll
-      for (int i = 0; i < NX; ++i) c[i] = a.c[ix(k, i, NX)];
+      loadn<NX * NX>(a.A, k, A);
+      loadn<NX * NU>(a.B, k, B);
+      loadn<NX>(a.c, k, c);
     } else {
 #pragma unroll
       for (int i = 0; i < NX * NX; ++i) A[i] = sh[SH::oA + i];
@@ -155,7 +184,7 @@ struct BoxQpIpm {
 #pragma unroll
       for (int i = 0; i < NX; ++i) x[i] = a.x0[i * bs + b];
       for (int k = 0; k < a.N; ++k) {
-        load_stage(k, A, B, c);
+        load_model(k, A, B, c);
 #pragma unroll
         for (int j = 0; j < NU; ++j) {
           T v = a.warm_U ? a.warm_U[ix(k, j, NU)] : T(0);
@@ -183,6 +212,7 @@ struct BoxQpIpm {
             g0 = acc > g0 ? acc : g0;
           }
         } else {
+          Stage st;
 #pragma unroll
           for (int i = 0; i < D; ++i) {
             const T zi = i < NU ? u[i] : xn[i - NU];
@@ -197,21 +227,39 @@ struct BoxQpIpm {
               s_u = s_u > T(1) ? s_u : T(1);
               l_u = mu0 / s_u;
             }
-            const int64_t o = ix(k, i, D);
-            z[o] = zi;
-            sl[o] = s_l;
-            su[o] = s_u;
-            ll[o] = l_l;
-            lu[o] = l_u;
-            ccl[o] = T(0);
-            ccu[o] = T(0);
+            st.z[i] = zi;
+            st.sl[i] = s_l;
+            st.su[i] = s_u;
+            st.ll[i] = l_l;
+            st.lu[i] = l_u;
           }
+          store_stage(k, st);
         }
 #pragma unroll
         for (int i = 0; i < NX; ++i) x[i] = xn[i];
       }
       if (pass == 0) mu0 = g0 > mu_scale ? g0 : mu_scale;
     }
+  }
+
+  MPC_HD void store_stage(int k, const Stage& s) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      const int64_t o = ix(k, i, D);
+      z[o] = s.z[i];
+      sl[o] = s.sl[i];
+      su[o] = s.su[i];
+      ll[o] = s.ll[i];
+      lu[o] = s.lu[i];
+    }
+  }
+
+  // second-order term cc = ds_aff * dlam_aff of one bound, recomputed from the stored dz_aff
+  // (affine direction: ds = +-dz + r, dlam = -lam - Sigma ds with Sigma = lam/s).
+  // Divisions: ONE reciprocal per bound and stage visit, rinv = 1/(s lam); 1/s = rinv lam, 1/lam = rinv s.
+  MPC_HD static T cc_of(T dz_signed, T r, T sig, T l) {
+    const T ds = dz_signed + r;
+    return ds * (-l - sig * ds);
   }
 
   // ---- backward sweep: (factorisation and) feed-forward terms of the Newton step.
@@ -223,10 +271,29 @@ struct BoxQpIpm {
     for (int i = 0; i < NX * NX; ++i) Pacc[i] = sh[SH::oPf + i];
 #pragma unroll
     for (int i = 0; i < NX; ++i) pacc[i] = T(0);
+    Stage cur, nxt;
+    T da[D], dan[D];
+    if (kPrefetch) {
+      load(a.N - 1, cur);
+      if (!FACTOR) loadn<D>(dza, a.N - 1, da);
+    }
     for (int k = a.N - 1; k >= 0; --k) {
-      T sig[D], rhs[D], zk[D];
-#pragma unroll
-      for (int i = 0; i < D; ++i) zk[i] = z[ix(k, i, D)];
+      if (kPrefetch) {
+        if (k > 0) {
+          load(k - 1, nxt);
+          if (!FACTOR) loadn<D>(dza, k - 1, dan);
+        }
+      } else {
+        load(k, cur);
+        if (!FACTOR) loadn<D>(dza, k, da);
+      }
+      T A[NX * NX], B[NX * NU], c[NX], K[NU * NX], Sinv[NU * NU];
+      load_model(k, A, B, c);
+      if (!FACTOR) {
+        loadn<NU * NX>(Kw, k, K);
+        loadn<NU * NU>(Sw, k, Sinv);
+      }
+      T sig[D], rhs[D];
       // -(H z): inputs weighted by R, state x_{k+1} by Q (Pf for the last stage)
       {
         const T* Qx = sh + (k == a.N - 1 ? SH::oPf : SH::oQ);
@@ -234,42 +301,41 @@ struct BoxQpIpm {
         for (int i = 0; i < NU; ++i) {
           T acc = T(0);
 #pragma unroll
-          for (int j = 0; j < NU; ++j) acc = fma_<T>(-sh[SH::oR + i * NU + j], zk[j], acc);
+          for (int j = 0; j < NU; ++j) acc = fma_<T>(-sh[SH::oR + i * NU + j], cur.z[j], acc);
           rhs[i] = acc;
         }
 #pragma unroll
         for (int i = 0; i < NX; ++i) {
           T acc = T(0);
 #pragma unroll
-          for (int j = 0; j < NX; ++j) acc = fma_<T>(-Qx[i * NX + j], zk[NU + j], acc);
+          for (int j = 0; j < NX; ++j) acc = fma_<T>(-Qx[i * NX + j], cur.z[NU + j], acc);
           rhs[NU + i] = acc;
         }
       }
 #pragma unroll
       for (int i = 0; i < D; ++i) {
-        const int64_t o = ix(k, i, D);
         T sg = T(0), r = rhs[i];
         if (hasl(i)) {
-          const T s = sl[o], l = ll[o];
-          const T inv = T(1) / s;
-          const T cc = FACTOR ? T(0) : ccl[o];
-          const T rl = zk[i] - lo(i) - s;
-          sg += l * inv;
-          r += (sig_mu - cc) * inv - l * inv * rl;
+          const T s = cur.sl[i], l = cur.ll[i];
+          const T inv = rcp_(s);
+          const T sgl = l * inv;
+          const T rl = cur.z[i] - lo(i) - s;
+          const T cc = FACTOR ? T(0) : cc_of(da[i], rl, sgl, l);
+          sg += sgl;
+          r += (sig_mu - cc) * inv - sgl * rl;
         }
         if (hasu(i)) {
-          const T s = su[o], l = lu[o];
-          const T inv = T(1) / s;
-          const T cc = FACTOR ? T(0) : ccu[o];
-          const T ru = hi(i) - zk[i] - s;
-          sg += l * inv;
-          r -= (sig_mu - cc) * inv - l * inv * ru;
+          const T s = cur.su[i], l = cur.lu[i];
+          const T inv = rcp_(s);
+          const T sgu = l * inv;
+          const T ru = hi(i) - cur.z[i] - s;
+          const T cc = FACTOR ? T(0) : cc_of(-da[i], ru, sgu, l);
+          sg += sgu;
+          r -= (sig_mu - cc) * inv - sgu * ru;
         }
         sig[i] = sg;
         rhs[i] = r;
       }
-      T A[NX * NX], B[NX * NU], c[NX], K[NU * NX], Sinv[NU * NU];
-      load_stage(k, A, B, c);
       if constexpr (FACTOR) {
         // P = Pacc + diag(Sigma_x);  S = R + diag(Sigma_u) + B'PB;  K = -S^-1 B'PA;
         // Pacc <- Q + A'(PA + PB K)
@@ -306,15 +372,8 @@ struct BoxQpIpm {
             Pacc[i * NX + j] = acc;
             Pacc[j * NX + i] = acc;
           }
-#pragma unroll
-        for (int i = 0; i < NU * NX; ++i) Kw[ix(k, i, NU * NX)] = K[i];
-#pragma unroll
-        for (int i = 0; i < NU * NU; ++i) Sw[ix(k, i, NU * NU)] = Sinv[i];
-      } else {
-#pragma unroll
-        for (int i = 0; i < NU * NX; ++i) K[i] = Kw[ix(k, i, NU * NX)];
-#pragma unroll
-        for (int i = 0; i < NU * NU; ++i) Sinv[i] = Sw[ix(k, i, NU * NU)];
+        storen<NU * NX>(Kw, k, K);
+        storen<NU * NU>(Sw, k, Sinv);
       }
       // h = -(rhs_x + pacc);  gu = rhs_u - B'h;  dff = Sinv gu;  pacc <- -A'h + K'gu
       T h[NX], gu[NU], dff[NU];
@@ -328,8 +387,7 @@ struct BoxQpIpm {
         gu[j] = acc;
       }
       mv<T, NU, NU, false>(Sinv, gu, dff);
-#pragma unroll
-      for (int j = 0; j < NU; ++j) dw[ix(k, j, NU)] = dff[j];
+      storen<NU>(dw, k, dff);
 #pragma unroll
       for (int i = 0; i < NX; ++i) {
         T acc = T(0);
@@ -338,6 +396,11 @@ struct BoxQpIpm {
 #pragma unroll
         for (int j = 0; j < NU; ++j) acc = fma_<T>(K[j * NX + i], gu[j], acc);
         pacc[i] = acc;
+      }
+      if (kPrefetch) {
+        cur = nxt;
+#pragma unroll
+        for (int i = 0; i < D; ++i) da[i] = dan[i];
       }
     }
   }
@@ -384,103 +447,151 @@ struct BoxQpIpm {
   }
 
   struct Acc {
-    T amin, s0, s1, s2, dzmax, rp;
+    T qmax, s0, s1, s2, dzmax, rp;  // qmax = max_i(-ds_i/s_i, -dlam_i/lam_i): largest feasible step = 1/qmax
+    MPC_HD T amin() const { return qmax > T(0) ? T(1) / qmax : T(1e30); }
   };
 
   // ---- forward sweep: dz by rollout with the stored gains; per element the slack / multiplier
-  // directions.  AFFINE: stores cc = ds*dlam (second-order term) and accumulates the sums that give
-  // mu_aff for any step length.  Otherwise stores dz and accumulates the step ratios / norms.
+  // directions.  AFFINE: stores dz_aff and accumulates the sums that give mu_aff for any step
+  // length.  Otherwise stores dz and accumulates the step ratios / norms.
   template <bool AFFINE>
   MPC_HD void forward(T sig_mu, Acc& acc) {
-    T x[NX], xn[NX], u[NU], A[NX * NX], B[NX * NU], c[NX];
-    acc.amin = T(1e30);
-    acc.s0 = acc.s1 = acc.s2 = acc.dzmax = acc.rp = T(0);
+    T x[NX], xn[NX], u[NU];
+    acc.qmax = acc.s0 = acc.s1 = acc.s2 = acc.dzmax = acc.rp = T(0);
 #pragma unroll
     for (int i = 0; i < NX; ++i) x[i] = T(0);  // dx_0 = 0
+    Stage cur, nxt;
+    T da[D], dan[D], K[NU * NX], Kn[NU * NX], dff[NU], dffn[NU];
+    if (kPrefetch) {
+      load(0, cur);
+      loadn<NU * NX>(Kw, 0, K);
+      loadn<NU>(dw, 0, dff);
+      if (!AFFINE) loadn<D>(dza, 0, da);
+    }
     for (int k = 0; k < a.N; ++k) {
-      load_stage(k, A, B, c);
-      T K[NU * NX];
+      if (kPrefetch) {
+        if (k + 1 < a.N) {
+          load(k + 1, nxt);
+          loadn<NU * NX>(Kw, k + 1, Kn);
+          loadn<NU>(dw, k + 1, dffn);
+          if (!AFFINE) loadn<D>(dza, k + 1, dan);
+        }
+      } else {
+        load(k, cur);
+        loadn<NU * NX>(Kw, k, K);
+        loadn<NU>(dw, k, dff);
+        if (!AFFINE) loadn<D>(dza, k, da);
+      }
+      T A[NX * NX], B[NX * NU], c[NX];
+      load_model(k, A, B, c);
 #pragma unroll
-      for (int i = 0; i < NU * NX; ++i) K[i] = Kw[ix(k, i, NU * NX)];
-#pragma unroll
-      for (int j = 0; j < NU; ++j) u[j] = dw[ix(k, j, NU)];
+      for (int j = 0; j < NU; ++j) u[j] = dff[j];
       mv<T, NU, NX, true>(K, x, u);
       mv<T, NX, NX, false>(A, x, xn);
       mv<T, NX, NU, true>(B, u, xn);
+      T dzv[D];
 #pragma unroll
       for (int i = 0; i < D; ++i) {
-        const int64_t o = ix(k, i, D);
         const T dz = i < NU ? u[i] : xn[i - NU];
-        const T zi = z[o];
+        dzv[i] = dz;
+        const T zi = cur.z[i];
         if (!AFFINE) {
-          zh[o] = dz;
           const T ad = dz < T(0) ? -dz : dz;
           acc.dzmax = ad > acc.dzmax ? ad : acc.dzmax;
         }
         if (hasl(i)) {
-          const T s = sl[o], l = ll[o];
+          const T s = cur.sl[i], l = cur.ll[i];
           const T r = zi - lo(i) - s;
           const T ds = dz + r;
-          const T cc = AFFINE ? T(0) : ccl[o];
-          const T dl = (sig_mu - cc) / s - l - l / s * ds;
-          if (ds < T(0)) { const T q = -s / ds; acc.amin = q < acc.amin ? q : acc.amin; }
-          if (dl < T(0)) { const T q = -l / dl; acc.amin = q < acc.amin ? q : acc.amin; }
+          const T rinv = rcp_(s * l), inv_s = rinv * l, inv_l = rinv * s;
+          const T sgl = l * inv_s;
+          const T cc = AFFINE ? T(0) : cc_of(da[i], r, sgl, l);
+          const T dl = (sig_mu - cc) * inv_s - l - sgl * ds;
+          const T qs = -ds * inv_s, ql = -dl * inv_l;  // step is limited to 1 / max(q)
+          acc.qmax = qs > acc.qmax ? qs : acc.qmax;
+          acc.qmax = ql > acc.qmax ? ql : acc.qmax;
           acc.s0 += s * l;
           acc.s1 += s * dl + l * ds;
           acc.s2 += ds * dl;
-          if (AFFINE) ccl[o] = ds * dl;
           const T ar = r < T(0) ? -r : r;
           acc.rp = ar > acc.rp ? ar : acc.rp;
         }
         if (hasu(i)) {
-          const T s = su[o], l = lu[o];
+          const T s = cur.su[i], l = cur.lu[i];
           const T r = hi(i) - zi - s;
           const T ds = -dz + r;
-          const T cc = AFFINE ? T(0) : ccu[o];
-          const T dl = (sig_mu - cc) / s - l - l / s * ds;
-          if (ds < T(0)) { const T q = -s / ds; acc.amin = q < acc.amin ? q : acc.amin; }
-          if (dl < T(0)) { const T q = -l / dl; acc.amin = q < acc.amin ? q : acc.amin; }
+          const T rinv = rcp_(s * l), inv_s = rinv * l, inv_l = rinv * s;
+          const T sgu = l * inv_s;
+          const T cc = AFFINE ? T(0) : cc_of(-da[i], r, sgu, l);
+          const T dl = (sig_mu - cc) * inv_s - l - sgu * ds;
+          const T qs = -ds * inv_s, ql = -dl * inv_l;
+          acc.qmax = qs > acc.qmax ? qs : acc.qmax;
+          acc.qmax = ql > acc.qmax ? ql : acc.qmax;
           acc.s0 += s * l;
           acc.s1 += s * dl + l * ds;
           acc.s2 += ds * dl;
-          if (AFFINE) ccu[o] = ds * dl;
           const T ar = r < T(0) ? -r : r;
           acc.rp = ar > acc.rp ? ar : acc.rp;
         }
       }
+      storen<D>(AFFINE ? dza : dzw, k, dzv);
 #pragma unroll
       for (int i = 0; i < NX; ++i) x[i] = xn[i];
+      if (kPrefetch) {
+        cur = nxt;
+#pragma unroll
+        for (int i = 0; i < NU * NX; ++i) K[i] = Kn[i];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) dff[i] = dffn[i];
+#pragma unroll
+        for (int i = 0; i < D; ++i) da[i] = dan[i];
+      }
     }
   }
 
-  // ---- step: (z, s, lam) += alpha * direction; returns max |z|
-  MPC_HD T update(T sig_mu, T alpha) {
+  // ---- step: (z, s, lam) += alpha * direction; returns max |z|.  Stages are independent here.
+  MPC_HD T update(T sig_mu, T alpha, bool second_order) {
     T zn = T(1);
     for (int k = 0; k < a.N; ++k) {
+      Stage st;
+      T da[D], dz[D];
+      load(k, st);
+      loadn<D>(dzw, k, dz);
+      if (second_order) {
+        loadn<D>(dza, k, da);
+      } else {
+#pragma unroll
+        for (int i = 0; i < D; ++i) da[i] = T(0);
+      }
 #pragma unroll
       for (int i = 0; i < D; ++i) {
-        const int64_t o = ix(k, i, D);
-        const T zi = z[o];
-        const T dz = zh[o];
+        const T zi = st.z[i];
         if (hasl(i)) {
-          const T s = sl[o], l = ll[o];
-          const T ds = dz + (zi - lo(i) - s);
-          const T dl = (sig_mu - ccl[o]) / s - l - l / s * ds;
-          sl[o] = s + alpha * ds;
-          ll[o] = l + alpha * dl;
+          const T s = st.sl[i], l = st.ll[i];
+          const T r = zi - lo(i) - s;
+          const T ds = dz[i] + r;
+          const T inv = rcp_(s), sgl = l * inv;
+          const T cc = second_order ? cc_of(da[i], r, sgl, l) : T(0);
+          const T dl = (sig_mu - cc) * inv - l - sgl * ds;
+          st.sl[i] = s + alpha * ds;
+          st.ll[i] = l + alpha * dl;
         }
         if (hasu(i)) {
-          const T s = su[o], l = lu[o];
-          const T ds = -dz + (hi(i) - zi - s);
-          const T dl = (sig_mu - ccu[o]) / s - l - l / s * ds;
-          su[o] = s + alpha * ds;
-          lu[o] = l + alpha * dl;
+          const T s = st.su[i], l = st.lu[i];
+          const T r = hi(i) - zi - s;
+          const T ds = -dz[i] + r;
+          const T inv = rcp_(s), sgu = l * inv;
+          const T cc = second_order ? cc_of(-da[i], r, sgu, l) : T(0);
+          const T dl = (sig_mu - cc) * inv - l - sgu * ds;
+          st.su[i] = s + alpha * ds;
+          st.lu[i] = l + alpha * dl;
         }
-        const T zn_i = zi + alpha * dz;
-        z[o] = zn_i;
+        const T zn_i = zi + alpha * dz[i];
+        st.z[i] = zn_i;
         const T az = zn_i < T(0) ? -zn_i : zn_i;
         zn = az > zn ? az : zn;
       }
+      store_stage(k, st);
     }
     return zn;
   }
@@ -496,15 +607,16 @@ struct BoxQpIpm {
       a.X[i * bs + b] = x[i];
     }
     for (int k = 0; k < a.N; ++k) {
-      load_stage(k, A, B, c);
+      Stage st;
+      load(k, st);
+      load_model(k, A, B, c);
 #pragma unroll
       for (int i = 0; i < D; ++i) {
-        const int64_t o = ix(k, i, D);
         int sat = 0;
-        if (hasl(i) && ll[o] > sl[o]) sat = -1;
-        if (hasu(i) && lu[o] > su[o]) sat = 1;
+        if (hasl(i) && st.ll[i] > st.sl[i]) sat = -1;
+        if (hasu(i) && st.lu[i] > st.su[i]) sat = 1;
         if (i < NU) {
-          u[i] = sat < 0 ? lo(i) : (sat > 0 ? hi(i) : z[o]);
+          u[i] = sat < 0 ? lo(i) : (sat > 0 ? hi(i) : st.z[i]);
           a.U[ix(k, i, NU)] = u[i];
           if (a.sat_u) a.sat_u[ix(k, i, NU)] = (int8_t)sat;
         } else if (a.sat_x) {
@@ -537,7 +649,7 @@ struct BoxQpIpm {
       Acc acc;
       backward<true>(T(0));
       forward<false>(T(0), acc);
-      update(T(0), T(1));
+      update(T(0), T(1), false);
       status = MPC_SOLVED;
       it = 1;
     }
@@ -548,7 +660,8 @@ struct BoxQpIpm {
       backward<true>(T(0));
       forward<true>(T(0), acc);
       const T mu = acc.s0 * inv_nc;
-      const T a_aff = acc.amin < T(1) ? acc.amin : T(1);
+      const T am_aff = acc.amin();
+      const T a_aff = am_aff < T(1) ? am_aff : T(1);
       const T mu_aff = (acc.s0 + a_aff * (acc.s1 + a_aff * acc.s2)) * inv_nc;
       T ratio = mu_aff / (mu > T(1e-300) ? mu : T(1e-300));
       T sigma = ratio * ratio * ratio;
@@ -556,9 +669,9 @@ struct BoxQpIpm {
       const T sig_mu = sigma * mu;
       backward<false>(sig_mu);
       forward<false>(sig_mu, acc);
-      T alpha = T(0.995) * acc.amin;
+      T alpha = T(0.995) * acc.amin();
       alpha = alpha < T(1) ? alpha : T(1);
-      zn = update(sig_mu, alpha);
+      zn = update(sig_mu, alpha, true);
       const T mu_new = (acc.s0 + alpha * (acc.s1 + alpha * acc.s2)) * inv_nc;
       rp = (T(1) - alpha) * acc.rp;
       const bool done = (mu_new <= a.eps * mu_scale) && (rp <= a.eps * zn) && (alpha * acc.dzmax <= T(1e-6) * zn);

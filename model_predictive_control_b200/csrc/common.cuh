@@ -131,6 +131,22 @@ MPC_HD float fma_<float>(float a, float b, float c) {
   return fmaf(a, b, c);
 }
 
+// reciprocal: one MUFU seed + Newton steps on the device (correctly rounded), plain division on the host
+MPC_HD double rcp_(double x) {
+#ifdef __CUDA_ARCH__
+  return __drcp_rn(x);
+#else
+  return 1.0 / x;
+#endif
+}
+MPC_HD float rcp_(float x) {
+#ifdef __CUDA_ARCH__
+  return __frcp_rn(x);
+#else
+  return 1.0f / x;
+#endif
+}
+
 // compile-time alignment (bytes, <= 32) of a densely packed row of CNT elements of T whose
 // base pointer is 32-byte aligned
 template <typename T, int CNT>

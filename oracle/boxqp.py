@@ -490,10 +490,13 @@ def ipm_riccati(A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi, c=None, warm_U=No
         return dz, np.where(has_l, dsl, 0.0), np.where(has_u, dsu, 0.0), dll, dlu
 
     def step_len(dsl, dsu, dll, dlu):
+        # largest step keeping s, lam > 0: 1 / max_i(-ds_i/s_i, -dlam_i/lam_i)
         with np.errstate(divide="ignore", invalid="ignore"):
-            r = np.minimum.reduce([np.where(dsl < 0, -sl / dsl, np.inf), np.where(dsu < 0, -su / dsu, np.inf),
-                                   np.where(dll < 0, -ll / dll, np.inf), np.where(dlu < 0, -lu / dlu, np.inf)])
-        return r.min(axis=(0, 2))
+            q = np.maximum.reduce([np.where(has_l, -dsl / sl, 0.0), np.where(has_u, -dsu / su, 0.0),
+                                   np.where(has_l, -dll / np.where(has_l, ll, 1.0), 0.0),
+                                   np.where(has_u, -dlu / np.where(has_u, lu, 1.0), 0.0)])
+            qmax = q.max(axis=(0, 2))
+            return np.where(qmax > 0, 1.0 / qmax, 1e30)
 
     zero = np.zeros(batch)
     for it in range(1, max_iter + 1):
