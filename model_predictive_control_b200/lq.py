@@ -162,6 +162,63 @@ def lq_solve(A, B, Q, R, Pf, x0, N, want_K=False, want_P0=False, out=None):
     return out
 
 
+class LqHostPipeline:
+    """End-to-end fused LQ solves for callers whose data lives in HOST memory.
+
+    ``submit(A, B, Q, R, Pf, x0)`` takes pinned host tensors of one batch and returns pinned host
+    tensors ``(X, U, V)``.  Consecutive submissions are software-pipelined over three CUDA streams
+    with double-buffered device storage: the H2D copy of batch i+1 overlaps the kernel and the D2H
+    copy of batch i (PCIe is full duplex), so the steady-state cost per batch is
+    max(H2D, D2H, kernel) rather than their sum.  ``wait()`` blocks until everything submitted has
+    landed in the returned host buffers.
+    """
+
+    def __init__(self, batch, n, m, N, dtype=torch.float64, device=None, per_scenario_model=True):
+        self.dev = device or torch.device("cuda", torch.cuda.current_device())
+        self.batch, self.n, self.m, self.N, self.dtype = batch, n, m, N, dtype
+        mb = (batch,) if per_scenario_model else ()
+        shapes = [mb + (n, n), mb + (n, m), mb + (n, n), mb + (m, m), mb + (n, n), (batch, n)]
+        self.dev_in = [[torch.empty(sh, dtype=dtype, device=self.dev) for sh in shapes] for _ in range(2)]
+        self.dev_out = [LqSolveBuffers(batch, n, m, N, dtype, self.dev) for _ in range(2)]
+        self.host_out = [[torch.empty(t.shape, dtype=dtype, pin_memory=True) for t in (o.X, o.U, o.V)]
+                         for o in self.dev_out]
+        self.s_in, self.s_c, self.s_out = (torch.cuda.Stream(self.dev) for _ in range(3))
+        self.ev_in = [torch.cuda.Event() for _ in range(2)]
+        self.ev_c = [torch.cuda.Event() for _ in range(2)]
+        self.ev_out = [torch.cuda.Event() for _ in range(2)]
+        self.count = 0
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.dev_in[0])
+        self.d2h_bytes = sum(t.numel() * t.element_size() for t in self.host_out[0])
+
+    def submit(self, A, B, Q, R, Pf, x0):
+        s = self.count % 2
+        first_use = self.count < 2
+        with torch.cuda.stream(self.s_in):
+            if not first_use:
+                self.s_in.wait_event(self.ev_c[s])        # the kernel that last read these inputs is done
+            for d, h in zip(self.dev_in[s], (A, B, Q, R, Pf, x0)):
+                d.copy_(h, non_blocking=True)
+            self.ev_in[s].record(self.s_in)
+        with torch.cuda.stream(self.s_c):
+            self.s_c.wait_event(self.ev_in[s])
+            if not first_use:
+                self.s_c.wait_event(self.ev_out[s])       # the D2H that last read these outputs is done
+            lq_solve(*self.dev_in[s], self.N, out=self.dev_out[s])
+            self.ev_c[s].record(self.s_c)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(self.ev_c[s])
+            o = self.dev_out[s]
+            for h, d in zip(self.host_out[s], (o.X, o.U, o.V)):
+                h.copy_(d, non_blocking=True)
+            self.ev_out[s].record(self.s_out)
+        self.count += 1
+        return self.host_out[s]
+
+    def wait(self):
+        for st in (self.s_in, self.s_c, self.s_out):
+            st.synchronize()
+
+
 def fma_peak(dtype=torch.float64):
     """Measured FMA-pipe FLOP/s of the current device (roofline denominator for fp kernels)."""
     import ctypes

@@ -270,3 +270,20 @@ def test_torch_in_torch_out_and_errors(mods, golden):
     # N = 0: P = [P_f], K = []
     P0, K0 = FHC.ricatti_recursion(arr(g["A"]), arr(g["B"]), arr(g["Q"]), arr(g["R"]), arr(g["Q"]), 0)
     assert len(P0) == 1 and len(K0) == 0
+
+
+def test_host_pipeline_matches_direct_call(mods):
+    _, _, _, lq, torch = mods
+    rng = np.random.default_rng(77)
+    batch, n, m, N = 5000, 4, 1, 20
+    A, B, Q, R = models(rng, batch, n, m)
+    pin = lambda a: torch.tensor(a, dtype=torch.float64).pin_memory()
+    pipe = lq.LqHostPipeline(batch, n, m, N)
+    outs = []
+    for i in range(5):   # more submissions than buffers: exercises the reuse hand-shakes
+        x0 = rng.uniform(-10, 10, (batch, n)) * (i + 1)
+        hX, hU, hV = pipe.submit(pin(A), pin(B), pin(Q), pin(R), pin(Q), pin(x0))
+        pipe.wait()
+        dev = lambda a: torch.tensor(a, dtype=torch.float64, device="cuda")
+        ref = lq.lq_solve(dev(A), dev(B), dev(Q), dev(R), dev(Q), dev(x0), N)
+        assert torch.equal(hX, ref.X.cpu()) and torch.equal(hU, ref.U.cpu()) and torch.equal(hV, ref.V.cpu())
