@@ -104,6 +104,76 @@ def terminal_cost_sweep(A, B, Q, R, P_f, x0, horizons=range(1, 10)):
     return V, float(np.squeeze(x0n.T @ P_inf @ x0n))
 
 
+def infinite_horizon(A, B, Q, R, tol=1e-13, max_horizon=1 << 16):
+    """(P_inf, K_inf) of the reference's infinite-horizon comparison (FHC.py:97-98,126), computed on
+    the GPU by running the Riccati recursion (K1) with doubling horizons until P stops changing --
+    the fixed point of the recursion is the stabilising DARE solution the reference gets from
+    scipy.linalg.solve_discrete_are.  K_inf = -(R + B'P B)^-1 B'P A is the converged first-stage gain."""
+    as_np = not io.any_tensor(A, B, Q, R)
+    dt = io.pick_dtype(A, B, Q, R)
+    Ad, Bd, Qd = (io.to_dev(M, dt) for M in (A, B, Q))
+    Rd = _prep_R(R, Bd.shape[-1], dt)
+    P, N = Qd, 64
+    while True:
+        K, Pn = lq.riccati(Ad, Bd, Qd, Rd, P, N, all_P=False)
+        P_new = Pn[0] if Ad.dim() == 2 else Pn
+        done = bool((P_new - P).abs().max() <= tol * P_new.abs().max())
+        P = P_new
+        if done or N >= max_horizon:
+            break
+        N *= 2
+    K0 = K[0, 0] if Ad.dim() == 2 else K[0]
+    return io.back(P, as_np), io.back(K0, as_np)
+
+
+def closed_loop_with_predictions(A, B, Q, R, P_f, x0, N, n_steps=30, gains=None):
+    """Numeric part of one panel of ``run_and_plot_traj`` (reference FHC.py:70-91): gains for horizon
+    N, the closed loop under gains[0] (``n_steps`` states, (n, batch, n_steps)) and, for every
+    closed-loop state x_t, the open-loop prediction of horizon N through ``LinearSystem.prediction``
+    (the reference loops over t; here all n_steps predictions are ONE batched rollout).
+    Returns (gains, x, bundle) with bundle[t] = prediction from x_t, shape (n_steps, n, batch, N)."""
+    if gains is None:
+        _, gains = ricatti_recursion(A, B, Q, R, P_f, N)
+    sys = AutoCruising(A, B)
+    sys.set_opti_gain(gains)
+    sys.simulate(x0, sys.control_law, n_steps)
+    x = sys.x
+    n, batch = x.shape[0], x.shape[1]
+    if io.is_tensor(x):
+        starts = x.permute(0, 2, 1).reshape(n, n_steps * batch)
+    else:
+        starts = np.ascontiguousarray(np.transpose(x, (0, 2, 1)).reshape(n, n_steps * batch))
+    pred = sys.prediction(starts, sys.pred, N)               # (n, n_steps*batch, N)
+    bundle = pred.reshape(n, n_steps, batch, pred.shape[-1])
+    bundle = bundle.permute(1, 0, 2, 3) if io.is_tensor(bundle) else np.transpose(bundle, (1, 0, 2, 3))
+    return gains, x, bundle
+
+
+def run_and_plot_traj(A, B, Q, R, P_f, x0):
+    """Reference FHC.py:64-114: closed loops and prediction bundles for N in (4, 6, 10) and for the
+    infinite-horizon gain.  Returns the numbers ({N: (x, bundle)}, (x_inf, bundle_inf)); the figures
+    are drawn only when matplotlib is importable."""
+    out = {}
+    for N in (4, 6, 10):
+        _, x, bundle = closed_loop_with_predictions(A, B, Q, R, P_f, x0, N)
+        out[N] = (x, bundle)
+    _, K_inf = infinite_horizon(A, B, Q, R)
+    _, x_inf, b_inf = closed_loop_with_predictions(A, B, Q, R, P_f, x0, 10, gains=[K_inf] * 10)
+    try:
+        import matplotlib.pyplot as plt
+    except ImportError:
+        return out, (x_inf, b_inf)
+    for idx, N in enumerate((4, 6, 10)):
+        x, bundle = out[N]
+        plt.figure(1)
+        plt.subplot(1, 3, idx + 1)
+        plt.plot(x[0, 0, :], x[1, 0, :], "x", linestyle="--")
+        for t in range(bundle.shape[0]):
+            plt.plot(bundle[t, 0, 0, :], bundle[t, 1, 0, :], "o", linestyle=":")
+    plt.show()
+    return out, (x_inf, b_inf)
+
+
 def compare_term_cost(A, B, Q, R, P_f, x0):
     """Reference FHC.py:117-131 (the plot needs matplotlib; the numbers do not)."""
     V, V_inf = terminal_cost_sweep(A, B, Q, R, P_f, x0)

@@ -71,10 +71,10 @@ extern "C" int mpc_boxqp_solve(const void* A, const void* B, const void* c, int 
               "mpc_boxqp_solve: the interior-point iteration runs in float64 only (barrier weights span > 1e10)");
   MPC_REQUIRE(n >= 1 && n <= MPC_MAX_NX && m >= 1 && m <= MPC_MAX_NU, MPC_ERR_SHAPE, "mpc_boxqp_solve: bad (n=%d, m=%d)", n, m);
   MPC_REQUIRE(N >= 1 && batch >= 0 && max_iter >= 1, MPC_ERR_SHAPE, "mpc_boxqp_solve: bad N / batch / max_iter");
+  if (batch == 0) return MPC_OK;  // nothing to do; pointers of an empty batch may be null
   MPC_REQUIRE(A && B && Q && R && Pf && u_lo && u_hi && x_lo && x_hi && x0 && U && X && cost && status && iters,
               MPC_ERR_NULL, "mpc_boxqp_solve: null pointer");
   MPC_REQUIRE(!ltv || c, MPC_ERR_NULL, "mpc_boxqp_solve: ltv model needs c");
-  if (batch == 0) return MPC_OK;
   MPC_REQUIRE(ws && ws_bytes >= mpc_boxqp_workspace_bytes(batch, n, m, N, dtype), MPC_ERR_WORKSPACE,
               "mpc_boxqp_solve: workspace too small (%lld < %lld bytes)", (long long)ws_bytes,
               (long long)mpc_boxqp_workspace_bytes(batch, n, m, N, dtype));

@@ -169,9 +169,9 @@ extern "C" int mpc_condense(const void* A, int64_t sA, const void* B, int64_t sB
   MPC_REQUIRE(dtype == MPC_F64 || dtype == MPC_F32, MPC_ERR_DTYPE, "mpc_condense: unknown dtype %d", dtype);
   MPC_REQUIRE(n >= 1 && n <= MPC_MAX_NX && m >= 1 && m <= MPC_MAX_NU && N >= 1 && batch >= 0, MPC_ERR_SHAPE,
               "mpc_condense: bad shape n=%d m=%d N=%d", n, m, N);
+  if (batch == 0) return MPC_OK;  // nothing to do; pointers of an empty batch may be null
   MPC_REQUIRE(A && B && Q && R && Pf, MPC_ERR_NULL, "mpc_condense: null model pointer");
   MPC_REQUIRE(sA >= 0 && sB >= 0 && sQ >= 0 && sR >= 0 && sPf >= 0, MPC_ERR_SHAPE, "mpc_condense: negative stride");
-  if (batch == 0) return MPC_OK;
   const size_t es = dtype == MPC_F64 ? 8 : 4;
   for (const void* p : {A, B, Q, R, Pf, (const void*)Phi, (const void*)Gamma, (const void*)H, (const void*)F})
     MPC_REQUIRE(!p || aligned(p, es), MPC_ERR_ALIGN, "mpc_condense: misaligned pointer");
@@ -197,12 +197,12 @@ extern "C" int mpc_condense(const void* A, int64_t sA, const void* B, int64_t sB
 extern "C" int mpc_summary(const void* cost, const void* viol, const int32_t* n_sat, const int32_t* status,
                            const int32_t* iters, int64_t batch, double* out8, int dtype, mpc_stream_t stream) {
   MPC_REQUIRE(dtype == MPC_F64 || dtype == MPC_F32, MPC_ERR_DTYPE, "mpc_summary: unknown dtype %d", dtype);
+  if (batch == 0) return MPC_OK;  // nothing to do; pointers of an empty batch may be null
   MPC_REQUIRE(out8, MPC_ERR_NULL, "mpc_summary: null output");
   MPC_REQUIRE(batch >= 0, MPC_ERR_SHAPE, "mpc_summary: negative batch");
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaMemsetAsync(out8, 0, 8 * sizeof(double), st);
   if (e != cudaSuccess) return fail((int)e, "mpc_summary: %s", cudaGetErrorString(e));
-  if (batch == 0) return MPC_OK;
   int64_t blocks = (batch + 255) / 256;
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
   if (dtype == MPC_F64)

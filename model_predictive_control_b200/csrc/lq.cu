@@ -372,10 +372,10 @@ extern "C" int mpc_riccati(const void* A, int64_t sA, const void* B, int64_t sB,
                            int dtype, mpc_stream_t stream) {
   CHECK_COMMON("mpc_riccati");
   MPC_REQUIRE(N >= 0, MPC_ERR_SHAPE, "mpc_riccati: negative horizon");
+  if (batch == 0) return MPC_OK;  // nothing to do; pointers of an empty batch may be null
   MPC_REQUIRE(A && B && Q && R && Pf, MPC_ERR_NULL, "mpc_riccati: null model pointer");
   MPC_REQUIRE(K || N == 0, MPC_ERR_NULL, "mpc_riccati: null K");
   MPC_REQUIRE(sA >= 0 && sB >= 0 && sQ >= 0 && sR >= 0 && sPf >= 0, MPC_ERR_SHAPE, "mpc_riccati: negative stride");
-  if (batch == 0) return MPC_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == MPC_F64) {
     MPC_REQUIRE(elem_aligned<double>({A, B, Q, R, Pf, K, P}), MPC_ERR_ALIGN, "mpc_riccati: misaligned pointer");
@@ -396,12 +396,12 @@ extern "C" int mpc_lq_rollout(const void* A, int64_t sA, const void* B, int64_t 
                               int64_t batch, int n, int m, int T, int dtype, mpc_stream_t stream) {
   CHECK_COMMON("mpc_lq_rollout");
   MPC_REQUIRE(T >= 1, MPC_ERR_SHAPE, "mpc_lq_rollout: need at least one state (T=%d)", T);
+  if (batch == 0) return MPC_OK;  // nothing to do; pointers of an empty batch may be null
   MPC_REQUIRE(A && B && x0 && X, MPC_ERR_NULL, "mpc_lq_rollout: null pointer");
   MPC_REQUIRE(K || T == 1, MPC_ERR_NULL, "mpc_lq_rollout: null gains");
   MPC_REQUIRE(!cost || (Q && R && Pf), MPC_ERR_NULL, "mpc_lq_rollout: cost needs Q, R, Pf");
   MPC_REQUIRE(gain_offset >= 0 && gain_step >= 0 && sA >= 0 && sB >= 0 && sK >= 0 && sK_stage >= 0,
               MPC_ERR_SHAPE, "mpc_lq_rollout: negative stride / gain index");
-  if (batch == 0) return MPC_OK;
   const int ng = (T >= 2) ? gain_offset + gain_step * (T - 2) + 1 : 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == MPC_F64) {
@@ -426,9 +426,9 @@ extern "C" int mpc_lq_solve(const void* A, int64_t sA, const void* B, int64_t sB
                             int64_t batch, int n, int m, int N, int dtype, mpc_stream_t stream) {
   CHECK_COMMON("mpc_lq_solve");
   MPC_REQUIRE(N >= 1, MPC_ERR_SHAPE, "mpc_lq_solve: horizon must be >= 1");
+  if (batch == 0) return MPC_OK;  // nothing to do; pointers of an empty batch may be null
   MPC_REQUIRE(A && B && Q && R && Pf && x0 && X && U && V, MPC_ERR_NULL, "mpc_lq_solve: null pointer");
   MPC_REQUIRE(sA >= 0 && sB >= 0 && sQ >= 0 && sR >= 0 && sPf >= 0, MPC_ERR_SHAPE, "mpc_lq_solve: negative stride");
-  if (batch == 0) return MPC_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == MPC_F64) {
     MPC_REQUIRE(elem_aligned<double>({A, B, Q, R, Pf, x0, X, U, V, K, P0}), MPC_ERR_ALIGN, "mpc_lq_solve: misaligned pointer");
@@ -447,9 +447,9 @@ extern "C" int mpc_lq_solve(const void* A, int64_t sA, const void* B, int64_t sB
 extern "C" int mpc_linear_step(const void* A, const void* B, const void* x, const void* u, void* xn,
                                int64_t batch, int n, int m, int dtype, mpc_stream_t stream) {
   CHECK_COMMON("mpc_linear_step");
+  if (batch == 0) return MPC_OK;  // nothing to do; pointers of an empty batch may be null
   MPC_REQUIRE(A && B && x && u && xn, MPC_ERR_NULL, "mpc_linear_step: null pointer");
   MPC_REQUIRE(xn != x, MPC_ERR_UNSUPPORTED, "mpc_linear_step: in-place step not supported");
-  if (batch == 0) return MPC_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = (unsigned)((batch + 255) / 256);
   if (dtype == MPC_F64) {

@@ -64,11 +64,11 @@ extern "C" int mpc_bicycle_rti_prepare(double lr, double lf, double accel, doubl
                                        void* B, void* c, int64_t batch, int N, int dtype, mpc_stream_t stream) {
   MPC_REQUIRE(dtype == MPC_F64, dtype == MPC_F32 ? MPC_ERR_UNSUPPORTED : MPC_ERR_DTYPE,
               "mpc_bicycle_rti_prepare: float64 only (dtype %d)", dtype);
+  if (batch == 0) return MPC_OK;  // nothing to do; pointers of an empty batch may be null
   MPC_REQUIRE(y && U_prev && warm_U && A && B && c, MPC_ERR_NULL, "mpc_bicycle_rti_prepare: null pointer");
   MPC_REQUIRE(N >= 1 && batch >= 0 && lr > 0 && lf >= 0 && ts > 0, MPC_ERR_SHAPE, "mpc_bicycle_rti_prepare: bad argument");
   MPC_REQUIRE(warm_U != U_prev, MPC_ERR_UNSUPPORTED, "mpc_bicycle_rti_prepare: warm_U must not alias U_prev");
   MPC_REQUIRE(al8({y, U_prev, warm_U, A, B, c}), MPC_ERR_ALIGN, "mpc_bicycle_rti_prepare: misaligned pointer");
-  if (batch == 0) return MPC_OK;
   BicycleModel<double> m{lr, lf, accel, ts, rk4 ? 1 : 0};
   rti_prepare_kernel<double><<<(unsigned)((batch + kRtiThreads - 1) / kRtiThreads), kRtiThreads, 0, (cudaStream_t)stream>>>(
       m, friction, (const double*)y, (const double*)U_prev, first, (double*)warm_U, (double*)A, (double*)B, (double*)c, N,
@@ -81,11 +81,11 @@ extern "C" int mpc_bicycle_plant_step(double lr, double lf, double accel, double
                                       int64_t batch, int dtype, mpc_stream_t stream) {
   MPC_REQUIRE(dtype == MPC_F64, dtype == MPC_F32 ? MPC_ERR_UNSUPPORTED : MPC_ERR_DTYPE,
               "mpc_bicycle_plant_step: float64 only (dtype %d)", dtype);
+  if (batch == 0) return MPC_OK;  // nothing to do; pointers of an empty batch may be null
   MPC_REQUIRE(friction && x && u && xn, MPC_ERR_NULL, "mpc_bicycle_plant_step: null pointer");
   MPC_REQUIRE(batch >= 0 && lr > 0 && ts > 0 && substeps >= 0 && (s_friction == 0 || s_friction == 1), MPC_ERR_SHAPE,
               "mpc_bicycle_plant_step: bad argument");
   MPC_REQUIRE(al8({friction, x, u, xn}), MPC_ERR_ALIGN, "mpc_bicycle_plant_step: misaligned pointer");
-  if (batch == 0) return MPC_OK;
   BicycleModel<double> m{lr, lf, accel, ts, 0};
   bicycle_plant_kernel<double><<<(unsigned)((batch + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       m, (const double*)friction, s_friction, substeps, (const double*)x, (const double*)u, (double*)xn, batch);
@@ -109,12 +109,12 @@ extern "C" int mpc_rti_closed_loop(double lr, double lf, double accel, double fr
                                    mpc_stream_t stream) {
   MPC_REQUIRE(dtype == MPC_F64, dtype == MPC_F32 ? MPC_ERR_UNSUPPORTED : MPC_ERR_DTYPE,
               "mpc_rti_closed_loop: float64 only (dtype %d)", dtype);
+  if (batch == 0) return MPC_OK;  // nothing to do; pointers of an empty batch may be null
   MPC_REQUIRE(friction_plant && Q && R && Pf && u_lo && u_hi && x_lo && x_hi && x0 && U_plan && X_pred && X_cl && U_cl &&
                   cost_cl && viol_cl && n_sat && n_fail && iters_total && last_status,
               MPC_ERR_NULL, "mpc_rti_closed_loop: null pointer");
   MPC_REQUIRE(N >= 1 && batch >= 0 && steps >= 0 && max_iter >= 1 && lr > 0 && ts > 0 && plant_substeps >= 0, MPC_ERR_SHAPE,
               "mpc_rti_closed_loop: bad argument");
-  if (batch == 0) return MPC_OK;
   MPC_REQUIRE(ws && ws_bytes >= mpc_rti_workspace_bytes(batch, N, dtype), MPC_ERR_WORKSPACE,
               "mpc_rti_closed_loop: workspace too small (%lld < %lld bytes)", (long long)ws_bytes,
               (long long)mpc_rti_workspace_bytes(batch, N, dtype));

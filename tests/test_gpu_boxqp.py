@@ -278,3 +278,32 @@ def test_cfg5_shape_n12_m4_N50(mods):
     np.testing.assert_array_equal(res.status.cpu().numpy(), port["status"])
     ok = port["status"] == 1
     assert np.abs(res.input_prediction.cpu().numpy()[ok] - port["U"].transpose(1, 0, 2)[ok]).max() <= 1e-6
+
+
+def test_edge_cases_boxqp(mods):
+    boxqp, problem, log, torch = mods
+    prob = problem.Problem(N=1)                      # horizon 1
+    res = problem.LinearMPC(prob).solve(np.array([-10.0, 40.0]))   # v_1 >= 40 - 0.3*20 = 34 > v_max: infeasible
+    assert int(res.status[0]) == bq.INFEASIBLE
+    res = problem.LinearMPC(prob).solve(np.array([-10.0, 3.0]))
+    ex = bq.solve_exact(prob.A, prob.B, prob.Q, prob.R, prob.Q, 1, np.array([-10.0, 3.0]), *bq.problem_bounds(bq.Problem(N=1)))
+    np.testing.assert_allclose(res.input_prediction[0].cpu().numpy(), ex["U"], rtol=1e-6, atol=1e-9)
+    # input bounds only (state bounds at infinity), one-sided state bound
+    prob = problem.Problem(N=10)
+    dev = lambda a: torch.tensor(np.asarray(a, dtype=np.float64), device="cuda")
+    x0 = np.array([[-30.0, 8.0], [-5.0, 2.0]])
+    res = boxqp.solve(dev(prob.A), dev(prob.B), dev(prob.Q), dev(prob.R), dev(prob.Q), 10, dev(x0.T.copy()),
+                      [prob.u_min], [prob.u_max], [-np.inf, -np.inf], [prob.p_max, np.inf])
+    for b in range(2):
+        ex = bq.solve_exact(prob.A, prob.B, prob.Q.astype(float), prob.R.astype(float), prob.Q.astype(float), 10, x0[b],
+                            np.array([prob.u_min]), np.array([prob.u_max]), np.array([-np.inf, -np.inf]),
+                            np.array([prob.p_max, np.inf]))
+        assert ex["status"] == bq.SOLVED and int(res.status[b]) == bq.SOLVED
+        np.testing.assert_allclose(res.input_prediction[b].cpu().numpy(), ex["U"], rtol=1e-6, atol=1e-7)
+        np.testing.assert_array_equal(res.sat_u.permute(2, 0, 1)[b].cpu().numpy(), ex["sat_u"])
+    # batch of one, and a batch that is not a multiple of the CTA size
+    for batch in (1, 129):
+        xb = np.tile(np.array([[-50.0, 5.0]]), (batch, 1))
+        r = problem.LinearMPC(problem.Problem(N=5)).solve(xb)
+        assert r.input_prediction.shape == (batch, 5, 1) and bool(r.solver_success.all())
+        assert torch.equal(r.U[:, :, 0], r.U[:, :, -1])

@@ -287,3 +287,56 @@ def test_host_pipeline_matches_direct_call(mods):
         dev = lambda a: torch.tensor(a, dtype=torch.float64, device="cuda")
         ref = lq.lq_solve(dev(A), dev(B), dev(Q), dev(R), dev(Q), dev(x0), N)
         assert torch.equal(hX, ref.X.cpu()) and torch.equal(hU, ref.U.cpu()) and torch.equal(hV, ref.V.cpu())
+
+
+def test_infinite_horizon_matches_dare_golden(mods, golden):
+    """P_inf / K_inf of FHC.py:97-98,126 (scipy DARE in the reference) as the fixed point of K1."""
+    FHC, *_ = mods
+    g = golden["cfg1"]
+    P_inf, K_inf = FHC.infinite_horizon(arr(g["A"]), arr(g["B"]), arr(g["Q"]), arr(g["R"]))
+    np.testing.assert_allclose(P_inf, arr(g["P_inf"]).reshape(2, 2), rtol=1e-9)
+    np.testing.assert_allclose(K_inf, arr(g["K_inf"]).reshape(1, 2), rtol=1e-9)
+
+
+def test_run_and_plot_traj_numbers(mods, golden):
+    """Closed loops + per-step prediction bundles of FHC.run_and_plot_traj (FHC.py:64-91)."""
+    FHC, *_ = mods
+    g = golden["cfg1"]
+    A, B, Q, R, x0 = arr(g["A"]), arr(g["B"]), arr(g["Q"]), arr(g["R"]), arr(g["x0"])
+    out, (x_inf, b_inf) = FHC.run_and_plot_traj(A, B, Q, R, Q, x0)
+    for N in (4, 6, 10):
+        x, bundle = out[N]
+        cl = g["closed_loop"][str(N)]
+        np.testing.assert_allclose(x, arr(cl["X"]), rtol=1e-8, atol=1e-12)
+        assert bundle.shape == (30, 2, 1, N)
+        for t, pr in zip((0, 1, 7), cl["pred_t0_t1_t7"]):
+            np.testing.assert_allclose(bundle[t], arr(pr), rtol=1e-8, atol=1e-12)
+    assert x_inf.shape == (2, 1, 30) and b_inf.shape == (30, 2, 1, 10)
+    assert np.abs(x_inf[:, 0, -1]).max() < 1e-5   # the infinite-horizon loop is stable
+
+
+def test_edge_cases_lq(mods):
+    FHC, LinearSystem, sol, lq, torch = mods
+    A, B = FHC.get_dynamics_discrete(0.5)
+    Q = np.eye(2); R = np.array([[0.1]])
+    P, K = FHC.ricatti_recursion(A, B, Q, R, Q, 1)
+    Po, Ko = olq.ricatti_recursion(A, B, Q, R, Q, 1)
+    np.testing.assert_allclose(K[0], Ko[0], rtol=1e-12)
+    sys = FHC.AutoCruising(A, B); sys.set_opti_gain(K)
+    sys.simulate(np.array([[1.0], [2.0]]), sys.control_law, 1)    # steps = 1: only x0
+    assert sys.x.shape == (2, 1, 1)
+    xp = sys.prediction(np.array([[1.0], [2.0]]), sys.pred, 1)    # horizon 1: no gain needed
+    assert xp.shape == (2, 1, 1)
+    with pytest.raises(IndexError):                                # reference: gains[1] does not exist
+        sys.prediction(np.array([[1.0], [2.0]]), sys.pred, 3)
+    with pytest.raises(ValueError):                                # x0 must be a column, as in the reference
+        sys.simulate(np.array([1.0, 2.0]), sys.control_law, 5)
+    # float32 tensors through the reference-shaped API stay float32 and meet 1e-4
+    t32 = lambda a: torch.tensor(a, dtype=torch.float32, device="cuda")
+    P32, K32 = FHC.ricatti_recursion(t32(A), t32(B), t32(Q), t32(R), t32(Q), 20)
+    Po, Ko = olq.ricatti_recursion(A, B, Q, R, Q, 20)
+    assert K32[0].dtype == torch.float32
+    assert np.abs(torch.stack(K32).cpu().numpy() - np.array(Ko)).max() <= 1e-4 * np.abs(np.array(Ko)).max()
+    # empty batch
+    out = lq.lq_solve(t32(A), t32(B), t32(Q), t32(R), t32(Q), torch.empty((0, 2), dtype=torch.float32, device="cuda"), 5)
+    assert out.X.shape == (6, 0, 2)
