@@ -366,7 +366,7 @@ def run_secondary(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    g = torch.Generator(device=dev); g.manual_seed(1234 + (3 if args.workload == "cfg3" else 4) + 1000 * rank)
+    g = torch.Generator(device=dev); g.manual_seed(1234 + int(args.workload[-1]) + 1000 * rank)
     rnd = lambda *shape: torch.rand(*shape, generator=g, device=dev, dtype=torch.float64)
     if args.workload == "cfg3":
         batch = args.batch or (1 << 18)
@@ -386,6 +386,27 @@ def run_secondary(args):
         solves_per_step = batch
         name = f"cfg3: session-2 Problem box-QP (input + state bounds), nx=2 nu=1 N=30, {batch} scenarios per GPU"
         io_bytes = 8 * (n + N * m + (N + 1) * n + 1) + 8 + N * (n + m)
+        host_in, host_out = [x0T], lambda r: [r.U, r.X, r.cost, r.status]
+    elif args.workload == "cfg5":
+        import numpy as np
+        batch = args.batch or (1 << 20)
+        n, m, N = 12, 4, 50
+        rng = np.random.default_rng(1234 + 5)      # the shared model is the same on every rank
+        Ts = 0.1
+        Ac = np.array([[1, Ts, Ts * Ts / 2], [0, 1, Ts], [0, 0, 1.0]]); Bc = np.array([[Ts**3 / 6], [Ts * Ts / 2], [Ts]])
+        A = torch.tensor(np.kron(np.eye(4), Ac) + 0.01 * rng.standard_normal((12, 12)), device=dev)
+        B = torch.tensor(np.kron(np.eye(4), Bc), device=dev)
+        Q = torch.eye(12, dtype=torch.float64, device=dev); R = 0.1 * torch.eye(4, dtype=torch.float64, device=dev)
+        x0T = rnd(12, batch) * 4 - 2
+        ws = boxqp.BoxQpWorkspace(batch, n, m, N, dev, sat=False)
+
+        def step():
+            return boxqp.solve(A, B, Q, R, Q, N, x0T, -1.0, 1.0, -5.0, 5.0, workspace=ws)
+
+        solves_per_step = batch
+        name = (f"cfg5: box-QP nx=12 nu=4 N=50 (four coupled triple integrators, |u|<=1, |x|<=5, x0~U[-2,2]^12), "
+                f"{batch} scenarios per GPU")
+        io_bytes = 8 * (n + N * m + (N + 1) * n + 1) + 8
         host_in, host_out = [x0T], lambda r: [r.U, r.X, r.cost, r.status]
     else:
         batch = args.batch or (1 << 16)
@@ -451,7 +472,7 @@ def run_secondary(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * solves_per_step * 3 / (float(t.item()) * 1e-3)
-    if args.workload == "cfg3":
+    if args.workload in ("cfg3", "cfg5"):
         summ = D.local_summary(cost=res.cost, status=res.status, iters=res.iters)
     else:
         summ = D.local_summary(cost=res.cost, violation=res.violation, n_saturated=res.n_saturated, iters=res.iters)
@@ -462,7 +483,7 @@ def run_secondary(args):
         iters_total = merged["sum_iters"] / world  # per rank (ranks run the same distribution)
         flops = iters_total * ipm_flops_per_iter(n, m, N)
         achieved = io_bytes * solves_per_step / (kern_ms * 1e-3) / 1e9
-        kname = "boxqp_ipm_kernel" if args.workload == "cfg3" else "rti_closed_loop_kernel"
+        kname = {"cfg3": "boxqp_ipm_kernel", "cfg4": "rti_closed_loop_kernel", "cfg5": "boxqp_ipm_coop_kernel"}[args.workload]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": kern_ms, "higher_is_better": True, "scaling": "weak",
@@ -495,9 +516,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--batch", type=int, default=0, help="scenarios per GPU (default: the named config's)")
-    ap.add_argument("--workload", default="cfg2b", choices=["cfg2b", "cfg3", "cfg4"],
+    ap.add_argument("--workload", default="cfg2b", choices=["cfg2b", "cfg3", "cfg4", "cfg5"],
                     help="cfg2b (default, BASELINE configs[1]); cfg3 = session-2 box-QP N=30, 256k scenarios; "
-                         "cfg4 = session-4 RTI closed loop, 64k scenarios x 200 steps")
+                         "cfg4 = session-4 RTI closed loop, 64k scenarios x 200 steps; "
+                         "cfg5 = nx=12 nu=4 N=50 box-QP, 2^20 scenarios per GPU (8M over 8 GPUs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -155,8 +155,9 @@ int mpc_summary(const void* cost, const void* viol, const int32_t* n_sat, const 
  *   Inputs at an active bound are returned exactly equal to the bound.
  *   ws: caller-owned workspace of mpc_boxqp_workspace_bytes(...) bytes.
  * Method: Mehrotra predictor-corrector interior point, Newton systems solved by Riccati sweeps;
- * float64 only (MPC_F32 -> MPC_ERR_UNSUPPORTED).  Supported (n, m): (2,1), (4,1), (4,2) register-resident;
- * (12,4) runs from thread-local memory (functional, not yet tuned).
+ * float64 only (MPC_F32 -> MPC_ERR_UNSUPPORTED).  Supported (n, m): (2,1), (4,1), (4,2) with one thread per
+ * scenario (register-resident matrices); (12,4) with a shared model (ltv = 0) on a persistent
+ * warp-per-scenario kernel whose workspace is one slot per resident warp, independent of the batch.
  */
 int64_t mpc_boxqp_workspace_bytes(int64_t batch, int n, int m, int N, int dtype);
 int mpc_boxqp_solve(const void* A, const void* B, const void* c, int ltv, const void* Q, const void* R,

@@ -5,6 +5,11 @@
 
 namespace mpc {
 
+// csrc/boxqp_coop.cu: warp-per-scenario variant for state dimensions beyond one thread's registers
+int64_t coop_ws_elems(int n, int m, int N, int64_t batch);
+bool coop_supported(int n, int m, int ltv);
+int launch_boxqp_coop(const BoxQpArgs<double>& a, int n, int m, cudaStream_t st);
+
 constexpr int kQpThreads = 128;
 
 // MINB = resident CTAs per SM the register allocation must allow (latency hiding for the streamed
@@ -56,6 +61,8 @@ using namespace mpc;
 extern "C" int64_t mpc_boxqp_workspace_bytes(int64_t batch, int n, int m, int N, int dtype) {
   if (batch < 0 || n < 1 || m < 1 || N < 1) return 0;
   const int64_t es = dtype == MPC_F32 ? 4 : 8;
+  // (12,4) runs on the persistent warp-per-scenario kernel: one slot per resident warp, not per scenario
+  if (coop_supported(n, m, 0)) return coop_ws_elems(n, m, N, batch) * es;
   return boxqp_ws_elems(n, m, N) * batch * es;
 }
 
@@ -90,6 +97,6 @@ extern "C" int mpc_boxqp_solve(const void* A, const void* B, const void* c, int 
   if (n == 2 && m == 1) return launch_boxqp<double, 2, 1>(a, st);
   if (n == 4 && m == 1) return launch_boxqp<double, 4, 1>(a, st);
   if (n == 4 && m == 2) return launch_boxqp<double, 4, 2>(a, st);
-  if (n == 12 && m == 4) return launch_boxqp<double, 12, 4>(a, st);
+  if (coop_supported(n, m, ltv)) return launch_boxqp_coop(a, n, m, st);
   return fail(MPC_ERR_UNSUPPORTED, "mpc_boxqp_solve: no kernel instantiated for n=%d m=%d", n, m);
 }

@@ -1,0 +1,605 @@
+// K4, cooperative variant: one WARP per scenario for state dimensions whose Riccati matrices do not
+// fit one thread's registers (n = 12, m = 4: BASELINE config 5).  Same algorithm, same passes and
+// the same arithmetic order per element as BoxQpIpm (csrc/boxqp_core.cuh); what changes is the
+// mapping:
+//   * the n x n / n x m / m x m matrices of the factorisation live in the warp's slice of shared
+//     memory and every product is computed lane-parallel over its output entries;
+//   * lane i < n + m owns element i of the stage vectors (z, slacks, multipliers, directions);
+//   * the kernel is persistent: grid = a fixed number of warps, each warp strides over scenarios and
+//     reuses ONE workspace slot, so the workspace does not grow with the batch (8M scenarios of
+//     72 KB state each would not fit any HBM) and no lane ever waits for another scenario.
+// Shared LTI model only (A, B staged once per CTA).
+#include <stdlib.h>
+
+#include "boxqp_core.cuh"
+
+namespace mpc {
+
+constexpr int kCoopWarps = 8;            // warps per CTA
+constexpr int kCoopMaxSlots = 148 * 32;  // upper bound of resident warps (workspace slots)
+
+template <int NX, int NU>
+struct CoopLayout {
+  static constexpr int D = NX + NU;
+  // per CTA
+  static constexpr int oA = 0;
+  static constexpr int oB = oA + NX * NX;
+  static constexpr int oQ = oB + NX * NU;
+  static constexpr int oR = oQ + NX * NX;
+  static constexpr int oPf = oR + NU * NU;
+  static constexpr int oLo = oPf + NX * NX;
+  static constexpr int oHi = oLo + D;
+  static constexpr int shared_total = oHi + D;
+  // per warp
+  static constexpr int wP = 0;
+  static constexpr int wW = wP + NX * NX;
+  static constexpr int wPB = wW + NX * NX;
+  static constexpr int wAug = wPB + NX * NU;  // [NU][2 NU] augmented matrix of the S inverse
+  static constexpr int wSi = wAug + NU * 2 * NU;
+  static constexpr int wK = wSi + NU * NU;
+  static constexpr int wG = wK + NU * NX;
+  static constexpr int wRhs = wG + NU * NX;
+  static constexpr int wSig = wRhs + D;
+  static constexpr int wZ = wSig + D;
+  static constexpr int wH = wZ + D;
+  static constexpr int wGu = wH + NX;
+  static constexpr int wDff = wGu + NU;
+  static constexpr int wPacc = wDff + NU;
+  static constexpr int wX = wPacc + NX;
+  static constexpr int wXn = wX + NX;
+  static constexpr int wU = wXn + NX;
+  static constexpr int warp_total = wU + NU;
+  // workspace slot (global), elements
+  __host__ __device__ static int64_t slot_elems(int N) { return (int64_t)N * (7 * D + NU * NX + NU * NU + NU); }
+};
+
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// C[M x Nn] (+)= op(A) B, lane-parallel over the output entries; A is [M x K] (TA: stored [K x M])
+template <int M, int K, int Nn, bool TA, bool ACC>
+__device__ __forceinline__ void wmm(const double* __restrict__ A, const double* __restrict__ B, double* C, int lane) {
+  for (int e = lane; e < M * Nn; e += 32) {
+    const int i = e / Nn, j = e % Nn;
+    double acc = ACC ? C[e] : 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc = fma(TA ? A[k * M + i] : A[i * K + k], B[k * Nn + j], acc);
+    C[e] = acc;
+  }
+}
+
+template <int NX, int NU>
+struct CoopIpm {
+  using L = CoopLayout<NX, NU>;
+  static constexpr int D = NX + NU;
+  const BoxQpArgs<double>& a;
+  const double* sh;  // CTA-shared model block
+  double* w;         // this warp's shared-memory slice
+  int lane;
+  int64_t b, bs;     // scenario, batch (I/O stride)
+  // workspace slot sections, each [N][per]
+  double *z, *sl, *su, *ll, *lu, *dza, *dzw, *Kw, *Sw, *dw;
+  double mu_scale, mu0;
+  bool hl, hu;   // this lane's element has a finite lower / upper bound
+  double lo, hi;
+
+  __device__ CoopIpm(const BoxQpArgs<double>& args, const double* shared, double* wsm, double* slot, int ln)
+      : a(args), sh(shared), w(wsm), lane(ln), b(0), bs(args.batch) {
+    const int64_t sec = (int64_t)a.N * D;
+    z = slot;
+    sl = z + sec;
+    su = sl + sec;
+    ll = su + sec;
+    lu = ll + sec;
+    dza = lu + sec;
+    dzw = dza + sec;
+    Kw = dzw + sec;
+    Sw = Kw + (int64_t)a.N * NU * NX;
+    dw = Sw + (int64_t)a.N * NU * NU;
+    mu_scale = 1.0;
+    for (int i = 0; i < NX * NX; ++i) mu_scale = fmax(mu_scale, fabs(sh[L::oQ + i]));
+    for (int i = 0; i < NU * NU; ++i) mu_scale = fmax(mu_scale, fabs(sh[L::oR + i]));
+    mu0 = mu_scale;
+    const int i = lane < D ? lane : 0;
+    lo = sh[L::oLo + i];
+    hi = sh[L::oHi + i];
+    hl = lane < D && lo > -kBigBound;
+    hu = lane < D && hi < kBigBound;
+  }
+
+  // x+ = A x + B u (lanes < NX), from / to the warp's vectors
+  __device__ void step_vec(const double* x, const double* u, double* xn) {
+    if (lane < NX) {
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < NX; ++j) acc = fma(sh[L::oA + lane * NX + j], x[j], acc);
+#pragma unroll
+      for (int j = 0; j < NU; ++j) acc = fma(sh[L::oB + lane * NU + j], u[j], acc);
+      xn[lane] = acc;
+    }
+  }
+
+  // (H z)_lane for the stage vector in w[wZ]: R u for inputs, Q x (Pf x at the last stage) for states
+  __device__ double hz(int k) const {
+    double acc = 0.0;
+    if (lane < NU) {
+#pragma unroll
+      for (int j = 0; j < NU; ++j) acc = fma(sh[L::oR + lane * NU + j], w[L::wZ + j], acc);
+    } else if (lane < D) {
+      const double* Qx = sh + (k == a.N - 1 ? L::oPf : L::oQ);
+      const int i = lane - NU;
+#pragma unroll
+      for (int j = 0; j < NX; ++j) acc = fma(Qx[i * NX + j], w[L::wZ + NU + j], acc);
+    }
+    return acc;
+  }
+
+  __device__ void init() {
+    double g0 = 0.0;
+    for (int pass = 0; pass < 2; ++pass) {
+      if (lane < NX) w[L::wX + lane] = a.x0[lane * bs + b];
+      __syncwarp();
+      for (int k = 0; k < a.N; ++k) {
+        if (lane < NU) {
+          double v = a.warm_U ? a.warm_U[((int64_t)k * NU + lane) * bs + b] : 0.0;
+          v = v < lo ? lo : v;
+          v = v > hi ? hi : v;
+          w[L::wU + lane] = v;
+        }
+        __syncwarp();
+        step_vec(w + L::wX, w + L::wU, w + L::wXn);
+        __syncwarp();
+        const double zi = lane < NU ? w[L::wU + lane] : (lane < D ? w[L::wXn + lane - NU] : 0.0);
+        if (lane < D) w[L::wZ + lane] = zi;
+        __syncwarp();
+        if (pass == 0) {
+          g0 = fmax(g0, fabs(hz(k)));
+        } else if (lane < D) {
+          double s_l = 1.0, s_u = 1.0, l_l = 0.0, l_u = 0.0;
+          if (hl) {
+            s_l = fmax(zi - lo, 1.0);
+            l_l = mu0 / s_l;
+          }
+          if (hu) {
+            s_u = fmax(hi - zi, 1.0);
+            l_u = mu0 / s_u;
+          }
+          const int64_t o = (int64_t)k * D + lane;
+          z[o] = zi;
+          sl[o] = s_l;
+          su[o] = s_u;
+          ll[o] = l_l;
+          lu[o] = l_u;
+        }
+        if (lane < NX) w[L::wX + lane] = w[L::wXn + lane];
+        __syncwarp();
+      }
+      if (pass == 0) {
+        g0 = warp_max(g0);
+        mu0 = g0 > mu_scale ? g0 : mu_scale;
+      }
+    }
+  }
+
+  static __device__ __forceinline__ double cc_of(double dz_signed, double r, double sig, double l) {
+    const double ds = dz_signed + r;
+    return ds * (-l - sig * ds);
+  }
+
+  template <bool FACTOR>
+  __device__ void backward(double sig_mu) {
+    for (int e = lane; e < NX * NX; e += 32) w[L::wP + e] = sh[L::oPf + e];  // Pacc
+    if (lane < NX) w[L::wPacc + lane] = 0.0;
+    __syncwarp();
+    for (int k = a.N - 1; k >= 0; --k) {
+      const int64_t o = (int64_t)k * D + lane;
+      double zi = 0.0, s_l = 1.0, s_u = 1.0, l_l = 0.0, l_u = 0.0, da = 0.0;
+      if (lane < D) {
+        zi = z[o];
+        s_l = sl[o];
+        s_u = su[o];
+        l_l = ll[o];
+        l_u = lu[o];
+        if (!FACTOR) da = dza[o];
+        w[L::wZ + lane] = zi;
+      }
+      if (!FACTOR) {
+        for (int e = lane; e < NU * NX; e += 32) w[L::wK + e] = Kw[(int64_t)k * NU * NX + e];
+        for (int e = lane; e < NU * NU; e += 32) w[L::wSi + e] = Sw[(int64_t)k * NU * NU + e];
+      }
+      __syncwarp();
+      double r = -hz(k), sg = 0.0;
+      if (hl) {
+        const double inv = rcp_(s_l), sgl = l_l * inv, rl = zi - lo - s_l;
+        const double cc = FACTOR ? 0.0 : cc_of(da, rl, sgl, l_l);
+        sg += sgl;
+        r += (sig_mu - cc) * inv - sgl * rl;
+      }
+      if (hu) {
+        const double inv = rcp_(s_u), sgu = l_u * inv, ru = hi - zi - s_u;
+        const double cc = FACTOR ? 0.0 : cc_of(-da, ru, sgu, l_u);
+        sg += sgu;
+        r -= (sig_mu - cc) * inv - sgu * ru;
+      }
+      if (lane < D) {
+        w[L::wRhs + lane] = r;
+        w[L::wSig + lane] = sg;
+      }
+      __syncwarp();
+      if (FACTOR) {
+        // P = Pacc + diag(Sigma_x)
+        if (lane < NX) w[L::wP + lane * NX + lane] += w[L::wSig + NU + lane];
+        __syncwarp();
+        wmm<NX, NX, NX, false, false>(w + L::wP, sh + L::oA, w + L::wW, lane);   // W  = P A
+        wmm<NX, NX, NU, false, false>(w + L::wP, sh + L::oB, w + L::wPB, lane);  // PB = P B
+        __syncwarp();
+        // augmented [S | I], S = R + diag(Sigma_u) + B'PB ;  G = B'W
+        for (int e = lane; e < NU * NU; e += 32) {
+          const int i = e / NU, j = e % NU;
+          double acc = sh[L::oR + e] + (i == j ? w[L::wSig + i] : 0.0);
+#pragma unroll
+          for (int l = 0; l < NX; ++l) acc = fma(sh[L::oB + l * NU + i], w[L::wPB + l * NU + j], acc);
+          w[L::wAug + i * 2 * NU + j] = acc;
+          w[L::wAug + i * 2 * NU + NU + j] = (i == j) ? 1.0 : 0.0;
+        }
+        wmm<NU, NX, NX, true, false>(sh + L::oB, w + L::wW, w + L::wG, lane);
+        __syncwarp();
+        // Gauss-Jordan without pivoting (S is symmetric positive definite); lanes over [NU][2 NU]
+        for (int p = 0; p < NU; ++p) {
+          const double inv = 1.0 / w[L::wAug + p * 2 * NU + p];
+          double newv = 0.0;
+          const int rr = lane / (2 * NU), cc = lane % (2 * NU);
+          const bool act = lane < NU * 2 * NU;
+          if (act) {
+            const double prow = w[L::wAug + p * 2 * NU + cc] * inv;
+            newv = (rr == p) ? prow : fma(-w[L::wAug + rr * 2 * NU + p], prow, w[L::wAug + rr * 2 * NU + cc]);
+          }
+          __syncwarp();
+          if (act) w[L::wAug + rr * 2 * NU + cc] = newv;
+          __syncwarp();
+        }
+        for (int e = lane; e < NU * NU; e += 32) w[L::wSi + e] = w[L::wAug + (e / NU) * 2 * NU + NU + e % NU];
+        __syncwarp();
+        // K = -Sinv G
+        for (int e = lane; e < NU * NX; e += 32) {
+          const int i = e / NX, j = e % NX;
+          double acc = 0.0;
+#pragma unroll
+          for (int l = 0; l < NU; ++l) acc = fma(w[L::wSi + i * NU + l], w[L::wG + l * NX + j], acc);
+          w[L::wK + e] = -acc;
+        }
+        __syncwarp();
+        wmm<NX, NU, NX, false, true>(w + L::wPB, w + L::wK, w + L::wW, lane);  // W += PB K
+        __syncwarp();
+        // Pacc <- Q + A'W, upper triangle mirrored
+        for (int e = lane; e < NX * NX; e += 32) {
+          const int i = e / NX, j = e % NX;
+          if (j >= i) {
+            double acc = sh[L::oQ + e];
+#pragma unroll
+            for (int l = 0; l < NX; ++l) acc = fma(sh[L::oA + l * NX + i], w[L::wW + l * NX + j], acc);
+            w[L::wP + i * NX + j] = acc;
+            w[L::wP + j * NX + i] = acc;
+          }
+        }
+        for (int e = lane; e < NU * NX; e += 32) Kw[(int64_t)k * NU * NX + e] = w[L::wK + e];
+        for (int e = lane; e < NU * NU; e += 32) Sw[(int64_t)k * NU * NU + e] = w[L::wSi + e];
+        __syncwarp();
+      }
+      // h = -(rhs_x + pacc);  gu = rhs_u - B'h;  dff = Sinv gu;  pacc <- -A'h + K'gu
+      if (lane < NX) w[L::wH + lane] = -(w[L::wRhs + NU + lane] + w[L::wPacc + lane]);
+      __syncwarp();
+      if (lane < NU) {
+        double acc = w[L::wRhs + lane];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) acc = fma(-sh[L::oB + i * NU + lane], w[L::wH + i], acc);
+        w[L::wGu + lane] = acc;
+      }
+      __syncwarp();
+      if (lane < NU) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < NU; ++j) acc = fma(w[L::wSi + lane * NU + j], w[L::wGu + j], acc);
+        dw[(int64_t)k * NU + lane] = acc;
+      }
+      if (lane < NX) {
+        double acc = 0.0;
+#pragma unroll
+        for (int l = 0; l < NX; ++l) acc = fma(-sh[L::oA + l * NX + lane], w[L::wH + l], acc);
+#pragma unroll
+        for (int j = 0; j < NU; ++j) acc = fma(w[L::wK + j * NX + lane], w[L::wGu + j], acc);
+        w[L::wPacc + lane] = acc;
+      }
+      __syncwarp();
+    }
+  }
+
+  struct Acc {
+    double qmax, s0, s1, s2, dzmax, rp;
+    __device__ double amin() const { return qmax > 0.0 ? 1.0 / qmax : 1e30; }
+  };
+
+  template <bool AFFINE>
+  __device__ void forward(double sig_mu, Acc& acc) {
+    double qmax = 0.0, s0 = 0.0, s1 = 0.0, s2 = 0.0, dzmax = 0.0, rp = 0.0;
+    if (lane < NX) w[L::wX + lane] = 0.0;  // dx_0 = 0
+    __syncwarp();
+    for (int k = 0; k < a.N; ++k) {
+      const int64_t o = (int64_t)k * D + lane;
+      double zi = 0.0, s_l = 1.0, s_u = 1.0, l_l = 0.0, l_u = 0.0, da = 0.0;
+      if (lane < D) {
+        zi = z[o];
+        s_l = sl[o];
+        s_u = su[o];
+        l_l = ll[o];
+        l_u = lu[o];
+        if (!AFFINE) da = dza[o];
+      }
+      for (int e = lane; e < NU * NX; e += 32) w[L::wK + e] = Kw[(int64_t)k * NU * NX + e];
+      if (lane < NU) w[L::wDff + lane] = dw[(int64_t)k * NU + lane];
+      __syncwarp();
+      if (lane < NU) {
+        double u = w[L::wDff + lane];
+#pragma unroll
+        for (int j = 0; j < NX; ++j) u = fma(w[L::wK + lane * NX + j], w[L::wX + j], u);
+        w[L::wU + lane] = u;
+      }
+      __syncwarp();
+      step_vec(w + L::wX, w + L::wU, w + L::wXn);
+      __syncwarp();
+      const double dz = lane < NU ? w[L::wU + lane] : (lane < D ? w[L::wXn + lane - NU] : 0.0);
+      if (lane < D) {
+        (AFFINE ? dza : dzw)[o] = dz;
+        if (!AFFINE) dzmax = fmax(dzmax, fabs(dz));
+      }
+      if (hl) {
+        const double r = zi - lo - s_l, ds = dz + r;
+        const double rinv = rcp_(s_l * l_l), inv_s = rinv * l_l, inv_l = rinv * s_l, sgl = l_l * inv_s;
+        const double cc = AFFINE ? 0.0 : cc_of(da, r, sgl, l_l);
+        const double dl = (sig_mu - cc) * inv_s - l_l - sgl * ds;
+        qmax = fmax(qmax, fmax(-ds * inv_s, -dl * inv_l));
+        s0 += s_l * l_l;
+        s1 += s_l * dl + l_l * ds;
+        s2 += ds * dl;
+        rp = fmax(rp, fabs(r));
+      }
+      if (hu) {
+        const double r = hi - zi - s_u, ds = -dz + r;
+        const double rinv = rcp_(s_u * l_u), inv_s = rinv * l_u, inv_l = rinv * s_u, sgu = l_u * inv_s;
+        const double cc = AFFINE ? 0.0 : cc_of(-da, r, sgu, l_u);
+        const double dl = (sig_mu - cc) * inv_s - l_u - sgu * ds;
+        qmax = fmax(qmax, fmax(-ds * inv_s, -dl * inv_l));
+        s0 += s_u * l_u;
+        s1 += s_u * dl + l_u * ds;
+        s2 += ds * dl;
+        rp = fmax(rp, fabs(r));
+      }
+      if (lane < NX) w[L::wX + lane] = w[L::wXn + lane];
+      __syncwarp();
+    }
+    acc.qmax = warp_max(qmax);
+    acc.s0 = warp_sum(s0);
+    acc.s1 = warp_sum(s1);
+    acc.s2 = warp_sum(s2);
+    acc.dzmax = warp_max(dzmax);
+    acc.rp = warp_max(rp);
+  }
+
+  __device__ double update(double sig_mu, double alpha, bool second_order) {
+    double zn = 1.0;
+    if (lane < D) {
+      for (int k = 0; k < a.N; ++k) {
+        const int64_t o = (int64_t)k * D + lane;
+        const double zi = z[o], dz = dzw[o], da = second_order ? dza[o] : 0.0;
+        if (hl) {
+          const double s = sl[o], l = ll[o], r = zi - lo - s, ds = dz + r;
+          const double inv = rcp_(s), sgl = l * inv;
+          const double cc = second_order ? cc_of(da, r, sgl, l) : 0.0;
+          const double dl = (sig_mu - cc) * inv - l - sgl * ds;
+          sl[o] = s + alpha * ds;
+          ll[o] = l + alpha * dl;
+        }
+        if (hu) {
+          const double s = su[o], l = lu[o], r = hi - zi - s, ds = -dz + r;
+          const double inv = rcp_(s), sgu = l * inv;
+          const double cc = second_order ? cc_of(-da, r, sgu, l) : 0.0;
+          const double dl = (sig_mu - cc) * inv - l - sgu * ds;
+          su[o] = s + alpha * ds;
+          lu[o] = l + alpha * dl;
+        }
+        const double zn_i = zi + alpha * dz;
+        z[o] = zn_i;
+        zn = fmax(zn, fabs(zn_i));
+      }
+    }
+    return warp_max(zn);
+  }
+
+  __device__ void output(int status, int iters) {
+    double cost = 0.0;
+    if (lane < NX) {
+      const double x = a.x0[lane * bs + b];
+      w[L::wX + lane] = x;
+      a.X[lane * bs + b] = x;
+    }
+    __syncwarp();
+    for (int k = 0; k < a.N; ++k) {
+      const int64_t o = (int64_t)k * D + lane;
+      int sat = 0;
+      double zi = 0.0;
+      if (lane < D) {
+        zi = z[o];
+        if (hl && ll[o] > sl[o]) sat = -1;
+        if (hu && lu[o] > su[o]) sat = 1;
+      }
+      if (lane < NU) {
+        const double u = sat < 0 ? lo : (sat > 0 ? hi : zi);
+        w[L::wU + lane] = u;
+        a.U[((int64_t)k * NU + lane) * bs + b] = u;
+        if (a.sat_u) a.sat_u[((int64_t)k * NU + lane) * bs + b] = (int8_t)sat;
+      } else if (lane < D && a.sat_x) {
+        a.sat_x[((int64_t)k * NX + lane - NU) * bs + b] = (int8_t)sat;
+      }
+      __syncwarp();
+      // stage cost x'Qx + u'Ru: lane i contributes x_i (Qx)_i or u_i (Ru)_i
+      if (lane < NX) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < NX; ++j) acc = fma(sh[L::oQ + lane * NX + j], w[L::wX + j], acc);
+        cost = fma(w[L::wX + lane], acc, cost);
+      }
+      if (lane < NU) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < NU; ++j) acc = fma(sh[L::oR + lane * NU + j], w[L::wU + j], acc);
+        cost = fma(w[L::wU + lane], acc, cost);
+      }
+      step_vec(w + L::wX, w + L::wU, w + L::wXn);
+      __syncwarp();
+      if (lane < NX) {
+        const double xn = w[L::wXn + lane];
+        w[L::wX + lane] = xn;
+        a.X[((int64_t)(k + 1) * NX + lane) * bs + b] = xn;
+      }
+      __syncwarp();
+    }
+    if (lane < NX) {
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < NX; ++j) acc = fma(sh[L::oPf + lane * NX + j], w[L::wX + j], acc);
+      cost = fma(w[L::wX + lane], acc, cost);
+    }
+    cost = warp_sum(cost);
+    if (lane == 0) {
+      a.cost[b] = cost;
+      a.status[b] = status;
+      a.iters[b] = iters;
+    }
+  }
+
+  __device__ void solve(int64_t scenario) {
+    b = scenario;
+    mu0 = mu_scale;
+    int ncons = 0;
+    for (int i = 0; i < D; ++i) ncons += (sh[L::oLo + i] > -kBigBound ? 1 : 0) + (sh[L::oHi + i] < kBigBound ? 1 : 0);
+    ncons *= a.N;
+    init();
+    int status = MPC_UNSOLVED, it = 0;
+    double rp = 0.0, zn = 1.0;
+    Acc acc;
+    if (ncons == 0) {
+      backward<true>(0.0);
+      forward<false>(0.0, acc);
+      update(0.0, 1.0, false);
+      status = MPC_SOLVED;
+      it = 1;
+    }
+    const double inv_nc = ncons ? 1.0 / (double)ncons : 0.0;
+    while (status == MPC_UNSOLVED && it < a.max_iter) {
+      ++it;
+      backward<true>(0.0);
+      forward<true>(0.0, acc);
+      const double mu = acc.s0 * inv_nc;
+      const double am_aff = acc.amin();
+      const double a_aff = am_aff < 1.0 ? am_aff : 1.0;
+      const double mu_aff = (acc.s0 + a_aff * (acc.s1 + a_aff * acc.s2)) * inv_nc;
+      const double ratio = mu_aff / (mu > 1e-300 ? mu : 1e-300);
+      double sigma = ratio * ratio * ratio;
+      sigma = sigma < 1.0 ? sigma : 1.0;
+      const double sig_mu = sigma * mu;
+      backward<false>(sig_mu);
+      forward<false>(sig_mu, acc);
+      double alpha = 0.995 * acc.amin();
+      alpha = alpha < 1.0 ? alpha : 1.0;
+      zn = update(sig_mu, alpha, true);
+      const double mu_new = (acc.s0 + alpha * (acc.s1 + alpha * acc.s2)) * inv_nc;
+      rp = (1.0 - alpha) * acc.rp;
+      const bool done = (mu_new <= a.eps * mu_scale) && (rp <= a.eps * zn) && (alpha * acc.dzmax <= 1e-6 * zn);
+      if (done) {
+        status = MPC_SOLVED;
+      } else if (!(alpha >= 1e-6) || !(mu_new <= 1e15 * mu0)) {
+        status = (rp <= 1e-6 * zn) ? MPC_MAX_ITER : MPC_INFEASIBLE;
+      }
+    }
+    if (status == MPC_UNSOLVED) status = (rp <= 1e-6 * zn) ? MPC_MAX_ITER : MPC_INFEASIBLE;
+    output(status, it);
+    __syncwarp();
+  }
+};
+
+template <int NX, int NU, int MINB>
+__global__ void __launch_bounds__(kCoopWarps * 32, MINB) boxqp_ipm_coop_kernel(BoxQpArgs<double> a, int nslots) {
+  using L = CoopLayout<NX, NU>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sh = reinterpret_cast<double*>(smem_raw);
+  for (int i = threadIdx.x; i < L::shared_total; i += blockDim.x) {
+    double v;
+    if (i < L::oB) v = a.A[i - L::oA];
+    else if (i < L::oQ) v = a.B[i - L::oB];
+    else if (i < L::oR) v = a.Q[i - L::oQ];
+    else if (i < L::oPf) v = a.R[i - L::oR];
+    else if (i < L::oLo) v = a.Pf[i - L::oPf];
+    else if (i < L::oLo + NU) v = a.u_lo[i - L::oLo];
+    else if (i < L::oHi) v = a.x_lo[i - L::oLo - NU];
+    else if (i < L::oHi + NU) v = a.u_hi[i - L::oHi];
+    else v = a.x_hi[i - L::oHi - NU];
+    sh[i] = v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slot = blockIdx.x * kCoopWarps + warp;
+  if (slot >= nslots) return;
+  double* wsm = sh + L::shared_total + warp * L::warp_total;
+  double* ws_slot = a.ws + (int64_t)slot * L::slot_elems(a.N);
+  CoopIpm<NX, NU> ipm(a, sh, wsm, ws_slot, lane);
+  for (int64_t b = slot; b < a.batch; b += nslots) ipm.solve(b);
+}
+
+int64_t coop_ws_elems(int n, int m, int N, int64_t batch) {
+  const int64_t slots = batch < kCoopMaxSlots ? batch : kCoopMaxSlots;
+  return (int64_t)N * (7 * (n + m) + m * n + m * m + m) * slots;
+}
+
+bool coop_supported(int n, int m, int ltv) { return n == 12 && m == 4 && !ltv; }
+
+template <int NX, int NU, int MINB>
+static int launch_coop_variant(const BoxQpArgs<double>& a, cudaStream_t st) {
+  using L = CoopLayout<NX, NU>;
+  const size_t smem = sizeof(double) * (size_t)(L::shared_total + kCoopWarps * L::warp_total);
+  auto kern = boxqp_ipm_coop_kernel<NX, NU, MINB>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail((int)e, "mpc_boxqp_solve: %s", cudaGetErrorString(e));
+  // persistent grid: exactly the CTAs that are resident at once (one workspace slot per warp)
+  int dev = 0, sms = kNumSMs, occ = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kCoopWarps * 32, smem);
+  if (e != cudaSuccess || occ < 1) return fail((int)e, "mpc_boxqp_solve: occupancy query failed");
+  int64_t slots = (int64_t)sms * occ * kCoopWarps;
+  if (slots > kCoopMaxSlots) slots = kCoopMaxSlots;
+  if (slots > a.batch) slots = a.batch;
+  const unsigned grid = (unsigned)((slots + kCoopWarps - 1) / kCoopWarps);
+  kern<<<grid, kCoopWarps * 32, smem, st>>>(a, (int)slots);
+  return check_launch("boxqp_ipm_coop_kernel");
+}
+
+int launch_boxqp_coop(const BoxQpArgs<double>& a, int n, int m, cudaStream_t st) {
+  if (n == 12 && m == 4) {
+    int minb = 4;  // measured on B200: 4 CTAs/SM (64 registers) is marginally the fastest
+    if (const char* env = getenv("MPC_COOP_MINB")) minb = atoi(env);
+    if (minb >= 4) return launch_coop_variant<12, 4, 4>(a, st);
+    if (minb == 3) return launch_coop_variant<12, 4, 3>(a, st);
+    return launch_coop_variant<12, 4, 2>(a, st);
+  }
+  return fail(MPC_ERR_UNSUPPORTED, "mpc_boxqp_solve: no cooperative kernel for n=%d m=%d", n, m);
+}
+
+}  // namespace mpc
