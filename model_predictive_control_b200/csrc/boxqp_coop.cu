@@ -525,7 +525,7 @@ struct CoopIpm {
       const bool done = (mu_new <= a.eps * mu_scale) && (rp <= a.eps * zn) && (alpha * acc.dzmax <= 1e-6 * zn);
       if (done) {
         status = MPC_SOLVED;
-      } else if (!(alpha >= 1e-6) || !(mu_new <= 1e15 * mu0)) {
+      } else if (!(alpha >= 1e-6) || !(mu_new <= 100.0 * mu0)) {
         status = (rp <= 1e-6 * zn) ? MPC_MAX_ITER : MPC_INFEASIBLE;
       }
     }

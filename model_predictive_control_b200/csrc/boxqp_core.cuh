@@ -677,8 +677,8 @@ struct BoxQpIpm {
       const bool done = (mu_new <= a.eps * mu_scale) && (rp <= a.eps * zn) && (alpha * acc.dzmax <= T(1e-6) * zn);
       if (done) {
         status = MPC_SOLVED;
-      } else if (!(alpha >= T(1e-6)) || !(mu_new <= T(1e15) * mu0)) {
-        // stalled: step length collapsed / barrier parameter exploded.  With a bound residual that
+      } else if (!(alpha >= T(1e-6)) || !(mu_new <= T(100) * mu0)) {
+        // stalled: step length collapsed / barrier parameter grew 100x above its start value.  With a bound residual that
         // cannot be closed the box and the dynamics do not meet: infeasible.
         status = (rp <= T(1e-6) * zn) ? MPC_MAX_ITER : MPC_INFEASIBLE;
       }

@@ -528,10 +528,10 @@ def ipm_riccati(A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi, c=None, warm_U=No
         done = active & (mu_new <= eps * mu_scale) & (rp <= eps * zn) & (step <= 1e-6 * zn)
         status[done] = SOLVED
         active &= ~done
-        # stalled: the step length collapses / the barrier parameter explodes.  With a bound
+        # stalled: the step length collapses / the barrier parameter grows 100x above its start value.  With a bound
         # residual that cannot be closed the problem is infeasible (box and dynamics do not meet).
         with np.errstate(invalid="ignore"):
-            stuck = active & (~(alpha >= 1e-6) | ~(mu_new <= 1e15 * mu0))
+            stuck = active & (~(alpha >= 1e-6) | ~(mu_new <= 100.0 * mu0))
             status[stuck & (rp <= 1e-6 * zn)] = MAX_ITER
             status[stuck & ~(rp <= 1e-6 * zn)] = INFEASIBLE
         active &= ~stuck
