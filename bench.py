@@ -342,6 +342,79 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_cfg2a(args):
+    """cfg 2a: shared model, 2^20 random initial states; K1 once (outside the timed steps, it is one
+    CTA), then per step ONE K2 launch: N-step rollout with the time-varying gains, X, U and cost written."""
+    import torch
+    import torch.distributed as dist
+    from model_predictive_control_b200 import lq
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dtype = torch.float64 if args.dtype == "f64" else torch.float32
+    w = 8 if args.dtype == "f64" else 4
+    n, m, N, batch = 4, 1, 20, args.batch or (1 << 20)
+    dd = dict(dtype=dtype, device=dev)
+    A = torch.eye(n, **dd) + 0.5 * torch.diag(torch.ones(n - 1, **dd), 1)
+    B = torch.zeros(n, m, **dd); B[-1, 0] = -0.5
+    C = torch.tensor([[1.0], [-2.0 / 3.0], [0.0], [0.0]], **dd)
+    Q = C @ C.t() + 1e-3 * torch.eye(n, **dd); R = torch.tensor([[0.1]], **dd)
+    g = torch.Generator(device=dev); g.manual_seed(1234 + 2 + 1000 * rank)
+    x0 = (torch.rand(n, batch, generator=g, device=dev, dtype=torch.float64) * 20 - 10).to(dtype)
+    K, P = lq.riccati(A, B, Q, R, Q, N, all_P=False)
+    Kg = K[:, 0].contiguous()
+
+    def step():
+        return lq.lq_rollout(A, B, Kg, x0, N + 1, gain_offset=0, gain_step=1, Q=Q, R=R, Pf=Q, want_U=True, want_cost=True)
+
+    for _ in range(max(args.warmup, 3)):
+        res = step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier(device_ids=[local])
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    t_spin = time.perf_counter()
+    while time.perf_counter() - t_spin < 0.3:
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        res = step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier(device_ids=[local])
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / args.steps
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        bytes_solve = w * (n + N * m + (N + 1) * n + 1)
+        achieved = bytes_solve * batch / (ms * 1e-3) / 1e9
+        line = {"metric": METRIC, "value": world * batch / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+                "config": {"workload": f"cfg2a: shared-model finite-horizon LQ, nx=4 nu=1 N=20, {batch} random initial states per GPU; "
+                                       "gains from one Riccati recursion, per-scenario optimal plan X, U and cost by K2",
+                           "batch_per_gpu": batch, "l2": f"{bytes_solve * batch / 1e6:.0f} MB per step > 126 MB L2"},
+                "roofline": {"bound": "hbm", "kernel": "rollout_shared_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": load_traffic("rollout_shared_kernel_" + args.dtype),
+                             "peak_source": peak_src, "bytes_per_solve": bytes_solve, "kernel_ms": ms},
+                "gpu_launches": args.steps, "clocks": clocks,
+                "summary": {"sum_cost": float(res["cost"].sum())}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def ipm_flops_per_iter(n, m, N):
     """Flops of one interior-point iteration as performed (csrc/boxqp_core.cuh): one factorising
     backward sweep, one feed-forward-only backward sweep, two forward sweeps, one update pass."""
@@ -516,8 +589,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--batch", type=int, default=0, help="scenarios per GPU (default: the named config's)")
-    ap.add_argument("--workload", default="cfg2b", choices=["cfg2b", "cfg3", "cfg4", "cfg5"],
-                    help="cfg2b (default, BASELINE configs[1]); cfg3 = session-2 box-QP N=30, 256k scenarios; "
+    ap.add_argument("--workload", default="cfg2b", choices=["cfg2b", "cfg2a", "cfg3", "cfg4", "cfg5"],
+                    help="cfg2b (default, BASELINE configs[1]); cfg2a = same shapes with ONE shared model: the Riccati "
+                         "recursion runs once, the per-scenario work is the K2 rollout (HBM-bound); cfg3 = session-2 box-QP N=30, 256k scenarios; "
                          "cfg4 = session-4 RTI closed loop, 64k scenarios x 200 steps; "
                          "cfg5 = nx=12 nu=4 N=50 box-QP, 2^20 scenarios per GPU (8M over 8 GPUs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -526,6 +600,8 @@ def main():
         run_reference_arm(args)
     elif args.workload == "cfg2b":
         run_ours(args)
+    elif args.workload == "cfg2a":
+        run_cfg2a(args)
     else:
         run_secondary(args)
 

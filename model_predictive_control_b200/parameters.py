@@ -1,50 +1,53 @@
-"""Drop-in for the reference's ``session_4/parameters.py``: ``VehicleParameters`` with the same field
-names and default values (/root/reference/session_4/parameters.py:4-54), so that code written
-against the reference (``VehicleParameters()``, ``params.friction *= 0.8``, ``params.max_steer``)
-runs unchanged.  Only the geometry, limits and the two kinematic-model parameters are used by the
-GPU path; the tyre and motor coefficients are carried for interface compatibility."""
-from dataclasses import dataclass
+"""``VehicleParameters`` for the session-4 path.
 
-import numpy as np
+Interface-compatible with the reference's ``session_4/parameters.py`` (a dataclass with these field
+names and default values, /root/reference/session_4/parameters.py:4-54), so that code written
+against the reference -- ``VehicleParameters()``, ``params.friction *= 0.8``, ``params.max_steer``
+-- runs unchanged.  The class is generated from the table below.  The GPU path uses the geometry
+(``axis_front``, ``axis_rear``), the input / state limits and the two kinematic-model parameters
+(``friction``, ``acceleration``); tyre and motor coefficients are carried for compatibility only.
+"""
+from dataclasses import make_dataclass, field
+import math
 
+#            name           default     meaning
+_FIELDS = [
+    ("length",        0.17,       "car length [m]"),
+    ("axis_front",    0.047,      "centre of gravity to front axis [m] (l_f of the kinematic model)"),
+    ("axis_rear",     0.05,       "centre of gravity to rear axis [m] (l_r of the kinematic model)"),
+    ("front",         0.08,       "centre of gravity to front end [m]"),
+    ("rear",          0.08,       "centre of gravity to rear end [m]"),
+    ("width",         0.08,       "car width [m]"),
+    ("height",        0.055,      "car height [m]"),
+    ("mass",          0.1735,     "mass [kg]"),
+    ("inertia",       18.3e-5,    "yaw inertia [kg m^2]"),
+    ("max_steer",     0.384,      "steering angle limit [rad] (input box, both signs)"),
+    ("max_drive",     1.0,        "largest normalised drive command"),
+    ("min_drive",     -1.0,       "largest reverse drive command"),
+    ("min_pos_x",     -3.0,       "state box: p_x lower [m]"),
+    ("max_pos_x",     3.0,        "state box: p_x upper [m]"),
+    ("min_pos_y",     -2.0,       "state box: p_y lower [m]"),
+    ("max_pos_y",     2.0,        "state box: p_y upper [m]"),
+    ("min_vel",       -0.5,       "state box: v lower [m/s]"),
+    ("max_vel",       0.5,        "state box: v upper [m/s]"),
+    ("max_heading",   2 * math.pi,  "state box: psi upper [rad]"),
+    ("min_heading",   -2 * math.pi, "state box: psi lower [rad]"),
+    ("bf",            3.1355,     "Pacejka front stiffness"),
+    ("cf",            2.1767,     "Pacejka front shape"),
+    ("df",            0.4399,     "Pacejka front peak"),
+    ("br",            2.8919,     "Pacejka rear stiffness"),
+    ("cr",            2.4431,     "Pacejka rear shape"),
+    ("dr",            0.6236,     "Pacejka rear peak"),
+    ("friction",      1,          "kinematic model: v' = acceleration * a - friction * v"),
+    ("acceleration",  2,          "kinematic model: drive-command gain"),
+    ("cm1",           0.3697,     "motor coefficient"),
+    ("cm2",           0.001295,   "motor coefficient"),
+    ("cr1",           0.1629,     "rolling-resistance coefficient"),
+    ("cr2",           0.02133,    "rolling-resistance coefficient"),
+]
 
-@dataclass
-class VehicleParameters:
-    # geometry [m], mass [kg], inertia [kg m^2]
-    length: float = 0.17
-    axis_front: float = 0.047
-    axis_rear: float = 0.05
-    front: float = 0.08
-    rear: float = 0.08
-    width: float = 0.08
-    height: float = 0.055
-    mass: float = 0.1735
-    inertia: float = 18.3e-5
-    # input limits
-    max_steer: float = 0.384
-    max_drive: float = 1.0
-    min_drive: float = -1.
-    # state limits
-    min_pos_x: float = -3.
-    max_pos_x: float = 3.
-    min_pos_y: float = -2.
-    max_pos_y: float = 2.
-    min_vel: float = -0.5
-    max_vel: float = 0.5
-    max_heading: float = 2 * np.pi
-    min_heading: float = -2 * np.pi
-    # Pacejka tyre coefficients (front / rear): stiffness, shape, peak
-    bf: float = 3.1355
-    cf: float = 2.1767
-    df: float = 0.4399
-    br: float = 2.8919
-    cr: float = 2.4431
-    dr: float = 0.6236
-    # kinematic approximation
-    friction: float = 1
-    acceleration: float = 2
-    # motor
-    cm1: float = 0.3697
-    cm2: float = 0.001295
-    cr1: float = 0.1629
-    cr2: float = 0.02133
+VehicleParameters = make_dataclass(
+    "VehicleParameters", [(name, float, field(default=default)) for name, default, _ in _FIELDS])
+VehicleParameters.__doc__ = "Vehicle geometry, limits and model coefficients:\n" + "\n".join(
+    f"    {name}: {doc} (default {default})" for name, default, doc in _FIELDS)
+VehicleParameters.__module__ = __name__
