@@ -295,6 +295,32 @@ def run_ours(args):
     e2e_value = world * batch * e2e_steps / (float(t.item()) * 1e-3)
     e2e_check = bool(torch.equal(host_res[2], out.V.cpu()))   # the host result is the device result
 
+    # ---- the other reading of configs[1] (cfg 2a: ONE shared model, random initial states): Riccati recursion once per
+    # step (a single CTA) + the K2 rollout kernel for every scenario.  Reported beside the headline, not instead of it.
+    A0 = torch.eye(n, dtype=dtype, device=dev) + 0.5 * torch.diag(torch.ones(n - 1, dtype=dtype, device=dev), 1)
+    B0 = torch.zeros(n, m, dtype=dtype, device=dev); B0[-1, 0] = -0.5
+    C0 = torch.tensor([[1.0], [-2.0 / 3.0], [0.0], [0.0]], dtype=dtype, device=dev)
+    Q0 = C0 @ C0.t() + 1e-3 * torch.eye(n, dtype=dtype, device=dev); R0 = torch.tensor([[0.1]], dtype=dtype, device=dev)
+    x0T = x0.t().contiguous()
+
+    def step2a():
+        K2a, _ = lq.riccati(A0, B0, Q0, R0, Q0, N, all_P=False)
+        return lq.lq_rollout(A0, B0, K2a[:, 0], x0T, N + 1, gain_offset=0, gain_step=1, Q=Q0, R=R0, Pf=Q0, want_U=True, want_cost=True)
+
+    for _ in range(5):
+        step2a()
+    barrier()
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ea.record()
+    for _ in range(args.steps):
+        step2a()
+    eb.record()
+    barrier()
+    t = torch.tensor([ea.elapsed_time(eb)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms2a = float(t.item()) / args.steps
+
     # ---- final gather of summaries over NCCL (outside the solve, outside the timed steps)
     summ = torch.stack([out.V.sum(), out.U[0].abs().max(), torch.tensor(float(batch), device=dev, dtype=dtype)]).double()
     if world > 1:
@@ -329,6 +355,11 @@ def run_ours(args):
                     "note": "lq.LqHostPipeline: pinned host buffers, all model/x0 inputs H2D and X/U/V D2H every step, "
                             "copies of consecutive steps overlapped on separate streams", "result_matches_device": e2e_check},
             "gpu_launches": args.steps, "clocks": clocks,
+            "cfg2a_shared_model": {"value": world * batch / (ms2a * 1e-3), "unit": UNIT, "ms_per_step": ms2a,
+                                   "kernels": "riccati_reg_kernel (1 CTA) + rollout_shared_kernel",
+                                   "bytes_per_solve": w * (n + N * m + (N + 1) * n + 1),
+                                   "hbm_frac": w * (n + N * m + (N + 1) * n + 1) * batch / (ms2a * 1e-3) / 1e9 / peak,
+                                   "note": "same shapes with ONE shared model: Riccati recursion once per step, optimal plan X, U, cost per scenario"},
             "summary": {"sum_cost": float(summ_all[:, 0].sum()), "max_abs_u0": float(summ_all[:, 1].max()),
                         "scenarios": int(summ_all[:, 2].sum())},
         }
@@ -364,11 +395,10 @@ def run_cfg2a(args):
     Q = C @ C.t() + 1e-3 * torch.eye(n, **dd); R = torch.tensor([[0.1]], **dd)
     g = torch.Generator(device=dev); g.manual_seed(1234 + 2 + 1000 * rank)
     x0 = (torch.rand(n, batch, generator=g, device=dev, dtype=torch.float64) * 20 - 10).to(dtype)
-    K, P = lq.riccati(A, B, Q, R, Q, N, all_P=False)
-    Kg = K[:, 0].contiguous()
-
     def step():
-        return lq.lq_rollout(A, B, Kg, x0, N + 1, gain_offset=0, gain_step=1, Q=Q, R=R, Pf=Q, want_U=True, want_cost=True)
+        # the whole solve of the batch: one Riccati recursion for the shared model (a single CTA), then the rollouts
+        K, P = lq.riccati(A, B, Q, R, Q, N, all_P=False)
+        return lq.lq_rollout(A, B, K[:, 0], x0, N + 1, gain_offset=0, gain_step=1, Q=Q, R=R, Pf=Q, want_U=True, want_cost=True)
 
     for _ in range(max(args.warmup, 3)):
         res = step()
@@ -408,7 +438,7 @@ def run_cfg2a(args):
                 "roofline": {"bound": "hbm", "kernel": "rollout_shared_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": load_traffic("rollout_shared_kernel_" + args.dtype),
                              "peak_source": peak_src, "bytes_per_solve": bytes_solve, "kernel_ms": ms},
-                "gpu_launches": args.steps, "clocks": clocks,
+                "gpu_launches": 2 * args.steps, "clocks": clocks,
                 "summary": {"sum_cost": float(res["cost"].sum())}}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -425,6 +455,54 @@ def ipm_flops_per_iter(n, m, N):
     fwd = 2 * n * m + 2 * n * n + 2 * n * m + 24 * d
     upd = 16 * d
     return N * (fac + 2 * (rhs + psweep) + 2 * fwd + upd)
+
+
+def _cpu_qp_worker(args):
+    """Exact CPU solves (HiGHS active set + KKT refinement, oracle/boxqp.py) of a slice of cfg3 / cfg5 scenarios."""
+    import numpy as np
+    from oracle import boxqp as obq
+    workload, seed, count = args
+    rng = np.random.default_rng(seed)
+    if workload == "cfg3":
+        p = obq.Problem(N=30)
+        A, B, Q, R, N = p.A, p.B, np.asarray(p.Q, float), np.asarray(p.R, float), 30
+        ulo, uhi, xlo, xhi = obq.problem_bounds(p)
+        x0 = np.stack([rng.uniform(-100, 0, count), rng.uniform(-10, 15, count)], 1)
+    else:
+        mrng = np.random.default_rng(1234 + 5)
+        Ts = 0.1
+        Ac = np.array([[1, Ts, Ts * Ts / 2], [0, 1, Ts], [0, 0, 1.0]]); Bc = np.array([[Ts**3 / 6], [Ts * Ts / 2], [Ts]])
+        A = np.kron(np.eye(4), Ac) + 0.01 * mrng.standard_normal((12, 12)); B = np.kron(np.eye(4), Bc)
+        Q, R, N = np.eye(12), 0.1 * np.eye(4), 50
+        ulo, uhi, xlo, xhi = -np.ones(4), np.ones(4), -5 * np.ones(12), 5 * np.ones(12)
+        x0 = rng.uniform(-2, 2, (count, 12))
+    t0 = time.perf_counter()
+    for b in range(count):
+        obq.solve_exact(A, B, Q, R, Q, N, x0[b], ulo, uhi, xlo, xhi)
+    return time.perf_counter() - t0, count
+
+
+def cpu_baseline_secondary(workload, cores):
+    """Bounded CPU sample of the secondary workloads (restated oracle, not reference code: the reference has no
+    solver for cfg 3/5 and its cfg-4 solver, CasADi + IPOPT, is not installable here)."""
+    import multiprocessing as mp
+    if workload in ("cfg3", "cfg5"):
+        per = 1500 if workload == "cfg3" else 8   # ~10-20 s of CPU work
+        with mp.get_context("spawn").Pool(cores) as pool:
+            res = pool.map(_cpu_qp_worker, [(workload, 7000 + i, per) for i in range(cores)])
+        rate = sum(r[1] for r in res) / max(r[0] for r in res)
+        return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"{per * cores} scenarios of {workload}, exact active-set QP solves (HiGHS + KKT refinement, oracle/boxqp.py), one process per core; restatement, not reference code"}
+    import numpy as np
+    from oracle import bicycle as obc
+    rng = np.random.default_rng(11)
+    nb, nsteps = 64, 48   # ~15 s of CPU work
+    x0 = np.array([0.6, -0.25, 0, 0]) + rng.uniform(-0.2, 0.2, (nb, 4)) * np.array([1, 1, 0.5, 0.2])
+    t0 = time.perf_counter()
+    obc.closed_loop(x0, nsteps, N=50, friction_plant=rng.uniform(0.7, 1.0, nb), qp="port")
+    dt = time.perf_counter() - t0
+    return {"value": nb * nsteps / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{nb} scenarios x {nsteps} control steps of cfg4, numpy restatement of the RTI loop and of the interior-point QP solver (oracle/bicycle.py, batched numpy, one process); restatement, not reference code"}
 
 
 def run_secondary(args):
@@ -576,6 +654,8 @@ def run_secondary(args):
                     "d2h_bytes_per_step": sum(t_.numel() * t_.element_size() for t_ in pin_out)},
             "gpu_launches": args.steps, "clocks": clocks, "summary": merged,
         }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline_secondary(args.workload, host_cores())
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
