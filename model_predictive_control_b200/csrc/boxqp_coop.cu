@@ -64,15 +64,25 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// C[M x Nn] (+)= op(A) B, lane-parallel over the output entries; A is [M x K] (TA: stored [K x M])
+// C[M x Nn] (+)= op(A) B, lane-parallel over the output entries; A is [M x K] (TA: stored [K x M]).
+// Shared-memory loads, not FMAs, bound this kernel (one wavefront per load, one per clock and SM,
+// against two FP64 warp instructions per clock), so each lane computes TWO adjacent outputs of a row
+// from one scalar load of A and one 16-byte load of B per k: 1 load per FMA instead of 2.
 template <int M, int K, int Nn, bool TA, bool ACC>
 __device__ __forceinline__ void wmm(const double* __restrict__ A, const double* __restrict__ B, double* C, int lane) {
-  for (int e = lane; e < M * Nn; e += 32) {
-    const int i = e / Nn, j = e % Nn;
-    double acc = ACC ? C[e] : 0.0;
+  static_assert(Nn % 2 == 0, "pairs of adjacent columns");
+  constexpr int H = Nn / 2;
+  for (int e = lane; e < M * H; e += 32) {
+    const int i = e / H, j = 2 * (e % H);
+    double2 acc = ACC ? *reinterpret_cast<const double2*>(C + i * Nn + j) : make_double2(0.0, 0.0);
 #pragma unroll
-    for (int k = 0; k < K; ++k) acc = fma(TA ? A[k * M + i] : A[i * K + k], B[k * Nn + j], acc);
-    C[e] = acc;
+    for (int k = 0; k < K; ++k) {
+      const double av = TA ? A[k * M + i] : A[i * K + k];
+      const double2 bv = *reinterpret_cast<const double2*>(B + k * Nn + j);
+      acc.x = fma(av, bv.x, acc.x);
+      acc.y = fma(av, bv.y, acc.y);
+    }
+    *reinterpret_cast<double2*>(C + i * Nn + j) = acc;
   }
 }
 
@@ -279,16 +289,19 @@ struct CoopIpm {
         __syncwarp();
         wmm<NX, NU, NX, false, true>(w + L::wPB, w + L::wK, w + L::wW, lane);  // W += PB K
         __syncwarp();
-        // Pacc <- Q + A'W, upper triangle mirrored
-        for (int e = lane; e < NX * NX; e += 32) {
-          const int i = e / NX, j = e % NX;
-          if (j >= i) {
-            double acc = sh[L::oQ + e];
-#pragma unroll
-            for (int l = 0; l < NX; ++l) acc = fma(sh[L::oA + l * NX + i], w[L::wW + l * NX + j], acc);
-            w[L::wP + i * NX + j] = acc;
-            w[L::wP + j * NX + i] = acc;
+        // Pacc <- Q + A'W on the upper triangle (NX (NX+1)/2 entries over the lanes), mirrored
+        for (int e = lane; e < NX * (NX + 1) / 2; e += 32) {
+          int i = 0, rem = e;
+          while (rem >= NX - i) {
+            rem -= NX - i;
+            ++i;
           }
+          const int j = i + rem;
+          double acc = sh[L::oQ + i * NX + j];
+#pragma unroll
+          for (int l = 0; l < NX; ++l) acc = fma(sh[L::oA + l * NX + i], w[L::wW + l * NX + j], acc);
+          w[L::wP + i * NX + j] = acc;
+          w[L::wP + j * NX + i] = acc;
         }
         for (int e = lane; e < NU * NX; e += 32) Kw[(int64_t)k * NU * NX + e] = w[L::wK + e];
         for (int e = lane; e < NU * NU; e += 32) Sw[(int64_t)k * NU * NU + e] = w[L::wSi + e];
