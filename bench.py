@@ -206,12 +206,18 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def load_traffic(key):
+def load_traffic(key, solves_per_launch=None):
+    """DRAM bytes per launch of kernel `key` from the committed ncu capture, scaled to this launch's size."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(path):
-        with open(path) as fh:
-            return json.load(fh).get(key)
-    return None
+    if not os.path.exists(path):
+        return None
+    with open(path) as fh:
+        ent = json.load(fh).get(key)
+    if not ent:
+        return None
+    if solves_per_launch is None:
+        return ent["bytes"]
+    return ent["bytes"] / ent["solves"] * solves_per_launch
 
 
 def run_ours(args):
@@ -346,7 +352,7 @@ def run_ours(args):
                        "batch_per_gpu": batch, "nx": n, "nu": m, "horizon": N, "parallelism": f"scenario-shard x{world}",
                        "l2": f"inputs+outputs {bytes_solve * batch / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)"},
             "roofline": {"bound": "hbm", "kernel": "lq_solve_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": load_traffic("lq_solve_kernel_" + args.dtype),
+                         "frac": achieved / peak, "traffic": load_traffic("lq_solve_kernel_" + args.dtype, batch),
                          "peak_source": peak_src, "bytes_per_solve": bytes_solve, "kernel_ms": kern_ms,
                          "fp_pipe": {"flops_per_solve": flops_solve, "achieved_tflops": flops_solve * batch / (kern_ms * 1e-3) / 1e12,
                                      "measured_fma_peak_tflops": fp_peak / 1e12,
@@ -436,7 +442,7 @@ def run_cfg2a(args):
                                        "gains from one Riccati recursion, per-scenario optimal plan X, U and cost by K2",
                            "batch_per_gpu": batch, "l2": f"{bytes_solve * batch / 1e6:.0f} MB per step > 126 MB L2"},
                 "roofline": {"bound": "hbm", "kernel": "rollout_shared_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": load_traffic("rollout_shared_kernel_" + args.dtype),
+                             "frac": achieved / peak, "traffic": load_traffic("rollout_shared_kernel_" + args.dtype, batch),
                              "peak_source": peak_src, "bytes_per_solve": bytes_solve, "kernel_ms": ms},
                 "gpu_launches": 2 * args.steps, "clocks": clocks,
                 "summary": {"sum_cost": float(res["cost"].sum())}}
@@ -643,7 +649,7 @@ def run_secondary(args):
                        "parallelism": f"scenario-shard x{world}",
                        "l2": "solver state is a per-scenario workspace streamed through L2/HBM every iteration (> 126 MB)"},
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": load_traffic(kname), "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": load_traffic(kname, solves_per_step), "peak_source": peak_src,
                          "note": "algorithmic I/O only; the kernel is bound by the FP64 pipe and its workspace traffic, see fp_pipe",
                          "kernel_ms": kern_ms,
                          "fp_pipe": {"mean_iters_per_solve": iters_total / solves_per_step,
