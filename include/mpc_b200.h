@@ -181,13 +181,17 @@ int mpc_boxqp_solve(const void* A, const void* B, const void* c, int ltv, const 
  *   model out from y [4][batch] and linearise:  U_prev [N][2][batch] -> warm_U [N][2][batch],
  *   A [N][16][batch], B [N][8][batch], c [N][4][batch]  (inputs of mpc_boxqp_solve with ltv = 1).
  * mpc_bicycle_plant_step: x [4][batch], u [2][batch] -> xn;  substeps = 0: forward Euler over ts
- *   (session4_sol.py:22-25), substeps > 0: RK4 sub-steps (stands in for odeint, :37-56);
+ *   (session4_sol.py:22-25), substeps > 0: RK4 sub-steps, substeps < 0: adaptive Dormand-Prince 5(4) with
+ *   rtol = atol = 10^substeps (the counterpart of the reference's odeint plant, :37-56);
  *   friction [batch] (s_friction = 1) or one shared value (s_friction = 0).
  * mpc_rti_closed_loop: `steps` control steps of prepare -> QP -> apply u_0 -> plant in ONE kernel.
  *   U_plan [N][2][batch] in/out (initial plan; zeros = cold start), X_pred [N+1][4][batch] (last
  *   prediction), X_cl [steps+1][4][batch], U_cl [steps][2][batch], cost_cl [batch] (sum of
  *   x'Qx + u'Ru along the closed loop), viol_cl [batch] (max state-bound violation), n_sat (applied
  *   inputs on a bound), n_fail (steps whose QP did not reach MPC_SOLVED), iters_total, last_status.
+ *   Optional prediction bundles (NULL = not written), the (time step x horizon x state) layout that
+ *   AnimateParking.bundle consumes (session_4/animation.py:75-83): X_bundle [steps][N+1][4][batch],
+ *   U_bundle [steps][N][2][batch].
  */
 int mpc_bicycle_rti_prepare(double lr, double lf, double accel, double friction, double ts, int rk4,
                             const void* y, const void* U_prev, int first, void* warm_U, void* A, void* B,
@@ -201,8 +205,8 @@ int mpc_rti_closed_loop(double lr, double lf, double accel, double friction_mode
                         const void* R, const void* Pf, const void* u_lo, const void* u_hi, const void* x_lo,
                         const void* x_hi, const void* x0, void* U_plan, void* X_pred, void* X_cl, void* U_cl,
                         void* cost_cl, void* viol_cl, int32_t* n_sat, int32_t* n_fail, int32_t* iters_total,
-                        int32_t* last_status, void* ws, int64_t ws_bytes, int64_t batch, int N, int max_iter,
-                        double eps, int dtype, mpc_stream_t stream);
+                        int32_t* last_status, void* X_bundle, void* U_bundle, void* ws, int64_t ws_bytes,
+                        int64_t batch, int N, int max_iter, double eps, int dtype, mpc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Device FP pipe probe: runs a register-resident FMA chain kernel and reports achieved

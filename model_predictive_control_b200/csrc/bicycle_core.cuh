@@ -117,16 +117,75 @@ MPC_HD void bicycle_discretize(const BicycleModel<T>& p, T friction, const T* x,
   for (int i = 0; i < 8; ++i) B[i] = w * (D1u[i] + T(2) * D2u[i] + T(2) * D3u[i] + D4u[i]);
 }
 
-// Plant: forward Euler over ts (substeps == 0; the nominal model of session4_sol.py:453) or classic
-// RK4 with `substeps` equal sub-steps (stands in for the reference's odeint plant,
-// session4_sol.py:37-56: a documented deviation).
+// Plant: forward Euler over ts (substeps == 0; the nominal model of session4_sol.py:453), classic
+// RK4 with `substeps` equal sub-steps (substeps > 0), or -- substeps < 0 -- the adaptive
+// Dormand-Prince 5(4) pair with rtol = atol = 10^substeps.  The adaptive mode is the counterpart of the
+// reference's exact_integration (scipy odeint / LSODA, session4_sol.py:37-56); the tests check it
+// against odeint itself.
 template <typename T>
 MPC_HD void bicycle_plant(const BicycleModel<T>& p, T friction, int substeps, T* x, const T* u) {
-  if (substeps <= 0) {
+  if (substeps == 0) {
     T f[4];
     bicycle_f(p, friction, x, u, f);
 #pragma unroll
     for (int i = 0; i < 4; ++i) x[i] = fma_<T>(p.ts, f[i], x[i]);
+    return;
+  }
+  if (substeps < 0) {
+    T tol = T(1);
+    for (int i = 0; i < -substeps; ++i) tol *= T(0.1);
+    T t = T(0), h = p.ts;
+    T k1[4], k2[4], k3[4], k4[4], k5[4], k6[4], k7[4], xs[4], xn[4];
+    bicycle_f(p, friction, x, u, k1);
+    for (int it = 0; it < 10000 && t < p.ts; ++it) {
+      if (t + h > p.ts) h = p.ts - t;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xs[i] = x[i] + h * (T(1.0 / 5.0) * k1[i]);
+      bicycle_f(p, friction, xs, u, k2);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xs[i] = x[i] + h * (T(3.0 / 40.0) * k1[i] + T(9.0 / 40.0) * k2[i]);
+      bicycle_f(p, friction, xs, u, k3);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        xs[i] = x[i] + h * (T(44.0 / 45.0) * k1[i] - T(56.0 / 15.0) * k2[i] + T(32.0 / 9.0) * k3[i]);
+      bicycle_f(p, friction, xs, u, k4);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        xs[i] = x[i] + h * (T(19372.0 / 6561.0) * k1[i] - T(25360.0 / 2187.0) * k2[i] + T(64448.0 / 6561.0) * k3[i] -
+                            T(212.0 / 729.0) * k4[i]);
+      bicycle_f(p, friction, xs, u, k5);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        xs[i] = x[i] + h * (T(9017.0 / 3168.0) * k1[i] - T(355.0 / 33.0) * k2[i] + T(46732.0 / 5247.0) * k3[i] +
+                            T(49.0 / 176.0) * k4[i] - T(5103.0 / 18656.0) * k5[i]);
+      bicycle_f(p, friction, xs, u, k6);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        xn[i] = x[i] + h * (T(35.0 / 384.0) * k1[i] + T(500.0 / 1113.0) * k3[i] + T(125.0 / 192.0) * k4[i] -
+                            T(2187.0 / 6784.0) * k5[i] + T(11.0 / 84.0) * k6[i]);
+      bicycle_f(p, friction, xn, u, k7);
+      T err = T(0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const T e = h * (T(71.0 / 57600.0) * k1[i] - T(71.0 / 16695.0) * k3[i] + T(71.0 / 1920.0) * k4[i] -
+                         T(17253.0 / 339200.0) * k5[i] + T(22.0 / 525.0) * k6[i] - T(1.0 / 40.0) * k7[i]);
+        const T ax = x[i] < T(0) ? -x[i] : x[i], an = xn[i] < T(0) ? -xn[i] : xn[i];
+        const T sc = tol + tol * (ax > an ? ax : an);
+        const T r = (e < T(0) ? -e : e) / sc;
+        err = r > err ? r : err;
+      }
+      if (err <= T(1)) {  // accept (first-same-as-last: k7 is the next k1)
+        t += h;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          x[i] = xn[i];
+          k1[i] = k7[i];
+        }
+      }
+      T fac = err > T(1e-30) ? T(0.9) * (T)pow((double)(T(1) / err), 0.2) : T(5);
+      fac = fac > T(5) ? T(5) : (fac < T(0.2) ? T(0.2) : fac);
+      h *= fac;
+    }
     return;
   }
   const T h = p.ts / T(substeps);
@@ -207,6 +266,8 @@ struct RtiLoopArgs {
   int32_t* n_sat;           // [batch] number of applied inputs on a bound
   int32_t* n_fail;          // [batch] number of steps whose QP did not reach MPC_SOLVED
   int32_t* iters_total;     // [batch]
+  T* X_bundle;              // optional [steps][N+1][4][batch]: the state prediction of every control step
+  T* U_bundle;              // optional [steps][N][2][batch]: the input plan of every control step
   BoxQpArgs<T> qp;          // ltv = 1; A/B/c = Acur/Bcur/ccur; x0 = xcur; warm_U = warm;
                             // U = plan buffer: initial plan on entry (zeros = cold start), last plan on exit
 };
@@ -232,6 +293,14 @@ MPC_HD void rti_closed_loop_body(const RtiLoopArgs<T>& a, const T* sh, int64_t b
                         bs, b);
     BoxQpIpm<T, 4, 2> ipm(a.qp, sh, b);
     ipm.solve();
+    if (a.X_bundle) {
+      T* dst = a.X_bundle + (int64_t)t * (N + 1) * 4 * bs;
+      for (int i = 0; i < (N + 1) * 4; ++i) dst[(int64_t)i * bs + b] = a.qp.X[(int64_t)i * bs + b];
+    }
+    if (a.U_bundle) {
+      T* dst = a.U_bundle + (int64_t)t * N * 2 * bs;
+      for (int i = 0; i < N * 2; ++i) dst[(int64_t)i * bs + b] = a.qp.U[(int64_t)i * bs + b];
+    }
     T u[2];
     u[0] = a.qp.U[(int64_t)0 * bs + b];
     u[1] = a.qp.U[(int64_t)1 * bs + b];

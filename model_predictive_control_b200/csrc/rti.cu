@@ -83,7 +83,7 @@ extern "C" int mpc_bicycle_plant_step(double lr, double lf, double accel, double
               "mpc_bicycle_plant_step: float64 only (dtype %d)", dtype);
   if (batch == 0) return MPC_OK;  // nothing to do; pointers of an empty batch may be null
   MPC_REQUIRE(friction && x && u && xn, MPC_ERR_NULL, "mpc_bicycle_plant_step: null pointer");
-  MPC_REQUIRE(batch >= 0 && lr > 0 && ts > 0 && substeps >= 0 && (s_friction == 0 || s_friction == 1), MPC_ERR_SHAPE,
+  MPC_REQUIRE(batch >= 0 && lr > 0 && ts > 0 && substeps >= -15 && (s_friction == 0 || s_friction == 1), MPC_ERR_SHAPE,
               "mpc_bicycle_plant_step: bad argument");
   MPC_REQUIRE(al8({friction, x, u, xn}), MPC_ERR_ALIGN, "mpc_bicycle_plant_step: misaligned pointer");
   BicycleModel<double> m{lr, lf, accel, ts, 0};
@@ -104,16 +104,16 @@ extern "C" int mpc_rti_closed_loop(double lr, double lf, double accel, double fr
                                    const void* R, const void* Pf, const void* u_lo, const void* u_hi,
                                    const void* x_lo, const void* x_hi, const void* x0, void* U_plan, void* X_pred,
                                    void* X_cl, void* U_cl, void* cost_cl, void* viol_cl, int32_t* n_sat,
-                                   int32_t* n_fail, int32_t* iters_total, int32_t* last_status, void* ws,
-                                   int64_t ws_bytes, int64_t batch, int N, int max_iter, double eps, int dtype,
-                                   mpc_stream_t stream) {
+                                   int32_t* n_fail, int32_t* iters_total, int32_t* last_status, void* X_bundle,
+                                   void* U_bundle, void* ws, int64_t ws_bytes, int64_t batch, int N, int max_iter,
+                                   double eps, int dtype, mpc_stream_t stream) {
   MPC_REQUIRE(dtype == MPC_F64, dtype == MPC_F32 ? MPC_ERR_UNSUPPORTED : MPC_ERR_DTYPE,
               "mpc_rti_closed_loop: float64 only (dtype %d)", dtype);
   if (batch == 0) return MPC_OK;  // nothing to do; pointers of an empty batch may be null
   MPC_REQUIRE(friction_plant && Q && R && Pf && u_lo && u_hi && x_lo && x_hi && x0 && U_plan && X_pred && X_cl && U_cl &&
                   cost_cl && viol_cl && n_sat && n_fail && iters_total && last_status,
               MPC_ERR_NULL, "mpc_rti_closed_loop: null pointer");
-  MPC_REQUIRE(N >= 1 && batch >= 0 && steps >= 0 && max_iter >= 1 && lr > 0 && ts > 0 && plant_substeps >= 0, MPC_ERR_SHAPE,
+  MPC_REQUIRE(N >= 1 && batch >= 0 && steps >= 0 && max_iter >= 1 && lr > 0 && ts > 0 && plant_substeps >= -15, MPC_ERR_SHAPE,
               "mpc_rti_closed_loop: bad argument");
   MPC_REQUIRE(ws && ws_bytes >= mpc_rti_workspace_bytes(batch, N, dtype), MPC_ERR_WORKSPACE,
               "mpc_rti_closed_loop: workspace too small (%lld < %lld bytes)", (long long)ws_bytes,
@@ -155,6 +155,8 @@ extern "C" int mpc_rti_closed_loop(double lr, double lf, double accel, double fr
   a.n_sat = n_sat;
   a.n_fail = n_fail;
   a.iters_total = iters_total;
+  a.X_bundle = (double*)X_bundle;
+  a.U_bundle = (double*)U_bundle;
   a.qp = BoxQpArgs<double>{Acur, Bcur, ccur, 1, (const double*)Q, (const double*)R, (const double*)Pf,
                            (const double*)u_lo, (const double*)u_hi, (const double*)x_lo, (const double*)x_hi, xcur, warm,
                            (double*)U_plan, (double*)X_pred, qp_cost, last_status, qp_iters, nullptr, nullptr,

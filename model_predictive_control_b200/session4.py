@@ -33,7 +33,7 @@ _lib.register("mpc_bicycle_rti_prepare", c_int, [c_double] * 5 + [c_int, c_void_
 _lib.register("mpc_bicycle_plant_step", c_int, [c_double] * 4 + [c_void_p, c_int64, c_int] + [c_void_p] * 3 +
               [c_int64, c_int, c_void_p])
 _lib.register("mpc_rti_workspace_bytes", c_int64, [c_int64, c_int, c_int])
-_lib.register("mpc_rti_closed_loop", c_int, [c_double] * 5 + [c_int, c_void_p, c_int, c_int] + [c_void_p] * 19 +
+_lib.register("mpc_rti_closed_loop", c_int, [c_double] * 5 + [c_int, c_void_p, c_int, c_int] + [c_void_p] * 21 +
               [c_int64, c_int64, c_int, c_int, c_double, c_int, c_void_p])
 
 F64 = torch.float64
@@ -101,8 +101,14 @@ def runge_kutta4(f, ts) -> Callable:
     return _Discrete(f, ts, "rk4", 1)
 
 
-def exact_integration(f, ts, substeps: int = 4) -> Callable:
-    """Accurate plant integration: RK4 with ``substeps`` sub-steps (the reference uses scipy odeint)."""
+def exact_integration(f, ts, substeps: int = 4, adaptive: bool = False, tol_exp: int = 10) -> Callable:
+    """Accurate plant integration (the reference uses scipy odeint, session4_sol.py:37-56): RK4 with
+    ``substeps`` sub-steps, or -- ``adaptive=True``, bicycle dynamics only -- the Dormand-Prince 5(4)
+    pair with rtol = atol = 10^-tol_exp on the GPU."""
+    if adaptive:
+        if not isinstance(f, KinematicBicycle):
+            raise ValueError("the adaptive integrator runs on the GPU and needs KinematicBicycle dynamics")
+        return _Discrete(f, ts, "rk4", -int(tol_exp))
     return _Discrete(f, ts, "rk4", int(substeps))
 
 
@@ -142,6 +148,13 @@ class RtiClosedLoopResult:
     n_failed: torch.Tensor     # [batch] steps whose QP did not report success
     iters: torch.Tensor        # [batch] interior-point iterations over all steps
     last_status: torch.Tensor  # [batch]
+    X_bundle: torch.Tensor = None  # [steps, N+1, 4, batch] state prediction of every control step (keep_predictions)
+    U_bundle: torch.Tensor = None  # [steps, N, 2, batch]
+
+    def bundle(self, scenario: int = 0):
+        """(time steps x horizon x states) array of one scenario, the layout AnimateParking.bundle takes
+        (reference session_4/animation.py:75-83)."""
+        return self.X_bundle[:, :, :, scenario]
 
     @property
     def states(self):          # (batch, steps+1, 4) view
@@ -239,14 +252,15 @@ class MPCController:
         return u[0] if (u.dim() if io.is_tensor(u) else u.ndim) == 2 else u[:, 0]
 
     # -- fused closed loop: `steps` x (prepare, QP, plant) in one kernel
-    def closed_loop(self, x0, n_steps, plant: _Discrete = None, friction_plant=None) -> RtiClosedLoopResult:
+    def closed_loop(self, x0, n_steps, plant: _Discrete = None, friction_plant=None,
+                    keep_predictions: bool = False) -> RtiClosedLoopResult:
         xd = io.to_dev(x0, F64)
         if xd.dim() == 1:
             xd = xd[None, :]
         x0T = xd.t().contiguous()
         batch, N, dev = x0T.shape[1], self.N, x0T.device
         pp = self.params if plant is None or not plant.fusable else plant.f.params
-        substeps = 4 if plant is None else (0 if plant.kind == "euler" else max(plant.substeps, 1))
+        substeps = 4 if plant is None else (0 if plant.kind == "euler" else (plant.substeps if plant.substeps < 0 else max(plant.substeps, 1)))
         if plant is not None and abs(plant.ts - self.ts) > 1e-15:
             raise ValueError("plant and controller sampling times differ")
         if friction_plant is None:
@@ -261,6 +275,8 @@ class MPCController:
         cost = torch.empty(batch, dtype=F64, device=dev)
         viol = torch.empty(batch, dtype=F64, device=dev)
         ints = [torch.empty(batch, dtype=torch.int32, device=dev) for _ in range(4)]
+        Xb = torch.empty((n_steps, N + 1, 4, batch), dtype=F64, device=dev) if keep_predictions else None
+        Ub = torch.empty((n_steps, N, 2, batch), dtype=F64, device=dev) if keep_predictions else None
         nbytes = _lib.lib().mpc_rti_workspace_bytes(batch, N, _lib.MPC_F64)
         ws = torch.empty(max(nbytes // 8, 1), dtype=F64, device=dev)
         i_lb, i_ub, s_lb, s_ub = (torch.as_tensor(v, dtype=F64, device=dev).contiguous() for v in self._boxes)
@@ -269,10 +285,11 @@ class MPCController:
             _lib.check(_lib.lib().mpc_rti_closed_loop(
                 *self._model_args(), _lib.ptr(fr), int(substeps), int(n_steps), _lib.ptr(Q), _lib.ptr(R), _lib.ptr(QT),
                 _lib.ptr(i_lb), _lib.ptr(i_ub), _lib.ptr(s_lb), _lib.ptr(s_ub), _lib.ptr(x0T), _lib.ptr(plan), _lib.ptr(Xp),
-                _lib.ptr(Xc), _lib.ptr(Uc), _lib.ptr(cost), _lib.ptr(viol), *[_lib.ptr(t) for t in ints], _lib.ptr(ws),
+                _lib.ptr(Xc), _lib.ptr(Uc), _lib.ptr(cost), _lib.ptr(viol), *[_lib.ptr(t) for t in ints], _lib.ptr(Xb), _lib.ptr(Ub),
+                _lib.ptr(ws),
                 nbytes, batch, N, int(self.max_iter), float(self.eps), _lib.MPC_F64, _lib.stream(dev)))
         self._plan = plan
-        return RtiClosedLoopResult(Xc, Uc, cost, viol, ints[0], ints[1], ints[2], ints[3])
+        return RtiClosedLoopResult(Xc, Uc, cost, viol, ints[0], ints[1], ints[2], ints[3], Xb, Ub)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -303,3 +320,23 @@ def simulate(x0, dynamics: Callable, n_steps: int, policy=None, friction_plant=N
         return out if out.ndim == 2 else np.swapaxes(out, 0, 1)
     out = torch.stack(xs)
     return out if out.dim() == 2 else out.transpose(0, 1)
+
+
+def build_test_policy():
+    """Open-loop test input of the reference (session4_sol.py:58-62)."""
+    acceleration = 1
+    return lambda y, t: np.array([acceleration, 0.1 * np.sin(t)])
+
+
+def compare_open_loop(ts: float, x0, steps: int, params: VehicleParameters = None):
+    """Numeric part of the reference's integrator comparison (session4_sol.py:65-104): open-loop
+    trajectories under the test policy with forward Euler, RK4 and the accurate integrator, and the
+    error norms against the accurate one.  Returns (results, errors) dictionaries keyed as in the
+    reference ("Forward Euler", "RK 4", "Ground truth")."""
+    bike = KinematicBicycle(params or VehicleParameters())
+    schemes = {"Forward Euler": forward_euler(bike, ts), "RK 4": runge_kutta4(bike, ts),
+               "Ground truth": exact_integration(bike, ts, adaptive=True)}
+    policy = build_test_policy()
+    results = {name: simulate(np.asarray(x0, dtype=float), dyn, steps, policy=policy) for name, dyn in schemes.items()}
+    errors = {name: np.linalg.norm(results["Ground truth"] - results[name], axis=1) for name in ("Forward Euler", "RK 4")}
+    return results, errors

@@ -131,6 +131,19 @@ def discretize(x, u, ts, par, friction, method="euler"):
     return xn, I + ts / 6.0 * (J1x + 2 * D2x + 2 * D3x + D4x), ts / 6.0 * (J1u + 2 * D2u + 2 * D3u + D4u)
 
 
+def exact_integration_odeint(x, u, ts, par, friction):
+    """The reference's own accurate plant: scipy odeint over [0, ts] (session4_sol.py:37-56), one state at a time."""
+    from scipy.integrate import odeint
+    lr, lf, acc = par.axis_rear, par.axis_front, par.acceleration
+    x = np.atleast_2d(np.asarray(x, float)); u = np.atleast_2d(np.asarray(u, float))
+    fr = np.broadcast_to(np.asarray(friction, float), (x.shape[0],))
+    out = np.zeros_like(x)
+    for b in range(x.shape[0]):
+        f_wrap = lambda xx, t: bicycle_f(xx, u[b], lr, lf, fr[b], acc)
+        out[b] = odeint(f_wrap, x[b], [0, ts], rtol=1e-12, atol=1e-12)[-1]
+    return out
+
+
 def plant_step(x, u, ts, par, friction, method="rk4", substeps=4):
     """Plant x+ : Euler (nominal model, session4_sol.py:453) or RK4 with fixed sub-steps (stands in for
     the reference's odeint plant, session4_sol.py:37-56 -- documented deviation)."""

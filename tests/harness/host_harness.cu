@@ -171,6 +171,8 @@ extern "C" int hh_rti_closed_loop(double lr, double lf, double accel, double fri
   a.steps = steps; a.x0 = x0; a.xcur = xcur; a.Acur = Acur; a.Bcur = Bcur; a.ccur = ccur; a.warm = warm;
   a.X_cl = X_cl; a.U_cl = U_cl; a.cost_cl = cost_cl; a.viol_cl = viol_cl; a.n_sat = n_sat; a.n_fail = n_fail;
   a.iters_total = iters_total;
+  a.X_bundle = nullptr;
+  a.U_bundle = nullptr;
   a.qp = BoxQpArgs<double>{Acur, Bcur, ccur, 1, Q, R, Pf, u_lo, u_hi, x_lo, x_hi, xcur, warm, U_plan, X_pred, qp_cost,
                            last_status, qp_iters, nullptr, nullptr, qp_ws, batch, N, max_iter, eps};
   for (int64_t b = 0; b < batch; ++b) rti_closed_loop_body<double>(a, sh.data(), b);

@@ -151,3 +151,48 @@ def test_full_size_properties_cfg4(mods):
     xt = X[:, 100].t().contiguous(); ut = U[:, 100].t().contiguous()
     xn = s4.plant_step(par, 0.05, xt, ut, friction=fr, substeps=4)
     assert torch.allclose(xn.t(), X[:, 101], rtol=1e-12, atol=1e-13)
+
+
+def test_adaptive_plant_and_open_loop_comparison(mods):
+    """exact_integration(adaptive=True) against scipy odeint (what the reference's exact_integration
+    calls), and the numbers of the reference's compare_open_loop (session4_sol.py:65-104)."""
+    s4, torch = mods
+    par = s4.VehicleParameters()
+    rng = np.random.default_rng(31)
+    x, fr = scenarios(rng, 12)
+    u = np.stack([rng.uniform(-1, 1, 12), rng.uniform(-0.384, 0.384, 12)], 1)
+    gt = s4.exact_integration(s4.KinematicBicycle(par), 0.25, adaptive=True)
+    np.testing.assert_allclose(gt(x, u), bc.exact_integration_odeint(x, u, 0.25, bc.VehicleParameters(), 1.0), rtol=0, atol=1e-9)
+    results, errors = s4.compare_open_loop(0.05, np.array([0.6, -0.25, 0.0, 0.0]), 40)
+    assert results["Ground truth"].shape == (41, 4)
+    assert errors["RK 4"].max() < 1e-5 < errors["Forward Euler"].max()   # RK4 is far more accurate than Euler
+    # ground truth by odeint, step by step with the same test policy
+    pol = s4.build_test_policy()
+    xs = [np.array([0.6, -0.25, 0.0, 0.0])]
+    for t in range(40):
+        xs.append(bc.exact_integration_odeint(xs[-1], pol(xs[-1], t), 0.05, bc.VehicleParameters(), 1.0)[0])
+    np.testing.assert_allclose(results["Ground truth"], np.array(xs), rtol=0, atol=1e-8)
+
+
+def test_prediction_bundles(mods):
+    s4, torch = mods
+    rng = np.random.default_rng(32)
+    x0, fr = scenarios(rng, 5)
+    N, steps = 15, 6
+    ctrl = s4.MPCController(N=N, ts=0.05, params=s4.VehicleParameters())
+    res = ctrl.closed_loop(x0, steps, friction_plant=fr, keep_predictions=True)
+    assert res.X_bundle.shape == (steps, N + 1, 4, 5) and res.U_bundle.shape == (steps, N, 2, 5)
+    assert res.bundle(2).shape == (steps, N + 1, 4)
+    # every prediction starts at the measured closed-loop state and its first input is the applied one
+    assert torch.equal(res.X_bundle[:, 0], res.X[:-1])
+    assert torch.equal(res.U_bundle[:, 0], res.U)
+    # the bundles are those of the step-by-step controller
+    ctrl2 = s4.MPCController(N=N, ts=0.05, params=s4.VehicleParameters())
+    sol = ctrl2.solve(x0)
+    np.testing.assert_allclose(res.X_bundle[0].permute(2, 0, 1).cpu().numpy(), sol["state_prediction"], rtol=0, atol=1e-12)
+    # a mismatched adaptive plant inside the fused loop
+    params = s4.VehicleParameters(); params.friction *= 0.8
+    plant = s4.exact_integration(s4.KinematicBicycle(params), 0.05, adaptive=True)
+    r2 = ctrl.closed_loop(x0, steps, plant=plant)
+    ref = bc.closed_loop(x0, steps, N=N, friction_plant=np.full(5, 0.8), plant_method="rk4", substeps=16, qp="port")
+    np.testing.assert_allclose(r2.states.cpu().numpy().transpose(1, 0, 2), ref["X"], rtol=0, atol=1e-7)

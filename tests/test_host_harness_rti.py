@@ -126,3 +126,23 @@ def test_closed_loop_matches_exact_qp_oracle(hh):
     ulo, uhi, _, _ = bc.bounds(par)
     np.testing.assert_array_equal(got["U"] == uhi, np.abs(ref["U"] - uhi) < 1e-12)
     np.testing.assert_array_equal(got["U"] == ulo, np.abs(ref["U"] - ulo) < 1e-12)
+
+
+def test_adaptive_plant_matches_scipy_odeint(hh):
+    """substeps < 0: Dormand-Prince 5(4).  Checked against scipy odeint, the integrator behind the
+    reference's exact_integration (session4_sol.py:37-56)."""
+    par = bc.VehicleParameters()
+    rng = np.random.default_rng(21)
+    batch = 9
+    x, fr = scenarios(rng, batch)
+    x[:, 3] = rng.uniform(-0.5, 0.5, batch)
+    u = np.stack([rng.uniform(-1, 1, batch), rng.uniform(-0.384, 0.384, batch)], 1)
+    for ts in (0.05, 0.5):
+        xn = np.zeros((4, batch))
+        assert hh.hh_plant_step(C.c_double(par.axis_rear), C.c_double(par.axis_front), C.c_double(par.acceleration),
+                                C.c_double(ts), p(c_(fr)), -10, p(c_(x.T)), p(c_(u.T)), p(xn), C.c_int64(batch)) == 0
+        ref = bc.exact_integration_odeint(x, u, ts, par, fr)
+        np.testing.assert_allclose(xn.T, ref, rtol=0, atol=1e-9)
+        # and the fixed RK4 x4 stand-in is close to it at the controller's sampling time
+        if ts == 0.05:
+            np.testing.assert_allclose(bc.plant_step(x, u, ts, par, fr, "rk4", 4), ref, rtol=0, atol=1e-8)
