@@ -1,5 +1,5 @@
 import os, sys, time, torch, numpy as np
-sys.path.insert(0, ".")
+sys.path.insert(0, ".")  # run from the repository root
 from model_predictive_control_b200 import boxqp, problem, session4
 dev = torch.device("cuda")
 prob = problem.Problem(N=30)

@@ -1,5 +1,5 @@
 import sys, torch, numpy as np
-sys.path.insert(0, "."); sys.path.insert(0, "tests")
+sys.path.insert(0, ".")  # run from the repository root; sys.path.insert(0, "tests")
 from test_gpu_boxqp import cfg5_model
 from model_predictive_control_b200 import boxqp
 A, B, Q, R = cfg5_model()

@@ -1,5 +1,5 @@
 import sys, torch
-sys.path.insert(0, ".")
+sys.path.insert(0, ".")  # run from the repository root
 from model_predictive_control_b200 import lq
 n, m, N, batch = 4, 1, 20, 1 << 20
 dd = dict(dtype=torch.float64, device="cuda")

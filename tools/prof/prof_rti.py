@@ -1,5 +1,5 @@
 import sys, torch
-sys.path.insert(0, ".")
+sys.path.insert(0, ".")  # run from the repository root
 from model_predictive_control_b200 import session4
 batch, steps = 32768, 10
 g = torch.Generator(device="cuda"); g.manual_seed(5)
