@@ -167,6 +167,19 @@ int mpc_boxqp_solve(const void* A, const void* B, const void* c, int ltv, const 
                     int64_t ws_bytes, int64_t batch, int n, int m, int N, int max_iter, double eps,
                     int dtype, mpc_stream_t stream);
 
+/* K4 with general stage rows (polytopic constraints):  additionally  Cg_k x_{k+1} >= hg_k,  k < N.
+ * Replaces, after linearisation, the collision constraints of the obstacle-avoidance controller
+ * (session_4/main.py:95-104: nine squared-distance constraints per stage).
+ *   Cg [N][nc*n][batch] (row-major rows), hg [N][nc][batch]; sat_c optional [N][nc][batch] (-1 = active).
+ * Instantiated: (n, m, nc) = (4, 2, 9) and (4, 2, 3). */
+int64_t mpc_boxqp_rows_workspace_bytes(int64_t batch, int n, int m, int N, int nc, int dtype);
+int mpc_boxqp_solve_rows(const void* A, const void* B, const void* c, int ltv, const void* Q, const void* R,
+                         const void* Pf, const void* u_lo, const void* u_hi, const void* x_lo, const void* x_hi,
+                         const void* Cg, const void* hg, int nc, const void* x0, const void* warm_U, void* U, void* X,
+                         void* cost, int32_t* status, int32_t* iters, int8_t* sat_u, int8_t* sat_x, int8_t* sat_c,
+                         void* ws, int64_t ws_bytes, int64_t batch, int n, int m, int N, int max_iter, double eps,
+                         int dtype, mpc_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * K5  session-4 kinematic bicycle, real-time-iteration (RTI) MPC.
  * Replaces, for a batch of scenarios, the per-step work of MPCController.__call__/solve

@@ -527,7 +527,9 @@ struct CoopIpm {
       const double ratio = mu_aff / (mu > 1e-300 ? mu : 1e-300);
       double sigma = ratio * ratio * ratio;
       sigma = sigma < 1.0 ? sigma : 1.0;
-      const double sig_mu = sigma * mu;
+      double sig_mu = sigma * mu;
+      const double mu_floor = 0.1 * a.eps * mu_scale;  // see BoxQpIpm::solve
+      sig_mu = sig_mu > mu_floor ? sig_mu : mu_floor;
       backward<false>(sig_mu);
       forward<false>(sig_mu, acc);
       double alpha = 0.995 * acc.amin();
@@ -535,7 +537,7 @@ struct CoopIpm {
       zn = update(sig_mu, alpha, true);
       const double mu_new = (acc.s0 + alpha * (acc.s1 + alpha * acc.s2)) * inv_nc;
       rp = (1.0 - alpha) * acc.rp;
-      const bool done = (mu_new <= a.eps * mu_scale) && (rp <= a.eps * zn) && (alpha * acc.dzmax <= 1e-6 * zn);
+      const bool done = (mu_new <= a.eps * mu_scale) && (rp <= a.eps * zn) && (alpha * acc.dzmax <= 1e-8 * zn);
       if (done) {
         status = MPC_SOLVED;
       } else if (!(alpha >= 1e-6) || !(mu_new <= 100.0 * mu0)) {

@@ -47,7 +47,11 @@ struct BoxQpArgs {
   int32_t* iters;                       // [batch]
   int8_t* sat_u;                        // optional [N][m][batch]: -1 lower, +1 upper, 0 free
   int8_t* sat_x;                        // optional [N][n][batch]
-  T* ws;                                // workspace, boxqp_ws_elems(n, m, N) * batch elements
+  // optional general stage rows  Cg_k x_{k+1} >= hg_k  (kernels instantiated with NC > 0 only):
+  const T* Cg;                          // [N][NC*n][batch]
+  const T* hg;                          // [N][NC][batch]
+  int8_t* sat_c;                        // optional [N][NC][batch]: -1 = row active
+  T* ws;                                // workspace, boxqp_ws_elems(n, m, N, nc) * batch elements
   int64_t batch;
   int N;
   int max_iter;
@@ -55,9 +59,9 @@ struct BoxQpArgs {
 };
 
 // workspace elements per scenario
-inline int64_t boxqp_ws_elems(int n, int m, int N) {
+inline int64_t boxqp_ws_elems(int n, int m, int N, int nc = 0) {
   const int d = n + m;
-  return (int64_t)N * (7 * d + m * n + m * m + m);
+  return (int64_t)N * (7 * d + m * n + m * m + m + 3 * nc);
 }
 
 // shared-parameter block (shared memory on the device)
@@ -74,7 +78,7 @@ struct BoxQpShared {
   static constexpr int total = oHi + D;
 };
 
-template <typename T, int NX, int NU>
+template <typename T, int NX, int NU, int NC = 0>
 struct BoxQpIpm {
   static constexpr int D = NX + NU;
   // small stages are double-buffered in registers (the next stage's operands are requested while
@@ -88,7 +92,7 @@ struct BoxQpIpm {
   T mu_scale;  // max(1, max|Q|, max|R|): scale of the complementarity tolerance
   T mu0;       // start value of the barrier parameter, per scenario: max(mu_scale, |H z0|_inf)
   // workspace sections, each [N][per][batch]
-  T *z, *sl, *su, *ll, *lu, *dza, *dzw, *Kw, *Sw, *dw;
+  T *z, *sl, *su, *ll, *lu, *dza, *dzw, *Kw, *Sw, *dw, *sc, *lc, *rc;  // general rows: slack, multiplier, residual C x - h - s
 
   MPC_HD BoxQpIpm(const BoxQpArgs<T>& args, const T* shared, int64_t scenario)
       : a(args), sh(shared), b(scenario), bs(args.batch) {
@@ -103,6 +107,9 @@ struct BoxQpIpm {
     Kw = dzw + sec;
     Sw = Kw + (int64_t)a.N * NU * NX * bs;
     dw = Sw + (int64_t)a.N * NU * NU * bs;
+    sc = dw + (int64_t)a.N * NU * bs;
+    lc = sc + (int64_t)a.N * NC * bs;
+    rc = lc + (int64_t)a.N * NC * bs;
     mu_scale = T(1);
     for (int i = 0; i < NX * NX; ++i) {
       const T v = sh[SH::oQ + i] < T(0) ? -sh[SH::oQ + i] : sh[SH::oQ + i];
@@ -149,6 +156,19 @@ struct BoxQpIpm {
   MPC_HD void storen(T* base, int k, const T* v) const {
 #pragma unroll
     for (int i = 0; i < PER; ++i) base[ix(k, i, PER)] = v[i];
+  }
+
+  // general row j of stage k: coefficients C[NX] and right-hand side h
+  MPC_HD T load_row_c(int k, int j, T* C) const {
+#pragma unroll
+    for (int i = 0; i < NX; ++i) C[i] = a.Cg[ix(k, j * NX + i, NC * NX)];
+    return a.hg[ix(k, j, NC)];
+  }
+  MPC_HD static T dotx(const T* C, const T* x) {
+    T acc = T(0);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) acc = fma_<T>(C[i], x[i], acc);
+    return acc;
   }
 
   MPC_HD void load_model(int k, T* A, T* B, T* c) const {
@@ -234,6 +254,20 @@ struct BoxQpIpm {
             st.lu[i] = l_u;
           }
           store_stage(k, st);
+          if constexpr (NC > 0) {
+#pragma unroll 1
+            for (int j = 0; j < NC; ++j) {
+              T C[NX];
+              const T h = load_row_c(k, j, C);
+              const T w = dotx(C, xn) - h;
+              const T s = w > T(1) ? w : T(1);
+              sc[ix(k, j, NC)] = s;
+              lc[ix(k, j, NC)] = mu0 / s;
+              // the row residual is carried, not recomputed: it decays exactly by (1 - alpha) per step, whereas
+              // C x - h - s recomputed from a dot product keeps ~1e-16 of rounding noise that Sigma ~ 1e12 amplifies
+              rc[ix(k, j, NC)] = w - s;
+            }
+          }
         }
 #pragma unroll
         for (int i = 0; i < NX; ++i) x[i] = xn[i];
@@ -335,6 +369,28 @@ struct BoxQpIpm {
         }
         sig[i] = sg;
         rhs[i] = r;
+      }
+      if constexpr (NC > 0) {
+        // general rows: value w = C x_{k+1}; adds C' Sigma_c C to the stage Hessian and C' rhs_c to the gradient
+#pragma unroll 1
+        for (int j = 0; j < NC; ++j) {
+          T C[NX];
+          const T h = load_row_c(k, j, C);
+          const T s = sc[ix(k, j, NC)], l = lc[ix(k, j, NC)];
+          const T inv = rcp_(s), sgc = l * inv;
+          const T r = rc[ix(k, j, NC)];
+          (void)h;
+          const T cc = FACTOR ? T(0) : cc_of(dotx(C, da + NU), r, sgc, l);
+          const T rhs_c = (sig_mu - cc) * inv - sgc * r;
+#pragma unroll
+          for (int i = 0; i < NX; ++i) rhs[NU + i] = fma_<T>(C[i], rhs_c, rhs[NU + i]);
+          if (FACTOR) {
+#pragma unroll
+            for (int i = 0; i < NX; ++i)
+#pragma unroll
+              for (int i2 = 0; i2 < NX; ++i2) Pacc[i * NX + i2] = fma_<T>(sgc * C[i], C[i2], Pacc[i * NX + i2]);
+          }
+        }
       }
       if constexpr (FACTOR) {
         // P = Pacc + diag(Sigma_x);  S = R + diag(Sigma_u) + B'PB;  K = -S^-1 B'PA;
@@ -534,6 +590,29 @@ struct BoxQpIpm {
           acc.rp = ar > acc.rp ? ar : acc.rp;
         }
       }
+      if constexpr (NC > 0) {
+#pragma unroll 1
+        for (int j = 0; j < NC; ++j) {
+          T C[NX];
+          const T h = load_row_c(k, j, C);
+          const T s = sc[ix(k, j, NC)], l = lc[ix(k, j, NC)];
+          const T r = rc[ix(k, j, NC)];
+          (void)h;
+          const T ds = dotx(C, xn) + r;
+          const T rinv = rcp_(s * l), inv_s = rinv * l, inv_l = rinv * s;
+          const T sgc = l * inv_s;
+          const T cc = AFFINE ? T(0) : cc_of(dotx(C, da + NU), r, sgc, l);
+          const T dl = (sig_mu - cc) * inv_s - l - sgc * ds;
+          const T qs = -ds * inv_s, ql = -dl * inv_l;
+          acc.qmax = qs > acc.qmax ? qs : acc.qmax;
+          acc.qmax = ql > acc.qmax ? ql : acc.qmax;
+          acc.s0 += s * l;
+          acc.s1 += s * dl + l * ds;
+          acc.s2 += ds * dl;
+          const T ar = r < T(0) ? -r : r;
+          acc.rp = ar > acc.rp ? ar : acc.rp;
+        }
+      }
       storen<D>(AFFINE ? dza : dzw, k, dzv);
 #pragma unroll
       for (int i = 0; i < NX; ++i) x[i] = xn[i];
@@ -562,6 +641,23 @@ struct BoxQpIpm {
       } else {
 #pragma unroll
         for (int i = 0; i < D; ++i) da[i] = T(0);
+      }
+      if constexpr (NC > 0) {
+#pragma unroll 1
+        for (int j = 0; j < NC; ++j) {
+          T C[NX];
+          const T h = load_row_c(k, j, C);
+          const T s = sc[ix(k, j, NC)], l = lc[ix(k, j, NC)];
+          const T r = rc[ix(k, j, NC)];
+          (void)h;
+          const T ds = dotx(C, dz + NU) + r;
+          const T inv = rcp_(s), sgc = l * inv;
+          const T cc = second_order ? cc_of(dotx(C, da + NU), r, sgc, l) : T(0);
+          const T dl = (sig_mu - cc) * inv - l - sgc * ds;
+          sc[ix(k, j, NC)] = s + alpha * ds;
+          lc[ix(k, j, NC)] = l + alpha * dl;
+          rc[ix(k, j, NC)] = (T(1) - alpha) * r;
+        }
       }
 #pragma unroll
       for (int i = 0; i < D; ++i) {
@@ -623,6 +719,12 @@ struct BoxQpIpm {
           a.sat_x[ix(k, i - NU, NX)] = (int8_t)sat;
         }
       }
+      if constexpr (NC > 0) {
+        if (a.sat_c) {
+#pragma unroll 1
+          for (int j = 0; j < NC; ++j) a.sat_c[ix(k, j, NC)] = lc[ix(k, j, NC)] > sc[ix(k, j, NC)] ? (int8_t)-1 : (int8_t)0;
+        }
+      }
       cost += quad<T, NX>(sh + SH::oQ, x) + quad<T, NU>(sh + SH::oR, u);
       step(A, B, c, x, u, xn);
 #pragma unroll
@@ -641,7 +743,7 @@ struct BoxQpIpm {
     int ncons = 0;
 #pragma unroll
     for (int i = 0; i < D; ++i) ncons += (hasl(i) ? 1 : 0) + (hasu(i) ? 1 : 0);
-    ncons *= a.N;
+    ncons = (ncons + NC) * a.N;
     init();
     int status = MPC_UNSOLVED, it = 0;
     T rp = T(0), zn = T(1);
@@ -666,7 +768,11 @@ struct BoxQpIpm {
       T ratio = mu_aff / (mu > T(1e-300) ? mu : T(1e-300));
       T sigma = ratio * ratio * ratio;
       sigma = sigma < T(1) ? sigma : T(1);
-      const T sig_mu = sigma * mu;
+      // centring target; never below a tenth of the complementarity tolerance: driving mu further only inflates
+      // the barrier weights (lam/s ~ lam^2/mu) and with them the rounding noise of the Newton step
+      T sig_mu = sigma * mu;
+      const T mu_floor = T(0.1) * a.eps * mu_scale;
+      sig_mu = sig_mu > mu_floor ? sig_mu : mu_floor;
       backward<false>(sig_mu);
       forward<false>(sig_mu, acc);
       T alpha = T(0.995) * acc.amin();
@@ -674,7 +780,7 @@ struct BoxQpIpm {
       zn = update(sig_mu, alpha, true);
       const T mu_new = (acc.s0 + alpha * (acc.s1 + alpha * acc.s2)) * inv_nc;
       rp = (T(1) - alpha) * acc.rp;
-      const bool done = (mu_new <= a.eps * mu_scale) && (rp <= a.eps * zn) && (alpha * acc.dzmax <= T(1e-6) * zn);
+      const bool done = (mu_new <= a.eps * mu_scale) && (rp <= a.eps * zn) && (alpha * acc.dzmax <= T(1e-8) * zn);
       if (done) {
         status = MPC_SOLVED;
       } else if (!(alpha >= T(1e-6)) || !(mu_new <= T(100) * mu0)) {

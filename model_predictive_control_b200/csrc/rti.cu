@@ -159,7 +159,7 @@ extern "C" int mpc_rti_closed_loop(double lr, double lf, double accel, double fr
   a.U_bundle = (double*)U_bundle;
   a.qp = BoxQpArgs<double>{Acur, Bcur, ccur, 1, (const double*)Q, (const double*)R, (const double*)Pf,
                            (const double*)u_lo, (const double*)u_hi, (const double*)x_lo, (const double*)x_hi, xcur, warm,
-                           (double*)U_plan, (double*)X_pred, qp_cost, last_status, qp_iters, nullptr, nullptr,
+                           (double*)U_plan, (double*)X_pred, qp_cost, last_status, qp_iters, nullptr, nullptr, nullptr, nullptr, nullptr,
                            qp_ws, batch, N, max_iter, eps};
   rti_closed_loop_kernel<double><<<(unsigned)((batch + kRtiThreads - 1) / kRtiThreads), kRtiThreads, 0, (cudaStream_t)stream>>>(a);
   return check_launch("rti_closed_loop_kernel");

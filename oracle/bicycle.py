@@ -213,3 +213,84 @@ def _plant(x, u, ts, par, friction, method, substeps):
         s1 = f(x, u); s2 = f(x + 0.5 * h * s1, u); s3 = f(x + 0.5 * h * s2, u); s4 = f(x + h * s3, u)
         x = x + h / 6.0 * (s1 + 2 * s2 + 2 * s3 + s4)
     return x
+
+
+# ------------------------------------------------------------------------------------------------
+# obstacle-avoidance variant (reference session_4/main.py:29-129)
+# ------------------------------------------------------------------------------------------------
+def create_cover_circles(l, w, n_c=3):
+    """Offsets of the n_c covering-circle centres along the vehicle axis and their radius
+    (main.py:191-200: d = l/(2 n_c), r = sqrt(d^2 + w^2/4), centres ((2k+1) d - l/2, 0))."""
+    d = l / (2 * n_c)
+    return np.array([(2 * k + 1) * d - l / 2 for k in range(n_c)]), float(np.sqrt(d * d + w * w / 4))
+
+
+def obstacle_weights():
+    """main.py:72-74: Q = diag(1, 6, .2, .05), Q_N = 100 Q, R = diag(1, .01)."""
+    Q = np.diag([1.0, 6.0, 0.2, 0.05])
+    return Q, 100.0 * Q, np.diag([1.0, 0.01])
+
+
+def obstacle_rows(xbar, x_obs, length=0.17, width=0.08, n_c=3):
+    """Linearisation at xbar [batch,4] of the n_c^2 collision constraints of main.py:95-104,
+    g_ij(x) = |c_i(x) - o_j|^2 >= (r + r_p)^2 with c_i(x) = p + a_i (cos psi, sin psi):
+    rows C x >= h with C = grad g(xbar), h = (r + r_p)^2 - g(xbar) + C xbar.  Returns C [batch, n_c^2, 4], h."""
+    a, r = create_cover_circles(length, width, n_c)
+    r2 = (2 * r) ** 2
+    x_obs = np.asarray(x_obs, float)
+    ox = x_obs[0] + a * np.cos(x_obs[2]); oy = x_obs[1] + a * np.sin(x_obs[2])
+    px, py, psi = xbar[:, 0], xbar[:, 1], xbar[:, 2]
+    C = np.zeros((xbar.shape[0], n_c * n_c, 4)); h = np.zeros((xbar.shape[0], n_c * n_c))
+    for i in range(n_c):
+        cx, cy = px + a[i] * np.cos(psi), py + a[i] * np.sin(psi)
+        for j in range(n_c):
+            dx, dy = cx - ox[j], cy - oy[j]
+            g = dx * dx + dy * dy
+            row = i * n_c + j
+            C[:, row, 0] = 2 * dx
+            C[:, row, 1] = 2 * dy
+            C[:, row, 2] = 2 * dx * (-a[i] * np.sin(psi)) + 2 * dy * (a[i] * np.cos(psi))
+            h[:, row] = r2 - g + np.einsum("bi,bi->b", C[:, row], xbar)
+    return C, h
+
+
+def closed_loop_obstacle(x0, x_obs, n_steps, N=30, ts=0.08, par=None, friction_plant=None, plant_method="rk4",
+                         substeps=4, qp="port", max_iter=60, length=0.17, width=0.08):
+    """RTI closed loop of the obstacle-avoidance controller (main.py:241-271 protocol): Euler prediction
+    model, box bounds as in session4_sol, plus the linearised collision rows on every predicted state."""
+    par = par or VehicleParameters()
+    x = np.atleast_2d(np.asarray(x0, float))
+    batch = x.shape[0]
+    fp = np.full(batch, par.friction, float) if friction_plant is None else np.broadcast_to(np.asarray(friction_plant, float), (batch,))
+    Q, QT, R = obstacle_weights()
+    ulo, uhi, xlo, xhi = bounds(par)
+    U_prev = np.zeros((N, batch, 2))
+    Xs, Us, Ss = [x], [], []
+    for t in range(n_steps):
+        Ubar, A, B, c, Xbar = rti_prepare(x, U_prev, ts, par, par.friction, "euler", first=(t == 0))
+        rows = [obstacle_rows(Xbar[k + 1], x_obs, length, width) for k in range(N)]
+        Cg = np.array([r_[0] for r_ in rows]); hg = np.array([r_[1] for r_ in rows])
+        if qp == "port":
+            r = bq.ipm_riccati(list(A), list(B), Q, R, QT, N, x, ulo, uhi, xlo, xhi, c=list(c), warm_U=Ubar, max_iter=max_iter,
+                               Cg=Cg, hg=hg)
+            U, status = r["U"], r["status"]
+        else:
+            U = np.zeros((N, batch, 2)); status = np.zeros(batch, dtype=np.int32)
+            for b in range(batch):
+                e = bq.solve_exact(A[:, b], B[:, b], Q, R, QT, N, x[b], ulo, uhi, xlo, xhi, c=c[:, b], Cg=Cg[:, b], hg=hg[:, b])
+                U[:, b], status[b] = e["U"], e["status"]
+        u0 = U[0]
+        x = _plant(x, u0, ts, par, fp, plant_method, substeps)
+        U_prev = U
+        Xs.append(x); Us.append(u0); Ss.append(status)
+    return {"X": np.array(Xs), "U": np.array(Us), "status": np.array(Ss)}
+
+
+def min_clearance(X, x_obs, length=0.17, width=0.08, n_c=3):
+    """Smallest |c_i - o_j| - 2 r over a trajectory X [..., 4] (negative = overlap of covering circles)."""
+    a, r = create_cover_circles(length, width, n_c)
+    x_obs = np.asarray(x_obs, float)
+    ox = x_obs[0] + a * np.cos(x_obs[2]); oy = x_obs[1] + a * np.sin(x_obs[2])
+    cx = X[..., 0, None] + a * np.cos(X[..., 2, None]); cy = X[..., 1, None] + a * np.sin(X[..., 2, None])
+    dist = np.sqrt((cx[..., :, None] - ox) ** 2 + (cy[..., :, None] - oy) ** 2)
+    return float(dist.min() - 2 * r)

@@ -144,7 +144,9 @@ def _highs_qp(H, g, G, lo, hi, lb, ub):
     return np.array(sol.col_value), status == hc.HighsModelStatus.kOptimal, status == hc.HighsModelStatus.kInfeasible
 
 
-def _condensed_qp(A, B, c, Q, R, Pf, x0, u_lo, u_hi, x_lo, x_hi):
+def _condensed_qp(A, B, c, Q, R, Pf, x0, u_lo, u_hi, x_lo, x_hi, Cg=None, hg=None):
+    """Condensed QP in U.  Optional general stage rows Cg[k] x_{k+1} >= hg[k] (Cg [N, nc, n], hg [N, nc])
+    are appended to the constraint matrix after the state-box rows."""
     N, n, m = B.shape
     Phi, Gam, g = ltv_prediction(A, B, c, x0)
     Qbar = np.kron(np.eye(N), Q); Qbar[-n:, -n:] = Pf
@@ -154,7 +156,15 @@ def _condensed_qp(A, B, c, Q, R, Pf, x0, u_lo, u_hi, x_lo, x_hi):
     grad = 2 * Gam.T @ Qbar @ free
     lo = np.tile(x_lo, N) - free
     hi = np.tile(x_hi, N) - free
-    return H, grad, Gam, lo, hi, np.tile(u_lo, N), np.tile(u_hi, N), free
+    G = Gam
+    if Cg is not None:
+        nc = Cg.shape[1]
+        rows = np.zeros((N * nc, Gam.shape[1])); rlo = np.zeros(N * nc)
+        for k in range(N):
+            rows[k * nc:(k + 1) * nc] = Cg[k] @ Gam[k * n:(k + 1) * n]
+            rlo[k * nc:(k + 1) * nc] = hg[k] - Cg[k] @ free[k * n:(k + 1) * n]
+        G = np.vstack([Gam, rows]); lo = np.concatenate([lo, rlo]); hi = np.concatenate([hi, np.full(N * nc, np.inf)])
+    return H, grad, G, lo, hi, np.tile(u_lo, N), np.tile(u_hi, N), free
 
 
 def stage_arrays(A, B, N, c=None):
@@ -212,7 +222,7 @@ def _kkt_refine(H, grad, Gam, lo, hi, lb, ub, U, tol=1e-6, max_rounds=50):
     return Un, False, side
 
 
-def solve_exact(A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi, c=None, method="highs", refine=True):
+def solve_exact(A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi, c=None, method="highs", refine=True, Cg=None, hg=None):
     """Exact solution of one scenario.  HiGHS (or SLSQP) identifies the active set, a dense KKT solve
     on that set gives the solution to rounding accuracy (HiGHS alone is only ~1e-6 accurate in U when
     the cost is flat).  Returns dict(U [N,m], X [N+1,n], cost, status, sat_u, sat_x)."""
@@ -220,7 +230,7 @@ def solve_exact(A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi, c=None, method="h
     Q, R, Pf = (np.asarray(M, float) for M in (Q, R, Pf))
     x0 = np.asarray(x0, float)
     n, m = B.shape[-2], B.shape[-1]
-    H, grad, Gam, lo, hi, lb, ub, free = _condensed_qp(A, B, c, Q, R, Pf, x0, u_lo, u_hi, x_lo, x_hi)
+    H, grad, Gam, lo, hi, lb, ub, free = _condensed_qp(A, B, c, Q, R, Pf, x0, u_lo, u_hi, x_lo, x_hi, Cg, hg)
     if method == "highs":
         U, ok, infeasible = _highs_qp(H, grad, Gam, lo, hi, lb, ub)
     elif method == "slsqp":
@@ -244,7 +254,9 @@ def solve_exact(A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi, c=None, method="h
     out = {"U": U, "X": X, "cost": cost_of(X, U, Q, R, Pf), "status": status}
     if side is not None:
         out["sat_u"] = side[:N * m].reshape(N, m).astype(np.int8)
-        out["sat_x"] = side[N * m:].reshape(N, n).astype(np.int8)
+        out["sat_x"] = side[N * m:N * m + N * n].reshape(N, n).astype(np.int8)
+        if Cg is not None:
+            out["sat_c"] = side[N * m + N * n:].reshape(N, -1).astype(np.int8)
     return out
 
 
@@ -392,7 +404,7 @@ def _bvec(v, batch):
 
 
 def ipm_riccati(A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi, c=None, warm_U=None, max_iter=60,
-                eps=1e-9, second_order=True, verbose=False):
+                eps=1e-9, second_order=True, verbose=False, Cg=None, hg=None):
     """Batched box-constrained LQ-MPC QP.  A, B, c are lists/arrays over stages; each stage entry is
     shared ([n,n]) or per scenario ([batch,n,n]).  x0 [batch, n].
 
@@ -402,6 +414,10 @@ def ipm_riccati(A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi, c=None, warm_U=No
       rhs   = -H z + (sigma mu - cc_l)/s_l - Sigma_l r_l - (sigma mu - cc_u)/s_u + Sigma_u r_u
     predictor: sigma = 0, cc = 0;  corrector: sigma = (mu_aff/mu)^3, cc = ds_aff * dlam_aff.
     One step length alpha = min(1, 0.995 * fraction to the boundary) for all variables.
+
+    Optional general stage rows Cg[k] x_{k+1} >= hg[k] (Cg [N, nc, n] shared or [N, batch, nc, n]; hg [N, nc] or
+    [N, batch, nc]): each row is treated like a lower-bounded element whose value is w = Cg x and whose direction is
+    dw = Cg dx; it adds Cg' diag(lam/s) Cg to the stage Hessian and Cg' rhs_c to the stage gradient.
     """
     if np.asarray(A).ndim == 2:
         A, B, c = stage_arrays(A, B, N, c)
@@ -419,6 +435,13 @@ def ipm_riccati(A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi, c=None, warm_U=No
     has_l, has_u = lo > -BIG, hi < BIG
     lo_f, hi_f = np.where(has_l, lo, 0.0), np.where(has_u, hi, 0.0)
     ncons = N * int(has_l.sum() + has_u.sum())
+    nc = 0
+    if Cg is not None:
+        Cg = np.asarray(Cg, float); hg = np.asarray(hg, float)
+        nc = Cg.shape[-2]
+        Cgb = [np.broadcast_to(Cg[k], (batch, nc, n)) for k in range(N)]
+        hgb = [np.broadcast_to(hg[k], (batch, nc)) for k in range(N)]
+        ncons += N * nc
     mv = lambda M, v: np.einsum("bij,bj->bi", M, v)
     mtv = lambda M, v: np.einsum("bji,bj->bi", M, v)
     dg = lambda v: np.einsum("bi,ij->bij", v, np.eye(v.shape[1]))
@@ -442,6 +465,14 @@ def ipm_riccati(A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi, c=None, warm_U=No
     ll = np.where(has_l, mu0 / sl, 0.0)
     lu = np.where(has_u, mu0 / su, 0.0)
     mu0 = mu0[0, :, 0]
+    sc = np.ones((N, batch, nc)); lc = np.zeros((N, batch, nc)); ccc = np.zeros((N, batch, nc)); dwc = np.zeros((N, batch, nc))
+    rcw = np.zeros((N, batch, nc))   # row residuals C x - h - s: carried and decayed by (1 - alpha), never recomputed
+    for k in range(N):
+        if nc:
+            w0 = mv(Cgb[k], z[k][:, m:]) - hgb[k]
+            sc[k] = np.maximum(w0, 1.0)
+            lc[k] = mu0[:, None] / sc[k]
+            rcw[k] = w0 - sc[k]
 
     status = np.zeros(batch, dtype=np.int32)
     iters = np.zeros(batch, dtype=np.int32)
@@ -463,8 +494,16 @@ def ipm_riccati(A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi, c=None, warm_U=No
             rhs = -Hz + np.where(has_l, (sig_mu[:, None] - ccl[k]) / sl[k] - Sl * rl, 0.0) - \
                 np.where(has_u, (sig_mu[:, None] - ccu[k]) / su[k] - Su * ru, 0.0)
             Sig = Sl + Su
+            if nc:
+                Sc = lc[k] / sc[k]
+                rc = rcw[k]
+                rhs_c = (sig_mu[:, None] - ccc[k]) / sc[k] - Sc * rc
+                rhs = rhs.copy()
+                rhs[:, m:] += mtv(Cgb[k], rhs_c)
             if factor:
                 P = Pacc + dg(Sig[:, m:])
+                if nc:
+                    P = P + np.einsum("bji,bj,bjl->bil", Cgb[k], Sc, Cgb[k])
                 PA, PB = P @ Ab[k], P @ Bb[k]
                 S = R + dg(Sig[:, :m]) + np.swapaxes(Bb[k], 1, 2) @ PB
                 Sinv[k] = np.linalg.inv(S)
@@ -481,6 +520,15 @@ def ipm_riccati(A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi, c=None, warm_U=No
             du = mv(K[k], dx) + dff[k]
             dx = mv(Ab[k], dx) + mv(Bb[k], du)
             zh[k, :, :m] = du; zh[k, :, m:] = dx
+            if nc:
+                dwc[k] = mv(Cgb[k], dx)
+
+    def rows_dir(sig_mu):
+        """Slack / multiplier directions of the general rows."""
+        rc = rcw
+        dsc = dwc + rc
+        dlc = (sig_mu[None, :, None] - ccc) / sc - lc - lc / sc * dsc
+        return dsc, dlc, rc
 
     def directions(sig_mu):
         dz = zh
@@ -496,36 +544,59 @@ def ipm_riccati(A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi, c=None, warm_U=No
                                    np.where(has_l, -dll / np.where(has_l, ll, 1.0), 0.0),
                                    np.where(has_u, -dlu / np.where(has_u, lu, 1.0), 0.0)])
             qmax = q.max(axis=(0, 2))
+            if nc:
+                qmax = np.maximum(qmax, np.maximum(-step_len.dsc / sc, -step_len.dlc / lc).max(axis=(0, 2)))
             return np.where(qmax > 0, 1.0 / qmax, 1e30)
 
     zero = np.zeros(batch)
     for it in range(1, max_iter + 1):
-        mu = (np.where(has_l, sl * ll, 0).sum(axis=(0, 2)) + np.where(has_u, su * lu, 0).sum(axis=(0, 2))) / ncons
-        ccl[:] = 0; ccu[:] = 0
+        mu = (np.where(has_l, sl * ll, 0).sum(axis=(0, 2)) + np.where(has_u, su * lu, 0).sum(axis=(0, 2)) +
+              (sc * lc).sum(axis=(0, 2))) / ncons
+        ccl[:] = 0; ccu[:] = 0; ccc[:] = 0
         backward(zero, True)
         forward()
         dz, dsl, dsu, dll, dlu = directions(zero)
+        if nc:
+            step_len.dsc, step_len.dlc, _ = rows_dir(zero)
         a_aff = np.minimum(1.0, step_len(dsl, dsu, dll, dlu))[None, :, None]
         mu_aff = (np.where(has_l, (sl + a_aff * dsl) * (ll + a_aff * dll), 0).sum(axis=(0, 2)) +
-                  np.where(has_u, (su + a_aff * dsu) * (lu + a_aff * dlu), 0).sum(axis=(0, 2))) / ncons
+                  np.where(has_u, (su + a_aff * dsu) * (lu + a_aff * dlu), 0).sum(axis=(0, 2)))
+        if nc:
+            mu_aff = mu_aff + ((sc + a_aff * step_len.dsc) * (lc + a_aff * step_len.dlc)).sum(axis=(0, 2))
+        mu_aff = mu_aff / ncons
         sigma = np.minimum(1.0, (mu_aff / np.maximum(mu, 1e-300)) ** 3)
         if second_order:
             ccl[:] = dsl * dll; ccu[:] = dsu * dlu
-        backward(sigma * mu, False)
+            if nc:
+                ccc[:] = step_len.dsc * step_len.dlc
+        sig_mu = np.maximum(sigma * mu, 0.1 * eps * mu_scale)   # centring target, floored (see BoxQpIpm::solve)
+        backward(sig_mu, False)
         forward()
-        dz, dsl, dsu, dll, dlu = directions(sigma * mu)
+        dz, dsl, dsu, dll, dlu = directions(sig_mu)
+        if nc:
+            step_len.dsc, step_len.dlc, _ = rows_dir(sig_mu)
         alpha = np.minimum(1.0, 0.995 * step_len(dsl, dsu, dll, dlu))
-        al = np.where(active, alpha, 0.0)[None, :, None]
-        z += al * dz; sl += al * dsl; su += al * dsu; ll += al * dll; lu += al * dlu
+        al = alpha[None, :, None]
+        act3 = active[None, :, None]          # retired scenarios are frozen (no 0 * nan leaks into them)
+
+        def upd(arr, d_):
+            arr[...] = np.where(act3, arr + al * d_, arr)
+        upd(z, dz); upd(sl, dsl); upd(su, dsu); upd(ll, dll); upd(lu, dlu)
+        if nc:
+            upd(sc, step_len.dsc); upd(lc, step_len.dlc)
+            rcw[...] = np.where(act3, (1.0 - al) * rcw, rcw)
         iters[active] = it
-        mu_new = (np.where(has_l, sl * ll, 0).sum(axis=(0, 2)) + np.where(has_u, su * lu, 0).sum(axis=(0, 2))) / ncons
+        mu_new = (np.where(has_l, sl * ll, 0).sum(axis=(0, 2)) + np.where(has_u, su * lu, 0).sum(axis=(0, 2)) +
+                  (sc * lc).sum(axis=(0, 2))) / ncons
         rp = np.maximum(np.where(has_l, np.abs(z - lo_f - sl), 0).max(axis=(0, 2)),
                         np.where(has_u, np.abs(hi_f - z - su), 0).max(axis=(0, 2)))
+        if nc:
+            rp = np.maximum(rp, np.abs(rows_dir(zero)[2]).max(axis=(0, 2)))
         zn = np.maximum(1.0, np.abs(z).max(axis=(0, 2)))
         step = alpha * np.abs(dz).max(axis=(0, 2))
         if verbose:
             print(it, "mu", mu_new.max(), "rp", rp.max(), "alpha", alpha.min(), "step", step.max())
-        done = active & (mu_new <= eps * mu_scale) & (rp <= eps * zn) & (step <= 1e-6 * zn)
+        done = active & (mu_new <= eps * mu_scale) & (rp <= eps * zn) & (step <= 1e-8 * zn)
         status[done] = SOLVED
         active &= ~done
         # stalled: the step length collapses / the barrier parameter grows 100x above its start value.  With a bound
@@ -535,11 +606,22 @@ def ipm_riccati(A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi, c=None, warm_U=No
             status[stuck & (rp <= 1e-6 * zn)] = MAX_ITER
             status[stuck & ~(rp <= 1e-6 * zn)] = INFEASIBLE
         active &= ~stuck
+        if stuck.any():
+            # the batched numpy code keeps evaluating retired scenarios: park diverged iterates on benign values
+            # (their outputs are only the status; the GPU threads simply leave the loop)
+            bad = stuck & ~np.isfinite(mu_new)
+            for arr in (sl, su, sc):
+                arr[:, bad] = 1.0
+            for arr in (ll, lu, lc):
+                arr[:, bad] = 1.0 if arr is lc else np.where(arr[:, bad] != 0, 1.0, 0.0)
+            z[:, bad] = np.nan_to_num(z[:, bad], nan=0.0, posinf=0.0, neginf=0.0)
         if not active.any():
             break
     # infeasible problems keep a bound residual that cannot be closed
     rp = np.maximum(np.where(has_l, np.abs(z - lo_f - sl), 0).max(axis=(0, 2)),
                     np.where(has_u, np.abs(hi_f - z - su), 0).max(axis=(0, 2)))
+    if nc:
+        rp = np.maximum(rp, np.abs(rows_dir(zero)[2]).max(axis=(0, 2)))
     zn = np.maximum(1.0, np.abs(z).max(axis=(0, 2)))
     status[active & ~(rp <= 1e-6 * zn)] = INFEASIBLE   # also catches diverged (non-finite) iterates
     status[active & (rp <= 1e-6 * zn)] = MAX_ITER
@@ -554,4 +636,4 @@ def ipm_riccati(A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi, c=None, warm_U=No
         + np.einsum("bi,ij,bj->b", X[-1], Pf, X[-1])
     sat = act_u.astype(np.int8) - act_l.astype(np.int8)
     return {"U": U, "X": X, "cost": cost, "status": status, "iters": iters, "sat_u": sat[:, :, :m],
-            "sat_x": sat[:, :, m:]}
+            "sat_x": sat[:, :, m:], "sat_c": (lc > sc).astype(np.int8) * -1}

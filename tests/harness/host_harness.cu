@@ -114,7 +114,7 @@ extern "C" int hh_boxqp_solve(const double* A, const double* B, const double* c,
                               double eps) {
   std::vector<double> ws((size_t)(boxqp_ws_elems(n, m, N) * batch));
   BoxQpArgs<double> a{A, B, c, ltv, Q, R, Pf, u_lo, u_hi, x_lo, x_hi, x0, warm_U, U, X, cost, status, iters,
-                      sat_u, sat_x, ws.data(), batch, N, max_iter, eps};
+                      sat_u, sat_x, nullptr, nullptr, nullptr, ws.data(), batch, N, max_iter, eps};
   if (n == 2 && m == 1) boxqp_loop<2, 1>(a);
   else if (n == 4 && m == 1) boxqp_loop<4, 1>(a);
   else if (n == 4 && m == 2) boxqp_loop<4, 2>(a);
@@ -174,7 +174,40 @@ extern "C" int hh_rti_closed_loop(double lr, double lf, double accel, double fri
   a.X_bundle = nullptr;
   a.U_bundle = nullptr;
   a.qp = BoxQpArgs<double>{Acur, Bcur, ccur, 1, Q, R, Pf, u_lo, u_hi, x_lo, x_hi, xcur, warm, U_plan, X_pred, qp_cost,
-                           last_status, qp_iters, nullptr, nullptr, qp_ws, batch, N, max_iter, eps};
+                           last_status, qp_iters, nullptr, nullptr, nullptr, nullptr, nullptr, qp_ws, batch, N, max_iter, eps};
   for (int64_t b = 0; b < batch; ++b) rti_closed_loop_body<double>(a, sh.data(), b);
+  return 0;
+}
+
+template <int NX, int NU, int NC>
+static void boxqp_rows_loop(const BoxQpArgs<double>& a) {
+  using SH = BoxQpShared<NX, NU>;
+  std::vector<double> sh(SH::total, 0.0);
+  if (!a.ltv) {
+    for (int i = 0; i < NX * NX; ++i) sh[SH::oA + i] = a.A[i];
+    for (int i = 0; i < NX * NU; ++i) sh[SH::oB + i] = a.B[i];
+  }
+  for (int i = 0; i < NX * NX; ++i) { sh[SH::oQ + i] = a.Q[i]; sh[SH::oPf + i] = a.Pf[i]; }
+  for (int i = 0; i < NU * NU; ++i) sh[SH::oR + i] = a.R[i];
+  for (int i = 0; i < NU; ++i) { sh[SH::oLo + i] = a.u_lo[i]; sh[SH::oHi + i] = a.u_hi[i]; }
+  for (int i = 0; i < NX; ++i) { sh[SH::oLo + NU + i] = a.x_lo[i]; sh[SH::oHi + NU + i] = a.x_hi[i]; }
+  for (int64_t b = 0; b < a.batch; ++b) {
+    BoxQpIpm<double, NX, NU, NC> ipm(a, sh.data(), b);
+    ipm.solve();
+  }
+}
+
+extern "C" int hh_boxqp_solve_rows(const double* A, const double* B, const double* c, int ltv, const double* Q,
+                                   const double* R, const double* Pf, const double* u_lo, const double* u_hi,
+                                   const double* x_lo, const double* x_hi, const double* Cg, const double* hg, int nc,
+                                   const double* x0, const double* warm_U, double* U, double* X, double* cost,
+                                   int32_t* status, int32_t* iters, int8_t* sat_u, int8_t* sat_x, int8_t* sat_c,
+                                   int64_t batch, int n, int m, int N, int max_iter, double eps) {
+  std::vector<double> ws((size_t)(boxqp_ws_elems(n, m, N, nc) * batch));
+  BoxQpArgs<double> a{A, B, c, ltv, Q, R, Pf, u_lo, u_hi, x_lo, x_hi, x0, warm_U, U, X, cost, status, iters,
+                      sat_u, sat_x, Cg, hg, sat_c, ws.data(), batch, N, max_iter, eps};
+  if (n == 4 && m == 2 && nc == 3) boxqp_rows_loop<4, 2, 3>(a);
+  else if (n == 4 && m == 2 && nc == 9) boxqp_rows_loop<4, 2, 9>(a);
+  else return -5;
   return 0;
 }

@@ -128,3 +128,54 @@ def test_unconstrained_is_the_lq_solution(hh):
         np.testing.assert_allclose(got["U"][:, b], U, rtol=1e-9, atol=1e-10)
         np.testing.assert_allclose(got["cost"][b], V, rtol=1e-10)
     assert np.all(got["status"] == bq.SOLVED) and np.all(got["iters"] == 1)
+
+
+def rows_problem(rng, batch, N, nc, n=4, m=2):
+    """LTV QPs with nc general stage rows Cg x_{k+1} >= hg, built so that some rows are active."""
+    A, B, c = random_ltv(rng, batch, N, n, m)
+    Q = np.diag(rng.uniform(0.5, 2.0, n)); R = np.diag(rng.uniform(0.05, 0.2, m)); Pf = 5 * Q
+    ulo, uhi = -np.ones(m), 0.5 * np.ones(m)
+    xlo, xhi = -2.0 * np.ones(n), 2.0 * np.ones(n)
+    x0 = rng.uniform(-1.0, 1.0, (batch, n))
+    base = bq.ipm_riccati(list(A), list(B), Q, R, Pf, N, x0, ulo, uhi, xlo, xhi, c=list(c))
+    Cg = rng.standard_normal((N, batch, nc, n))
+    low = -0.03 if nc <= 3 else -0.004   # a few rows cut into the box-only optimum, the rest are slack
+    hg = np.einsum("kbji,kbi->kbj", Cg, base["X"][1:]) - rng.uniform(low, 0.3, (N, batch, nc))
+    return A, B, c, Q, R, Pf, ulo, uhi, xlo, xhi, x0, Cg, hg
+
+
+@pytest.mark.parametrize("nc", [3, 9])
+def test_general_stage_rows(hh, nc):
+    """Polytopic stage constraints Cg x >= hg (the linearised collision constraints of
+    session_4/main.py:95-104 have this form) against the numpy restatement and the exact oracle."""
+    rng = np.random.default_rng(40 + nc)
+    batch, N, n, m = 10, 10, 4, 2
+    A, B, c, Q, R, Pf, ulo, uhi, xlo, xhi, x0, Cg, hg = rows_problem(rng, batch, N, nc)
+    U = np.zeros((N, m, batch)); X = np.zeros((N + 1, n, batch)); cost = np.zeros(batch)
+    status = np.zeros(batch, dtype=np.int32); iters = np.zeros(batch, dtype=np.int32)
+    su = np.zeros((N, m, batch), dtype=np.int8); sx = np.zeros((N, n, batch), dtype=np.int8)
+    scn = np.zeros((N, nc, batch), dtype=np.int8)
+    I8 = C.POINTER(C.c_int8); I32 = C.POINTER(C.c_int32)
+    rc = hh.hh_boxqp_solve_rows(p(c_(A.reshape(N, batch, n * n).transpose(0, 2, 1))), p(c_(B.reshape(N, batch, n * m).transpose(0, 2, 1))),
+                                p(c_(c.transpose(0, 2, 1))), 1, p(c_(Q)), p(c_(R)), p(c_(Pf)), p(c_(ulo)), p(c_(uhi)), p(c_(xlo)),
+                                p(c_(xhi)), p(c_(Cg.reshape(N, batch, nc * n).transpose(0, 2, 1))), p(c_(hg.transpose(0, 2, 1))), nc,
+                                p(c_(x0.T)), None, p(U), p(X), p(cost), status.ctypes.data_as(I32), iters.ctypes.data_as(I32),
+                                su.ctypes.data_as(I8), sx.ctypes.data_as(I8), scn.ctypes.data_as(I8), C.c_int64(batch), n, m, N,
+                                60, C.c_double(1e-9))
+    assert rc == 0
+    port = bq.ipm_riccati(list(A), list(B), Q, R, Pf, N, x0, ulo, uhi, xlo, xhi, c=list(c), Cg=Cg, hg=hg)
+    np.testing.assert_array_equal(status, port["status"])
+    ok = status == bq.SOLVED
+    assert ok.sum() >= batch // 2
+    np.testing.assert_allclose(U.transpose(0, 2, 1)[:, ok], port["U"][:, ok], rtol=1e-7, atol=1e-8)
+    n_active = 0
+    for b in np.nonzero(ok)[0]:
+        ex = bq.solve_exact(A[:, b], B[:, b], Q, R, Pf, N, x0[b], ulo, uhi, xlo, xhi, c=c[:, b], Cg=Cg[:, b], hg=hg[:, b])
+        assert ex["status"] == bq.SOLVED
+        assert np.abs(U[:, :, b] - ex["U"]).max() <= 1e-6 * max(1.0, np.abs(ex["U"]).max())
+        np.testing.assert_array_equal(su[:, :, b], ex["sat_u"])
+        np.testing.assert_array_equal(sx[:, :, b], ex["sat_x"])
+        np.testing.assert_array_equal(scn[:, :, b], ex["sat_c"])
+        n_active += int(np.abs(ex["sat_c"]).sum())
+        assert np.all(np.einsum("kji,ki->kj", Cg[:, b], X[1:, :, b]) >= hg[:, b] - 1e-7)   # rows hold on the rollout
+    assert n_active > 0
