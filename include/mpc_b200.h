@@ -209,6 +209,14 @@ int mpc_boxqp_solve_rows(const void* A, const void* B, const void* c, int ltv, c
 int mpc_bicycle_rti_prepare(double lr, double lf, double accel, double friction, double ts, int rk4,
                             const void* y, const void* U_prev, int first, void* warm_U, void* A, void* B,
                             void* c, int64_t batch, int N, int dtype, mpc_stream_t stream);
+/* Obstacle-avoidance variant (session_4/main.py:29-129): as mpc_bicycle_rti_prepare, and additionally the nine
+ * collision constraints between the three covering circles of the vehicle and of the parked obstacle
+ * (main.py:49-56,95-104,191-200), linearised at the rolled-out states:  Cg [N][9*4][batch], hg [N][9][batch],
+ * the general rows of mpc_boxqp_solve_rows.  x_obs is a HOST pointer to the obstacle pose [p_x, p_y, psi, v]. */
+int mpc_bicycle_rti_prepare_obstacle(double lr, double lf, double accel, double friction, double ts, int rk4,
+                                     double length, double width, const double* x_obs, const void* y,
+                                     const void* U_prev, int first, void* warm_U, void* A, void* B, void* c, void* Cg,
+                                     void* hg, int64_t batch, int N, int dtype, mpc_stream_t stream);
 int mpc_bicycle_plant_step(double lr, double lf, double accel, double ts, const void* friction,
                            int64_t s_friction, int substeps, const void* x, const void* u, void* xn,
                            int64_t batch, int dtype, mpc_stream_t stream);

@@ -22,6 +22,11 @@ _lib.register("mpc_boxqp_solve", c_int,
               [c_void_p] * 3 + [c_int] + [c_void_p] * 16 + [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int,
                                                            c_double, c_int, c_void_p])
 
+_lib.register("mpc_boxqp_rows_workspace_bytes", c_int64, [c_int64, c_int, c_int, c_int, c_int, c_int])
+_lib.register("mpc_boxqp_solve_rows", c_int,
+              [c_void_p] * 3 + [c_int] + [c_void_p] * 9 + [c_int] + [c_void_p] * 11 + [c_int64, c_int64, c_int, c_int, c_int, c_int,
+                                                                                  c_double, c_int, c_void_p])
+
 BIG = 1e20  # "no bound"
 
 
@@ -35,6 +40,7 @@ class BoxQpResult:
     iters: torch.Tensor    # int32 [batch]
     sat_u: torch.Tensor    # int8 [N, m, batch]: -1 lower, +1 upper, 0 free
     sat_x: torch.Tensor    # int8 [N, n, batch]
+    sat_c: torch.Tensor = None   # int8 [N, nc, batch]: -1 where a general row C x >= h is active
 
     @property
     def solver_success(self):
@@ -52,9 +58,12 @@ class BoxQpResult:
 class BoxQpWorkspace:
     """Caller-owned scratch + outputs, reusable across solves of the same shape."""
 
-    def __init__(self, batch, n, m, N, device, sat=True):
+    def __init__(self, batch, n, m, N, device, sat=True, nc=0):
         dd = dict(dtype=torch.float64, device=device)
-        nbytes = _lib.lib().mpc_boxqp_workspace_bytes(batch, n, m, N, _lib.MPC_F64)
+        nbytes = (_lib.lib().mpc_boxqp_rows_workspace_bytes(batch, n, m, N, nc, _lib.MPC_F64) if nc else
+                  _lib.lib().mpc_boxqp_workspace_bytes(batch, n, m, N, _lib.MPC_F64))
+        self.sat_c = torch.empty((N, nc, batch), dtype=torch.int8, device=device) if (sat and nc) else None
+        self.nc = nc
         self.ws = torch.empty(max(nbytes // 8, 1), **dd)
         self.nbytes = nbytes
         self.U = torch.empty((N, m, batch), **dd)
@@ -78,12 +87,13 @@ def _vec(v, k, device, name):
 
 
 def solve(A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi, c=None, warm_U=None, max_iter=60, eps=1e-9,
-          workspace=None):
+          workspace=None, Cg=None, hg=None):
     """Solve ``batch`` QPs.  x0 [n, batch] (CUDA, float64).
 
     LTI: A [n,n], B [n,m] shared (c must be None).
     LTV: A [N, n*n, batch], B [N, n*m, batch], c [N, n, batch] per scenario and stage.
     Bounds are per coordinate, shared by all stages and scenarios; +-inf = unbounded.
+    Optional general stage rows  Cg_k x_{k+1} >= hg_k:  Cg [N, nc*n, batch] (row-major rows), hg [N, nc, batch].
     """
     _lib.require_cuda(A, B, Q, R, Pf, x0)
     if x0.dtype != torch.float64:
@@ -118,9 +128,26 @@ def solve(A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi, c=None, warm_U=None, ma
         if tuple(warm_U.shape) != (N, m, batch):
             raise ValueError(f"warm_U must be (N, m, batch) = {(N, m, batch)}")
         warm_U = warm_U.contiguous()
-    w = workspace if workspace is not None else BoxQpWorkspace(batch, n, m, N, dev)
-    if w.shape != (batch, n, m, N):
-        raise ValueError(f"workspace was built for {w.shape}, need {(batch, n, m, N)}")
+    nc = 0
+    if Cg is not None:
+        if hg is None or Cg.dim() != 3 or Cg.shape[0] != N or Cg.shape[2] != batch or Cg.shape[1] % n:
+            raise ValueError("rows must be Cg [N, nc*n, batch] with hg [N, nc, batch]")
+        nc = Cg.shape[1] // n
+        if tuple(hg.shape) != (N, nc, batch):
+            raise ValueError(f"hg must be {(N, nc, batch)}")
+        Cg, hg = Cg.contiguous(), hg.contiguous()
+    w = workspace if workspace is not None else BoxQpWorkspace(batch, n, m, N, dev, nc=nc)
+    if w.shape != (batch, n, m, N) or getattr(w, "nc", 0) != nc:
+        raise ValueError(f"workspace was built for {w.shape} (nc={getattr(w, 'nc', 0)}), need {(batch, n, m, N)} (nc={nc})")
+    if nc:
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().mpc_boxqp_solve_rows(
+                _lib.ptr(A), _lib.ptr(B), _lib.ptr(c), 1 if ltv else 0, _lib.ptr(Q), _lib.ptr(R), _lib.ptr(Pf),
+                _lib.ptr(ulo), _lib.ptr(uhi), _lib.ptr(xlo), _lib.ptr(xhi), _lib.ptr(Cg), _lib.ptr(hg), nc, _lib.ptr(x0),
+                _lib.ptr(warm_U), _lib.ptr(w.U), _lib.ptr(w.X), _lib.ptr(w.cost), _lib.ptr(w.status), _lib.ptr(w.iters),
+                _lib.ptr(w.sat_u), _lib.ptr(w.sat_x), _lib.ptr(w.sat_c), _lib.ptr(w.ws), w.nbytes, batch, n, m, N,
+                int(max_iter), float(eps), _lib.MPC_F64, _lib.stream(dev)))
+        return BoxQpResult(w.U, w.X, w.cost, w.status, w.iters, w.sat_u, w.sat_x, w.sat_c)
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().mpc_boxqp_solve(
             _lib.ptr(A), _lib.ptr(B), _lib.ptr(c), 1 if ltv else 0, _lib.ptr(Q), _lib.ptr(R), _lib.ptr(Pf),

@@ -206,15 +206,53 @@ MPC_HD void bicycle_plant(const BicycleModel<T>& p, T friction, int substeps, T*
   }
 }
 
+// Covering circles of the obstacle-avoidance variant (reference session_4/main.py:49-56,191-200): NCIRC
+// circles of radius r along the vehicle axis at offsets a_i, the same for the parked obstacle at pose
+// x_obs; constraint |c_i(x) - o_j|^2 >= (2 r)^2 for every pair.
+constexpr int kObsCircles = 3;
+template <typename T>
+struct ObstacleParams {
+  T a[kObsCircles];               // centre offsets along the vehicle axis
+  T ox[kObsCircles], oy[kObsCircles];  // obstacle circle centres (world frame)
+  T r2;                           // (r + r_p)^2
+};
+
+// Linearisation at xbar of the kObsCircles^2 collision constraints: rows C x >= h with
+// C = grad g(xbar), h = r2 - g(xbar) + C xbar  (g_ij(x) = |p + a_i (cos psi, sin psi) - o_j|^2).
+template <typename T>
+MPC_HD void obstacle_rows(const ObstacleParams<T>& ob, const T* xbar, T* Cg, T* hg, int64_t stride) {
+  T sp, cp;
+  sincos(xbar[2], &sp, &cp);
+#pragma unroll
+  for (int i = 0; i < kObsCircles; ++i) {
+    const T cx = xbar[0] + ob.a[i] * cp, cy = xbar[1] + ob.a[i] * sp;
+#pragma unroll
+    for (int j = 0; j < kObsCircles; ++j) {
+      const T dx = cx - ob.ox[j], dy = cy - ob.oy[j];
+      const T g = dx * dx + dy * dy;
+      const T c0 = T(2) * dx, c1 = T(2) * dy;
+      const T c2 = T(2) * dx * (-ob.a[i] * sp) + T(2) * dy * (ob.a[i] * cp);
+      const int row = i * kObsCircles + j;
+      Cg[(int64_t)(row * 4 + 0) * stride] = c0;
+      Cg[(int64_t)(row * 4 + 1) * stride] = c1;
+      Cg[(int64_t)(row * 4 + 2) * stride] = c2;
+      Cg[(int64_t)(row * 4 + 3) * stride] = T(0);
+      hg[(int64_t)row * stride] = ob.r2 - g + c0 * xbar[0] + c1 * xbar[1] + c2 * xbar[2];
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // RTI preparation for one scenario: shift the previous plan (first == 0), roll the nonlinear model
 // out from the measured state y, linearise along the trajectory:
 //   warm[k] = first ? Uprev[k] : Uprev[min(k+1, N-1)]
 //   xbar_{k+1} = f_d(xbar_k, warm[k]);  A_k, B_k its Jacobians;  c_k = xbar_{k+1} - A_k xbar_k - B_k warm[k]
 // Layouts: y [4][batch], Uprev / warm [N][2][batch], A [N][16][batch], B [N][8][batch], c [N][4][batch].
+// Optional: obstacle rows Cg [N][9*4][batch], hg [N][9][batch] linearised at xbar_{k+1} (ob != nullptr).
 template <typename T>
 MPC_HD void rti_prepare_body(const BicycleModel<T>& p, T friction, const T* y, const T* Uprev, int first, T* warm,
-                             T* A, T* B, T* c, int N, int64_t bs, int64_t b) {
+                             T* A, T* B, T* c, int N, int64_t bs, int64_t b, const ObstacleParams<T>* ob = nullptr,
+                             T* Cg = nullptr, T* hg = nullptr) {
   T x[4], xn[4], u[2], Ak[16], Bk[8];
 #pragma unroll
   for (int i = 0; i < 4; ++i) x[i] = y[i * bs + b];
@@ -237,6 +275,10 @@ MPC_HD void rti_prepare_body(const BicycleModel<T>& p, T friction, const T* y, c
       acc = fma_<T>(-Bk[i * 2 + 0], u[0], acc);
       acc = fma_<T>(-Bk[i * 2 + 1], u[1], acc);
       c[((int64_t)k * 4 + i) * bs + b] = acc;
+    }
+    if (ob) {
+      constexpr int R = kObsCircles * kObsCircles;
+      obstacle_rows<T>(*ob, xn, Cg + (int64_t)k * R * 4 * bs + b, hg + (int64_t)k * R * bs + b, bs);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) x[i] = xn[i];

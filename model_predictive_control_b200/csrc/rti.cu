@@ -14,6 +14,15 @@ __global__ void __launch_bounds__(kRtiThreads) rti_prepare_kernel(BicycleModel<T
 }
 
 template <typename T>
+__global__ void __launch_bounds__(kRtiThreads) rti_prepare_obstacle_kernel(BicycleModel<T> model, T friction,
+                                                                           ObstacleParams<T> ob, const T* y,
+                                                                           const T* Uprev, int first, T* warm, T* A, T* B,
+                                                                           T* c, T* Cg, T* hg, int N, int64_t batch) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < batch) rti_prepare_body<T>(model, friction, y, Uprev, first, warm, A, B, c, N, batch, b, &ob, Cg, hg);
+}
+
+template <typename T>
 __global__ void __launch_bounds__(256) bicycle_plant_kernel(BicycleModel<T> model, const T* friction, int64_t sfr,
                                                             int substeps, const T* x, const T* u, T* xn, int64_t batch) {
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -74,6 +83,37 @@ extern "C" int mpc_bicycle_rti_prepare(double lr, double lf, double accel, doubl
       m, friction, (const double*)y, (const double*)U_prev, first, (double*)warm_U, (double*)A, (double*)B, (double*)c, N,
       batch);
   return check_launch("rti_prepare_kernel");
+}
+
+extern "C" int mpc_bicycle_rti_prepare_obstacle(double lr, double lf, double accel, double friction, double ts, int rk4,
+                                                double length, double width, const double* x_obs, const void* y,
+                                                const void* U_prev, int first, void* warm_U, void* A, void* B, void* c,
+                                                void* Cg, void* hg, int64_t batch, int N, int dtype,
+                                                mpc_stream_t stream) {
+  MPC_REQUIRE(dtype == MPC_F64, dtype == MPC_F32 ? MPC_ERR_UNSUPPORTED : MPC_ERR_DTYPE,
+              "mpc_bicycle_rti_prepare_obstacle: float64 only (dtype %d)", dtype);
+  if (batch == 0) return MPC_OK;
+  MPC_REQUIRE(x_obs && y && U_prev && warm_U && A && B && c && Cg && hg, MPC_ERR_NULL,
+              "mpc_bicycle_rti_prepare_obstacle: null pointer");
+  MPC_REQUIRE(N >= 1 && batch >= 0 && lr > 0 && lf >= 0 && ts > 0 && length > 0 && width > 0, MPC_ERR_SHAPE,
+              "mpc_bicycle_rti_prepare_obstacle: bad argument");
+  MPC_REQUIRE(warm_U != U_prev, MPC_ERR_UNSUPPORTED, "mpc_bicycle_rti_prepare_obstacle: warm_U must not alias U_prev");
+  MPC_REQUIRE(al8({y, U_prev, warm_U, A, B, c, Cg, hg}), MPC_ERR_ALIGN, "mpc_bicycle_rti_prepare_obstacle: misaligned pointer");
+  BicycleModel<double> m{lr, lf, accel, ts, rk4 ? 1 : 0};
+  // covering circles (x_obs is a HOST pointer to the obstacle pose [p_x, p_y, psi, v])
+  ObstacleParams<double> ob;
+  const double d = length / (2.0 * kObsCircles);
+  const double r = sqrt(d * d + width * width / 4.0);
+  ob.r2 = (2.0 * r) * (2.0 * r);
+  for (int k = 0; k < kObsCircles; ++k) {
+    ob.a[k] = (2 * k + 1) * d - length / 2.0;
+    ob.ox[k] = x_obs[0] + ob.a[k] * cos(x_obs[2]);
+    ob.oy[k] = x_obs[1] + ob.a[k] * sin(x_obs[2]);
+  }
+  rti_prepare_obstacle_kernel<double><<<(unsigned)((batch + kRtiThreads - 1) / kRtiThreads), kRtiThreads, 0, (cudaStream_t)stream>>>(
+      m, friction, ob, (const double*)y, (const double*)U_prev, first, (double*)warm_U, (double*)A, (double*)B, (double*)c,
+      (double*)Cg, (double*)hg, N, batch);
+  return check_launch("rti_prepare_obstacle_kernel");
 }
 
 extern "C" int mpc_bicycle_plant_step(double lr, double lf, double accel, double ts, const void* friction,

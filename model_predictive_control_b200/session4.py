@@ -36,6 +36,9 @@ _lib.register("mpc_rti_workspace_bytes", c_int64, [c_int64, c_int, c_int])
 _lib.register("mpc_rti_closed_loop", c_int, [c_double] * 5 + [c_int, c_void_p, c_int, c_int] + [c_void_p] * 21 +
               [c_int64, c_int64, c_int, c_int, c_double, c_int, c_void_p])
 
+_lib.register("mpc_bicycle_rti_prepare_obstacle", c_int, [c_double] * 5 + [c_int, c_double, c_double, c_void_p, c_void_p,
+              c_void_p, c_int] + [c_void_p] * 6 + [c_int64, c_int, c_int, c_void_p])
+
 F64 = torch.float64
 
 
@@ -293,6 +296,78 @@ class MPCController:
 
 
 # ------------------------------------------------------------------------------------------------
+# obstacle-avoidance controller (reference session_4/main.py)
+# ------------------------------------------------------------------------------------------------
+def x2T(x, symbolic: bool = False):
+    """Homogeneous transform of a pose [p_x, p_y, psi, ...] (reference main.py:173-188)."""
+    c, s_ = np.cos(x[2]), np.sin(x[2])
+    return np.array([[c, -s_, x[0]], [s_, c, x[1]], [0.0, 0.0, 0.0]])
+
+
+def create_cover_circles(l, w, n_c: int):
+    """Centres (homogeneous, vehicle frame) and radius of the n_c covering circles (reference main.py:191-200)."""
+    d = l / (2 * n_c)
+    r = np.sqrt(d ** 2 + (w ** 2) / 4)
+    return [np.array([(2 * k + 1) * d - l / 2, 0, 1]) for k in range(n_c)], r
+
+
+class ObstacleMPCController(MPCController):
+    """RTI counterpart of the obstacle-avoidance controller of the reference's ``session_4/main.py``
+    (:29-129): same constructor arguments ``(N, ts, params, model, x_obs)``, weights
+    Q = diag(1, 6, .2, .05), Q_N = 100 Q, R = diag(1, .01) (:72-74), forward-Euler prediction model
+    (:76), input box, state box, and the nine collision constraints between the three covering
+    circles of the vehicle and of the obstacle parked at ``x_obs`` (:49-56, :95-104).  Every control
+    step linearises the collision constraints along the rolled-out plan and solves ONE QP with
+    polytopic stage constraints on the GPU (K4 with general rows)."""
+
+    def __init__(self, N: int, ts: float, params: VehicleParameters, model=None, x_obs=None, max_iter: int = 60,
+                 eps: float = 1e-9):
+        if x_obs is None:
+            raise ValueError("x_obs (pose of the parked obstacle) is required")
+        super().__init__(N, ts, params=params, integrator="euler", max_iter=max_iter, eps=eps)
+        self.model = model
+        self.x_obs = np.asarray(x_obs, dtype=np.float64).reshape(-1)
+        self.Q = np.diag([1.0, 6.0, 0.2, 0.05])
+        self.QT = 100.0 * self.Q
+        self.R = np.diag([1.0, 0.01])
+        n_c = 3
+        self.bounds["lbg"] = np.tile(np.concatenate([self._boxes[2], np.full(n_c * n_c, self.collision_radius2())]), self.N)
+        self.bounds["ubg"] = np.tile(np.concatenate([self._boxes[3], np.full(n_c * n_c, np.inf)]), self.N)
+
+    def collision_radius2(self):
+        _, r = create_cover_circles(self.params.length, self.params.width, 3)
+        return float((2 * r) ** 2)
+
+    def _solve_dev(self, yT):
+        batch, N = yT.shape[1], self.N
+        dev = yT.device
+        first = self._plan is None or self._plan.shape[2] != batch or self._plan.device != dev
+        if first:
+            self._plan = torch.zeros((N, 2, batch), dtype=F64, device=dev)
+            self._lin = [torch.empty((N, k, batch), dtype=F64, device=dev) for k in (2, 16, 8, 4, 36, 9)]
+            self._qp_ws = boxqp.BoxQpWorkspace(batch, 4, 2, N, dev, nc=9)
+        warm, A, B, c, Cg, hg = self._lin
+        from ctypes import POINTER
+        xo = (c_double * 4)(*[float(v) for v in self.x_obs[:4]])
+        p = self.params
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().mpc_bicycle_rti_prepare_obstacle(
+                *self._model_args(), float(p.length), float(p.width), xo, _lib.ptr(yT), _lib.ptr(self._plan),
+                1 if first else 0, _lib.ptr(warm), _lib.ptr(A), _lib.ptr(B), _lib.ptr(c), _lib.ptr(Cg), _lib.ptr(hg), batch, N,
+                _lib.MPC_F64, _lib.stream(dev)))
+        i_lb, i_ub, s_lb, s_ub = self._boxes
+        Q, R, QT = (torch.as_tensor(M, dtype=F64, device=dev) for M in (self.Q, self.R, self.QT))
+        res = boxqp.solve(A, B, Q, R, QT, N, yT, i_lb, i_ub, s_lb, s_ub, c=c, warm_U=warm, max_iter=self.max_iter,
+                          eps=self.eps, workspace=self._qp_ws, Cg=Cg, hg=hg)
+        self._plan.copy_(res.U)
+        return res
+
+    def closed_loop(self, *args, **kwargs):
+        raise NotImplementedError("the fused closed-loop kernel covers the box-constrained controller; drive this "
+                                  "controller step by step (simulate(x0, dynamics, n_steps, policy=controller))")
+
+
+# ------------------------------------------------------------------------------------------------
 # closed-loop driver (the reference imports it from rcracers.simulator)
 # ------------------------------------------------------------------------------------------------
 def simulate(x0, dynamics: Callable, n_steps: int, policy=None, friction_plant=None):
@@ -301,13 +376,16 @@ def simulate(x0, dynamics: Callable, n_steps: int, policy=None, friction_plant=N
     the whole loop is one fused kernel; any other callables run step by step.  The policy is called
     as ``policy(y)`` or ``policy(y, t)`` depending on its signature, as the course simulator does."""
     as_np = not io.is_tensor(x0)
-    if isinstance(policy, MPCController) and isinstance(dynamics, _Discrete) and dynamics.fusable:
+    if (isinstance(policy, MPCController) and not isinstance(policy, ObstacleMPCController)
+            and isinstance(dynamics, _Discrete) and dynamics.fusable):
         policy.reset()
         res = policy.closed_loop(x0, int(n_steps), plant=dynamics, friction_plant=friction_plant)
         X = res.states
         single = (np.ndim(x0) if as_np else x0.dim()) == 1
         return io.back(X[0] if single else X, as_np)
     import inspect
+    if isinstance(policy, MPCController):
+        policy.reset()
     takes_t = policy is not None and len(inspect.signature(policy).parameters) >= 2
     x = x0
     xs = [x]

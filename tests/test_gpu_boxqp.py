@@ -307,3 +307,33 @@ def test_edge_cases_boxqp(mods):
         r = problem.LinearMPC(problem.Problem(N=5)).solve(xb)
         assert r.input_prediction.shape == (batch, 5, 1) and bool(r.solver_success.all())
         assert torch.equal(r.U[:, :, 0], r.U[:, :, -1])
+
+
+@pytest.mark.parametrize("nc", [3, 9])
+def test_general_stage_rows_gpu(mods, nc):
+    """K4 with polytopic stage constraints Cg x_{k+1} >= hg against the exact oracle."""
+    boxqp, problem, log, torch = mods
+    from test_host_harness_boxqp import rows_problem
+    rng = np.random.default_rng(60 + nc)
+    batch, N, n, m = 48, 12, 4, 2
+    A, B, c, Q, R, Pf, ulo, uhi, xlo, xhi, x0, Cg, hg = rows_problem(rng, batch, N, nc)
+    dev = lambda a: torch.tensor(np.ascontiguousarray(a), dtype=torch.float64, device="cuda")
+    res = boxqp.solve(dev(A.reshape(N, batch, n * n).transpose(0, 2, 1)), dev(B.reshape(N, batch, n * m).transpose(0, 2, 1)),
+                      dev(Q), dev(R), dev(Pf), N, dev(x0.T), ulo, uhi, xlo, xhi, c=dev(c.transpose(0, 2, 1)),
+                      Cg=dev(Cg.reshape(N, batch, nc * n).transpose(0, 2, 1)), hg=dev(hg.transpose(0, 2, 1)))
+    status = res.status.cpu().numpy()
+    port = bq.ipm_riccati(list(A), list(B), Q, R, Pf, N, x0, ulo, uhi, xlo, xhi, c=list(c), Cg=Cg, hg=hg)
+    np.testing.assert_array_equal(status, port["status"])
+    U = res.input_prediction.cpu().numpy(); satc = res.sat_c.permute(2, 0, 1).cpu().numpy()
+    nact = 0
+    for b in range(0, batch, 3):
+        ex = bq.solve_exact(A[:, b], B[:, b], Q, R, Pf, N, x0[b], ulo, uhi, xlo, xhi, c=c[:, b], Cg=Cg[:, b], hg=hg[:, b])
+        if ex["status"] != bq.SOLVED:
+            assert status[b] != bq.SOLVED or ex["status"] == bq.MAX_ITER
+            continue
+        assert status[b] == bq.SOLVED
+        assert np.abs(U[b] - ex["U"]).max() <= 1e-6 * max(1.0, np.abs(ex["U"]).max())
+        np.testing.assert_array_equal(satc[b], ex["sat_c"])
+        np.testing.assert_array_equal(res.sat_u.permute(2, 0, 1)[b].cpu().numpy(), ex["sat_u"])
+        nact += int(np.abs(ex["sat_c"]).sum())
+    assert nact > 0

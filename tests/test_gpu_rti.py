@@ -196,3 +196,28 @@ def test_prediction_bundles(mods):
     r2 = ctrl.closed_loop(x0, steps, plant=plant)
     ref = bc.closed_loop(x0, steps, N=N, friction_plant=np.full(5, 0.8), plant_method="rk4", substeps=16, qp="port")
     np.testing.assert_allclose(r2.states.cpu().numpy().transpose(1, 0, 2), ref["X"], rtol=0, atol=1e-7)
+
+
+def test_obstacle_avoidance_controller(mods):
+    """the obstacle-avoidance controller of the reference's session_4/main.py
+    (:29-129, protocol :241-271) as RTI with linearised collision rows, against the CPU restatement."""
+    s4, torch = mods
+    horizon, ts, steps = 30, 0.08, 40
+    params = s4.VehicleParameters()
+    x_obs = np.array([0.25, 0, 0.0, 0.0])
+    x0 = np.array([[0.3, -0.1, 0.0, 0.0], [0.35, -0.12, 0.1, 0.0], [0.4, 0.12, 0.0, 0.0]])
+    controller = s4.ObstacleMPCController(horizon, ts, params, s4.KinematicBicycle(params, symbolic=True), x_obs)
+    assert controller.bounds["lbg"].shape == (horizon * 13,)
+    sol = controller.solve(x0[0])
+    assert controller.reshape_input(sol).shape == (horizon, 2) and bool(sol["success"])
+    dynamics_accurate = s4.exact_integration(s4.KinematicBicycle(params), ts)
+    X = s4.simulate(x0, dynamics_accurate, n_steps=steps, policy=controller)
+    assert X.shape == (3, steps + 1, 4)
+    ref = bc.closed_loop_obstacle(x0, x_obs, steps, N=horizon, ts=ts, qp="port")
+    assert np.all(ref["status"] == 1)
+    np.testing.assert_allclose(X.transpose(1, 0, 2), ref["X"], rtol=0, atol=2e-6)
+    assert bc.min_clearance(X, x_obs) > -1e-3          # the covering circles do not overlap (up to linearisation error)
+    assert np.abs(X[:, -1, :2]).max() < 0.08            # and the car reaches the parking spot
+    # exact-QP restatement on the first steps
+    ref2 = bc.closed_loop_obstacle(x0[:1], x_obs, 6, N=horizon, ts=ts, qp="exact")
+    np.testing.assert_allclose(X[0, :7], ref2["X"][:, 0], rtol=0, atol=2e-6)
