@@ -33,7 +33,8 @@ struct CoopLayout {
   // per warp
   static constexpr int wP = 0;
   static constexpr int wW = wP + NX * NX;
-  static constexpr int wPB = wW + NX * NX;
+  static constexpr int wAcl = wW + NX * NX;  // closed-loop matrix A + B K
+  static constexpr int wPB = wAcl + NX * NX;
   static constexpr int wAug = wPB + NX * NU;  // [NU][2 NU] augmented matrix of the S inverse
   static constexpr int wSi = wAug + NU * 2 * NU;
   static constexpr int wK = wSi + NU * NU;
@@ -248,10 +249,11 @@ struct CoopIpm {
         // P = Pacc + diag(Sigma_x)
         if (lane < NX) w[L::wP + lane * NX + lane] += w[L::wSig + NU + lane];
         __syncwarp();
-        wmm<NX, NX, NX, false, false>(w + L::wP, sh + L::oA, w + L::wW, lane);   // W  = P A
+        // Joseph form (see BoxQpIpm::backward): PB = P B, S = Rt + B'PB, K = -S^-1 (PB)'A, Acl = A + B K,
+        // Pacc <- Q + Acl' P Acl + K' Rt K with Rt = R + diag(Sigma_u)
         wmm<NX, NX, NU, false, false>(w + L::wP, sh + L::oB, w + L::wPB, lane);  // PB = P B
         __syncwarp();
-        // augmented [S | I], S = R + diag(Sigma_u) + B'PB ;  G = B'W
+        // augmented [S | I], S = Rt + B'PB ;  G = (PB)'A
         for (int e = lane; e < NU * NU; e += 32) {
           const int i = e / NU, j = e % NU;
           double acc = sh[L::oR + e] + (i == j ? w[L::wSig + i] : 0.0);
@@ -260,7 +262,7 @@ struct CoopIpm {
           w[L::wAug + i * 2 * NU + j] = acc;
           w[L::wAug + i * 2 * NU + NU + j] = (i == j) ? 1.0 : 0.0;
         }
-        wmm<NU, NX, NX, true, false>(sh + L::oB, w + L::wW, w + L::wG, lane);
+        wmm<NU, NX, NX, true, false>(w + L::wPB, sh + L::oA, w + L::wG, lane);
         __syncwarp();
         // Gauss-Jordan without pivoting (S is symmetric positive definite); lanes over [NU][2 NU]
         for (int p = 0; p < NU; ++p) {
@@ -287,9 +289,25 @@ struct CoopIpm {
           w[L::wK + e] = -acc;
         }
         __syncwarp();
-        wmm<NX, NU, NX, false, true>(w + L::wPB, w + L::wK, w + L::wW, lane);  // W += PB K
+        // Acl = A + B K (into wAcl = the PB.. no: its own buffer wW2), G <- Rt K
+        for (int e = lane; e < NX * NX; e += 32) {
+          const int i = e / NX, j = e % NX;
+          double acc = sh[L::oA + e];
+#pragma unroll
+          for (int l = 0; l < NU; ++l) acc = fma(sh[L::oB + i * NU + l], w[L::wK + l * NX + j], acc);
+          w[L::wAcl + e] = acc;
+        }
+        for (int e = lane; e < NU * NX; e += 32) {
+          const int i = e / NX, j = e % NX;
+          double acc = 0.0;
+#pragma unroll
+          for (int l = 0; l < NU; ++l) acc = fma(sh[L::oR + i * NU + l] + (i == l ? w[L::wSig + i] : 0.0), w[L::wK + l * NX + j], acc);
+          w[L::wG + e] = acc;
+        }
         __syncwarp();
-        // Pacc <- Q + A'W on the upper triangle (NX (NX+1)/2 entries over the lanes), mirrored
+        wmm<NX, NX, NX, false, false>(w + L::wP, w + L::wAcl, w + L::wW, lane);  // T = P Acl
+        __syncwarp();
+        // Pacc <- Q + Acl'T + K'(Rt K) on the upper triangle (NX (NX+1)/2 entries over the lanes), mirrored
         for (int e = lane; e < NX * (NX + 1) / 2; e += 32) {
           int i = 0, rem = e;
           while (rem >= NX - i) {
@@ -299,7 +317,9 @@ struct CoopIpm {
           const int j = i + rem;
           double acc = sh[L::oQ + i * NX + j];
 #pragma unroll
-          for (int l = 0; l < NX; ++l) acc = fma(sh[L::oA + l * NX + i], w[L::wW + l * NX + j], acc);
+          for (int l = 0; l < NX; ++l) acc = fma(w[L::wAcl + l * NX + i], w[L::wW + l * NX + j], acc);
+#pragma unroll
+          for (int l = 0; l < NU; ++l) acc = fma(w[L::wK + l * NX + i], w[L::wG + l * NX + j], acc);
           w[L::wP + i * NX + j] = acc;
           w[L::wP + j * NX + i] = acc;
         }
@@ -528,7 +548,7 @@ struct CoopIpm {
       double sigma = ratio * ratio * ratio;
       sigma = sigma < 1.0 ? sigma : 1.0;
       double sig_mu = sigma * mu;
-      const double mu_floor = 0.1 * a.eps * mu_scale;  // see BoxQpIpm::solve
+      const double mu_floor = 1e-3 * a.eps * mu_scale;  // see BoxQpIpm::solve
       sig_mu = sig_mu > mu_floor ? sig_mu : mu_floor;
       backward<false>(sig_mu);
       forward<false>(sig_mu, acc);

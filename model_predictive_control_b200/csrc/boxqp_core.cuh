@@ -393,21 +393,26 @@ struct BoxQpIpm {
         }
       }
       if constexpr (FACTOR) {
-        // P = Pacc + diag(Sigma_x);  S = R + diag(Sigma_u) + B'PB;  K = -S^-1 B'PA;
-        // Pacc <- Q + A'(PA + PB K)
+        // P = Pacc + diag(Sigma_x) (+ rows' C' Sigma_c C, added above)
 #pragma unroll
         for (int i = 0; i < NX; ++i) Pacc[i * NX + i] += sig[NU + i];
-        T PA[NX * NX], PB[NX * NU], S[NU * NU];
-        mm<T, NX, NX, NX, false>(Pacc, A, PA);
+        // Joseph (symmetric) form of the Riccati update:
+        //   PB = P B,  S = Rt + B'PB,  K = -S^-1 (PB)'A,  Acl = A + B K,  Pacc <- Q + Acl' P Acl + K' Rt K
+        // with Rt = R + diag(Sigma_u).  Every term is a positive semidefinite sum: the huge barrier weights inside P
+        // (lam/s ~ 1e12 on active states / rows) meet closed-loop rows Acl_i ~ 1/Sigma and drop out, whereas the short
+        // form Q + A'(PA + PB K) subtracts two O(Sigma) products and loses eps * Sigma of absolute accuracy.
+        T PB[NX * NU], S[NU * NU], Rt[NU * NU];
         mm<T, NX, NX, NU, false>(Pacc, B, PB);
 #pragma unroll
-        for (int i = 0; i < NU * NU; ++i) S[i] = sh[SH::oR + i];
+        for (int i = 0; i < NU * NU; ++i) Rt[i] = sh[SH::oR + i];
 #pragma unroll
-        for (int i = 0; i < NU; ++i) S[i * NU + i] += sig[i];
+        for (int i = 0; i < NU; ++i) Rt[i * NU + i] += sig[i];
+#pragma unroll
+        for (int i = 0; i < NU * NU; ++i) S[i] = Rt[i];
         mtm<T, NU, NX, NU, true>(B, PB, S);
         sym_inverse(S, Sinv);
         T G[NU * NX];
-        mtm<T, NU, NX, NX, false>(B, PA, G);
+        mtm<T, NU, NX, NX, false>(PB, A, G);  // (PB)'A
 #pragma unroll
         for (int i = 0; i < NU; ++i)
 #pragma unroll
@@ -417,14 +422,21 @@ struct BoxQpIpm {
             for (int l = 0; l < NU; ++l) acc = fma_<T>(Sinv[i * NU + l], G[l * NX + j], acc);
             K[i * NX + j] = -acc;
           }
-        mm<T, NX, NU, NX, true>(PB, K, PA);  // PA <- PA + PB K
+        T Acl[NX * NX], Tm[NX * NX];
+#pragma unroll
+        for (int i = 0; i < NX * NX; ++i) Acl[i] = A[i];
+        mm<T, NX, NU, NX, true>(B, K, Acl);
+        mm<T, NX, NX, NX, false>(Pacc, Acl, Tm);
+        mm<T, NU, NU, NX, false>(Rt, K, G);  // G <- Rt K
 #pragma unroll
         for (int i = 0; i < NX; ++i)
 #pragma unroll
           for (int j = i; j < NX; ++j) {
             T acc = sh[SH::oQ + i * NX + j];
 #pragma unroll
-            for (int l = 0; l < NX; ++l) acc = fma_<T>(A[l * NX + i], PA[l * NX + j], acc);
+            for (int l = 0; l < NX; ++l) acc = fma_<T>(Acl[l * NX + i], Tm[l * NX + j], acc);
+#pragma unroll
+            for (int l = 0; l < NU; ++l) acc = fma_<T>(K[l * NX + i], G[l * NX + j], acc);
             Pacc[i * NX + j] = acc;
             Pacc[j * NX + i] = acc;
           }
@@ -768,10 +780,10 @@ struct BoxQpIpm {
       T ratio = mu_aff / (mu > T(1e-300) ? mu : T(1e-300));
       T sigma = ratio * ratio * ratio;
       sigma = sigma < T(1) ? sigma : T(1);
-      // centring target; never below a tenth of the complementarity tolerance: driving mu further only inflates
+      // centring target; never below 1e-3 of the complementarity tolerance: driving mu further only inflates
       // the barrier weights (lam/s ~ lam^2/mu) and with them the rounding noise of the Newton step
       T sig_mu = sigma * mu;
-      const T mu_floor = T(0.1) * a.eps * mu_scale;
+      const T mu_floor = T(1e-3) * a.eps * mu_scale;
       sig_mu = sig_mu > mu_floor ? sig_mu : mu_floor;
       backward<false>(sig_mu);
       forward<false>(sig_mu, acc);

@@ -504,11 +504,14 @@ def ipm_riccati(A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi, c=None, warm_U=No
                 P = Pacc + dg(Sig[:, m:])
                 if nc:
                     P = P + np.einsum("bji,bj,bjl->bil", Cgb[k], Sc, Cgb[k])
-                PA, PB = P @ Ab[k], P @ Bb[k]
-                S = R + dg(Sig[:, :m]) + np.swapaxes(Bb[k], 1, 2) @ PB
+                # Joseph form (see BoxQpIpm::backward): positive semidefinite sums only
+                PB = P @ Bb[k]
+                Rt = R + dg(Sig[:, :m])
+                S = Rt + np.swapaxes(Bb[k], 1, 2) @ PB
                 Sinv[k] = np.linalg.inv(S)
-                K[k] = -Sinv[k] @ (np.swapaxes(Bb[k], 1, 2) @ PA)
-                Pacc = Q + np.swapaxes(Ab[k], 1, 2) @ (PA + PB @ K[k])
+                K[k] = -Sinv[k] @ (np.swapaxes(PB, 1, 2) @ Ab[k])
+                Acl = Ab[k] + Bb[k] @ K[k]
+                Pacc = Q + np.swapaxes(Acl, 1, 2) @ (P @ Acl) + np.swapaxes(K[k], 1, 2) @ (Rt @ K[k])
             h = -(rhs[:, m:] + pacc)
             gu = rhs[:, :m] - mtv(Bb[k], h)
             dff[k] = mv(Sinv[k], gu)
@@ -569,7 +572,7 @@ def ipm_riccati(A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi, c=None, warm_U=No
             ccl[:] = dsl * dll; ccu[:] = dsu * dlu
             if nc:
                 ccc[:] = step_len.dsc * step_len.dlc
-        sig_mu = np.maximum(sigma * mu, 0.1 * eps * mu_scale)   # centring target, floored (see BoxQpIpm::solve)
+        sig_mu = np.maximum(sigma * mu, 1e-3 * eps * mu_scale)   # centring target, floored (see BoxQpIpm::solve)
         backward(sig_mu, False)
         forward()
         dz, dsl, dsu, dll, dlu = directions(sig_mu)
