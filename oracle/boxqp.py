@@ -141,6 +141,7 @@ def _highs_qp(H, g, G, lo, hi, lb, ub):
     h.run()
     status = h.getModelStatus()
     sol = h.getSolution()
+    _highs_qp.last_duals = (np.array(sol.col_dual), np.array(sol.row_dual))
     return np.array(sol.col_value), status == hc.HighsModelStatus.kOptimal, status == hc.HighsModelStatus.kInfeasible
 
 
@@ -188,7 +189,7 @@ def cost_of(X, U, Q, R, Pf):
     return float(sum(X[k] @ Q @ X[k] + U[k] @ R @ U[k] for k in range(U.shape[0])) + X[-1] @ Pf @ X[-1])
 
 
-def _kkt_refine(H, grad, Gam, lo, hi, lb, ub, U, tol=1e-6, max_rounds=50):
+def _kkt_refine(H, grad, Gam, lo, hi, lb, ub, U, tol=1e-6, max_rounds=50, duals=None):
     """Exact (to rounding) solution on the active set identified near U: solve the equality-
     constrained KKT system densely, then check primal feasibility and multiplier signs; constraints
     with a wrong-sign multiplier are dropped, violated ones added (a few primal active-set rounds)."""
@@ -198,6 +199,12 @@ def _kkt_refine(H, grad, Gam, lo, hi, lb, ub, U, tol=1e-6, max_rounds=50):
     val = C_all @ U
     scale = np.maximum(1.0, np.abs(val))
     side = np.where(np.abs(val - l_all) <= tol * scale, -1, np.where(np.abs(val - u_all) <= tol * scale, 1, 0))
+    if duals is not None:
+        # degenerate vertices: constraints that sit on their bound with a zero multiplier are only weakly active and
+        # must not enter the equality set (they make it rank deficient); keep the ones the solver's duals support
+        dual = np.concatenate(duals)
+        strong = np.abs(dual) > 1e-7 * max(1.0, np.abs(dual).max())
+        side = np.where(strong, side, 0)
     for _ in range(max_rounds):
         idx = np.nonzero(side)[0]
         C = C_all[idx]; dvec = np.where(side[idx] < 0, l_all[idx], u_all[idx])
@@ -243,12 +250,22 @@ def solve_exact(A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi, c=None, method="h
         U, ok, infeasible = res.x, res.success, not res.success
     else:
         raise ValueError(method)
+    if method == "highs" and not ok and not infeasible:
+        # HiGHS' active-set QP occasionally stops without a verdict on degenerate problems: second opinion
+        alt = solve_exact(A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi, c=c, method="slsqp", refine=refine, Cg=Cg, hg=hg)
+        if alt["status"] == SOLVED:
+            return alt
     status = SOLVED if ok else (INFEASIBLE if infeasible else MAX_ITER)
     side = None
     if ok and refine:
-        U, ok2, side = _kkt_refine(H, grad, Gam, lo, hi, lb, ub, U)
+        U_raw = U
+        duals = getattr(_highs_qp, "last_duals", None) if method == "highs" else None
+        U, ok2, side = _kkt_refine(H, grad, Gam, lo, hi, lb, ub, U_raw, duals=duals)
+        if not ok2 and duals is not None:
+            U, ok2, side = _kkt_refine(H, grad, Gam, lo, hi, lb, ub, U_raw)
         if not ok2:
             status = MAX_ITER
+            U = U_raw
     U = U.reshape(N, m)
     X = rollout(A, B, c, x0, U)
     out = {"U": U, "X": X, "cost": cost_of(X, U, Q, R, Pf), "status": status}
