@@ -557,7 +557,7 @@ struct CoopIpm {
       zn = update(sig_mu, alpha, true);
       const double mu_new = (acc.s0 + alpha * (acc.s1 + alpha * acc.s2)) * inv_nc;
       rp = (1.0 - alpha) * acc.rp;
-      const bool done = (mu_new <= a.eps * mu_scale) && (rp <= a.eps * zn) && (alpha * acc.dzmax <= 1e-8 * zn);
+      const bool done = (mu_new <= a.eps * mu_scale) && (rp <= a.eps * zn) && (alpha * acc.dzmax <= 1e-6 * zn);
       if (done) {
         status = MPC_SOLVED;
       } else if (!(alpha >= 1e-6) || !(mu_new <= 100.0 * mu0)) {

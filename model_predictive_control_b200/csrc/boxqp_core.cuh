@@ -792,7 +792,7 @@ struct BoxQpIpm {
       zn = update(sig_mu, alpha, true);
       const T mu_new = (acc.s0 + alpha * (acc.s1 + alpha * acc.s2)) * inv_nc;
       rp = (T(1) - alpha) * acc.rp;
-      const bool done = (mu_new <= a.eps * mu_scale) && (rp <= a.eps * zn) && (alpha * acc.dzmax <= T(1e-8) * zn);
+      const bool done = (mu_new <= a.eps * mu_scale) && (rp <= a.eps * zn) && (alpha * acc.dzmax <= T(1e-6) * zn);
       if (done) {
         status = MPC_SOLVED;
       } else if (!(alpha >= T(1e-6)) || !(mu_new <= T(100) * mu0)) {

@@ -616,7 +616,7 @@ def ipm_riccati(A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi, c=None, warm_U=No
         step = alpha * np.abs(dz).max(axis=(0, 2))
         if verbose:
             print(it, "mu", mu_new.max(), "rp", rp.max(), "alpha", alpha.min(), "step", step.max())
-        done = active & (mu_new <= eps * mu_scale) & (rp <= eps * zn) & (step <= 1e-8 * zn)
+        done = active & (mu_new <= eps * mu_scale) & (rp <= eps * zn) & (step <= 1e-6 * zn)
         status[done] = SOLVED
         active &= ~done
         # stalled: the step length collapses / the barrier parameter grows 100x above its start value.  With a bound
