@@ -252,7 +252,7 @@ MPC_HD void obstacle_rows(const ObstacleParams<T>& ob, const T* xbar, T* Cg, T* 
 template <typename T>
 MPC_HD void rti_prepare_body(const BicycleModel<T>& p, T friction, const T* y, const T* Uprev, int first, T* warm,
                              T* A, T* B, T* c, int N, int64_t bs, int64_t b, const ObstacleParams<T>* ob = nullptr,
-                             T* Cg = nullptr, T* hg = nullptr) {
+                             T* Cg = nullptr, T* hg = nullptr, T* pack = nullptr) {
   T x[4], xn[4], u[2], Ak[16], Bk[8];
 #pragma unroll
   for (int i = 0; i < 4; ++i) x[i] = y[i * bs + b];
@@ -263,10 +263,7 @@ MPC_HD void rti_prepare_body(const BicycleModel<T>& p, T friction, const T* y, c
     warm[((int64_t)k * 2 + 0) * bs + b] = u[0];
     warm[((int64_t)k * 2 + 1) * bs + b] = u[1];
     bicycle_discretize(p, friction, x, u, xn, Ak, Bk);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) A[((int64_t)k * 16 + i) * bs + b] = Ak[i];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) B[((int64_t)k * 8 + i) * bs + b] = Bk[i];
+    T ck[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       T acc = xn[i];
@@ -274,7 +271,21 @@ MPC_HD void rti_prepare_body(const BicycleModel<T>& p, T friction, const T* y, c
       for (int j = 0; j < 4; ++j) acc = fma_<T>(-Ak[i * 4 + j], x[j], acc);
       acc = fma_<T>(-Bk[i * 2 + 0], u[0], acc);
       acc = fma_<T>(-Bk[i * 2 + 1], u[1], acc);
-      c[((int64_t)k * 4 + i) * bs + b] = acc;
+      ck[i] = acc;
+    }
+    if (pack) {
+      // forward-Euler model only: the entries of A, B that are not structurally 0 or 1 (see BoxQpIpm, MODEL = 1)
+      const T v[kBicyclePack] = {Ak[2], Ak[3], Ak[6], Ak[7], Ak[11], Ak[15], Bk[1], Bk[3], Bk[5], Bk[6],
+                                 ck[0], ck[1], ck[2], ck[3]};
+#pragma unroll
+      for (int i = 0; i < kBicyclePack; ++i) pack[((int64_t)k * kBicyclePack + i) * bs + b] = v[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) A[((int64_t)k * 16 + i) * bs + b] = Ak[i];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) B[((int64_t)k * 8 + i) * bs + b] = Bk[i];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) c[((int64_t)k * 4 + i) * bs + b] = ck[i];
     }
     if (ob) {
       constexpr int R = kObsCircles * kObsCircles;
@@ -314,7 +325,8 @@ struct RtiLoopArgs {
                             // U = plan buffer: initial plan on entry (zeros = cold start), last plan on exit
 };
 
-template <typename T>
+// PACKED = the prediction model is forward Euler: stage matrices in the packed 14-value form (a.Acur holds them).
+template <typename T, bool PACKED>
 MPC_HD void rti_closed_loop_body(const RtiLoopArgs<T>& a, const T* sh, int64_t b) {
   using SH = BoxQpShared<4, 2>;
   const int64_t bs = a.qp.batch;
@@ -332,8 +344,8 @@ MPC_HD void rti_closed_loop_body(const RtiLoopArgs<T>& a, const T* sh, int64_t b
 #pragma unroll
     for (int i = 0; i < 4; ++i) a.xcur[i * bs + b] = x[i];
     rti_prepare_body<T>(a.model, a.friction_model, a.xcur, a.qp.U, t == 0 ? 1 : 0, a.warm, a.Acur, a.Bcur, a.ccur, N,
-                        bs, b);
-    BoxQpIpm<T, 4, 2> ipm(a.qp, sh, b);
+                        bs, b, nullptr, nullptr, nullptr, PACKED ? a.Acur : nullptr);
+    BoxQpIpm<T, 4, 2, 0, PACKED ? 1 : 0> ipm(a.qp, sh, b);
     ipm.solve();
     if (a.X_bundle) {
       T* dst = a.X_bundle + (int64_t)t * (N + 1) * 4 * bs;

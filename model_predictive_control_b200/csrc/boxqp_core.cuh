@@ -78,7 +78,14 @@ struct BoxQpShared {
   static constexpr int total = oHi + D;
 };
 
-template <typename T, int NX, int NU, int NC = 0>
+// MODEL = 0: generic dense model (shared LTI, or per-scenario LTV A [N][n*n][batch], B, c).
+// MODEL = 1: forward-Euler kinematic bicycle (NX = 4, NU = 2), per-scenario LTV in PACKED form: only the 10 entries of
+//            A = I + ts J_x and B = ts J_u that are not structurally 0 or 1, plus c: a.A -> [N][14][batch]
+//            {a02, a03, a12, a13, a23, a33, b01, b11, b21, b30, c0..c3}.  The structural zeros and ones are written
+//            as literals, so the unrolled register algebra drops the corresponding multiplications at compile time.
+constexpr int kBicyclePack = 14;
+
+template <typename T, int NX, int NU, int NC = 0, int MODEL = 0>
 struct BoxQpIpm {
   static constexpr int D = NX + NU;
   // small stages are double-buffered in registers (the next stage's operands are requested while
@@ -172,6 +179,31 @@ struct BoxQpIpm {
   }
 
   MPC_HD void load_model(int k, T* A, T* B, T* c) const {
+    if constexpr (MODEL == 1) {
+      static_assert(MODEL == 0 || (NX == 4 && NU == 2), "packed bicycle model is 4 x 2");
+      T v[kBicyclePack];
+      loadn<kBicyclePack>(a.A, k, v);
+#pragma unroll
+      for (int i = 0; i < NX * NX; ++i) A[i] = T(0);
+#pragma unroll
+      for (int i = 0; i < NX * NU; ++i) B[i] = T(0);
+      A[0] = T(1);
+      A[2] = v[0];
+      A[3] = v[1];
+      A[5] = T(1);
+      A[6] = v[2];
+      A[7] = v[3];
+      A[10] = T(1);
+      A[11] = v[4];
+      A[15] = v[5];
+      B[1] = v[6];
+      B[3] = v[7];
+      B[5] = v[8];
+      B[6] = v[9];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) c[i] = v[10 + i];
+      return;
+    }
     if (a.ltv) {
       loadn<NX * NX>(a.A, k, A);
       loadn<NX * NU>(a.B, k, B);

@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(256) bicycle_plant_kernel(BicycleModel<T> mode
   for (int i = 0; i < 4; ++i) xn[i * batch + b] = xv[i];
 }
 
-template <typename T>
+template <typename T, bool PACKED>
 __global__ void __launch_bounds__(kRtiThreads) rti_closed_loop_kernel(RtiLoopArgs<T> a) {
   using SH = BoxQpShared<4, 2>;
   __shared__ T sh[SH::total];
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(kRtiThreads) rti_closed_loop_kernel(RtiLoopArg
   }
   __syncthreads();
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < a.qp.batch) rti_closed_loop_body<T>(a, sh, b);
+  if (b < a.qp.batch) rti_closed_loop_body<T, PACKED>(a, sh, b);
 }
 
 }  // namespace mpc
@@ -201,6 +201,10 @@ extern "C" int mpc_rti_closed_loop(double lr, double lf, double accel, double fr
                            (const double*)u_lo, (const double*)u_hi, (const double*)x_lo, (const double*)x_hi, xcur, warm,
                            (double*)U_plan, (double*)X_pred, qp_cost, last_status, qp_iters, nullptr, nullptr, nullptr, nullptr, nullptr,
                            qp_ws, batch, N, max_iter, eps};
-  rti_closed_loop_kernel<double><<<(unsigned)((batch + kRtiThreads - 1) / kRtiThreads), kRtiThreads, 0, (cudaStream_t)stream>>>(a);
+  const unsigned grid = (unsigned)((batch + kRtiThreads - 1) / kRtiThreads);
+  if (rk4)
+    rti_closed_loop_kernel<double, false><<<grid, kRtiThreads, 0, (cudaStream_t)stream>>>(a);
+  else  // forward-Euler prediction model: packed sparse stage matrices
+    rti_closed_loop_kernel<double, true><<<grid, kRtiThreads, 0, (cudaStream_t)stream>>>(a);
   return check_launch("rti_closed_loop_kernel");
 }

@@ -175,7 +175,10 @@ extern "C" int hh_rti_closed_loop(double lr, double lf, double accel, double fri
   a.U_bundle = nullptr;
   a.qp = BoxQpArgs<double>{Acur, Bcur, ccur, 1, Q, R, Pf, u_lo, u_hi, x_lo, x_hi, xcur, warm, U_plan, X_pred, qp_cost,
                            last_status, qp_iters, nullptr, nullptr, nullptr, nullptr, nullptr, qp_ws, batch, N, max_iter, eps};
-  for (int64_t b = 0; b < batch; ++b) rti_closed_loop_body<double>(a, sh.data(), b);
+  for (int64_t b = 0; b < batch; ++b) {
+    if (rk4) rti_closed_loop_body<double, false>(a, sh.data(), b);
+    else rti_closed_loop_body<double, true>(a, sh.data(), b);
+  }
   return 0;
 }
 
