@@ -82,6 +82,31 @@ def cfg2b_flops_per_solve(n=4, m=1, N=20):
     return N * (f_ric + f_roll) + 2 * n * n + 2 * n
 
 
+def cfg2b_flops_per_solve_krylov(n=4, N=20):
+    """Flops lq_solve_krylov_kernel performs per single-input solve (lq_core.cuh, mul+add = 2):
+    set-up: n Krylov mat-vecs 2n^3, adjugate + determinant (n=4: 127), the two Frobenius norms 4n^2,
+    -a = C^-1 A^n b and z0 = C^-1 x0 4n^2+2n, the two congruences C'QC, C'PfC 2(2n^3+n^2(n+1));
+    backward stage: w = -Pa 2n^2, S and its reciprocal 2, K n, upper triangle of P+ 3n(n-1)/2 + 2n + (n-1) + 2n;
+    forward stage: u = Kz 2n, z+ 2n, x = Cz 2n^2;  V = z0'P0 z0 2n^2+2n."""
+    adj = 127 if n == 4 else 7
+    setup = 2 * n**3 + adj + 4 * n * n + 4 + 4 * n * n + 2 * n + 2 * (2 * n**3 + n * n * (n + 1))
+    back = 2 * n * n + 2 + n + 3 * n * (n - 1) // 2 + 2 * n + (n - 1) + 2 * n
+    fwd = 2 * n + 2 * n + 2 * n * n
+    return setup + N * (back + fwd) + 2 * n * n + 2 * n
+
+
+def krylov_path_fraction(A, B, cond_max=1e3):
+    """Share of the scenarios lq_solve_krylov_kernel accepts (cond_F of [b, Ab, A^2b, A^3b] <= cond_max);
+    the others take the dense recursion inside the same launch.  torch on the device, outside any timed region."""
+    import torch
+    cols = [B[:, :, 0]]
+    for _ in range(A.shape[-1] - 1):
+        cols.append(torch.einsum("bij,bj->bi", A, cols[-1]))
+    C = torch.stack(cols, dim=2)
+    cond = torch.linalg.matrix_norm(C) * torch.linalg.matrix_norm(torch.linalg.inv(C))
+    return float((cond <= cond_max).double().mean())
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU arms (oracle = restated reference; the only place bench.py executes oracle/)
 # ------------------------------------------------------------------------------------------------
@@ -339,7 +364,13 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = load_peaks()
         bytes_solve = cfg2b_bytes_per_solve(w, n, m, N)
-        flops_solve = cfg2b_flops_per_solve(n, m, N)
+        kernel = lq.lq_solve_kernel_name(n, m, dtype)
+        if kernel == "lq_solve_krylov_kernel":
+            kfrac = krylov_path_fraction(A, B, float(os.environ.get("MPC_LQ_KRYLOV_COND", "1e3")))
+            flops_solve = kfrac * cfg2b_flops_per_solve_krylov(n, N) + (1 - kfrac) * cfg2b_flops_per_solve(n, m, N)
+        else:
+            kfrac = 0.0
+            flops_solve = cfg2b_flops_per_solve(n, m, N)
         kern_ms = sum(per_launch) / len(per_launch)
         achieved = bytes_solve * batch / (kern_ms * 1e-3) / 1e9
         fp_peak = lq.fma_peak(dtype)
@@ -351,8 +382,9 @@ def run_ours(args):
                                    f"{batch} scenarios per GPU, per-scenario model and initial state",
                        "batch_per_gpu": batch, "nx": n, "nu": m, "horizon": N, "parallelism": f"scenario-shard x{world}",
                        "l2": f"inputs+outputs {bytes_solve * batch / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)"},
-            "roofline": {"bound": "hbm", "kernel": "lq_solve_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": load_traffic("lq_solve_kernel_" + args.dtype, batch),
+            "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": load_traffic(kernel + "_" + args.dtype, batch),
+                         "krylov_path_fraction": kfrac,
                          "peak_source": peak_src, "bytes_per_solve": bytes_solve, "kernel_ms": kern_ms,
                          "fp_pipe": {"flops_per_solve": flops_solve, "achieved_tflops": flops_solve * batch / (kern_ms * 1e-3) / 1e12,
                                      "measured_fma_peak_tflops": fp_peak / 1e12,

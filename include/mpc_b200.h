@@ -114,7 +114,15 @@ int mpc_linear_step(const void* A, const void* B, const void* x, const void* u, 
  *   x0 [batch][n];  outputs stage-major:  X [N+1][batch][n], U [N][batch][m], V [batch];
  *   optional K [N][batch][m][n], P0 [batch][n][n].
  * Supported (n, m): n <= 4, m <= 2 (register-resident); others -> MPC_ERR_UNSUPPORTED.
+ * Q and Pf must be symmetric (their upper triangles are used).
+ * Single-input fp64 solves (m = 1, n = 2 or 4) that do not ask for K / P0 run the same recursion
+ * in Krylov coordinates x = [b, Ab, .., A^{n-1}b] z, where a stage costs O(n^2) instead of O(n^3);
+ * a scenario whose controllability matrix has cond_F > 1e3 (env MPC_LQ_KRYLOV_COND, 0 = never)
+ * takes the dense recursion inside the same launch, so the result stays within the 1e-6 parity bar
+ * for every input.  mpc_lq_solve_variant tells which kernel a call with these arguments launches:
+ * 0 = lq_solve_kernel (dense stages), 1 = lq_solve_krylov_kernel.
  */
+int mpc_lq_solve_variant(int n, int m, int dtype, int wants_gains_or_P0);
 int mpc_lq_solve(const void* A, int64_t sA, const void* B, int64_t sB, const void* Q, int64_t sQ,
                  const void* R, int64_t sR, const void* Pf, int64_t sPf, const void* x0, void* X,
                  void* U, void* V, void* K, void* P0, int64_t batch, int n, int m, int N, int dtype,

@@ -48,6 +48,7 @@ SIGNATURES = {
     "mpc_lq_solve": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
                              c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p]),
+    "mpc_lq_solve_variant": (c_int, [c_int, c_int, c_int, c_int]),
     "mpc_fma_peak_probe": (c_int, [c_int, POINTER(c_double)]),
 }
 

@@ -290,4 +290,190 @@ MPC_HD void lq_solve_body(const LqSolveArgs<T>& a, int64_t b, T* Ks, int kstride
   }
 }
 
+// ----------------------------------------------------------------- K1 + K2, single input (m = 1)
+// Same solve in Krylov coordinates.  For a single-input model the change of variables x = C z with
+// the controllability matrix C = [b, Ab, ..., A^{n-1}b] turns (A, b) into
+//   A_o = C^-1 A C = [e_2, ..., e_n, -a]   (shifts and ONE dense column),   C^-1 b = e_1,
+// where a = -C^-1 A^n b holds the characteristic-polynomial coefficients.  In these coordinates a
+// backward Riccati stage (FHC.py:56-57 applied to A_o, e_1, Q_c = C'QC) is O(n^2):
+//   P b = P[:,0],  S = R + P_00,  W = P A_o = [P[:,1..n-1], w],  w = -P a,  K = -W[0,:]/S,
+//   M = W + P[:,0] K,  P+ = Q_c + A_o' M  (row i < n-1 of A_o'M is row i+1 of M, the last row is -a'M),
+// and so is a forward stage: u = K z, z+ = [u, z_0, .., z_{n-2}] - a z_{n-1}, x = C z (the plan u_k is
+// coordinate-free).  Per solve at n=4, N=20: ~2 100 FP64 instructions instead of ~3 900.
+// The transformation loses about cond(C)^2 * eps: the body measures cond_F(C)^2 and returns false
+// (nothing but X[0] written) when it exceeds `cond2_max`; the caller then runs lq_solve_body.
+// Symmetric Q, Pf assumed (the upper triangles of C'QC and C'PfC are used), as in lq_solve_body.
+
+// adjugate and determinant of a small matrix (row-major); inverse = adj / det
+template <int NX>
+MPC_HD double adjugate(const double* m, double* adj);
+
+template <>
+MPC_HD double adjugate<2>(const double* m, double* adj) {
+  adj[0] = m[3];
+  adj[1] = -m[1];
+  adj[2] = -m[2];
+  adj[3] = m[0];
+  return fma(m[0], m[3], -m[1] * m[2]);
+}
+
+template <>
+MPC_HD double adjugate<4>(const double* m, double* adj) {
+#define MPC_D2(a, b, c, d) fma(m[a], m[b], -(m[c] * m[d]))
+  const double s0 = MPC_D2(0, 5, 4, 1), s1 = MPC_D2(0, 6, 4, 2), s2 = MPC_D2(0, 7, 4, 3);
+  const double s3 = MPC_D2(1, 6, 5, 2), s4 = MPC_D2(1, 7, 5, 3), s5 = MPC_D2(2, 7, 6, 3);
+  const double c5 = MPC_D2(10, 15, 14, 11), c4 = MPC_D2(9, 15, 13, 11), c3 = MPC_D2(9, 14, 13, 10);
+  const double c2 = MPC_D2(8, 15, 12, 11), c1 = MPC_D2(8, 14, 12, 10), c0 = MPC_D2(8, 13, 12, 9);
+#undef MPC_D2
+  adj[0] = fma(m[5], c5, fma(-m[6], c4, m[7] * c3));
+  adj[1] = fma(-m[1], c5, fma(m[2], c4, -(m[3] * c3)));
+  adj[2] = fma(m[13], s5, fma(-m[14], s4, m[15] * s3));
+  adj[3] = fma(-m[9], s5, fma(m[10], s4, -(m[11] * s3)));
+  adj[4] = fma(-m[4], c5, fma(m[6], c2, -(m[7] * c1)));
+  adj[5] = fma(m[0], c5, fma(-m[2], c2, m[3] * c1));
+  adj[6] = fma(-m[12], s5, fma(m[14], s2, -(m[15] * s1)));
+  adj[7] = fma(m[8], s5, fma(-m[10], s2, m[11] * s1));
+  adj[8] = fma(m[4], c4, fma(-m[5], c2, m[7] * c0));
+  adj[9] = fma(-m[0], c4, fma(m[1], c2, -(m[3] * c0)));
+  adj[10] = fma(m[12], s4, fma(-m[13], s2, m[15] * s0));
+  adj[11] = fma(-m[8], s4, fma(m[9], s2, -(m[11] * s0)));
+  adj[12] = fma(-m[4], c3, fma(m[5], c1, -(m[6] * c0)));
+  adj[13] = fma(m[0], c3, fma(-m[1], c1, m[2] * c0));
+  adj[14] = fma(-m[12], s3, fma(m[13], s1, -(m[14] * s0)));
+  adj[15] = fma(m[8], s3, fma(-m[9], s1, m[10] * s0));
+  return fma(s0, c5, fma(-s1, c4, fma(s2, c3, fma(s3, c2, fma(-s4, c1, s5 * c0)))));
+}
+
+// upper triangle (mirrored storage: only entries i <= j are defined) of C' S C for a full S
+template <int NX>
+MPC_HD void congruence_upper(const double* C, const double* S, double* out) {
+  double T[NX * NX];
+  mm<double, NX, NX, NX, false>(S, C, T);
+#pragma unroll
+  for (int i = 0; i < NX; ++i)
+#pragma unroll
+    for (int j = i; j < NX; ++j) {
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < NX; ++k) acc = fma(C[k * NX + i], T[k * NX + j], acc);
+      out[i * NX + j] = acc;
+    }
+}
+
+#define MPC_SYM(P, i, j) ((i) <= (j) ? (P)[(i) * NX + (j)] : (P)[(j) * NX + (i)])
+
+template <int NX, bool AL>
+MPC_HD bool lq_solve_krylov_body(const LqSolveArgs<double>& a, int64_t b, double* Ks, int kstride,
+                                 double cond2_max) {
+  using T = double;
+  constexpr int ANN = AL ? RowAlign<T, NX * NX>::value : 8;
+  constexpr int AN = AL ? RowAlign<T, NX>::value : 8;
+  T C[NX * NX], na[NX], z[NX], x[NX];
+  load_row<T, NX, AN>(a.x0 + b * NX, x);
+  store_row<T, NX, AN>(a.X + b * NX, x);
+  {
+    T A[NX * NX], col[NX], nxt[NX], adj[NX * NX];
+    load_row<T, NX * NX, ANN>(a.A + b * a.sA, A);
+    load_row<T, NX, AN>(a.B + b * a.sB, col);
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) C[i * NX + j] = col[i];
+      mv<T, NX, NX, false>(A, col, nxt);  // after the last column: nxt = A^n b
+#pragma unroll
+      for (int i = 0; i < NX; ++i) col[i] = nxt[i];
+    }
+    const T det = adjugate<NX>(C, adj);
+    T nC = T(0), nAdj = T(0);
+#pragma unroll
+    for (int i = 0; i < NX * NX; ++i) {
+      nC = fma(C[i], C[i], nC);
+      nAdj = fma(adj[i], adj[i], nAdj);
+    }
+    const T rdet = rcp_(det);
+    // cond_F(C)^2 = |C|_F^2 |adj|_F^2 / det^2; NaN/inf (singular C, non-finite data) compare false
+    if (!(nC * nAdj * rdet * rdet <= cond2_max)) return false;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      T s = T(0), t = T(0);
+#pragma unroll
+      for (int k = 0; k < NX; ++k) {
+        s = fma(adj[i * NX + k], col[k], s);
+        t = fma(adj[i * NX + k], x[k], t);
+      }
+      na[i] = s * rdet;  // -a = C^-1 A^n b
+      z[i] = t * rdet;   // z_0 = C^-1 x_0
+    }
+  }
+  T P[NX * NX], Q[NX * NX], R;
+  {
+    T S[NX * NX];
+    load_row<T, NX * NX, ANN>(a.Q + b * a.sQ, S);
+    congruence_upper<NX>(C, S, Q);
+    load_row<T, NX * NX, ANN>(a.Pf + b * a.sPf, S);
+    congruence_upper<NX>(C, S, P);
+    R = a.R[b * a.sR];
+  }
+  for (int k = a.N - 1; k >= 0; --k) {
+    const T nrS = -rcp_(R + P[0]);
+    T w[NX], K[NX], mc[NX], Pn[NX * NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {  // w = -P a
+      T s = T(0);
+#pragma unroll
+      for (int l = 0; l < NX; ++l) s = fma(MPC_SYM(P, i, l), na[l], s);
+      w[i] = s;
+    }
+#pragma unroll
+    for (int j = 0; j + 1 < NX; ++j) K[j] = P[j + 1] * nrS;  // G = W[0,:] = [P_01 .. P_0,n-1, w_0]
+    K[NX - 1] = w[0] * nrS;
+#pragma unroll
+    for (int e = 0; e < NX; ++e) Ks[(k * NX + e) * kstride] = K[e];
+    // rows 0..n-2 of P+ = Q_c + rows 1..n-1 of M,  M(r,c) = W(r,c) + P_0r K_c
+#pragma unroll
+    for (int i = 0; i + 1 < NX; ++i)
+#pragma unroll
+      for (int j = i; j + 1 < NX; ++j)
+        Pn[i * NX + j] = fma(P[i + 1], K[j], Q[i * NX + j] + MPC_SYM(P, i + 1, j + 1));
+#pragma unroll
+    for (int r = 0; r < NX; ++r) mc[r] = fma(P[r], K[NX - 1], w[r]);  // last column of M
+#pragma unroll
+    for (int i = 0; i + 1 < NX; ++i) Pn[i * NX + NX - 1] = Q[i * NX + NX - 1] + mc[i + 1];
+    T last = Q[NX * NX - 1];
+#pragma unroll
+    for (int r = 0; r < NX; ++r) last = fma(na[r], mc[r], last);
+    Pn[NX * NX - 1] = last;
+#pragma unroll
+    for (int i = 0; i < NX; ++i)
+#pragma unroll
+      for (int j = i; j < NX; ++j) P[i * NX + j] = Pn[i * NX + j];
+  }
+  {
+    // V_N(x0) = x0' P_0 x0 = z0' P_c z0 (FHC.py:123-124)
+    T v = T(0);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      T r = T(0);
+#pragma unroll
+      for (int j = 0; j < NX; ++j) r = fma(MPC_SYM(P, i, j), z[j], r);
+      v = fma(z[i], r, v);
+    }
+    a.V[b] = v;
+  }
+  for (int k = 0; k < a.N; ++k) {
+    T u = T(0);
+#pragma unroll
+    for (int e = 0; e < NX; ++e) u = fma(Ks[(k * NX + e) * kstride], z[e], u);
+    a.U[(int64_t)k * a.batch + b] = u;
+    const T zl = z[NX - 1];
+#pragma unroll
+    for (int i = NX - 1; i >= 1; --i) z[i] = fma(na[i], zl, z[i - 1]);
+    z[0] = fma(na[0], zl, u);
+    mv<T, NX, NX, false>(C, z, x);
+    store_row<T, NX, AN>(a.X + ((int64_t)(k + 1) * a.batch + b) * NX, x);
+  }
+  return true;
+}
+#undef MPC_SYM
+
 }  // namespace mpc

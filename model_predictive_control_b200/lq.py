@@ -162,6 +162,14 @@ def lq_solve(A, B, Q, R, Pf, x0, N, want_K=False, want_P0=False, out=None):
     return out
 
 
+def lq_solve_kernel_name(n, m, dtype, want_K=False, want_P0=False):
+    """Name of the kernel :func:`lq_solve` launches for these arguments (``mpc_lq_solve_variant``):
+    single-input fp64 solves without K/P0 outputs run in Krylov coordinates."""
+    enum = 0 if dtype == torch.float64 else 1
+    v = _lib.lib().mpc_lq_solve_variant(int(n), int(m), enum, int(bool(want_K or want_P0)))
+    return "lq_solve_krylov_kernel" if v == 1 else "lq_solve_kernel"
+
+
 class LqHostPipeline:
     """End-to-end fused LQ solves for callers whose data lives in HOST memory.
 

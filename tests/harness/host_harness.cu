@@ -88,6 +88,29 @@ extern "C" int hh_lq_solve(const double* A, int64_t sA, const double* B, int64_t
   return 0;
 }
 
+// Krylov-coordinate body of the single-input solve; `used[b]` = 1 where it accepted the scenario,
+// 0 where it asked for the dense body (which is then run, exactly as the kernel does).
+template <int NX>
+static void lq_solve_krylov_loop(const LqSolveArgs<double>& a, double cond2_max, uint8_t* used) {
+  std::vector<double> Ks((size_t)a.N * NX);
+  for (int64_t b = 0; b < a.batch; ++b) {
+    const bool ok = lq_solve_krylov_body<NX, false>(a, b, Ks.data(), 1, cond2_max);
+    if (!ok) lq_solve_body<double, NX, 1, false>(a, b, Ks.data(), 1);
+    if (used) used[b] = ok ? 1 : 0;
+  }
+}
+
+extern "C" int hh_lq_solve_krylov(const double* A, int64_t sA, const double* B, int64_t sB, const double* Q,
+                                  int64_t sQ, const double* R, int64_t sR, const double* Pf, int64_t sPf,
+                                  const double* x0, double* X, double* U, double* V, int64_t batch, int n,
+                                  int N, double cond_max, uint8_t* used) {
+  LqSolveArgs<double> a{A, B, Q, R, Pf, sA, sB, sQ, sR, sPf, x0, X, U, V, nullptr, nullptr, batch, N};
+  if (n == 2) lq_solve_krylov_loop<2>(a, cond_max * cond_max, used);
+  else if (n == 4) lq_solve_krylov_loop<4>(a, cond_max * cond_max, used);
+  else return -5;
+  return 0;
+}
+
 template <int NX, int NU>
 static void boxqp_loop(const BoxQpArgs<double>& a) {
   using SH = BoxQpShared<NX, NU>;

@@ -225,6 +225,49 @@ def test_lq_solve_fused(mods, n, m, dtype, shared):
         assert np.abs(out.P0[b].cpu().numpy() - Pb[0]).max() <= rtol * np.abs(Pb[0]).max() * 10
 
 
+@pytest.mark.parametrize("n", [2, 4])
+@pytest.mark.parametrize("shared", [False, True])
+def test_lq_solve_krylov_kernel(mods, n, shared, monkeypatch):
+    """Single-input fp64 solve without K/P0 outputs = lq_solve_krylov_kernel: against the oracle's dense
+    recursion (FHC.py:51-61), bit-identical to the dense kernel where the conditioning guard rejects a
+    scenario (uncontrollable pair, b = 0, nearly dependent Krylov columns), and within 1e-8 of it elsewhere."""
+    _, _, _, lq, torch = mods
+    rng = np.random.default_rng(300 + n)
+    batch, N, m = 1500, 20, 1
+    A, B, Q, R = models(rng, 1 if shared else batch, n, m)
+    if not shared:
+        A[0] = np.eye(n); B[1] = 0.0
+        A[2] = np.diag(1.0 + 1e-6 * np.arange(n)); B[2] = 1.0
+    x0 = rng.uniform(-10, 10, (batch, n))
+    dev = lambda a: torch.tensor(a, dtype=torch.float64, device="cuda")
+    sq = (lambda a: a[0]) if shared else (lambda a: a)
+    args = (dev(sq(A)), dev(sq(B)), dev(sq(Q)), dev(sq(R)), dev(sq(Q)), dev(x0), N)
+    assert lq.lq_solve_kernel_name(n, m, torch.float64) == "lq_solve_krylov_kernel"
+    out = lq.lq_solve(*args)
+    monkeypatch.setenv("MPC_LQ_KRYLOV_COND", "0")
+    assert lq.lq_solve_kernel_name(n, m, torch.float64) == "lq_solve_kernel"
+    dense = lq.lq_solve(*args)
+    monkeypatch.delenv("MPC_LQ_KRYLOV_COND")
+    if not shared:
+        for t_k, t_d in ((out.X, dense.X), (out.U, dense.U)):
+            assert torch.equal(t_k[:, :3], t_d[:, :3]), "guarded scenarios must take the dense body"
+        assert torch.equal(out.V[:3], dense.V[:3])
+        differ = (out.U != dense.U).any(dim=0).any(dim=-1)
+        assert differ[3:].double().mean().item() > 0.5, "the Krylov path does not seem to be taken"
+    sx = dense.X.abs().amax(dim=(0, 2)).clamp_min(1.0)[None, :, None]
+    su = dense.U.abs().amax(dim=(0, 2)).clamp_min(1.0)[None, :, None]
+    assert ((out.X - dense.X).abs() / sx).max().item() < 1e-8
+    assert ((out.U - dense.U).abs() / su).max().item() < 1e-8
+    assert torch.allclose(out.V, dense.V, rtol=1e-8, atol=1e-12)
+    X, U, V = out.X.cpu().numpy(), out.U.cpu().numpy(), out.V.cpu().numpy()
+    for b in list(range(0, 8)) + list(range(8, batch, 149)):
+        i = 0 if shared else b
+        Xb, Ub, Vb, _, _ = olq.lq_open_loop(A[i], B[i], Q[i], R[i], Q[i], x0[b], N)
+        assert np.abs(X[:, b] - Xb).max() <= 1e-8 * max(1.0, np.abs(Xb).max())
+        assert np.abs(U[:, b] - Ub).max() <= 1e-8 * max(1.0, np.abs(Ub).max())
+        assert abs(V[b] - Vb) <= 1e-8 * abs(Vb)
+
+
 def test_full_size_properties_cfg2(mods):
     """1M scenarios (BASELINE config 2): size-independent properties of the fused solve:
     V == x0' P0 x0, X satisfies the dynamics, U = K X, linearity in x0, and agreement with the
@@ -246,9 +289,20 @@ def test_full_size_properties_cfg2(mods):
     Xn = torch.einsum("bij,kbj->kbi", A, out.X[:-1]) + torch.einsum("bij,kbj->kbi", Bm, out.U)
     assert torch.allclose(out.X[1:], Xn, rtol=1e-10, atol=1e-9)
     assert torch.allclose(out.U, torch.einsum("kbij,kbj->kbi", out.K, out.X[:-1]), rtol=1e-10, atol=1e-9)
+    # without K/P0 outputs a single-input fp64 solve runs in Krylov coordinates (lq_solve_krylov_kernel):
+    # same plan within 1e-8 of each scenario's scale (bar: 1e-6), exactly linear in x0, and its X obeys
+    # the dynamics of the ORIGINAL model
+    out1 = lq.lq_solve(A, Bm, Q, R, Q, x0, N)
+    sx = out.X.abs().amax(dim=(0, 2)).clamp_min(1.0)[None, :, None]
+    su = out.U.abs().amax(dim=(0, 2)).clamp_min(1.0)[None, :, None]
+    assert ((out1.X - out.X).abs() / sx).max().item() < 1e-8
+    assert ((out1.U - out.U).abs() / su).max().item() < 1e-8
+    assert torch.allclose(out1.V, out.V, rtol=1e-8)
+    Xn1 = torch.einsum("bij,kbj->kbi", A, out1.X[:-1]) + torch.einsum("bij,kbj->kbi", Bm, out1.U)
+    assert ((out1.X[1:] - Xn1).abs() / sx).max().item() < 1e-8
     out2 = lq.lq_solve(A, Bm, Q, R, Q, 2.0 * x0, N)
-    assert torch.allclose(out2.U, 2.0 * out.U, rtol=1e-12, atol=1e-12)
-    assert torch.allclose(out2.V, 4.0 * out.V, rtol=1e-12)
+    assert torch.allclose(out2.U, 2.0 * out1.U, rtol=1e-12, atol=1e-12)
+    assert torch.allclose(out2.V, 4.0 * out1.V, rtol=1e-12)
     K, P = lq.riccati(A, Bm, Q, R, Q, N, all_P=False)
     assert torch.allclose(K, out.K, rtol=1e-12, atol=1e-14) and torch.allclose(P, out.P0, rtol=1e-12)
     res = lq.lq_rollout(A, Bm, K, x0.t().contiguous(), N + 1, gain_offset=0, gain_step=1)

@@ -134,3 +134,30 @@ def test_lq_solve_body(hh, n, m):
         np.testing.assert_allclose(V[b], x0[b] @ Pb[0] @ x0[b], rtol=1e-9)  # V = x0' P0 x0 (FHC.py:123-124)
         np.testing.assert_allclose(K[:, b], np.array(Kb), rtol=1e-9, atol=1e-12)
         np.testing.assert_allclose(P0[b], Pb[0], rtol=1e-10)
+
+
+@pytest.mark.parametrize("n", [2, 4])
+def test_lq_solve_krylov_body(hh, n):
+    """Single-input solve in Krylov coordinates (lq_solve_krylov_body) against the oracle's dense
+    recursion, and the conditioning guard: ill-conditioned scenarios are handed to the dense body."""
+    rng = np.random.default_rng(5)
+    batch, N, m = 64, 20, 1
+    A, B, Q, R = models(rng, batch, n, m)
+    # three scenarios the guard must reject: uncontrollable pair, b = 0, nearly dependent Krylov columns
+    A[0] = np.eye(n); B[1] = 0.0
+    A[2] = np.diag(1.0 + 1e-6 * np.arange(n)); B[2] = 1.0
+    x0 = c(rng.uniform(-10, 10, (batch, n)))
+    X = np.zeros((N + 1, batch, n)); U = np.zeros((N, batch, m)); V = np.zeros(batch)
+    used = np.zeros(batch, dtype=np.uint8)
+    rc = hh.hh_lq_solve_krylov(p(A), C.c_int64(n * n), p(B), C.c_int64(n * m), p(Q), C.c_int64(n * n), p(R),
+                               C.c_int64(m * m), p(Q), C.c_int64(n * n), p(x0), p(X), p(U), p(V), C.c_int64(batch),
+                               n, N, C.c_double(1e3), used.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    assert not used[:3].any()
+    assert used[3:].mean() > 0.8, "the well-conditioned scenarios must take the Krylov path"
+    for b in range(batch):
+        Xb, Ub, Vb, Pb, Kb = lq.lq_open_loop(A[b], B[b], Q[b], R[b], Q[b], x0[b], N)
+        scale = max(1.0, np.abs(Xb).max())
+        np.testing.assert_allclose(X[:, b], Xb, rtol=0, atol=1e-8 * scale)
+        np.testing.assert_allclose(U[:, b], Ub, rtol=0, atol=1e-8 * max(1.0, np.abs(Ub).max()))
+        np.testing.assert_allclose(V[b], Vb, rtol=1e-8)
