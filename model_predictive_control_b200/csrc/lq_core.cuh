@@ -460,10 +460,17 @@ MPC_HD bool lq_solve_krylov_body(const LqSolveArgs<double>& a, int64_t b, double
     }
     a.V[b] = v;
   }
+  T Kc[NX];
+#pragma unroll
+  for (int e = 0; e < NX; ++e) Kc[e] = Ks[e * kstride];
   for (int k = 0; k < a.N; ++k) {
     T u = T(0);
 #pragma unroll
-    for (int e = 0; e < NX; ++e) u = fma(Ks[(k * NX + e) * kstride], z[e], u);
+    for (int e = 0; e < NX; ++e) u = fma(Kc[e], z[e], u);
+    if (k + 1 < a.N) {  // next stage's gain leaves shared memory while this stage is computed
+#pragma unroll
+      for (int e = 0; e < NX; ++e) Kc[e] = Ks[((k + 1) * NX + e) * kstride];
+    }
     a.U[(int64_t)k * a.batch + b] = u;
     const T zl = z[NX - 1];
 #pragma unroll

@@ -11,7 +11,7 @@ import bench
 from model_predictive_control_b200 import lq
 
 
-def timed(fn, iters=20, warm=5):
+def timed(fn, iters=60, warm=10):
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -33,20 +33,30 @@ def main():
     torch.cuda.synchronize()
     Xr, Ur, Vr = ref.X.clone(), ref.U.clone(), ref.V.clone()
     out = lq.LqSolveBuffers(batch, 4, 1, N, torch.float64, dev)
-    for spec in sys.argv[1:] or ["-"]:
-        for k in [k for k in os.environ if k.startswith("MPC_LQ_")]:
-            del os.environ[k]
-        if spec != "-":
-            for kv in spec.split(","):
-                k, v = kv.split("=")
-                os.environ[k] = v
-        ms = timed(lambda: lq.lq_solve(A, B, Q, R, Pf, x0, N, out=out))
-        ex = ((out.X - Xr).abs().amax() / Xr.abs().amax()).item()
-        eu = ((out.U - Ur).abs().amax() / Ur.abs().amax()).item()
-        ev = ((out.V - Vr).abs() / Vr.abs()).amax().item()
-        rel_row = ((out.X - Xr).abs().amax(dim=(0, 2)) / Xr.abs().amax(dim=(0, 2))).amax().item()
-        print(f"{spec:40s} {ms:8.4f} ms  {batch / ms * 1e-6:7.3f} Gsolves/s  {1296 * batch / ms * 1e-6:8.1f} GB/s  "
-              f"errX {ex:.2e} (per-scenario {rel_row:.2e}) errU {eu:.2e} errV {ev:.2e}", flush=True)
+    specs = sys.argv[1:] or ["-"]
+    rounds = int(os.environ.get("EXP_ROUNDS", "5"))
+    times = {s: [] for s in specs}
+    errs = {}
+    for r in range(rounds):   # round-robin: clocks drift with the power/thermal state, so interleave the variants
+        for spec in specs:
+            for k in [k for k in os.environ if k.startswith("MPC_LQ_")]:
+                del os.environ[k]
+            if spec != "-":
+                for kv in spec.split(","):
+                    k, v = kv.split("=")
+                    os.environ[k] = v
+            times[spec].append(timed(lambda: lq.lq_solve(A, B, Q, R, Pf, x0, N, out=out), iters=30, warm=3))
+            if r == 0:
+                ex = ((out.X - Xr).abs().amax(dim=(0, 2)) / Xr.abs().amax(dim=(0, 2))).amax().item()
+                eu = ((out.U - Ur).abs().amax() / Ur.abs().amax()).item()
+                ev = ((out.V - Vr).abs() / Vr.abs()).amax().item()
+                errs[spec] = (ex, eu, ev)
+    for spec in specs:
+        t = sorted(times[spec])
+        ms = t[len(t) // 2]
+        ex, eu, ev = errs[spec]
+        print(f"{spec:44s} median {ms:7.4f} ms (min {t[0]:.4f} max {t[-1]:.4f})  {batch / ms * 1e-6:6.3f} Gsolves/s  "
+              f"{1296 * batch / ms * 1e-6:7.1f} GB/s  errX {ex:.1e} errU {eu:.1e} errV {ev:.1e}", flush=True)
 
 
 if __name__ == "__main__":
