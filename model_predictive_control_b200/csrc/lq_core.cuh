@@ -362,6 +362,42 @@ MPC_HD void congruence_upper(const double* C, const double* S, double* out) {
 
 #define MPC_SYM(P, i, j) ((i) <= (j) ? (P)[(i) * NX + (j)] : (P)[(j) * NX + (i)])
 
+// One backward stage in Krylov coordinates: Pn = Q + A_o'(P A_o + P e_1 K), K = -(e_1'P A_o)/(R + P_00); K -> Ks.
+// Upper triangles only (entries i <= j of P, Pn, Q).
+template <int NX>
+MPC_HD void krylov_stage(const double* P, double* Pn, const double* Q, const double* na, double R, double* Ks,
+                         int kstride) {
+  using T = double;
+  const T nrS = -rcp_(R + P[0]);
+  T w[NX], K[NX], mc[NX];
+#pragma unroll
+  for (int i = 0; i < NX; ++i) {  // w = -P a
+    T s = T(0);
+#pragma unroll
+    for (int l = 0; l < NX; ++l) s = fma(MPC_SYM(P, i, l), na[l], s);
+    w[i] = s;
+  }
+#pragma unroll
+  for (int j = 0; j + 1 < NX; ++j) K[j] = P[j + 1] * nrS;  // G = W[0,:] = [P_01 .. P_0,n-1, w_0]
+  K[NX - 1] = w[0] * nrS;
+#pragma unroll
+  for (int e = 0; e < NX; ++e) Ks[e * kstride] = K[e];
+  // rows 0..n-2 of P+ = Q_c + rows 1..n-1 of M,  M(r,c) = W(r,c) + P_0r K_c
+#pragma unroll
+  for (int i = 0; i + 1 < NX; ++i)
+#pragma unroll
+    for (int j = i; j + 1 < NX; ++j)
+      Pn[i * NX + j] = fma(P[i + 1], K[j], Q[i * NX + j] + MPC_SYM(P, i + 1, j + 1));
+#pragma unroll
+  for (int r = 0; r < NX; ++r) mc[r] = fma(P[r], K[NX - 1], w[r]);  // last column of M
+#pragma unroll
+  for (int i = 0; i + 1 < NX; ++i) Pn[i * NX + NX - 1] = Q[i * NX + NX - 1] + mc[i + 1];
+  T last = Q[NX * NX - 1];
+#pragma unroll
+  for (int r = 0; r < NX; ++r) last = fma(na[r], mc[r], last);
+  Pn[NX * NX - 1] = last;
+}
+
 template <int NX, bool AL>
 MPC_HD bool lq_solve_krylov_body(const LqSolveArgs<double>& a, int64_t b, double* Ks, int kstride,
                                  double cond2_max) {
@@ -414,39 +450,19 @@ MPC_HD bool lq_solve_krylov_body(const LqSolveArgs<double>& a, int64_t b, double
     congruence_upper<NX>(C, S, P);
     R = a.R[b * a.sR];
   }
-  for (int k = a.N - 1; k >= 0; --k) {
-    const T nrS = -rcp_(R + P[0]);
-    T w[NX], K[NX], mc[NX], Pn[NX * NX];
-#pragma unroll
-    for (int i = 0; i < NX; ++i) {  // w = -P a
-      T s = T(0);
-#pragma unroll
-      for (int l = 0; l < NX; ++l) s = fma(MPC_SYM(P, i, l), na[l], s);
-      w[i] = s;
-    }
-#pragma unroll
-    for (int j = 0; j + 1 < NX; ++j) K[j] = P[j + 1] * nrS;  // G = W[0,:] = [P_01 .. P_0,n-1, w_0]
-    K[NX - 1] = w[0] * nrS;
-#pragma unroll
-    for (int e = 0; e < NX; ++e) Ks[(k * NX + e) * kstride] = K[e];
-    // rows 0..n-2 of P+ = Q_c + rows 1..n-1 of M,  M(r,c) = W(r,c) + P_0r K_c
-#pragma unroll
-    for (int i = 0; i + 1 < NX; ++i)
-#pragma unroll
-      for (int j = i; j + 1 < NX; ++j)
-        Pn[i * NX + j] = fma(P[i + 1], K[j], Q[i * NX + j] + MPC_SYM(P, i + 1, j + 1));
-#pragma unroll
-    for (int r = 0; r < NX; ++r) mc[r] = fma(P[r], K[NX - 1], w[r]);  // last column of M
-#pragma unroll
-    for (int i = 0; i + 1 < NX; ++i) Pn[i * NX + NX - 1] = Q[i * NX + NX - 1] + mc[i + 1];
-    T last = Q[NX * NX - 1];
-#pragma unroll
-    for (int r = 0; r < NX; ++r) last = fma(na[r], mc[r], last);
-    Pn[NX * NX - 1] = last;
+  // two stages per trip, ping-ponging between P and P2, so that no stage ends with a register copy
+  int k = a.N - 1;
+  T P2[NX * NX];
+  for (; k >= 1; k -= 2) {
+    krylov_stage<NX>(P, P2, Q, na, R, Ks + (int64_t)k * NX * kstride, kstride);
+    krylov_stage<NX>(P2, P, Q, na, R, Ks + (int64_t)(k - 1) * NX * kstride, kstride);
+  }
+  if (k == 0) {
+    krylov_stage<NX>(P, P2, Q, na, R, Ks, kstride);
 #pragma unroll
     for (int i = 0; i < NX; ++i)
 #pragma unroll
-      for (int j = i; j < NX; ++j) P[i * NX + j] = Pn[i * NX + j];
+      for (int j = i; j < NX; ++j) P[i * NX + j] = P2[i * NX + j];
   }
   {
     // V_N(x0) = x0' P_0 x0 = z0' P_c z0 (FHC.py:123-124)
