@@ -56,6 +56,7 @@ struct BoxQpArgs {
   int N;
   int max_iter;
   T eps;
+  int pf_dist = 0;  // stages of L2 prefetch ahead of each sweep's loads (device only; 0 = off)
 };
 
 // workspace elements per scenario
@@ -151,6 +152,56 @@ struct BoxQpIpm {
       s.lu[i] = lu[o];
     }
   }
+  // ---- L2 prefetch of the rows a later stage visit will load.  The workspace is streamed from HBM once per pass
+  // (it is far larger than L2); a `prefetch.global.L2` per row, issued pf_dist stage visits early, turns the
+  // ~1 us DRAM round trip of those loads into an L2 hit without holding registers for the data in flight.
+  MPC_HD static void pf(const T* p) {
+#ifdef __CUDA_ARCH__
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+  }
+  template <int PER>
+  MPC_HD void pf_rows(const T* base, int k) const {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) pf(base + ix(k, i, PER));
+  }
+  // rows every pass reads: the iterate of stage k (+ the per-scenario model)
+  MPC_HD void pf_stage(int k) const {
+#ifdef __CUDA_ARCH__
+    if constexpr (kPrefetch) return;  // small stages are already double-buffered in registers (measured: no gain)
+    if (a.pf_dist <= 0 || k < 0 || k >= a.N) return;
+    pf_rows<D>(z, k);
+    pf_rows<D>(sl, k);
+    pf_rows<D>(su, k);
+    pf_rows<D>(ll, k);
+    pf_rows<D>(lu, k);
+    if constexpr (MODEL == 1) {
+      pf_rows<kBicyclePack>(a.A, k);
+    } else if (a.ltv) {
+      pf_rows<NX * NX>(a.A, k);
+      pf_rows<NX * NU>(a.B, k);
+      pf_rows<NX>(a.c, k);
+    }
+#else
+    (void)k;
+#endif
+  }
+  MPC_HD void pf_extra(int k, bool gains, bool sinv, bool ff, bool aff, bool dir) const {
+#ifdef __CUDA_ARCH__
+    if constexpr (kPrefetch) return;
+    if (a.pf_dist <= 0 || k < 0 || k >= a.N) return;
+    if (gains) pf_rows<NU * NX>(Kw, k);
+    if (sinv) pf_rows<NU * NU>(Sw, k);
+    if (ff) pf_rows<NU>(dw, k);
+    if (aff) pf_rows<D>(dza, k);
+    if (dir) pf_rows<D>(dzw, k);
+#else
+    (void)k; (void)gains; (void)sinv; (void)ff; (void)aff; (void)dir;
+#endif
+  }
+
   MPC_HD void load_vec(const T* base, int k, int per, T* v) const {
     for (int i = 0; i < per; ++i) v[i] = base[ix(k, i, per)];
   }
@@ -344,6 +395,8 @@ struct BoxQpIpm {
       if (!FACTOR) loadn<D>(dza, a.N - 1, da);
     }
     for (int k = a.N - 1; k >= 0; --k) {
+      pf_stage(k - a.pf_dist);
+      pf_extra(k - a.pf_dist, !FACTOR, !FACTOR, false, !FACTOR, false);
       if (kPrefetch) {
         if (k > 0) {
           load(k - 1, nxt);
@@ -569,6 +622,8 @@ struct BoxQpIpm {
       if (!AFFINE) loadn<D>(dza, 0, da);
     }
     for (int k = 0; k < a.N; ++k) {
+      pf_stage(k + a.pf_dist);
+      pf_extra(k + a.pf_dist, true, false, true, !AFFINE, false);
       if (kPrefetch) {
         if (k + 1 < a.N) {
           load(k + 1, nxt);
@@ -676,6 +731,8 @@ struct BoxQpIpm {
   MPC_HD T update(T sig_mu, T alpha, bool second_order) {
     T zn = T(1);
     for (int k = 0; k < a.N; ++k) {
+      pf_stage(k + a.pf_dist);
+      pf_extra(k + a.pf_dist, false, false, false, second_order, true);
       Stage st;
       T da[D], dz[D];
       load(k, st);
