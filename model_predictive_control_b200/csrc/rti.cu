@@ -39,8 +39,8 @@ __global__ void __launch_bounds__(256) bicycle_plant_kernel(BicycleModel<T> mode
   for (int i = 0; i < 4; ++i) xn[i * batch + b] = xv[i];
 }
 
-template <typename T, bool PACKED>
-__global__ void __launch_bounds__(kRtiThreads) rti_closed_loop_kernel(RtiLoopArgs<T> a) {
+template <typename T, bool PACKED, int MINB>
+__global__ void __launch_bounds__(kRtiThreads, MINB) rti_closed_loop_kernel(RtiLoopArgs<T> a) {
   using SH = BoxQpShared<4, 2>;
   __shared__ T sh[SH::total];
   for (int i = threadIdx.x; i < SH::total; i += blockDim.x) {
@@ -206,9 +206,19 @@ extern "C" int mpc_rti_closed_loop(double lr, double lf, double accel, double fr
   a.qp.pf_dist = 4;  // measured on B200, cfg 4: 5.46 s (off) -> 4.44 s (2) -> 4.38 s (4) per 13.1 M QPs
   if (const char* env = getenv("MPC_QP_PREFETCH")) a.qp.pf_dist = atoi(env);
   const unsigned grid = (unsigned)((batch + kRtiThreads - 1) / kRtiThreads);
-  if (rk4)
-    rti_closed_loop_kernel<double, false><<<grid, kRtiThreads, 0, (cudaStream_t)stream>>>(a);
-  else  // forward-Euler prediction model: packed sparse stage matrices
-    rti_closed_loop_kernel<double, true><<<grid, kRtiThreads, 0, (cudaStream_t)stream>>>(a);
+  // MINB = resident CTAs per SM the register allocation must allow.  2 (255 registers, no spills) is the faster
+  // per-warp code; 4 (128 registers, spills) wins only when it lets the whole batch run as ONE wave instead of a full
+  // wave plus a partial one (measured at 65 536 scenarios: 4.19 s vs 3.93 s; 3 CTAs/SM quantises worst: 5.33 s).
+  const int64_t wave2 = (int64_t)kNumSMs * 2 * kRtiThreads, wave4 = (int64_t)kNumSMs * 4 * kRtiThreads;
+  int minb = (batch > wave2 && batch <= wave4) ? 4 : 2;
+  if (const char* env = getenv("MPC_RTI_MINB")) minb = atoi(env);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rk4) {
+    rti_closed_loop_kernel<double, false, 2><<<grid, kRtiThreads, 0, st>>>(a);
+  } else {  // forward-Euler prediction model: packed sparse stage matrices
+    if (minb >= 4) rti_closed_loop_kernel<double, true, 4><<<grid, kRtiThreads, 0, st>>>(a);
+    else if (minb == 3) rti_closed_loop_kernel<double, true, 3><<<grid, kRtiThreads, 0, st>>>(a);
+    else rti_closed_loop_kernel<double, true, 2><<<grid, kRtiThreads, 0, st>>>(a);
+  }
   return check_launch("rti_closed_loop_kernel");
 }
