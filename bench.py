@@ -699,6 +699,219 @@ def run_secondary(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# SURVEY 8(f) rows ("next"): the callers either side of the solve, each with its own bench line
+# ------------------------------------------------------------------------------------------------
+def run_next(args):
+    """--workload obstacle | bundles | dare | plant: one JSON line (same schema) per SURVEY 8(f) item.
+    obstacle: session_4/main.py controller as RTI with linearised collision rows, step-wise closed loop;
+    bundles : prediction bundles of FHC.run_and_plot_traj (closed loop + one prediction per closed-loop state);
+    dare    : infinite-horizon cost-to-go / gain as the Riccati fixed point, one per scenario model;
+    plant   : the accurate plant step (adaptive Dormand-Prince 5(4)) of session4_sol.exact_integration."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from model_predictive_control_b200 import FHC, lq, session4
+
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    seed = 1234 + 6 + 1000 * rank
+    g = torch.Generator(device=dev); g.manual_seed(seed)
+    rnd = lambda *shape: torch.rand(*shape, generator=g, device=dev, dtype=torch.float64)
+    w = args.workload
+    launches = 1
+    cpu = None
+    if w == "obstacle":
+        batch = args.batch or (1 << 14)
+        N, ts, steps_cl = 30, 0.08, 10
+        par = session4.VehicleParameters()
+        x_obs = np.array([0.25, 0.0, 0.0, 0.0])
+        x0 = torch.tensor([0.3, -0.1, 0.0, 0.0], device=dev, dtype=torch.float64) + (rnd(batch, 4) * 0.1 - 0.05) * \
+            torch.tensor([1, 1, 1, 0.0], device=dev, dtype=torch.float64)
+        ctrl = session4.ObstacleMPCController(N, ts, par, session4.KinematicBicycle(par, symbolic=True), x_obs)
+        plant = session4.exact_integration(session4.KinematicBicycle(par), ts)
+
+        def step():
+            return session4.simulate(x0, plant, n_steps=steps_cl, policy=ctrl)
+
+        units, n, m = batch * steps_cl, 4, 2
+        launches = 3 * steps_cl   # rti_prepare_obstacle_kernel + boxqp_ipm_rows_kernel + bicycle_plant_kernel per control step
+        name = (f"8(f).1 obstacle-avoidance RTI closed loop (session_4/main.py controller, 9 linearised collision rows per stage), "
+                f"nx=4 nu=2 N={N}, {batch} scenarios x {steps_cl} control steps per GPU, step-wise driver")
+        kname, io_bytes = "boxqp_ipm_rows_kernel", 8 * 6
+        host_in, host_out = [x0], lambda r: [r]
+
+        def cpu_fn():
+            from oracle import bicycle as obc
+            nb, ns = 8, 4
+            t0 = time.perf_counter()
+            obc.closed_loop_obstacle(x0[:nb].cpu().numpy(), x_obs, ns, N=N, ts=ts, qp="port")
+            dt = time.perf_counter() - t0
+            return {"value": nb * ns / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                    "sample": f"{nb} scenarios x {ns} control steps, numpy restatement of the obstacle RTI loop (oracle/bicycle.py); restatement, not reference code"}
+        cpu = cpu_fn
+    elif w == "bundles":
+        batch = args.batch or (1 << 18)
+        n, m, N, n_steps = 2, 1, 10, 30
+        A, B = FHC.get_dynamics_discrete(0.5)
+        C = np.array([[1.0], [-2.0 / 3.0]])
+        Q = C @ C.T + 1e-3 * np.eye(2); R = np.array([0.1])
+        dv = lambda a: torch.tensor(np.asarray(a, dtype=np.float64), device=dev)
+        Ad, Bd, Qd, Rd = dv(A), dv(B), dv(Q), dv(R)
+        x0 = rnd(2, batch) * 20 - 10
+        _, gains = FHC.ricatti_recursion(Ad, Bd, Qd, Rd, Qd, N)
+
+        def step():
+            return FHC.closed_loop_with_predictions(Ad, Bd, Qd, Rd, Qd, x0, N, n_steps=n_steps, gains=gains)[2]
+
+        units = batch * n_steps              # one open-loop prediction per closed-loop state
+        launches = 2                         # closed-loop rollout + the batched prediction rollout (rollout_shared_kernel)
+        name = (f"8(f).2 prediction bundles of FHC.run_and_plot_traj (FHC.py:87-91): {batch} scenarios x {n_steps} closed-loop "
+                f"states x horizon-{N} predictions, nx=2 nu=1")
+        kname, io_bytes = "rollout_shared_kernel", 8 * n * (N + 1)   # per prediction: read the start state, write N states
+        host_in, host_out = [x0], lambda r: [r]
+
+        def cpu_fn():
+            from oracle import lq as olq
+            nb = 20000
+            xs = x0[:, :nb].cpu().numpy()
+            Po, Ko = olq.ricatti_recursion(A, B, Q, R, Q, N)
+            t0 = time.perf_counter()
+            X = olq.simulate(A, B, xs, Ko, n_steps, mode="receding")
+            for t in range(n_steps):
+                olq.prediction(A, B, X[:, :, t], Ko, N)
+            dt = time.perf_counter() - t0
+            return {"value": nb * n_steps / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                    "sample": f"{nb} scenarios, column-batched numpy port of LinearSystem.simulate/prediction (the reference's own code runs column-batched unchanged)"}
+        cpu = cpu_fn
+    elif w == "dare":
+        batch = args.batch or (1 << 16)
+        n, m, N = 4, 1, 0
+        A, B, Q, R, _, _ = cfg2b_inputs_torch(batch, seed, dev, torch.float64)
+
+        def step():
+            return FHC.infinite_horizon(A, B, Q, R)
+
+        units = batch
+        launches = 5                         # riccati_reg_kernel per doubling of the horizon (64, 128, ...), data dependent
+        name = (f"8(f).3 infinite-horizon cost-to-go and gain (FHC.py:97-98,126) as the Riccati fixed point, one per scenario model, "
+                f"nx=4 nu=1, {batch} models per GPU")
+        kname, io_bytes = "riccati_reg_kernel", 8 * (3 * n * n + n * m + m * m) + 8 * (n * n + m * n)
+        host_in, host_out = [A, B, Q, R], lambda r: [r[0], r[1]]
+
+        def cpu_fn():
+            from scipy import linalg
+            nb = 2000
+            An, Bn, Qn, Rn = (t_[:nb].cpu().numpy() for t_ in (A, B, Q, R))
+            t0 = time.perf_counter()
+            for i in range(nb):
+                P = linalg.solve_discrete_are(An[i], Bn[i], Qn[i], Rn[i])
+                -np.linalg.inv(Rn[i] + Bn[i].T @ P @ Bn[i]) @ Bn[i].T @ P @ An[i]
+            dt = time.perf_counter() - t0
+            return {"value": nb / dt, "unit": UNIT, "cores": 1, "kind": "reference",
+                    "sample": f"{nb} models, scipy.linalg.solve_discrete_are + K_inf exactly as the reference calls them (FHC.py:97-98,126), python loop"}
+        cpu = cpu_fn
+    else:  # plant
+        batch = args.batch or (1 << 20)
+        n, m, N = 4, 2, 0
+        par = session4.VehicleParameters()
+        ts = 0.05
+        x = torch.stack([rnd(batch) * 2 - 1, rnd(batch) * 2 - 1, rnd(batch) * 2 - 1, rnd(batch) - 0.5], 0)
+        u = torch.stack([rnd(batch) * 2 - 1, rnd(batch) * 0.768 - 0.384], 0)
+
+        def step():
+            return session4.plant_step(par, ts, x, u, substeps=-10)   # adaptive Dormand-Prince, rtol = atol = 1e-10
+
+        units = batch
+        name = (f"8(f).4 accurate plant step (session4_sol.exact_integration, :37-56) as adaptive Dormand-Prince 5(4), "
+                f"rtol=atol=1e-10, ts={ts}, {batch} states per GPU")
+        kname, io_bytes = "bicycle_plant_kernel", 8 * (4 + 2 + 4)
+        host_in, host_out = [x, u], lambda r: [r]
+
+        def cpu_fn():
+            from oracle import bicycle as obc
+            nb = 2000
+            xs, us = x[:, :nb].t().cpu().numpy(), u[:, :nb].t().cpu().numpy()
+            op = obc.VehicleParameters()
+            t0 = time.perf_counter()
+            for i in range(nb):
+                obc.exact_integration_odeint(xs[i], us[i], ts, op, op.friction)
+            dt = time.perf_counter() - t0
+            return {"value": nb / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                    "sample": f"{nb} states, scipy odeint over [0, ts] per state as the reference's exact_integration does, python loop"}
+        cpu = cpu_fn
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        res = step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        res = step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms = total_ms / args.steps
+    value = world * units * args.steps / (total_ms * 1e-3)
+    pin_in = [torch.empty(t_.shape, dtype=t_.dtype, pin_memory=True).copy_(t_) for t_ in host_in]
+    pin_out = [torch.empty(t_.shape, dtype=t_.dtype, pin_memory=True) for t_ in host_out(res)]
+
+    def e2e_step():
+        for d_, h_ in zip(host_in, pin_in):
+            d_.copy_(h_, non_blocking=True)
+        r = step()
+        for h_, d_ in zip(pin_out, host_out(r)):
+            h_.copy_(d_, non_blocking=True)
+
+    e2e_step(); barrier()
+    e0.record()
+    for _ in range(3):
+        e2e_step()
+    e1.record(); barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * units * 3 / (float(t.item()) * 1e-3)
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        achieved = io_bytes * units / (ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": name, "batch_per_gpu": batch, "nx": n, "nu": m, "horizon": N,
+                       "parallelism": f"scenario-shard x{world}",
+                       "l2": "per-step footprint (inputs, outputs, solver workspace) exceeds the 126 MB L2; no flush needed"},
+            "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "bytes_per_unit": io_bytes,
+                         "note": "algorithmic I/O of the dominant kernel per unit of work; step time includes the other launches of the step"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": sum(t_.numel() * t_.element_size() for t_ in pin_in),
+                    "d2h_bytes_per_step": sum(t_.numel() * t_.element_size() for t_ in pin_out)},
+            "gpu_launches": launches * args.steps, "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu()
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -707,11 +920,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--batch", type=int, default=0, help="scenarios per GPU (default: the named config's)")
-    ap.add_argument("--workload", default="cfg2b", choices=["cfg2b", "cfg2a", "cfg3", "cfg4", "cfg5"],
+    ap.add_argument("--workload", default="cfg2b", choices=["cfg2b", "cfg2a", "cfg3", "cfg4", "cfg5", "obstacle", "bundles", "dare", "plant"],
                     help="cfg2b (default, BASELINE configs[1]); cfg2a = same shapes with ONE shared model: the Riccati "
                          "recursion runs once, the per-scenario work is the K2 rollout (HBM-bound); cfg3 = session-2 box-QP N=30, 256k scenarios; "
                          "cfg4 = session-4 RTI closed loop, 64k scenarios x 200 steps; "
-                         "cfg5 = nx=12 nu=4 N=50 box-QP, 2^20 scenarios per GPU (8M over 8 GPUs)")
+                         "cfg5 = nx=12 nu=4 N=50 box-QP, 2^20 scenarios per GPU (8M over 8 GPUs); "
+                         "obstacle | bundles | dare | plant = the SURVEY 8(f) rows (see run_next)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -720,6 +934,8 @@ def main():
         run_ours(args)
     elif args.workload == "cfg2a":
         run_cfg2a(args)
+    elif args.workload in ("obstacle", "bundles", "dare", "plant"):
+        run_next(args)
     else:
         run_secondary(args)
 
