@@ -453,9 +453,12 @@ MPC_HD bool lq_solve_krylov_body(const LqSolveArgs<double>& a, int64_t b, double
   // two stages per trip, ping-ponging between P and P2, so that no stage ends with a register copy
   int k = a.N - 1;
   T P2[NX * NX];
+  double* Kb = Ks + (int64_t)k * NX * kstride;  // slot of stage k, walked downwards
+  const int kdec = NX * kstride;
   for (; k >= 1; k -= 2) {
-    krylov_stage<NX>(P, P2, Q, na, R, Ks + (int64_t)k * NX * kstride, kstride);
-    krylov_stage<NX>(P2, P, Q, na, R, Ks + (int64_t)(k - 1) * NX * kstride, kstride);
+    krylov_stage<NX>(P, P2, Q, na, R, Kb, kstride);
+    krylov_stage<NX>(P2, P, Q, na, R, Kb - kdec, kstride);
+    Kb -= 2 * kdec;
   }
   if (k == 0) {
     krylov_stage<NX>(P, P2, Q, na, R, Ks, kstride);
@@ -476,24 +479,32 @@ MPC_HD bool lq_solve_krylov_body(const LqSolveArgs<double>& a, int64_t b, double
     }
     a.V[b] = v;
   }
+  // forward sweep with running pointers; the next stage's gain leaves shared memory while this stage is computed
+  // (the last trip re-reads its own slot instead of branching)
   T Kc[NX];
+  const double* Kp = Ks;
+  const int kinc = NX * kstride;
+  double* Up = a.U + b;
+  double* Xp = a.X + (a.batch + b) * NX;
+  const int64_t xinc = a.batch * NX;
 #pragma unroll
-  for (int e = 0; e < NX; ++e) Kc[e] = Ks[e * kstride];
+  for (int e = 0; e < NX; ++e) Kc[e] = Kp[e * kstride];
   for (int k = 0; k < a.N; ++k) {
     T u = T(0);
 #pragma unroll
     for (int e = 0; e < NX; ++e) u = fma(Kc[e], z[e], u);
-    if (k + 1 < a.N) {  // next stage's gain leaves shared memory while this stage is computed
+    Kp += (k + 1 < a.N) ? kinc : 0;
 #pragma unroll
-      for (int e = 0; e < NX; ++e) Kc[e] = Ks[((k + 1) * NX + e) * kstride];
-    }
-    a.U[(int64_t)k * a.batch + b] = u;
+    for (int e = 0; e < NX; ++e) Kc[e] = Kp[e * kstride];
+    *Up = u;
+    Up += a.batch;
     const T zl = z[NX - 1];
 #pragma unroll
     for (int i = NX - 1; i >= 1; --i) z[i] = fma(na[i], zl, z[i - 1]);
     z[0] = fma(na[0], zl, u);
     mv<T, NX, NX, false>(C, z, x);
-    store_row<T, NX, AN>(a.X + ((int64_t)(k + 1) * a.batch + b) * NX, x);
+    store_row<T, NX, AN>(Xp, x);
+    Xp += xinc;
   }
   return true;
 }
