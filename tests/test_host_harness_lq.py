@@ -161,3 +161,60 @@ def test_lq_solve_krylov_body(hh, n):
         np.testing.assert_allclose(X[:, b], Xb, rtol=0, atol=1e-8 * scale)
         np.testing.assert_allclose(U[:, b], Ub, rtol=0, atol=1e-8 * max(1.0, np.abs(Ub).max()))
         np.testing.assert_allclose(V[b], Vb, rtol=1e-8)
+
+
+def test_lq_solve_krylov_body_against_extended_precision(hh):
+    """Where the Krylov-coordinate path and the dense fp64 recursion disagree most (fast, badly conditioned models:
+    spectral radius 2-3, |P| ~ 1e7), extended precision (numpy longdouble) says which one is off: the accepted
+    Krylov-path solves stay within 1e-8 of the exact plan, the dense recursion -- the reference's own arithmetic --
+    is the one that drifts (up to ~1e-6 on this distribution)."""
+    if np.finfo(np.longdouble).eps > 1e-18:
+        pytest.skip("no extended-precision long double on this platform")
+    rng = np.random.default_rng(3)
+    batch, n, m, N = 20000, 4, 1, 20
+    A = c(np.eye(n) + 0.5 * np.diag(np.ones(n - 1), 1) + 0.5 * rng.standard_normal((batch, n, n)))
+    B = np.zeros((n, m)); B[-1, 0] = -0.5
+    B = c(B + 0.5 * rng.standard_normal((batch, n, m)))
+    G = rng.standard_normal((batch, n, n))
+    Q = c(G @ G.transpose(0, 2, 1) / n + 0.01 * np.eye(n))
+    R = c(0.1 * (1 + rng.random((batch, 1, 1))))
+    x0 = c(rng.uniform(-10, 10, (batch, n)))
+    out = {}
+    for name in ("krylov", "dense"):
+        X = np.zeros((N + 1, batch, n)); U = np.zeros((N, batch, m)); V = np.zeros(batch)
+        used = np.zeros(batch, dtype=np.uint8)
+        common = (p(A), C.c_int64(n * n), p(B), C.c_int64(n * m), p(Q), C.c_int64(n * n), p(R), C.c_int64(1), p(Q),
+                  C.c_int64(n * n), p(x0), p(X), p(U), p(V))
+        if name == "krylov":
+            rc = hh.hh_lq_solve_krylov(*common, C.c_int64(batch), n, N, C.c_double(1e3), used.ctypes.data_as(C.c_void_p))
+        else:
+            rc = hh.hh_lq_solve(*common, None, None, C.c_int64(batch), n, m, N)
+        assert rc == 0
+        out[name] = (U[:, :, 0], used)
+    Uk, used = out["krylov"]
+    Ud = out["dense"][0]
+    assert used.mean() > 0.8
+    scale = np.maximum(np.abs(Ud).max(0), 1.0)
+    gap = np.abs(Uk - Ud).max(0) / scale
+    L = np.longdouble
+    worst_k = 0.0
+    for b in np.argsort(gap)[-12:]:
+        Ab, Bb, Qb, Rb = (M[b].astype(L) for M in (A, B, Q, R))
+        P = Qb.copy(); Ks = []
+        for _ in range(N):
+            K = -(Bb.T @ P @ Ab) / (Rb + Bb.T @ P @ Bb)
+            P = Qb + Ab.T @ P @ (Ab + Bb @ K)
+            Ks.append(K)
+        x = x0[b].astype(L)[:, None]; Ue = []
+        for K in Ks[::-1]:
+            u = K @ x
+            x = Ab @ x + Bb @ u
+            Ue.append(u[0, 0])
+        Ue = np.array(Ue, dtype=L)
+        s = max(1.0, float(np.abs(Ue).max()))
+        ek = float(np.abs(Uk[:, b] - Ue).max()) / s
+        ed = float(np.abs(Ud[:, b] - Ue).max()) / s
+        if used[b]:
+            worst_k = max(worst_k, ek)
+            assert ek <= max(1e-8, ed), (b, ek, ed)
+    assert worst_k <= 1e-8
