@@ -1,4 +1,4 @@
-"""Generate tests/golden/session1.json by RUNNING THE REFERENCE'S OWN CODE.
+"""Generate tests/golden/session1.json and tests/golden/session234.json by RUNNING THE REFERENCE'S OWN CODE.
 
 Run in the build container only (needs /root/reference):
     python tests/golden/make_golden.py
@@ -140,5 +140,100 @@ def main():
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+
+def _fields(obj, names):
+    out = {}
+    for k in names:
+        v = getattr(obj, k)
+        out[k] = tolist(v) if isinstance(v, np.ndarray) else (float(v) if isinstance(v, (int, float, np.floating, np.integer)) else v)
+    return out
+
+
+def main_sessions234():
+    """Sessions 2-4: what the reference DOES define there, produced by its own (unmodified) code:
+    the Problem data of session_2/3 (problem.py), VehicleParameters (parameters.py), the integrators of
+    session4_sol.py:22-56, and the OCPs of session4_sol.py:131-217 / main.py:41-113 evaluated numerically
+    (cost f(U; x0), constraint vector g(U; x0), bound vectors) through oracle.ref_loader.NumericCasadi.
+    The only ingredient that is NOT the reference's is the bicycle ODE behind rcracers' KinematicBicycle
+    (package absent and unpinned): oracle/bicycle.py's definition is plugged in, as documented in DESIGN.md."""
+    out = {"_meta": {"numpy": np.__version__, "scipy": scipy.__version__, "generated_by": "tests/golden/make_golden.py",
+                     "source": "/root/reference/session_{2,3}/problem.py, session_4/{parameters,session4_sol,main}.py run "
+                               "through oracle/ref_loader.py (numeric casadi stand-in; bicycle ODE = oracle/bicycle.py)"}}
+    names = ["Ts", "Q", "R", "p_min", "p_max", "v_min", "v_max", "u_min", "u_max", "N", "A", "B", "n_state", "n_input"]
+    out["problem"] = {}
+    for s in (2, 3):
+        Problem = ref_loader.load_problem(s)
+        out["problem"][str(s)] = {"default": _fields(Problem(), names), "N30": _fields(Problem(N=30), names),
+                                  "Ts01_N7": _fields(Problem(Ts=0.1, N=7), names)}
+    VP = ref_loader.load_parameters()
+    vp = VP()
+    out["parameters"] = {k: float(getattr(vp, k)) for k in VP.__dataclass_fields__}
+
+    rng = np.random.default_rng(4321)
+    sol, cs = ref_loader.load_session4("session4_sol")
+    bike = sol.KinematicBicycle(vp)
+    # ---- integrators (session4_sol.py:22-56) on the bicycle, nominal and mismatched friction (:461-463)
+    cases = []
+    for i in range(6):
+        x = np.array([0.6, -0.25, 0.0, 0.0]) + rng.uniform(-0.3, 0.3, 4)
+        u = np.array([rng.uniform(-1, 1), rng.uniform(-0.384, 0.384)])
+        ts = [0.05, 0.08, 0.2][i % 3]
+        vpm = VP(); vpm.friction = vp.friction * (0.8 if i % 2 else 1.0)
+        bk = sol.KinematicBicycle(vpm)
+        cases.append({"x": tolist(x), "u": tolist(u), "ts": ts, "friction": float(vpm.friction),
+                      "f": tolist(bk(x, u)),
+                      "forward_euler": tolist(sol.forward_euler(bk, ts)(x, u)),
+                      "runge_kutta4": tolist(sol.runge_kutta4(bk, ts)(x, u)),
+                      "exact_integration": tolist(sol.exact_integration(bk, ts)(x, u))})
+    out["integrators"] = cases
+    pol = sol.build_test_policy()
+    out["test_policy"] = [tolist(pol(None, t)) for t in (0, 1, 2.5)]
+    # open-loop protocol of compare_open_loop (:65-104): simulate(x0, dynamics, steps, policy) with the three integrators
+    x0 = np.zeros(4)
+    out["open_loop"] = {"x0": tolist(x0), "ts": 0.05, "steps": 40,
+                        "forward_euler": tolist(sol.simulate(x0, sol.forward_euler(bike, 0.05), 40, policy=pol)),
+                        "runge_kutta4": tolist(sol.simulate(x0, sol.runge_kutta4(bike, 0.05), 40, policy=pol)),
+                        "exact_integration": tolist(sol.simulate(x0, sol.exact_integration(bike, 0.05), 40, policy=pol))}
+
+    # ---- session4_sol.MPCController.build_ocp, numerically
+    def ocp_cases(make, N, nrep, spread):
+        res = []
+        for _ in range(nrep):
+            xv = np.array([0.6, -0.25, 0.0, 0.0]) + rng.uniform(-1, 1, 4) * spread
+            U = np.stack([rng.uniform(-1, 1, N), rng.uniform(-0.384, 0.384, N)], 1)
+            cs_, ctrl = make()
+            cs_.values = {"x0": xv, **{f"u_{t}": U[t] for t in range(N)}}
+            c = ctrl()
+            nlp = c.ipopt_solver.nlp
+            res.append({"x0": tolist(xv), "U": tolist(U), "f": float(np.squeeze(nlp["f"])), "g": tolist(np.ravel(nlp["g"])),
+                        "x": tolist(np.ravel(nlp["x"])), "p": tolist(np.ravel(nlp["p"]))})
+        bounds = {k: tolist(np.ravel(np.asarray(v, dtype=float))) for k, v in c.bounds.items()}
+        return res, bounds
+
+    N = 5
+    res, bounds = ocp_cases(lambda: (cs, lambda: sol.MPCController(N, 0.05, params=vp)), N, 4, np.array([0.2, 0.2, 0.5, 0.2]))
+    out["ocp_sol"] = {"N": N, "ts": 0.05, "cases": res, "bounds": bounds}
+    cs.values = {"x0": np.zeros(4), **{f"u_{t}": np.zeros(2) for t in range(50)}}
+    c50 = sol.MPCController(50, 0.05, params=vp)
+    out["ocp_sol"]["N50_bounds"] = {k: tolist(np.ravel(np.asarray(v, dtype=float))) for k, v in c50.bounds.items()}
+
+    # ---- main.MPCController.build_ocp (obstacle avoidance), numerically
+    mn, cs2 = ref_loader.load_session4("main")
+    x_obs = np.array([0.25, 0.0, 0.0, 0.0])
+    N = 4
+    res, bounds = ocp_cases(lambda: (cs2, lambda: mn.MPCController(N, 0.08, vp, mn.KinematicBicycle(vp, symbolic=True), x_obs)),
+                            N, 4, np.array([0.3, 0.2, 0.6, 0.2]))
+    centers, r = mn.create_cover_circles(vp.length, vp.width, 3)
+    out["ocp_main"] = {"N": N, "ts": 0.08, "x_obs": tolist(x_obs), "cases": res, "bounds": bounds,
+                       "cover_circles": {"centers": [tolist(c_) for c_ in centers], "r": float(r)},
+                       "x2T": tolist(mn.x2T(np.array([0.3, -0.1, 0.7, 0.0]), False))}
+    path = os.path.join(ROOT, "tests", "golden", "session234.json")
+    with open(path, "w") as fh:
+        json.dump(out, fh)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
-    main()
+    if "--only-234" not in sys.argv:
+        main()
+    main_sessions234()

@@ -221,3 +221,55 @@ def test_obstacle_avoidance_controller(mods):
     # exact-QP restatement on the first steps
     ref2 = bc.closed_loop_obstacle(x0[:1], x_obs, 6, N=horizon, ts=ts, qp="exact")
     np.testing.assert_allclose(X[0, :7], ref2["X"][:, 0], rtol=0, atol=2e-6)
+
+
+def test_device_kernels_against_reference_fixture(mods):
+    """tests/golden/session234.json = outputs of the reference's own session-4 code (integrators of
+    session4_sol.py:22-56; OCP of main.py:41-113 evaluated numerically).  The device plant steps reproduce the
+    reference's integrators, and the linearisation kernels reproduce -- at the linearisation point -- the reference's
+    predicted states and collision-constraint values."""
+    import ctypes
+    import json
+    import os
+    s4, torch = mods
+    from model_predictive_control_b200 import _lib
+    with open(os.path.join(os.path.dirname(__file__), "golden", "session234.json")) as fh:
+        g = json.load(fh)
+    dev = lambda a: torch.tensor(np.asarray(a, dtype=np.float64), device="cuda")
+    for c in g["integrators"]:
+        p = s4.VehicleParameters(); p.friction = c["friction"]
+        bike = s4.KinematicBicycle(p)
+        x, u = np.asarray(c["x"]), np.asarray(c["u"])
+        np.testing.assert_allclose(s4.forward_euler(bike, c["ts"])(x, u), c["forward_euler"], rtol=1e-13, atol=1e-15)
+        np.testing.assert_allclose(s4.runge_kutta4(bike, c["ts"])(x, u), c["runge_kutta4"], rtol=1e-13, atol=1e-15)
+        # the reference's ground truth is odeint at its default tolerances (~1.5e-8)
+        np.testing.assert_allclose(s4.exact_integration(bike, c["ts"], adaptive=True)(x, u), c["exact_integration"], rtol=0, atol=2e-8)
+        np.testing.assert_allclose(s4.exact_integration(bike, c["ts"], substeps=16)(x, u), c["exact_integration"], rtol=0, atol=2e-8)
+    o = g["ocp_main"]
+    N, ts, x_obs = o["N"], o["ts"], np.asarray(o["x_obs"])
+    p = s4.VehicleParameters()
+    a_c, r_c = bc.create_cover_circles(p.length, p.width, 3)
+    r2 = (2 * r_c) ** 2
+    for c in o["cases"]:
+        y = dev(c["x0"]).reshape(4, 1).contiguous()
+        plan = dev(c["U"]).reshape(N, 2, 1).contiguous()
+        warm, A, B, cc, Cg, hg = (torch.empty((N, k, 1), dtype=torch.float64, device="cuda") for k in (2, 16, 8, 4, 36, 9))
+        xo = (ctypes.c_double * 4)(*[float(v) for v in x_obs])
+        _lib.check(_lib.lib().mpc_bicycle_rti_prepare_obstacle(
+            p.axis_rear, p.axis_front, float(p.acceleration), float(p.friction), ts, 0, float(p.length), float(p.width), xo,
+            _lib.ptr(y), _lib.ptr(plan), 1, _lib.ptr(warm), _lib.ptr(A), _lib.ptr(B), _lib.ptr(cc), _lib.ptr(Cg), _lib.ptr(hg),
+            1, N, _lib.MPC_F64, _lib.stream(y.device)))
+        torch.cuda.synchronize()
+        gref = np.asarray(c["g"]).reshape(N, 13)
+        U = np.asarray(c["U"])
+        A_, B_, c_ = A[:, :, 0].cpu().numpy().reshape(N, 4, 4), B[:, :, 0].cpu().numpy().reshape(N, 4, 2), cc[:, :, 0].cpu().numpy()
+        x = np.asarray(c["x0"])
+        for k in range(N):
+            # affine model of stage k at the linearisation point reproduces the reference's Euler rollout (its g rows 0..3)
+            xn = A_[k] @ x + B_[k] @ U[k] + c_[k]
+            np.testing.assert_allclose(xn, gref[k, :4], rtol=1e-12, atol=1e-14)
+            rows = Cg[k, :, 0].cpu().numpy().reshape(9, 4)
+            vals = r2 - hg[k, :, 0].cpu().numpy() + rows @ gref[k, :4]
+            np.testing.assert_allclose(vals, gref[k, 4:], rtol=1e-10, atol=1e-13)   # squared centre distances, main.py:95-104
+            x = gref[k, :4]
+        np.testing.assert_array_equal(warm[:, :, 0].cpu().numpy(), U)
