@@ -1,10 +1,15 @@
 """CPU oracle for the session-4 path (TEST INFRASTRUCTURE): kinematic bicycle, integrators, the
 real-time-iteration (RTI) step and the closed-loop driver.
 
-PARITY UNPINNED BY THE REFERENCE.  The reference solves the nonlinear OCP with CasADi + IPOPT
-(/root/reference/session_4/session4_sol.py:113-230) and takes the vehicle model from ``rcracers``
-(``KinematicBicycle``, call sites session4_sol.py:11,74,191,452); neither dependency is vendored,
-pinned or installed, so nothing here can be checked against reference outputs.  What follows the
+OCP DATA AND INTEGRATORS PINNED, ODE AND SOLVER PARITY UNPINNED BY THE REFERENCE.  The reference
+solves the nonlinear OCP with CasADi + IPOPT (/root/reference/session_4/session4_sol.py:113-230) and
+takes the vehicle model from ``rcracers`` (``KinematicBicycle``, call sites session4_sol.py:11,74,191,452);
+neither dependency is vendored, pinned or installed, so the converged NLP solution and the ODE cannot be
+checked against reference outputs.  Everything else is: tests/golden/session234.json holds outputs of
+the reference's own parameters.py, integrators (session4_sol.py:22-56) and of MPCController.build_ocp of
+session4_sol.py and main.py evaluated numerically (cost, constraint vector, bounds) with this module's
+ODE plugged in for rcracers (oracle/ref_loader.py::load_session4, NumericCasadi), and
+tests/test_oracle_golden_s234.py checks this restatement against them.  What follows the
 reference: state order [p_x, p_y, psi, v] and input order [a, delta] (session4_sol.py:176-181),
 weights Q = diag(1, 3, .1, .01), Q_T = 10 Q, R = diag(1, .01) (:166-169), bounds from
 VehicleParameters (:176-181, parameters.py:17-29), N = 50, ts = 0.05, x0 = [.6, -.25, 0, 0]

@@ -1,10 +1,12 @@
 """CPU oracle for the box-constrained linear MPC QP of sessions 2/3 (TEST INFRASTRUCTURE).
 
-PARITY UNPINNED BY THE REFERENCE: /root/reference ships only the problem *data*
+DATA PINNED, SOLVER PARITY UNPINNED BY THE REFERENCE: /root/reference ships only the problem *data*
 (session_2/problem.py:4-32, session_3/problem.py:8-36) and the per-solve log schema
-(session_2/log.py:8-12); the solver file of the course is not in the repository and
-``problem.py`` itself does not import on Python >= 3.11.  The oracle is therefore pinned by
-agreement of independent exact CPU solvers on the same QP (tests/test_oracle_boxqp.py):
+(session_2/log.py:8-12); the solver file of the course is not in the repository.  The data
+(fields, __post_init__ matrices, properties) is pinned to tests/golden/session234.json, produced by
+the reference's own problem.py (tests/golden/make_golden.py, oracle/ref_loader.py::load_problem;
+tests/test_oracle_golden_s234.py).  The *solution* has no reference output to be pinned to; it is
+pinned by agreement of independent exact CPU solvers on the same QP (tests/test_oracle_boxqp.py):
   * HiGHS active-set QP (scipy's bundled ``scipy.optimize._highspy``),
   * scipy SLSQP,
   * our own numpy restatement of the algorithm the GPU runs (``admm_riccati``).
