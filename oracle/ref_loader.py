@@ -196,3 +196,19 @@ def load_session4(which: str = "session4_sol"):
         mod = _import_file(path, "_ref_s4_" + which, extra_path=os.path.join(REFERENCE_ROOT, "session_4"))
         sys.modules.pop("parameters", None)
     return mod, cs
+
+
+def load_log(session: int = 2):
+    """``ControllerLog`` of /root/reference/session_{2,3}/log.py (source unmodified; rcracers' absent
+    ``BaseControllerLog`` is replaced by an empty dataclass base)."""
+    if not available():
+        raise RuntimeError("reference not mounted at " + REFERENCE_ROOT)
+    import dataclasses
+    import types
+    core = types.ModuleType("rcracers.simulator.core")
+    core.BaseControllerLog = dataclasses.make_dataclass("BaseControllerLog", [])
+    stubs = {"rcracers": types.ModuleType("rcracers"), "rcracers.simulator": types.ModuleType("rcracers.simulator"),
+             "rcracers.simulator.core": core}
+    with mock.patch.dict(sys.modules, stubs):
+        mod = _import_file(os.path.join(REFERENCE_ROOT, f"session_{session}", "log.py"), f"_ref_log_s{session}")
+    return mod.ControllerLog

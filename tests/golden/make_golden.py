@@ -165,6 +165,11 @@ def main_sessions234():
         Problem = ref_loader.load_problem(s)
         out["problem"][str(s)] = {"default": _fields(Problem(), names), "N30": _fields(Problem(N=30), names),
                                   "Ts01_N7": _fields(Problem(Ts=0.1, N=7), names)}
+    out["log_fields"] = {}
+    for s in (2, 3):
+        Log = ref_loader.load_log(s)
+        lg = Log()
+        out["log_fields"][str(s)] = {f.name: type(getattr(lg, f.name)).__name__ for f in __import__("dataclasses").fields(Log)}
     VP = ref_loader.load_parameters()
     vp = VP()
     out["parameters"] = {k: float(getattr(vp, k)) for k in VP.__dataclass_fields__}

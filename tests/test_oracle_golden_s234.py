@@ -51,6 +51,15 @@ def test_problem_data(g234, session):
     np.testing.assert_array_equal(xlo, [d["p_min"], d["v_min"]]); np.testing.assert_array_equal(xhi, [d["p_max"], d["v_max"]])
 
 
+def test_controller_log_schema(g234):
+    """session_{2,3}/log.py:8-12: three list fields, empty at construction."""
+    import dataclasses
+    from model_predictive_control_b200.log import ControllerLog
+    ours = {f.name: type(getattr(ControllerLog(), f.name)).__name__ for f in dataclasses.fields(ControllerLog)}
+    assert ours == g234["log_fields"]["2"] == g234["log_fields"]["3"]
+    assert all(getattr(ControllerLog(), k) == [] for k in ours)
+
+
 def test_vehicle_parameters(g234):
     ref = g234["parameters"]
     from model_predictive_control_b200.parameters import VehicleParameters
