@@ -352,6 +352,17 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms2a = float(t.item()) / args.steps
 
+    # ---- the same launch timed alone after a cool-down (burst clocks), like MEASURED_PEAKS.json's copy bandwidth
+    # (best of 10): the timed loop above runs power-capped (sw_power_cap), which the burst figure separates from the kernel
+    time.sleep(1.0)
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    burst = []
+    for _ in range(10):
+        b0.record(); step(); b1.record()
+        torch.cuda.synchronize()
+        burst.append(b0.elapsed_time(b1))
+    barrier()
+
     # ---- final gather of summaries over NCCL (outside the solve, outside the timed steps)
     summ = torch.stack([out.V.sum(), out.U[0].abs().max(), torch.tensor(float(batch), device=dev, dtype=dtype)]).double()
     if world > 1:
@@ -385,6 +396,11 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": load_traffic(kernel + "_" + args.dtype, batch),
                          "krylov_path_fraction": kfrac,
+                         "burst": {"best_ms": min(burst), "median_ms": sorted(burst)[len(burst) // 2],
+                                   "achieved": bytes_solve * batch / (min(burst) * 1e-3) / 1e9,
+                                   "frac": bytes_solve * batch / (min(burst) * 1e-3) / 1e9 / peak,
+                                   "note": "same launch timed alone after a 1 s cool-down, best of 10 (how the peak itself was "
+                                           "measured); achieved/frac above are the average over the timed loop, which runs power-capped"},
                          "peak_source": peak_src, "bytes_per_solve": bytes_solve, "kernel_ms": kern_ms,
                          "fp_pipe": {"flops_per_solve": flops_solve, "achieved_tflops": flops_solve * batch / (kern_ms * 1e-3) / 1e12,
                                      "measured_fma_peak_tflops": fp_peak / 1e12,
