@@ -575,8 +575,9 @@ def run_secondary(args):
     rnd = lambda *shape: torch.rand(*shape, generator=g, device=dev, dtype=torch.float64)
     if args.workload == "cfg3":
         batch = args.batch or (1 << 18)
-        prob = problem.Problem(N=30)
-        n, m, N = 2, 1, 30
+        N = args.horizon or 30
+        prob = problem.Problem(N=N)
+        n, m = 2, 1
         x0 = torch.stack([rnd(batch) * 100 - 100, rnd(batch) * 25 - 10], dim=1)
         mpc = problem.LinearMPC(prob)
         x0T = x0.t().contiguous()
@@ -589,7 +590,7 @@ def run_secondary(args):
             return boxqp.solve(A, B, Q, R, Q, N, x0T, u_lo, u_hi, x_lo, x_hi, workspace=ws)
 
         solves_per_step = batch
-        name = f"cfg3: session-2 Problem box-QP (input + state bounds), nx=2 nu=1 N=30, {batch} scenarios per GPU"
+        name = f"cfg3: session-2 Problem box-QP (input + state bounds), nx=2 nu=1 N={N}, {batch} scenarios per GPU"
         io_bytes = 8 * (n + N * m + (N + 1) * n + 1) + 8 + N * (n + m)
         host_in, host_out = [x0T], lambda r: [r.U, r.X, r.cost, r.status]
     elif args.workload == "cfg5":
@@ -942,6 +943,8 @@ def main():
                          "cfg4 = session-4 RTI closed loop, 64k scenarios x 200 steps; "
                          "cfg5 = nx=12 nu=4 N=50 box-QP, 2^20 scenarios per GPU (8M over 8 GPUs); "
                          "obstacle | bundles | dare | plant = the SURVEY 8(f) rows (see run_next)")
+    ap.add_argument("--horizon", type=int, default=0, help="cfg3 only: horizon N (default 30, the BASELINE config; the north star's "
+                                                          "throughput target is quoted at N = 20)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
