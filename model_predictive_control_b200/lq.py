@@ -138,7 +138,11 @@ class LqSolveBuffers:
 def lq_solve(A, B, Q, R, Pf, x0, N, want_K=False, want_P0=False, out=None):
     """Fused per-scenario finite-horizon LQ solve (K1+K2): x0 [batch, n] ->
     X [N+1, batch, n], U [N, batch, m], V [batch] (+ K [N, batch, m, n], P0 [batch, n, n]).
-    Models shared ([n,n]) or per scenario ([batch,n,n])."""
+    Models shared ([n,n]) or per scenario ([batch,n,n]).  Q and P_f must be symmetric (their upper
+    triangles are used).  Single-input float64 solves without K/P0 run in Krylov coordinates
+    (``lq_solve_kernel_name``; env ``MPC_LQ_KRYLOV_COND`` = conditioning bound of the guard, 0 = off):
+    same plan as the dense recursion within ~1e-10 of each scenario's scale on well-conditioned
+    models, with a per-scenario fallback to the dense recursion otherwise."""
     _lib.require_cuda(A, B, Q, R, Pf, x0)
     n, m = A.shape[-1], B.shape[-1]
     if x0.dim() != 2 or x0.shape[1] != n:
