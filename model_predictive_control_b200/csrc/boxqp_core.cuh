@@ -848,14 +848,9 @@ struct BoxQpIpm {
     init();
     int status = MPC_UNSOLVED, it = 0;
     T rp = T(0), zn = T(1);
-    if (ncons == 0) {  // no finite bound: one Newton step is the LQ optimum
-      Acc acc;
-      backward<true>(T(0));
-      forward<false>(T(0), acc);
-      update(T(0), T(1), false);
-      status = MPC_SOLVED;
-      it = 1;
-    }
+    // (no finite bound at all: the first iteration below is one exact Newton step onto the LQ optimum -- all barrier
+    // terms vanish, alpha = 1 -- and the loop stops after it.  One call site per pass keeps the kernel's code, which
+    // is far larger than the instruction caches, as small as it can be.)
     const T inv_nc = ncons ? T(1) / T(ncons) : T(0);
     while (status == MPC_UNSOLVED && it < a.max_iter) {
       ++it;
@@ -881,7 +876,8 @@ struct BoxQpIpm {
       zn = update(sig_mu, alpha, true);
       const T mu_new = (acc.s0 + alpha * (acc.s1 + alpha * acc.s2)) * inv_nc;
       rp = (T(1) - alpha) * acc.rp;
-      const bool done = (mu_new <= a.eps * mu_scale) && (rp <= a.eps * zn) && (alpha * acc.dzmax <= T(1e-6) * zn);
+      const bool done = (ncons == 0) ||
+                        ((mu_new <= a.eps * mu_scale) && (rp <= a.eps * zn) && (alpha * acc.dzmax <= T(1e-6) * zn));
       if (done) {
         status = MPC_SOLVED;
       } else if (!(alpha >= T(1e-6)) || !(mu_new <= T(100) * mu0)) {
