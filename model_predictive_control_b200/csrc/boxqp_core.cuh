@@ -381,8 +381,7 @@ struct BoxQpIpm {
 
   // ---- backward sweep: (factorisation and) feed-forward terms of the Newton step.
   // rhs_i = -(H z)_i + (sig_mu - cc_l)/s_l - Sigma_l r_l - (sig_mu - cc_u)/s_u + Sigma_u r_u
-  template <bool FACTOR>
-  MPC_HD void backward(T sig_mu) {
+  MPC_HD void backward(const bool FACTOR, T sig_mu) {
     T Pacc[NX * NX], pacc[NX];
 #pragma unroll
     for (int i = 0; i < NX * NX; ++i) Pacc[i] = sh[SH::oPf + i];
@@ -390,6 +389,8 @@ struct BoxQpIpm {
     for (int i = 0; i < NX; ++i) pacc[i] = T(0);
     Stage cur, nxt;
     T da[D], dan[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) da[i] = dan[i] = T(0);
     if (kPrefetch) {
       load(a.N - 1, cur);
       if (!FACTOR) loadn<D>(dza, a.N - 1, da);
@@ -477,7 +478,7 @@ struct BoxQpIpm {
           }
         }
       }
-      if constexpr (FACTOR) {
+      if (FACTOR) {
         // P = Pacc + diag(Sigma_x) (+ rows' C' Sigma_c C, added above)
 #pragma unroll
         for (int i = 0; i < NX; ++i) Pacc[i * NX + i] += sig[NU + i];
@@ -607,14 +608,15 @@ struct BoxQpIpm {
   // ---- forward sweep: dz by rollout with the stored gains; per element the slack / multiplier
   // directions.  AFFINE: stores dz_aff and accumulates the sums that give mu_aff for any step
   // length.  Otherwise stores dz and accumulates the step ratios / norms.
-  template <bool AFFINE>
-  MPC_HD void forward(T sig_mu, Acc& acc) {
+  MPC_HD void forward(const bool AFFINE, T sig_mu, Acc& acc) {
     T x[NX], xn[NX], u[NU];
     acc.qmax = acc.s0 = acc.s1 = acc.s2 = acc.dzmax = acc.rp = T(0);
 #pragma unroll
     for (int i = 0; i < NX; ++i) x[i] = T(0);  // dx_0 = 0
     Stage cur, nxt;
     T da[D], dan[D], K[NU * NX], Kn[NU * NX], dff[NU], dffn[NU];
+#pragma unroll
+    for (int i = 0; i < D; ++i) da[i] = dan[i] = T(0);
     if (kPrefetch) {
       load(0, cur);
       loadn<NU * NX>(Kw, 0, K);
@@ -855,22 +857,29 @@ struct BoxQpIpm {
     while (status == MPC_UNSOLVED && it < a.max_iter) {
       ++it;
       Acc acc;
-      backward<true>(T(0));
-      forward<true>(T(0), acc);
-      const T mu = acc.s0 * inv_nc;
-      const T am_aff = acc.amin();
-      const T a_aff = am_aff < T(1) ? am_aff : T(1);
-      const T mu_aff = (acc.s0 + a_aff * (acc.s1 + a_aff * acc.s2)) * inv_nc;
-      T ratio = mu_aff / (mu > T(1e-300) ? mu : T(1e-300));
-      T sigma = ratio * ratio * ratio;
-      sigma = sigma < T(1) ? sigma : T(1);
-      // centring target; never below 1e-3 of the complementarity tolerance: driving mu further only inflates
-      // the barrier weights (lam/s ~ lam^2/mu) and with them the rounding noise of the Newton step
-      T sig_mu = sigma * mu;
-      const T mu_floor = T(1e-3) * a.eps * mu_scale;
-      sig_mu = sig_mu > mu_floor ? sig_mu : mu_floor;
-      backward<false>(sig_mu);
-      forward<false>(sig_mu, acc);
+      T sig_mu = T(0);
+      // predictor (phase 0: factorise, sigma = 0, no second-order term) and corrector (phase 1) run through the SAME
+      // code: one copy of each sweep in the kernel instead of two
+#pragma unroll 1
+      for (int phase = 0; phase < 2; ++phase) {
+        const bool predictor = (phase == 0);
+        backward(predictor, sig_mu);
+        forward(predictor, sig_mu, acc);
+        if (predictor) {
+          const T mu = acc.s0 * inv_nc;
+          const T am_aff = acc.amin();
+          const T a_aff = am_aff < T(1) ? am_aff : T(1);
+          const T mu_aff = (acc.s0 + a_aff * (acc.s1 + a_aff * acc.s2)) * inv_nc;
+          T ratio = mu_aff / (mu > T(1e-300) ? mu : T(1e-300));
+          T sigma = ratio * ratio * ratio;
+          sigma = sigma < T(1) ? sigma : T(1);
+          // centring target; never below 1e-3 of the complementarity tolerance: driving mu further only inflates
+          // the barrier weights (lam/s ~ lam^2/mu) and with them the rounding noise of the Newton step
+          sig_mu = sigma * mu;
+          const T mu_floor = T(1e-3) * a.eps * mu_scale;
+          sig_mu = sig_mu > mu_floor ? sig_mu : mu_floor;
+        }
+      }
       T alpha = T(0.995) * acc.amin();
       alpha = alpha < T(1) ? alpha : T(1);
       zn = update(sig_mu, alpha, true);
