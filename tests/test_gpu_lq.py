@@ -268,6 +268,45 @@ def test_lq_solve_krylov_kernel(mods, n, shared, monkeypatch):
         assert abs(V[b] - Vb) <= 1e-8 * abs(Vb)
 
 
+@pytest.mark.parametrize("N,batch", [(1, 1), (2, 63), (7, 65), (33, 1000), (120, 257)])
+@pytest.mark.parametrize("misaligned", [False, True])
+def test_lq_solve_krylov_edge_shapes(mods, N, batch, misaligned, monkeypatch):
+    """Horizons 1 / odd / long (on-chip gains up to 120 stages), ragged batches, and inputs that are only 8-byte
+    aligned (views at an odd element offset: the kernel's non-vectorised path): Krylov path == dense kernel == oracle."""
+    _, _, _, lq, torch = mods
+    rng = np.random.default_rng(1000 + N + batch)
+    n, m = 4, 1
+    A, B, Q, R = models(rng, batch, n, m)
+    x0 = rng.uniform(-10, 10, (batch, n))
+
+    def dev(a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        if not misaligned:
+            return torch.tensor(a, device="cuda")
+        buf = torch.zeros(a.size + 1, dtype=torch.float64, device="cuda")
+        view = buf[1:].view(a.shape)          # 8-byte aligned, not 16/32
+        view.copy_(torch.tensor(a, device="cuda"))
+        assert view.data_ptr() % 16 == 8
+        return view
+    args = (dev(A), dev(B), dev(Q), dev(R), dev(Q), dev(x0), N)
+    out = lq.lq_solve(*args)
+    monkeypatch.setenv("MPC_LQ_KRYLOV_COND", "0")
+    dense = lq.lq_solve(*args)
+    monkeypatch.delenv("MPC_LQ_KRYLOV_COND")
+    assert out.X.shape == (N + 1, batch, n) and out.U.shape == (N, batch, m) and out.V.shape == (batch,)
+    sx = dense.X.abs().amax(dim=(0, 2)).clamp_min(1.0)[None, :, None]
+    su = dense.U.abs().amax(dim=(0, 2)).clamp_min(1.0)[None, :, None]
+    assert ((out.X - dense.X).abs() / sx).max().item() < 1e-8
+    assert ((out.U - dense.U).abs() / su).max().item() < 1e-8
+    assert torch.allclose(out.V, dense.V, rtol=1e-8, atol=1e-12)
+    assert torch.equal(out.X[0], args[5])
+    for b in sorted({0, batch // 2, batch - 1}):
+        Xb, Ub, Vb, _, _ = olq.lq_open_loop(A[b], B[b], Q[b], R[b], Q[b], x0[b], N)
+        assert np.abs(out.X[:, b].cpu().numpy() - Xb).max() <= 1e-8 * max(1.0, np.abs(Xb).max())
+        assert np.abs(out.U[:, b].cpu().numpy() - Ub).max() <= 1e-8 * max(1.0, np.abs(Ub).max())
+        assert abs(out.V[b].item() - Vb) <= 1e-8 * abs(Vb)
+
+
 def test_full_size_properties_cfg2(mods):
     """1M scenarios (BASELINE config 2): size-independent properties of the fused solve:
     V == x0' P0 x0, X satisfies the dynamics, U = K X, linearity in x0, and agreement with the
