@@ -406,8 +406,10 @@ def run_ours(args):
                                      "measured_fma_peak_tflops": fp_peak / 1e12,
                                      "frac": flops_solve * batch / (kern_ms * 1e-3) / fp_peak}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "d2h_gbs_per_gpu": d2h * (e2e_value / world / batch) / 1e9, "h2d_gbs_per_gpu": h2d * (e2e_value / world / batch) / 1e9,
                     "note": "lq.LqHostPipeline: pinned host buffers, all model/x0 inputs H2D and X/U/V D2H every step, "
-                            "copies of consecutive steps overlapped on separate streams", "result_matches_device": e2e_check},
+                            "copies of consecutive steps overlapped on separate streams (full duplex); the D2H stream "
+                            "(840 B per solve) runs at the PCIe link rate, which bounds this figure", "result_matches_device": e2e_check},
             "gpu_launches": args.steps, "clocks": clocks,
             "cfg2a_shared_model": {"value": world * batch / (ms2a * 1e-3), "unit": UNIT, "ms_per_step": ms2a,
                                    "kernels": "riccati_reg_kernel (1 CTA) + rollout_shared_kernel",
