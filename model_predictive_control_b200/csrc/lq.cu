@@ -232,43 +232,48 @@ __global__ void __launch_bounds__(256) linear_step_kernel(const T* __restrict__ 
 }
 
 // ================================================================== K1 + K2 fused
+// L2 prefetch of `count` elements starting at p (16-byte aligned start and size): one instruction, no
+// registers or shared memory held while the data is in flight.
+template <typename T>
+__device__ __forceinline__ void prefetch_l2(const T* p, int64_t count) {
+  if (count > 0)
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"((unsigned)(count * sizeof(T))) : "memory");
+}
+
+// Thread 0 of a CTA pulls the per-scenario inputs of the CTA `dist` positions later in the grid into L2 (see
+// launch_lq_solve for the distance): that CTA's first loads are then L2 hits instead of ~1 us DRAM round trips with
+// nothing else to do.  Needs 32-byte aligned, densely packed inputs (the AL kernels).
+template <typename T, int NX, int NU>
+__device__ __forceinline__ void prefetch_next_inputs(const LqSolveArgs<T>& a, int dist) {
+  if (dist <= 0 || threadIdx.x != 0) return;
+  const int64_t b0 = ((int64_t)blockIdx.x + dist) * blockDim.x;
+  const int64_t cnt = min((int64_t)blockDim.x, a.batch - b0) & ~(int64_t)3;  // multiples of 16 bytes for every array
+  if (cnt <= 0) return;
+  if (a.sA) prefetch_l2(a.A + b0 * a.sA, cnt * (NX * NX));
+  if (a.sQ) prefetch_l2(a.Q + b0 * a.sQ, cnt * (NX * NX));
+  if (a.sPf) prefetch_l2(a.Pf + b0 * a.sPf, cnt * (NX * NX));
+  if (a.sB) prefetch_l2(a.B + b0 * a.sB, cnt * (NX * NU));
+  if (a.sR) prefetch_l2(a.R + b0 * a.sR, cnt * (NU * NU));
+  prefetch_l2(a.x0 + b0 * NX, cnt * NX);
+}
+
 template <typename T, int NX, int NU, bool AL>
-__global__ void __launch_bounds__(kLqThreads) lq_solve_kernel(LqSolveArgs<T> a) {
+__global__ void __launch_bounds__(kLqThreads) lq_solve_kernel(LqSolveArgs<T> a, int prefetch_dist) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* Ks = reinterpret_cast<T*>(smem_raw) + threadIdx.x;
+  if (AL) prefetch_next_inputs<T, NX, NU>(a, prefetch_dist);
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b < a.batch) lq_solve_body<T, NX, NU, AL>(a, b, Ks, blockDim.x);
 }
 
 // Single-input models, fp64: the solve in Krylov coordinates (lq_solve_krylov_body); scenarios whose
 // controllability matrix is too ill-conditioned for the 1e-6 parity bar take the dense body instead.
-// L2 prefetch of `count` doubles starting at p (16-byte aligned, count even): one instruction, no
-// registers or shared memory held while the data is in flight.
-__device__ __forceinline__ void prefetch_l2(const double* p, int64_t count) {
-  if (count > 0)
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"((unsigned)(count * 8)) : "memory");
-}
-
 template <int NX, bool AL>
 __global__ void __launch_bounds__(kLqThreads) lq_solve_krylov_kernel(LqSolveArgs<double> a, double cond2_max,
                                                                      int prefetch_dist) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* Ks = reinterpret_cast<double*>(smem_raw) + threadIdx.x;
-  if (AL && prefetch_dist > 0 && threadIdx.x == 0) {
-    // The CTA that will take this CTA's place on the SM about one CTA lifetime from now is
-    // blockIdx.x + (resident CTAs of the grid): pull its per-scenario inputs into L2 now, so that its
-    // first loads are L2 hits instead of ~1 us DRAM round trips with nothing else to do.
-    const int64_t b0 = ((int64_t)blockIdx.x + prefetch_dist) * blockDim.x;
-    const int64_t cnt = min((int64_t)blockDim.x, a.batch - b0) & ~(int64_t)1;
-    if (cnt > 0) {
-      if (a.sA) prefetch_l2(a.A + b0 * a.sA, cnt * (NX * NX));
-      if (a.sQ) prefetch_l2(a.Q + b0 * a.sQ, cnt * (NX * NX));
-      if (a.sPf) prefetch_l2(a.Pf + b0 * a.sPf, cnt * (NX * NX));
-      if (a.sB) prefetch_l2(a.B + b0 * a.sB, cnt * NX);
-      if (a.sR) prefetch_l2(a.R + b0 * a.sR, cnt);
-      prefetch_l2(a.x0 + b0 * NX, cnt * NX);
-    }
-  }
+  if (AL) prefetch_next_inputs<double, NX, 1>(a, prefetch_dist);
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= a.batch) return;
   if (!lq_solve_krylov_body<NX, AL>(a, b, Ks, blockDim.x, cond2_max))
@@ -379,6 +384,13 @@ static int launch_lq_solve(const LqSolveArgs<T>& a, cudaStream_t st) {
   const size_t smem = per_thread * threads;
   MPC_REQUIRE(smem <= 220 * 1024, MPC_ERR_SHAPE, "mpc_lq_solve: horizon %d too long for on-chip gains", a.N);
   const unsigned grid = (unsigned)((a.batch + threads - 1) / threads);
+  // L2 prefetch distance in CTAs: 48 scenarios per SM ahead of the CTA that issues it, i.e. about
+  // 1/7 of the scenarios in flight (5 CTAs x 64 per SM).  Measured on B200 (tools/prof/
+  // exp_lq_variants.py, cfg 2b, sustained clocks): 0.288 ms without prefetch, 0.2505 ms for 74..148 CTAs
+  // of 64, 0.265 ms at 370, no gain at the full resident set (740): lines prefetched too early are
+  // evicted by the write stream before they are used.
+  int pf = (48 * kNumSMs) / threads;
+  if (const char* env = getenv("MPC_LQ_PREFETCH")) pf = atoi(env);
   if constexpr (std::is_same<T, double>::value && NU == 1 && (NX == 2 || NX == 4)) {
     const double cond_max = krylov_cond_max();
     if (cond_max > 0 && !a.K && !a.P0) {
@@ -386,13 +398,6 @@ static int launch_lq_solve(const LqSolveArgs<T>& a, cudaStream_t st) {
       if (al) {
         auto kern = lq_solve_krylov_kernel<NX, true>;
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        // L2 prefetch distance in CTAs: 48 scenarios per SM ahead of the CTA that issues it, i.e. about
-        // 1/7 of the scenarios in flight (5 CTAs x 64 per SM).  Measured on B200 (tools/prof/
-        // exp_lq_variants.py, cfg 2b, sustained clocks): 0.288 ms without prefetch, 0.2505 ms for 74..148 CTAs
-        // of 64, 0.265 ms at 370, no gain at the full resident set (740): lines prefetched too early are
-        // evicted by the write stream before they are used.
-        int pf = (48 * kNumSMs) / threads;
-        if (const char* env = getenv("MPC_LQ_PREFETCH")) pf = atoi(env);
         kern<<<grid, threads, smem, st>>>(a, c2, pf);
       } else {
         auto kern = lq_solve_krylov_kernel<NX, false>;
@@ -405,11 +410,11 @@ static int launch_lq_solve(const LqSolveArgs<T>& a, cudaStream_t st) {
   if (al) {
     auto kern = lq_solve_kernel<T, NX, NU, true>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<grid, threads, smem, st>>>(a);
+    kern<<<grid, threads, smem, st>>>(a, pf);
   } else {
     auto kern = lq_solve_kernel<T, NX, NU, false>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<grid, threads, smem, st>>>(a);
+    kern<<<grid, threads, smem, st>>>(a, 0);
   }
   return check_launch("lq_solve_kernel");
 }
