@@ -158,11 +158,34 @@ def lq_solve(A, B, Q, R, Pf, x0, N, want_K=False, want_P0=False, out=None):
     N = int(N)
     if out is None:
         out = LqSolveBuffers(batch, n, m, N, x0.dtype, x0.device, want_K, want_P0)
+    if (n, m) not in FUSED_SHAPES:
+        return _lq_solve_composed(A, B, Q, R, Pf, x0, N, out)
     with torch.cuda.device(x0.device):
         _lib.check(_lib.lib().mpc_lq_solve(
             _lib.ptr(A), sA, _lib.ptr(B), sB, _lib.ptr(Q), sQ, _lib.ptr(R), sR, _lib.ptr(Pf), sP,
             _lib.ptr(x0), _lib.ptr(out.X), _lib.ptr(out.U), _lib.ptr(out.V), _lib.ptr(out.K),
             _lib.ptr(out.P0), batch, n, m, N, _lib.dtype_enum(x0), _lib.stream(x0.device)))
+    return out
+
+
+FUSED_SHAPES = {(2, 1), (4, 1), (4, 2)}   # (n, m) with a register-resident fused kernel behind mpc_lq_solve
+
+
+def _lq_solve_composed(A, B, Q, R, Pf, x0, N, out):
+    """Same result for shapes without a fused kernel (n <= 32, m <= 16): the recursion (mpc_riccati, K1) followed by the
+    gain rollout (mpc_lq_rollout, K2) -- two launches, the gains take a round trip through HBM -- and
+    V = x0' P_0 x0 (FHC.py:123-124).  Still entirely on the device."""
+    batch, n = x0.shape
+    K, P0 = riccati(A, B, Q, R, Pf, N, all_P=False)            # K [N, 1 or batch, m, n], P0 [1 or batch, n, n]
+    res = lq_rollout(A, B, K if K.shape[1] > 1 else K[:, 0], x0.t().contiguous(), N + 1, gain_offset=0, gain_step=1,
+                     want_U=True)
+    out.X.copy_(res["X"].permute(0, 2, 1))
+    out.U.copy_(res["U"].permute(0, 2, 1))
+    out.V.copy_(torch.einsum("bi,bij,bj->b", x0, P0.expand(batch, n, n), x0))
+    if out.K is not None:
+        out.K.copy_(K.expand(N, batch, K.shape[2], n))
+    if out.P0 is not None:
+        out.P0.copy_(P0.expand(batch, n, n))
     return out
 
 

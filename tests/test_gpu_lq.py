@@ -307,6 +307,30 @@ def test_lq_solve_krylov_edge_shapes(mods, N, batch, misaligned, monkeypatch):
         assert abs(out.V[b].item() - Vb) <= 1e-8 * abs(Vb)
 
 
+@pytest.mark.parametrize("n,m,shared", [(3, 1, False), (6, 2, False), (12, 4, True), (5, 3, True)])
+def test_lq_solve_other_shapes(mods, n, m, shared):
+    """Shapes without a fused kernel: lq_solve composes K1 + K2 on the device; same contract, same oracle."""
+    _, _, _, lq, torch = mods
+    rng = np.random.default_rng(500 + n + m)
+    batch, N = 33, 15
+    A, B, Q, R = models(rng, 1 if shared else batch, n, m)
+    for j in range(2, m):
+        B[:, j % n, j] += 0.2
+    x0 = rng.uniform(-5, 5, (batch, n))
+    dev = lambda a: torch.tensor(a, dtype=torch.float64, device="cuda")
+    sq = (lambda a: a[0]) if shared else (lambda a: a)
+    out = lq.lq_solve(dev(sq(A)), dev(sq(B)), dev(sq(Q)), dev(sq(R)), dev(sq(Q)), dev(x0), N, want_K=True, want_P0=True)
+    assert out.X.shape == (N + 1, batch, n) and out.U.shape == (N, batch, m) and out.K.shape == (N, batch, m, n)
+    for b in range(0, batch, 8):
+        i = 0 if shared else b
+        Xb, Ub, Vb, Pb, Kb = olq.lq_open_loop(A[i], B[i], Q[i], R[i], Q[i], x0[b], N)
+        np.testing.assert_allclose(out.X[:, b].cpu().numpy(), Xb, rtol=1e-9, atol=1e-9 * max(1.0, np.abs(Xb).max()))
+        np.testing.assert_allclose(out.U[:, b].cpu().numpy(), Ub, rtol=1e-9, atol=1e-9 * max(1.0, np.abs(Ub).max()))
+        np.testing.assert_allclose(out.V[b].item(), Vb, rtol=1e-9)
+        np.testing.assert_allclose(out.K[:, b].cpu().numpy(), np.array(Kb), rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(out.P0[b].cpu().numpy(), Pb[0], rtol=1e-9, atol=1e-12)
+
+
 def test_full_size_properties_cfg2(mods):
     """1M scenarios (BASELINE config 2): size-independent properties of the fused solve:
     V == x0' P0 x0, X satisfies the dynamics, U = K X, linearity in x0, and agreement with the
