@@ -337,3 +337,56 @@ def test_general_stage_rows_gpu(mods, nc):
         np.testing.assert_array_equal(res.sat_u.permute(2, 0, 1)[b].cpu().numpy(), ex["sat_u"])
         nact += int(np.abs(ex["sat_c"]).sum())
     assert nact > 0
+
+
+@pytest.mark.parametrize("shape", ["lti21", "ltv42", "lti124"])
+def test_boxqp_writes_stay_inside_buffers(mods, shape):
+    """Guard bands around every output and around the solver workspace (ragged batch): the kernels write nothing
+    outside what mpc_boxqp_workspace_bytes / the output shapes promise."""
+    boxqp, problem, log, torch = mods
+    rng = np.random.default_rng(99)
+    pad = 512
+    dd = dict(dtype=torch.float64, device="cuda")
+    if shape == "lti21":
+        prob = problem.Problem(N=9)
+        n, m, N, batch = 2, 1, 9, 193
+        A, B = torch.tensor(prob.A, **dd), torch.tensor(prob.B, **dd)
+        Q, R = torch.tensor(prob.Q.astype(float), **dd), torch.tensor(prob.R.astype(float), **dd)
+        lo_u, hi_u, lo_x, hi_x = [prob.u_min], [prob.u_max], [prob.p_min, prob.v_min], [prob.p_max, prob.v_max]
+        x0 = torch.tensor(session_x0(rng, batch).T.copy(), **dd)
+        kw = {}
+    elif shape == "ltv42":
+        n, m, N, batch = 4, 2, 11, 161
+        A0 = np.eye(n) + 0.1 * np.diag(np.ones(n - 1), 1)
+        B0 = np.zeros((n, m)); B0[-1, 0] = 0.1; B0[-2, 1] = 0.1
+        A = torch.tensor((A0 + 0.02 * rng.standard_normal((N, batch, n, n))).transpose(0, 2, 3, 1).reshape(N, n * n, batch).copy(), **dd)
+        B = torch.tensor((B0 + 0.02 * rng.standard_normal((N, batch, n, m))).transpose(0, 2, 3, 1).reshape(N, n * m, batch).copy(), **dd)
+        kw = {"c": torch.tensor(0.01 * rng.standard_normal((N, n, batch)), **dd)}
+        Q, R = torch.eye(n, **dd), 0.1 * torch.eye(m, **dd)
+        lo_u, hi_u, lo_x, hi_x = [-1.0] * m, [0.5] * m, [-2.0] * n, [2.0] * n
+        x0 = torch.tensor(rng.uniform(-1.5, 1.5, (n, batch)), **dd)
+    else:
+        n, m, N, batch = 12, 4, 6, 77
+        Ts = 0.1
+        Ac = np.array([[1, Ts, Ts * Ts / 2], [0, 1, Ts], [0, 0, 1.0]]); Bc = np.array([[Ts**3 / 6], [Ts * Ts / 2], [Ts]])
+        A = torch.tensor(np.kron(np.eye(4), Ac) + 0.01 * rng.standard_normal((12, 12)), **dd)
+        B = torch.tensor(np.kron(np.eye(4), Bc), **dd)
+        Q, R = torch.eye(n, **dd), 0.1 * torch.eye(m, **dd)
+        lo_u, hi_u, lo_x, hi_x = [-1.0] * m, [1.0] * m, [-5.0] * n, [5.0] * n
+        x0 = torch.tensor(rng.uniform(-1, 1, (n, batch)), **dd)
+        kw = {}
+    ws = boxqp.BoxQpWorkspace(batch, n, m, N, "cuda")
+    guards = {}
+    for name in ("ws", "U", "X", "cost", "status", "iters", "sat_u", "sat_x"):
+        t = getattr(ws, name)
+        fill = -7 if t.dtype in (torch.int8, torch.int32) else -7.25
+        buf = torch.full((t.numel() + 2 * pad,), fill, dtype=t.dtype, device="cuda")
+        setattr(ws, name, buf[pad:pad + t.numel()].view(t.shape))
+        guards[name] = (buf, fill)
+    res = boxqp.solve(A, B, Q, R, Q, N, x0, lo_u, hi_u, lo_x, hi_x, workspace=ws, **kw)
+    torch.cuda.synchronize()
+    for name, (buf, fill) in guards.items():
+        assert bool((buf[:pad] == fill).all()) and bool((buf[-pad:] == fill).all()), name
+    assert int((res.status == 0).sum()) == 0                      # every scenario got a status
+    for name in ("U", "X", "cost"):
+        assert not bool((getattr(res, name) == -7.25).any()), name

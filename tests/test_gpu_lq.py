@@ -331,6 +331,39 @@ def test_lq_solve_other_shapes(mods, n, m, shared):
         np.testing.assert_allclose(out.P0[b].cpu().numpy(), Pb[0], rtol=1e-9, atol=1e-12)
 
 
+@pytest.mark.parametrize("want_K", [False, True])
+def test_lq_solve_writes_stay_inside_the_outputs(mods, want_K):
+    """Guard bands around every output buffer (ragged batch, odd horizon): both fused kernels write exactly their
+    outputs and nothing else (compute-sanitizer is not available on the GPU pool)."""
+    _, _, _, lq, torch = mods
+    rng = np.random.default_rng(4242)
+    batch, n, m, N, pad = 193, 4, 1, 7, 256
+    A, B, Q, R = models(rng, batch, n, m)
+    x0 = rng.uniform(-10, 10, (batch, n))
+    dev = lambda a: torch.tensor(a, dtype=torch.float64, device="cuda")
+
+    def guarded(shape):
+        numel = int(np.prod(shape))
+        buf = torch.full((numel + 2 * pad,), -7.25, dtype=torch.float64, device="cuda")
+        return buf, buf[pad:pad + numel].view(shape)
+    out = lq.LqSolveBuffers(1, n, m, N, torch.float64, "cuda")
+    bufs = {}
+    for name, shape in (("X", (N + 1, batch, n)), ("U", (N, batch, m)), ("V", (batch,)), ("K", (N, batch, m, n)), ("P0", (batch, n, n))):
+        if name in ("K", "P0") and not want_K:
+            setattr(out, name, None)
+            continue
+        bufs[name], view = guarded(shape)
+        setattr(out, name, view)
+    res = lq.lq_solve(dev(A), dev(B), dev(Q), dev(R), dev(Q), dev(x0), N, out=out)
+    torch.cuda.synchronize()
+    assert lq.lq_solve_kernel_name(n, m, torch.float64, want_K, want_K) == ("lq_solve_kernel" if want_K else "lq_solve_krylov_kernel")
+    for name, buf in bufs.items():
+        assert bool((buf[:pad] == -7.25).all()) and bool((buf[-pad:] == -7.25).all()), name
+        assert not bool((getattr(res, name) == -7.25).any()), name      # and every output element was written
+    Xb, Ub, Vb, _, _ = olq.lq_open_loop(A[batch - 1], B[batch - 1], Q[batch - 1], R[batch - 1], Q[batch - 1], x0[batch - 1], N)
+    np.testing.assert_allclose(res.U[:, batch - 1].cpu().numpy(), Ub, rtol=0, atol=1e-8 * max(1.0, np.abs(Ub).max()))
+
+
 def test_full_size_properties_cfg2(mods):
     """1M scenarios (BASELINE config 2): size-independent properties of the fused solve:
     V == x0' P0 x0, X satisfies the dynamics, U = K X, linearity in x0, and agreement with the
