@@ -745,7 +745,7 @@ def run_next(args):
     launches = 1
     cpu = None
     if w == "obstacle":
-        batch = args.batch or (1 << 14)
+        batch = args.batch or (1 << 16)
         N, ts, steps_cl = 30, 0.08, 10
         par = session4.VehicleParameters()
         x_obs = np.array([0.25, 0.0, 0.0, 0.0])
