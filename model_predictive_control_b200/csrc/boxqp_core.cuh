@@ -171,7 +171,7 @@ struct BoxQpIpm {
   MPC_HD void pf_stage(int k) const {
 #ifdef __CUDA_ARCH__
     if constexpr (kPrefetch) return;  // small stages are already double-buffered in registers (measured: no gain)
-    if constexpr (NC > 0) return;     // general rows: measured 6.1e5 QPs/s with, 6.9e5 without (obstacle workload)
+    if constexpr (NC > 0) return;     // general rows: measured 6.1e5 QPs/s with, 6.2-6.9e5 without (obstacle workload)
     if (a.pf_dist <= 0 || k < 0 || k >= a.N) return;
     pf_rows<D>(z, k);
     pf_rows<D>(sl, k);
