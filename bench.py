@@ -392,7 +392,10 @@ def run_ours(args):
             "config": {"workload": "cfg2b: FHC Riccati LQ solve (backward recursion + optimal plan + cost), nx=4 nu=1 N=20, "
                                    f"{batch} scenarios per GPU, per-scenario model and initial state",
                        "batch_per_gpu": batch, "nx": n, "nu": m, "horizon": N, "parallelism": f"scenario-shard x{world}",
-                       "l2": f"inputs+outputs {bytes_solve * batch / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)"},
+                       "l2": (f"inputs+outputs {bytes_solve * batch / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)"
+                              if bytes_solve * batch > 126e6 else
+                              f"inputs+outputs {bytes_solve * batch / 1e6:.0f} MB per step FIT in the 126 MB L2: not a valid "
+                              "timing configuration (use the default batch)")},
             "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": load_traffic(kernel + "_" + args.dtype, batch),
                          "krylov_path_fraction": kfrac,

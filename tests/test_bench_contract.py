@@ -1,0 +1,51 @@
+"""bench.py's output contract (one JSON line per run; keys the driver and the judge read)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches"}
+
+
+def run_bench(*args, env=None):
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True,
+                         cwd=ROOT, timeout=600, env={**os.environ, **(env or {})})
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, res.stdout[-2000:]
+    return json.loads(lines[0])
+
+
+def test_reference_arm_line():
+    """--impl reference: the CPU arm (oracle port of the reference's loop on the host cores), rank 0 only."""
+    d = run_bench("--impl", "reference", "--steps", "1", "--warmup", "0")
+    assert BASE_KEYS <= set(d) and d["impl"] == "reference"
+    assert d["value"] > 0 and d["unit"] == "solves/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert "workload" in d["config"] and d["gpu_launches"] == 0
+    # other ranks of a torchrun launch print nothing and exit 0
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, cwd=ROOT, timeout=600, env={**os.environ, "RANK": "1", "WORLD_SIZE": "2"})
+    assert res.returncode == 0 and res.stdout.strip() == ""
+
+
+@pytest.mark.gpu
+def test_default_line_on_gpu():
+    d = run_bench("--steps", "3", "--warmup", "3", "--batch", "65536", "--no-cpu")
+    assert BASE_KEYS <= set(d) and "impl" not in d
+    assert d["dtype"] == "f64" and d["scaling"] == "weak" and d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] >= 3
+    r = d["roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic", "kernel"} <= set(r)
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert r["kernel"] == "lq_solve_krylov_kernel" and r["krylov_path_fraction"] > 0.99
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 65536 * 456 and e["d2h_bytes_per_step"] == 65536 * 840
+    assert e["result_matches_device"] is True
+    assert d["gpu_launches"] == d["steps"] and {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+    assert "workload" in d["config"] and "l2" in d["config"]
