@@ -266,6 +266,16 @@ def test_lq_solve_krylov_kernel(mods, n, shared, monkeypatch):
         assert np.abs(X[:, b] - Xb).max() <= 1e-8 * max(1.0, np.abs(Xb).max())
         assert np.abs(U[:, b] - Ub).max() <= 1e-8 * max(1.0, np.abs(Ub).max())
         assert abs(V[b] - Vb) <= 1e-8 * abs(Vb)
+    # terminal weight different from Q
+    Pf = 2.5 * Q + 0.1 * np.eye(n)
+    Pf[::2] = Q[::2]                          # every other scenario keeps P_f = Q
+    out2 = lq.lq_solve(*args[:4], dev(sq(Pf)), *args[5:])
+    U2 = out2.U.cpu().numpy()
+    for b in list(range(0, 8)) + list(range(8, batch, 149)):
+        i = 0 if shared else b
+        _, Ub, Vb, _, _ = olq.lq_open_loop(A[i], B[i], Q[i], R[i], Pf[i], x0[b], N)
+        assert np.abs(U2[:, b] - Ub).max() <= 1e-8 * max(1.0, np.abs(Ub).max())
+        assert abs(out2.V[b].item() - Vb) <= 1e-8 * abs(Vb)
 
 
 @pytest.mark.parametrize("N,batch", [(1, 1), (2, 63), (7, 65), (33, 1000), (120, 257)])

@@ -149,14 +149,16 @@ def test_lq_solve_krylov_body(hh, n):
     x0 = c(rng.uniform(-10, 10, (batch, n)))
     X = np.zeros((N + 1, batch, n)); U = np.zeros((N, batch, m)); V = np.zeros(batch)
     used = np.zeros(batch, dtype=np.uint8)
+    Pf = c(2.5 * Q + 0.1 * np.eye(n))
+    Pf[::2] = Q[::2]   # half of the scenarios keep P_f = Q
     rc = hh.hh_lq_solve_krylov(p(A), C.c_int64(n * n), p(B), C.c_int64(n * m), p(Q), C.c_int64(n * n), p(R),
-                               C.c_int64(m * m), p(Q), C.c_int64(n * n), p(x0), p(X), p(U), p(V), C.c_int64(batch),
+                               C.c_int64(m * m), p(Pf), C.c_int64(n * n), p(x0), p(X), p(U), p(V), C.c_int64(batch),
                                n, N, C.c_double(1e3), used.ctypes.data_as(C.c_void_p))
     assert rc == 0
     assert not used[:3].any()
     assert used[3:].mean() > 0.8, "the well-conditioned scenarios must take the Krylov path"
     for b in range(batch):
-        Xb, Ub, Vb, Pb, Kb = lq.lq_open_loop(A[b], B[b], Q[b], R[b], Q[b], x0[b], N)
+        Xb, Ub, Vb, Pb, Kb = lq.lq_open_loop(A[b], B[b], Q[b], R[b], Pf[b], x0[b], N)
         scale = max(1.0, np.abs(Xb).max())
         np.testing.assert_allclose(X[:, b], Xb, rtol=0, atol=1e-8 * scale)
         np.testing.assert_allclose(U[:, b], Ub, rtol=0, atol=1e-8 * max(1.0, np.abs(Ub).max()))
