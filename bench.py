@@ -173,7 +173,7 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw,power.limit")
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
@@ -201,7 +201,7 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, pw, pl = [], [], set(), [], []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             parts = [p.strip() for p in ln.split(",")]
@@ -214,10 +214,18 @@ class ClockSampler:
             for nme, val in zip(names, parts[2:6]):
                 if val.lower().startswith("active"):
                     reasons.add(nme)
+            try:
+                pw.append(float(parts[6])); pl.append(float(parts[7]))
+            except (ValueError, IndexError):
+                pass
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        sm.sort(); pw.sort()
+        out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        if pw:
+            out["power_w"] = pw[len(pw) // 2]
+            out["power_limit_w"] = max(pl) if pl else None
+        return out
 
 
 # ------------------------------------------------------------------------------------------------
