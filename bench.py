@@ -546,6 +546,18 @@ def ipm_flops_per_iter(n, m, N):
     return N * (fac + 2 * (rhs + psweep) + 2 * fwd + upd)
 
 
+def ipm_workspace_bytes_per_iter(n, m, N, model_doubles_per_stage):
+    """HBM bytes one interior-point iteration moves BY DESIGN in the thread-per-scenario kernels (csrc/boxqp_core.cuh):
+    the solver state lives in a [stage][element][batch] workspace that is streamed once per pass.  Per stage and
+    iteration, in doubles: the iterate (z, s_l, s_u, lam_l, lam_u = 5(n+m)) is read by the five passes and written by the
+    update (x6); the gains K (mn) are written once and read three times; S^-1 (m^2) written + read; the feed-forward
+    (m) written twice + read twice; dz_aff (n+m) written + read three times; dz (n+m) written + read; the per-scenario
+    stage model (LTV only) is read by all five passes."""
+    d = n + m
+    per_stage = 6 * 5 * d + 4 * m * n + 2 * m * m + 4 * m + 4 * d + 2 * d + 5 * model_doubles_per_stage
+    return 8 * N * per_stage
+
+
 def _cpu_qp_worker(args):
     """Exact CPU solves (HiGHS active set + KKT refinement, oracle/boxqp.py) of a slice of cfg3 / cfg5 scenarios."""
     import numpy as np
@@ -736,6 +748,12 @@ def run_secondary(args):
                          "frac": achieved / peak, "traffic": load_traffic(kname, solves_per_step), "peak_source": peak_src,
                          "note": "algorithmic I/O only; the kernel is bound by the FP64 pipe and its workspace traffic, see fp_pipe",
                          "kernel_ms": kern_ms,
+                         "workspace_stream": (None if args.workload == "cfg5" else (lambda wb: {
+                             "bytes_per_iter": wb, "achieved": wb * iters_total / (kern_ms * 1e-3) / 1e9,
+                             "frac": wb * iters_total / (kern_ms * 1e-3) / 1e9 / peak,
+                             "note": "HBM bytes the kernel moves by design (solver workspace streamed once per pass, "
+                                     "ipm_workspace_bytes_per_iter) x iterations performed: the roofline this kernel actually "
+                                     "runs against"})(ipm_workspace_bytes_per_iter(n, m, N, 14 if args.workload == "cfg4" else 0))),
                          "fp_pipe": {"mean_iters_per_solve": iters_total / solves_per_step,
                                      "flops_per_iter": ipm_flops_per_iter(n, m, N),
                                      "achieved_tflops": flops / (kern_ms * 1e-3) / 1e12,
