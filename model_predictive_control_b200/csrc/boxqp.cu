@@ -39,10 +39,15 @@ __global__ void __launch_bounds__(kQpThreads, MINB) boxqp_ipm_kernel(BoxQpArgs<T
 }
 
 template <typename T, int NX, int NU>
-static int launch_boxqp(const BoxQpArgs<T>& a, cudaStream_t st) {
-  const unsigned grid = (unsigned)((a.batch + kQpThreads - 1) / kQpThreads);
-  int minb = (NX + NU <= 3) ? 3 : 2;  // measured on B200: (2,1) best at 3 CTAs/SM (168 regs), (4,x) at 2 (255 regs)
+static int launch_boxqp(const BoxQpArgs<T>& a_in, cudaStream_t st) {
+  const unsigned grid = (unsigned)((a_in.batch + kQpThreads - 1) / kQpThreads);
+  // measured on B200 (tools/prof/exp_q3.sh, cfg 3): (2,1) best at 4 CTAs/SM (128 registers) with the L2 prefetch two
+  // stage visits ahead (21.8 ms per 2^18 solves; 3 CTAs: 23.1, 6: 22.4+, distance 4: 25.5); (4,x) at 2 CTAs (255
+  // registers) and four visits ahead
+  int minb = (NX + NU <= 3) ? 4 : 2;
   if (const char* env = getenv("MPC_QP_MINB")) minb = atoi(env);
+  BoxQpArgs<T> a = a_in;
+  if (NX + NU <= 3 && !getenv("MPC_QP_PREFETCH")) a.pf_dist = 2;
   if constexpr (NX + NU > 8) {
     boxqp_ipm_kernel<T, NX, NU, 1><<<grid, kQpThreads, 0, st>>>(a);
   } else {

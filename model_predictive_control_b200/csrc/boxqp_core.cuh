@@ -89,9 +89,10 @@ constexpr int kBicyclePack = 14;
 template <typename T, int NX, int NU, int NC = 0, int MODEL = 0>
 struct BoxQpIpm {
   static constexpr int D = NX + NU;
-  // small stages are double-buffered in registers (the next stage's operands are requested while
-  // the current one is being computed); larger ones rely on occupancy to hide the loads
-  static constexpr bool kPrefetch = (D <= 3);
+  // Loads of a stage visit are hidden by resident warps plus an L2 prefetch of the rows a few visits ahead (pf_stage).
+  // Double-buffering the next stage in REGISTERS (an earlier version, for n + m <= 3) cost more than it hid: 168
+  // registers with 245 M local-memory sectors of spill traffic per 65 536 solves (ncu); without it the (2,1) kernel
+  // has no spills at 152 registers and runs 1.2x faster at 4 CTAs/SM.
   using SH = BoxQpShared<NX, NU>;
 
   const BoxQpArgs<T>& a;
@@ -170,7 +171,6 @@ struct BoxQpIpm {
   // rows every pass reads: the iterate of stage k (+ the per-scenario model)
   MPC_HD void pf_stage(int k) const {
 #ifdef __CUDA_ARCH__
-    if constexpr (kPrefetch) return;  // small stages are already double-buffered in registers (measured: no gain)
     if constexpr (NC > 0) return;     // general rows: measured 6.1e5 QPs/s with, 6.2-6.9e5 without (obstacle workload)
     if (a.pf_dist <= 0 || k < 0 || k >= a.N) return;
     pf_rows<D>(z, k);
@@ -191,7 +191,6 @@ struct BoxQpIpm {
   }
   MPC_HD void pf_extra(int k, bool gains, bool sinv, bool ff, bool aff, bool dir) const {
 #ifdef __CUDA_ARCH__
-    if constexpr (kPrefetch) return;
     if constexpr (NC > 0) return;
     if (a.pf_dist <= 0 || k < 0 || k >= a.N) return;
     if (gains) pf_rows<NU * NX>(Kw, k);
@@ -389,26 +388,15 @@ struct BoxQpIpm {
     for (int i = 0; i < NX * NX; ++i) Pacc[i] = sh[SH::oPf + i];
 #pragma unroll
     for (int i = 0; i < NX; ++i) pacc[i] = T(0);
-    Stage cur, nxt;
-    T da[D], dan[D];
+    Stage cur;
+    T da[D];
 #pragma unroll
-    for (int i = 0; i < D; ++i) da[i] = dan[i] = T(0);
-    if (kPrefetch) {
-      load(a.N - 1, cur);
-      if (!FACTOR) loadn<D>(dza, a.N - 1, da);
-    }
+    for (int i = 0; i < D; ++i) da[i] = T(0);
     for (int k = a.N - 1; k >= 0; --k) {
       pf_stage(k - a.pf_dist);
       pf_extra(k - a.pf_dist, !FACTOR, !FACTOR, false, !FACTOR, false);
-      if (kPrefetch) {
-        if (k > 0) {
-          load(k - 1, nxt);
-          if (!FACTOR) loadn<D>(dza, k - 1, dan);
-        }
-      } else {
-        load(k, cur);
-        if (!FACTOR) loadn<D>(dza, k, da);
-      }
+      load(k, cur);
+      if (!FACTOR) loadn<D>(dza, k, da);
       T A[NX * NX], B[NX * NU], c[NX], K[NU * NX], Sinv[NU * NU];
       load_model(k, A, B, c);
       if (!FACTOR) {
@@ -553,11 +541,6 @@ struct BoxQpIpm {
         for (int j = 0; j < NU; ++j) acc = fma_<T>(K[j * NX + i], gu[j], acc);
         pacc[i] = acc;
       }
-      if (kPrefetch) {
-        cur = nxt;
-#pragma unroll
-        for (int i = 0; i < D; ++i) da[i] = dan[i];
-      }
     }
   }
 
@@ -615,32 +598,17 @@ struct BoxQpIpm {
     acc.qmax = acc.s0 = acc.s1 = acc.s2 = acc.dzmax = acc.rp = T(0);
 #pragma unroll
     for (int i = 0; i < NX; ++i) x[i] = T(0);  // dx_0 = 0
-    Stage cur, nxt;
-    T da[D], dan[D], K[NU * NX], Kn[NU * NX], dff[NU], dffn[NU];
+    Stage cur;
+    T da[D], K[NU * NX], dff[NU];
 #pragma unroll
-    for (int i = 0; i < D; ++i) da[i] = dan[i] = T(0);
-    if (kPrefetch) {
-      load(0, cur);
-      loadn<NU * NX>(Kw, 0, K);
-      loadn<NU>(dw, 0, dff);
-      if (!AFFINE) loadn<D>(dza, 0, da);
-    }
+    for (int i = 0; i < D; ++i) da[i] = T(0);
     for (int k = 0; k < a.N; ++k) {
       pf_stage(k + a.pf_dist);
       pf_extra(k + a.pf_dist, true, false, true, !AFFINE, false);
-      if (kPrefetch) {
-        if (k + 1 < a.N) {
-          load(k + 1, nxt);
-          loadn<NU * NX>(Kw, k + 1, Kn);
-          loadn<NU>(dw, k + 1, dffn);
-          if (!AFFINE) loadn<D>(dza, k + 1, dan);
-        }
-      } else {
-        load(k, cur);
-        loadn<NU * NX>(Kw, k, K);
-        loadn<NU>(dw, k, dff);
-        if (!AFFINE) loadn<D>(dza, k, da);
-      }
+      load(k, cur);
+      loadn<NU * NX>(Kw, k, K);
+      loadn<NU>(dw, k, dff);
+      if (!AFFINE) loadn<D>(dza, k, da);
       T A[NX * NX], B[NX * NU], c[NX];
       load_model(k, A, B, c);
 #pragma unroll
@@ -719,15 +687,6 @@ struct BoxQpIpm {
       storen<D>(AFFINE ? dza : dzw, k, dzv);
 #pragma unroll
       for (int i = 0; i < NX; ++i) x[i] = xn[i];
-      if (kPrefetch) {
-        cur = nxt;
-#pragma unroll
-        for (int i = 0; i < NU * NX; ++i) K[i] = Kn[i];
-#pragma unroll
-        for (int i = 0; i < NU; ++i) dff[i] = dffn[i];
-#pragma unroll
-        for (int i = 0; i < D; ++i) da[i] = dan[i];
-      }
     }
   }
 
