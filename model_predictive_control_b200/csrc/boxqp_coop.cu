@@ -266,7 +266,7 @@ struct CoopIpm {
         __syncwarp();
         // Gauss-Jordan without pivoting (S is symmetric positive definite); lanes over [NU][2 NU]
         for (int p = 0; p < NU; ++p) {
-          const double inv = 1.0 / w[L::wAug + p * 2 * NU + p];
+          const double inv = rcp_(w[L::wAug + p * 2 * NU + p]);
           double newv = 0.0;
           const int rr = lane / (2 * NU), cc = lane % (2 * NU);
           const bool act = lane < NU * 2 * NU;
