@@ -547,10 +547,10 @@ struct BoxQpIpm {
   // inverse of a small symmetric positive definite matrix
   MPC_HD static void sym_inverse(const T* S, T* Si) {
     if constexpr (NU == 1) {
-      Si[0] = T(1) / S[0];
+      Si[0] = rcp_(S[0]);
     } else if constexpr (NU == 2) {
       const T det = S[0] * S[3] - S[1] * S[2];
-      const T id = T(1) / det;
+      const T id = rcp_(det);
       Si[0] = S[3] * id;
       Si[1] = -S[1] * id;
       Si[2] = -S[2] * id;
@@ -565,7 +565,7 @@ struct BoxQpIpm {
       }
 #pragma unroll
       for (int p = 0; p < NU; ++p) {
-        const T inv = T(1) / M[p * NU + p];
+        const T inv = rcp_(M[p * NU + p]);
 #pragma unroll
         for (int j = 0; j < NU; ++j) {
           M[p * NU + j] *= inv;

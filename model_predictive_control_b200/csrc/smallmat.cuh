@@ -66,7 +66,7 @@ template <typename T, int M, int N>
 MPC_HD void neg_solve(T* S, T* G) {
 #pragma unroll
   for (int p = 0; p < M; ++p) {
-    const T inv = T(1) / S[p * M + p];
+    const T inv = rcp_(S[p * M + p]);
 #pragma unroll
     for (int j = p + 1; j < M; ++j) S[p * M + j] *= inv;
 #pragma unroll
