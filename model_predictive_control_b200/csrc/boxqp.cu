@@ -140,7 +140,7 @@ static int boxqp_solve_impl(const void* A, const void* B, const void* c, int ltv
                       sat_c, (double*)ws, batch, N,
                       max_iter, eps};
   cudaStream_t st = (cudaStream_t)stream;
-  a.pf_dist = 4;  // measured on B200, cfg 4: 5.46 s (off) -> 4.44 s (2) -> 4.38 s (4) per 13.1 M QPs
+  a.pf_dist = 0;  // (4,x) stages: the kernels are bandwidth-bound on their workspace, see launch_boxqp and rti.cu
   if (const char* env = getenv("MPC_QP_PREFETCH")) a.pf_dist = atoi(env);
   if (nc > 0) {
     if (n == 4 && m == 2 && nc == 9) return launch_boxqp_rows<double, 4, 2, 9>(a, st);

@@ -203,14 +203,16 @@ extern "C" int mpc_rti_closed_loop(double lr, double lf, double accel, double fr
                            (const double*)u_lo, (const double*)u_hi, (const double*)x_lo, (const double*)x_hi, xcur, warm,
                            (double*)U_plan, (double*)X_pred, qp_cost, last_status, qp_iters, nullptr, nullptr, nullptr, nullptr, nullptr,
                            qp_ws, batch, N, max_iter, eps};
-  a.qp.pf_dist = 4;  // measured on B200, cfg 4: 5.46 s (off) -> 4.44 s (2) -> 4.38 s (4) per 13.1 M QPs
+  a.qp.pf_dist = 0;
   if (const char* env = getenv("MPC_QP_PREFETCH")) a.qp.pf_dist = atoi(env);
   const unsigned grid = (unsigned)((batch + kRtiThreads - 1) / kRtiThreads);
-  // MINB = resident CTAs per SM the register allocation must allow.  2 (255 registers, no spills) is the faster
-  // per-warp code; 4 (128 registers, spills) wins only when it lets the whole batch run as ONE wave instead of a full
-  // wave plus a partial one (measured at 65 536 scenarios: 4.19 s vs 3.93 s; 3 CTAs/SM quantises worst: 5.33 s).
-  const int64_t wave2 = (int64_t)kNumSMs * 2 * kRtiThreads, wave4 = (int64_t)kNumSMs * 4 * kRtiThreads;
-  int minb = (batch > wave2 && batch <= wave4) ? 4 : 2;
+  // MINB = resident CTAs per SM the register allocation must allow: 2 (255 registers) is the default.  Measured at
+  // cfg 4 with the final code of round 1 (tools/prof/exp_rti_minb.sh, 13.1 M QPs): 2 CTAs/SM 2.74 s, 4 CTAs/SM (128
+  // registers, spills, one wave instead of 1.7) 3.15 s, 3 CTAs/SM 3.96 s; with the L2 prefetch of the workspace rows
+  // 3.44 s at 2 CTAs/SM -- the kernel streams its workspace at ~70 % of the DRAM peak, so prefetches that are evicted
+  // before use only add traffic.  (Earlier in the round, with 25 % more code and an 11-instruction reciprocal, the
+  // same kernel was latency-bound and both the prefetch and the one-wave variant paid.)
+  int minb = 2;
   if (const char* env = getenv("MPC_RTI_MINB")) minb = atoi(env);
   cudaStream_t st = (cudaStream_t)stream;
   if (rk4) {
