@@ -42,8 +42,9 @@ template <typename T, int NX, int NU>
 static int launch_boxqp(const BoxQpArgs<T>& a_in, cudaStream_t st) {
   const unsigned grid = (unsigned)((a_in.batch + kQpThreads - 1) / kQpThreads);
   // measured on B200 (tools/prof/exp_q3.sh, cfg 3): (2,1) best at 4 CTAs/SM (128 registers) with the L2 prefetch two
-  // stage visits ahead (21.8 ms per 2^18 solves; 3 CTAs: 23.1, 6: 22.4+, distance 4: 25.5); (4,x) at 2 CTAs (255
-  // registers) and four visits ahead
+  // stage visits ahead (20.1 ms per 2^18 solves; 3 CTAs: 20.4, without prefetch 21.9-22.1); (4,x) at 2 CTAs (255
+  // registers) WITHOUT prefetch: those kernels stream their workspace at ~70 % of the DRAM peak, and lines prefetched
+  // and evicted before use are extra traffic (tools/prof/exp_rti_minb.sh)
   int minb = (NX + NU <= 3) ? 4 : 2;
   if (const char* env = getenv("MPC_QP_MINB")) minb = atoi(env);
   BoxQpArgs<T> a = a_in;

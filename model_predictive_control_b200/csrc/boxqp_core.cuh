@@ -155,7 +155,9 @@ struct BoxQpIpm {
   }
   // ---- L2 prefetch of the rows a later stage visit will load.  The workspace is streamed from HBM once per pass
   // (it is far larger than L2); a `prefetch.global.L2` per row, issued pf_dist stage visits early, turns the
-  // ~1 us DRAM round trip of those loads into an L2 hit without holding registers for the data in flight.
+  // ~1 us DRAM round trip of those loads into an L2 hit without holding registers for the data in flight.  It pays
+  // while a kernel is latency-bound (the (2,1) kernel: pf_dist = 2) and costs once it is bandwidth-bound, because lines
+  // evicted before use are fetched twice (the (4,2) kernels and the fused RTI loop: pf_dist = 0); the launchers decide.
   MPC_HD static void pf(const T* p) {
 #ifdef __CUDA_ARCH__
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
