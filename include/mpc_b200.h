@@ -162,10 +162,15 @@ int mpc_summary(const void* cost, const void* viol, const int32_t* n_sat, const 
  *   sat_u [N][m][batch] / sat_x [N][n][batch] optional int8: -1 at lower bound, +1 at upper, 0 free.
  *   Inputs at an active bound are returned exactly equal to the bound.
  *   ws: caller-owned workspace of mpc_boxqp_workspace_bytes(...) bytes.
- * Method: Mehrotra predictor-corrector interior point, Newton systems solved by Riccati sweeps;
- * float64 only (MPC_F32 -> MPC_ERR_UNSUPPORTED).  Supported (n, m): (2,1), (4,1), (4,2) with one thread per
- * scenario (register-resident matrices); (12,4) with a shared model (ltv = 0) on a persistent
+ * Method: Mehrotra predictor-corrector interior point, Newton systems solved by Riccati sweeps; arithmetic is float64
+ * for both dtypes.  MPC_F64: float64 arrays; the workspace keeps the iterate, gains and steps in float64 and slacks /
+ * multipliers in float32 (env MPC_QP_STORE=f64: everything float64).  MPC_F32: float32 arrays and workspace
+ * (north-star tolerance 1e-4).  Supported (n, m): (2,1), (4,1), (4,2) with one thread per
+ * scenario (register-resident matrices); (12,4), MPC_F64, with a shared model (ltv = 0) on a persistent
  * warp-per-scenario kernel whose workspace is one slot per resident warp, independent of the batch.
+ * status: MPC_SOLVED; MPC_INFEASIBLE when the iteration stalls (step length < 1e-6 or barrier parameter 100x above its
+ * start) with a bound residual that does not close; MPC_MAX_ITER otherwise (iteration limit without that signature).
+ * ws must be 16-byte aligned.
  */
 int64_t mpc_boxqp_workspace_bytes(int64_t batch, int n, int m, int N, int dtype);
 int mpc_boxqp_solve(const void* A, const void* B, const void* c, int ltv, const void* Q, const void* R,
@@ -196,7 +201,7 @@ int mpc_boxqp_solve_rows(const void* A, const void* B, const void* c, int ltv, c
  * nonlinear OCP with CasADi + IPOPT; here ONE linearised QP (K4, ltv = 1) is solved per control
  * step.  The bicycle ODE is our definition (rcracers is not vendored), see csrc/bicycle_core.cuh:
  *   state [p_x, p_y, psi, v], input [a, delta], parameters lr = axis_rear, lf = axis_front,
- *   friction, accel = acceleration (session_4/parameters.py:7-8,47-48).  float64 only.
+ *   friction, accel = acceleration (session_4/parameters.py:7-8,47-48).  MPC_F64 or MPC_F32 arrays (float64 arithmetic).
  *
  * mpc_bicycle_rti_prepare: shift the previous plan (first == 0) or keep it (first != 0), roll the
  *   model out from y [4][batch] and linearise:  U_prev [N][2][batch] -> warm_U [N][2][batch],
@@ -205,14 +210,22 @@ int mpc_boxqp_solve_rows(const void* A, const void* B, const void* c, int ltv, c
  *   (session4_sol.py:22-25), substeps > 0: RK4 sub-steps, substeps < 0: adaptive Dormand-Prince 5(4) with
  *   rtol = atol = 10^substeps (the counterpart of the reference's odeint plant, :37-56);
  *   friction [batch] (s_friction = 1) or one shared value (s_friction = 0).
- * mpc_rti_closed_loop: `steps` control steps of prepare -> QP -> apply u_0 -> plant in ONE kernel.
+ * mpc_rti_closed_loop: `steps` control steps of  sqp_iters x (prepare -> QP) -> apply u_0 -> plant  in ONE kernel.
+ *   Prediction model (lr, lf, accel, friction_model, ts, rk4) and plant (plant_lr, plant_lf, plant_accel, per-scenario
+ *   friction_plant [batch], plant_substeps as in mpc_bicycle_plant_step) are separate, as in the reference's mismatch
+ *   study (session4_sol.py:461-465).  sqp_iters = 1: real-time iteration.  sqp_iters > 1: the OCP is re-linearised at
+ *   the new plan and solved again (full-step SQP towards the converged solution IPOPT returns in the reference,
+ *   session4_sol.py:126-130); a round that moves the plan by <= sqp_tol * max(1, |U|) ends the step (0 = run all).
+ *   nc = 0: box constraints.  nc = 9: additionally the nine linearised collision rows of the obstacle-avoidance
+ *   controller (session_4/main.py:95-104) for an obstacle at the HOST pose x_obs, vehicle length / width
+ *   (forward-Euler prediction model only); clear_cl optional [batch] = smallest |c_i - o_j|^2 - (2r)^2 along the loop.
  *   U_plan [N][2][batch] in/out (initial plan; zeros = cold start), X_pred [N+1][4][batch] (last
  *   prediction), X_cl [steps+1][4][batch], U_cl [steps][2][batch], cost_cl [batch] (sum of
  *   x'Qx + u'Ru along the closed loop), viol_cl [batch] (max state-bound violation), n_sat (applied
- *   inputs on a bound), n_fail (steps whose QP did not reach MPC_SOLVED), iters_total, last_status.
+ *   inputs on a bound), n_fail (QPs that did not reach MPC_SOLVED), iters_total, last_status.
  *   Optional prediction bundles (NULL = not written), the (time step x horizon x state) layout that
  *   AnimateParking.bundle consumes (session_4/animation.py:75-83): X_bundle [steps][N+1][4][batch],
- *   U_bundle [steps][N][2][batch].
+ *   U_bundle [steps][N][2][batch].  ws: mpc_rti_workspace_bytes(batch, N, nc, dtype) bytes, 16-byte aligned.
  */
 int mpc_bicycle_rti_prepare(double lr, double lf, double accel, double friction, double ts, int rk4,
                             const void* y, const void* U_prev, int first, void* warm_U, void* A, void* B,
@@ -228,14 +241,16 @@ int mpc_bicycle_rti_prepare_obstacle(double lr, double lf, double accel, double 
 int mpc_bicycle_plant_step(double lr, double lf, double accel, double ts, const void* friction,
                            int64_t s_friction, int substeps, const void* x, const void* u, void* xn,
                            int64_t batch, int dtype, mpc_stream_t stream);
-int64_t mpc_rti_workspace_bytes(int64_t batch, int N, int dtype);
+int64_t mpc_rti_workspace_bytes(int64_t batch, int N, int nc, int dtype);
 int mpc_rti_closed_loop(double lr, double lf, double accel, double friction_model, double ts, int rk4,
-                        const void* friction_plant, int plant_substeps, int steps, const void* Q,
-                        const void* R, const void* Pf, const void* u_lo, const void* u_hi, const void* x_lo,
-                        const void* x_hi, const void* x0, void* U_plan, void* X_pred, void* X_cl, void* U_cl,
-                        void* cost_cl, void* viol_cl, int32_t* n_sat, int32_t* n_fail, int32_t* iters_total,
-                        int32_t* last_status, void* X_bundle, void* U_bundle, void* ws, int64_t ws_bytes,
-                        int64_t batch, int N, int max_iter, double eps, int dtype, mpc_stream_t stream);
+                        double plant_lr, double plant_lf, double plant_accel, const void* friction_plant,
+                        int plant_substeps, int steps, int sqp_iters, double sqp_tol, const void* Q, const void* R,
+                        const void* Pf, const void* u_lo, const void* u_hi, const void* x_lo, const void* x_hi, int nc,
+                        double length, double width, const double* x_obs, const void* x0, void* U_plan, void* X_pred,
+                        void* X_cl, void* U_cl, void* cost_cl, void* viol_cl, void* clear_cl, int32_t* n_sat,
+                        int32_t* n_fail, int32_t* iters_total, int32_t* last_status, void* X_bundle, void* U_bundle,
+                        void* ws, int64_t ws_bytes, int64_t batch, int N, int max_iter, double eps, int dtype,
+                        mpc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Device FP pipe probe: runs a register-resident FMA chain kernel and reports achieved

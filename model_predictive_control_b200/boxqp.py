@@ -58,13 +58,17 @@ class BoxQpResult:
 class BoxQpWorkspace:
     """Caller-owned scratch + outputs, reusable across solves of the same shape."""
 
-    def __init__(self, batch, n, m, N, device, sat=True, nc=0):
-        dd = dict(dtype=torch.float64, device=device)
-        nbytes = (_lib.lib().mpc_boxqp_rows_workspace_bytes(batch, n, m, N, nc, _lib.MPC_F64) if nc else
-                  _lib.lib().mpc_boxqp_workspace_bytes(batch, n, m, N, _lib.MPC_F64))
+    def __init__(self, batch, n, m, N, device, sat=True, nc=0, dtype=torch.float64):
+        if dtype not in (torch.float64, torch.float32):
+            raise ValueError("the box-QP solver takes float64 or float32 arrays")
+        dd = dict(dtype=dtype, device=device)
+        en = _lib.MPC_F64 if dtype == torch.float64 else _lib.MPC_F32
+        nbytes = (_lib.lib().mpc_boxqp_rows_workspace_bytes(batch, n, m, N, nc, en) if nc else
+                  _lib.lib().mpc_boxqp_workspace_bytes(batch, n, m, N, en))
         self.sat_c = torch.empty((N, nc, batch), dtype=torch.int8, device=device) if (sat and nc) else None
         self.nc = nc
-        self.ws = torch.empty(max(nbytes // 8, 1), **dd)
+        self.dtype = dtype
+        self.ws = torch.empty(max(nbytes // 8, 1) + 2, dtype=torch.float64, device=device)   # 16-byte aligned scratch
         self.nbytes = nbytes
         self.U = torch.empty((N, m, batch), **dd)
         self.X = torch.empty((N + 1, n, batch), **dd)
@@ -76,19 +80,22 @@ class BoxQpWorkspace:
         self.shape = (batch, n, m, N)
 
 
-def _vec(v, k, device, name):
+def _vec(v, k, device, name, dtype=torch.float64):
     t = torch.as_tensor(v, dtype=torch.float64, device=device).reshape(-1)
     if t.numel() == 1 and k > 1:
         t = t.expand(k)
     if t.numel() != k:
         raise ValueError(f"{name} must have {k} entries, got {t.numel()}")
-    t = torch.nan_to_num(t, posinf=BIG, neginf=-BIG)
-    return t.contiguous()
+    if bool(torch.isnan(t).any()):
+        raise ValueError(f"{name} contains NaN (use +-inf for 'no bound')")
+    t = torch.clamp(t, min=-BIG, max=BIG)   # +-inf -> "no bound"
+    return t.to(dtype).contiguous()
 
 
 def solve(A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi, c=None, warm_U=None, max_iter=60, eps=1e-9,
           workspace=None, Cg=None, hg=None):
-    """Solve ``batch`` QPs.  x0 [n, batch] (CUDA, float64).
+    """Solve ``batch`` QPs.  x0 [n, batch] (CUDA; float64 = the reference's arithmetic, or float32: float32 arrays
+    and solver workspace, float64 arithmetic inside the kernel -- the north star's 1e-4 tolerance class).
 
     LTI: A [n,n], B [n,m] shared (c must be None).
     LTV: A [N, n*n, batch], B [N, n*m, batch], c [N, n, batch] per scenario and stage.
@@ -96,8 +103,13 @@ def solve(A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi, c=None, warm_U=None, ma
     Optional general stage rows  Cg_k x_{k+1} >= hg_k:  Cg [N, nc*n, batch] (row-major rows), hg [N, nc, batch].
     """
     _lib.require_cuda(A, B, Q, R, Pf, x0)
-    if x0.dtype != torch.float64:
-        raise ValueError("the box-QP solver computes in float64 (the reference's arithmetic)")
+    dt = x0.dtype
+    if dt not in (torch.float64, torch.float32):
+        raise ValueError("x0 must be float64 (the reference's arithmetic) or float32")
+    for name, t in (("A", A), ("B", B), ("c", c), ("warm_U", warm_U), ("Cg", Cg), ("hg", hg)):
+        if t is not None and (t.dtype != dt or t.device != x0.device):
+            raise ValueError(f"{name} must share dtype and device with x0 ({dt}, {x0.device}); got {t.dtype}, {t.device}")
+    en = _lib.MPC_F64 if dt == torch.float64 else _lib.MPC_F32
     dev = x0.device
     N = int(N)
     ltv = A.dim() == 3
@@ -117,11 +129,11 @@ def solve(A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi, c=None, warm_U=None, ma
             raise ValueError(f"x0 must be (n={n}, batch), got {tuple(x0.shape)}")
         batch = x0.shape[1]
     A, B, x0 = A.contiguous(), B.contiguous(), x0.contiguous()
-    Q, R, Pf = (torch.as_tensor(M, dtype=torch.float64, device=dev).contiguous() for M in (Q, R, Pf))
+    Q, R, Pf = (torch.as_tensor(M, device=dev).to(dt).contiguous() for M in (Q, R, Pf))
     if tuple(Q.shape) != (n, n) or tuple(R.shape) != (m, m) or tuple(Pf.shape) != (n, n):
         raise ValueError("Q, Pf must be (n,n) and R (m,m)")
-    ulo, uhi = _vec(u_lo, m, dev, "u_lo"), _vec(u_hi, m, dev, "u_hi")
-    xlo, xhi = _vec(x_lo, n, dev, "x_lo"), _vec(x_hi, n, dev, "x_hi")
+    ulo, uhi = _vec(u_lo, m, dev, "u_lo", dt), _vec(u_hi, m, dev, "u_hi", dt)
+    xlo, xhi = _vec(x_lo, n, dev, "x_lo", dt), _vec(x_hi, n, dev, "x_hi", dt)
     if bool((ulo > uhi).any()) or bool((xlo > xhi).any()):
         raise ValueError("lower bound above upper bound")
     if warm_U is not None:
@@ -136,9 +148,10 @@ def solve(A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi, c=None, warm_U=None, ma
         if tuple(hg.shape) != (N, nc, batch):
             raise ValueError(f"hg must be {(N, nc, batch)}")
         Cg, hg = Cg.contiguous(), hg.contiguous()
-    w = workspace if workspace is not None else BoxQpWorkspace(batch, n, m, N, dev, nc=nc)
-    if w.shape != (batch, n, m, N) or getattr(w, "nc", 0) != nc:
-        raise ValueError(f"workspace was built for {w.shape} (nc={getattr(w, 'nc', 0)}), need {(batch, n, m, N)} (nc={nc})")
+    w = workspace if workspace is not None else BoxQpWorkspace(batch, n, m, N, dev, nc=nc, dtype=dt)
+    if w.shape != (batch, n, m, N) or getattr(w, "nc", 0) != nc or w.dtype != dt or w.U.device != dev:
+        raise ValueError(f"workspace was built for {w.shape} (nc={getattr(w, 'nc', 0)}, {w.dtype}, {w.U.device}), "
+                         f"need {(batch, n, m, N)} (nc={nc}, {dt}, {dev})")
     if nc:
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().mpc_boxqp_solve_rows(
@@ -146,7 +159,7 @@ def solve(A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi, c=None, warm_U=None, ma
                 _lib.ptr(ulo), _lib.ptr(uhi), _lib.ptr(xlo), _lib.ptr(xhi), _lib.ptr(Cg), _lib.ptr(hg), nc, _lib.ptr(x0),
                 _lib.ptr(warm_U), _lib.ptr(w.U), _lib.ptr(w.X), _lib.ptr(w.cost), _lib.ptr(w.status), _lib.ptr(w.iters),
                 _lib.ptr(w.sat_u), _lib.ptr(w.sat_x), _lib.ptr(w.sat_c), _lib.ptr(w.ws), w.nbytes, batch, n, m, N,
-                int(max_iter), float(eps), _lib.MPC_F64, _lib.stream(dev)))
+                int(max_iter), float(eps), en, _lib.stream(dev)))
         return BoxQpResult(w.U, w.X, w.cost, w.status, w.iters, w.sat_u, w.sat_x, w.sat_c)
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().mpc_boxqp_solve(
@@ -154,7 +167,7 @@ def solve(A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi, c=None, warm_U=None, ma
             _lib.ptr(ulo), _lib.ptr(uhi), _lib.ptr(xlo), _lib.ptr(xhi), _lib.ptr(x0), _lib.ptr(warm_U),
             _lib.ptr(w.U), _lib.ptr(w.X), _lib.ptr(w.cost), _lib.ptr(w.status), _lib.ptr(w.iters),
             _lib.ptr(w.sat_u), _lib.ptr(w.sat_x), _lib.ptr(w.ws), w.nbytes, batch, n, m, N, int(max_iter),
-            float(eps), _lib.MPC_F64, _lib.stream(dev)))
+            float(eps), en, _lib.stream(dev)))
     return BoxQpResult(w.U, w.X, w.cost, w.status, w.iters, w.sat_u, w.sat_x)
 
 

@@ -219,8 +219,8 @@ struct ObstacleParams {
 
 // Linearisation at xbar of the kObsCircles^2 collision constraints: rows C x >= h with
 // C = grad g(xbar), h = r2 - g(xbar) + C xbar  (g_ij(x) = |p + a_i (cos psi, sin psi) - o_j|^2).
-template <typename T>
-MPC_HD void obstacle_rows(const ObstacleParams<T>& ob, const T* xbar, T* Cg, T* hg, int64_t stride) {
+template <typename T, typename TIO>
+MPC_HD void obstacle_rows(const ObstacleParams<T>& ob, const T* xbar, TIO* Cg, TIO* hg, int64_t stride) {
   T sp, cp;
   sincos(xbar[2], &sp, &cp);
 #pragma unroll
@@ -233,13 +233,32 @@ MPC_HD void obstacle_rows(const ObstacleParams<T>& ob, const T* xbar, T* Cg, T* 
       const T c0 = T(2) * dx, c1 = T(2) * dy;
       const T c2 = T(2) * dx * (-ob.a[i] * sp) + T(2) * dy * (ob.a[i] * cp);
       const int row = i * kObsCircles + j;
-      Cg[(int64_t)(row * 4 + 0) * stride] = c0;
-      Cg[(int64_t)(row * 4 + 1) * stride] = c1;
-      Cg[(int64_t)(row * 4 + 2) * stride] = c2;
-      Cg[(int64_t)(row * 4 + 3) * stride] = T(0);
-      hg[(int64_t)row * stride] = ob.r2 - g + c0 * xbar[0] + c1 * xbar[1] + c2 * xbar[2];
+      Cg[(int64_t)(row * 4 + 0) * stride] = (TIO)c0;
+      Cg[(int64_t)(row * 4 + 1) * stride] = (TIO)c1;
+      Cg[(int64_t)(row * 4 + 2) * stride] = (TIO)c2;
+      Cg[(int64_t)(row * 4 + 3) * stride] = TIO(0);
+      hg[(int64_t)row * stride] = (TIO)(ob.r2 - g + c0 * xbar[0] + c1 * xbar[1] + c2 * xbar[2]);
     }
   }
+}
+
+// smallest clearance  min_ij |c_i(x) - o_j|^2 - r2  of a pose (negative = the covering circles overlap)
+template <typename T>
+MPC_HD T obstacle_clearance(const ObstacleParams<T>& ob, const T* x) {
+  T sp, cp;
+  sincos(x[2], &sp, &cp);
+  T best = T(1e300);
+#pragma unroll
+  for (int i = 0; i < kObsCircles; ++i) {
+    const T cx = x[0] + ob.a[i] * cp, cy = x[1] + ob.a[i] * sp;
+#pragma unroll
+    for (int j = 0; j < kObsCircles; ++j) {
+      const T dx = cx - ob.ox[j], dy = cy - ob.oy[j];
+      const T g = dx * dx + dy * dy - ob.r2;
+      best = g < best ? g : best;
+    }
+  }
+  return best;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -249,20 +268,29 @@ MPC_HD void obstacle_rows(const ObstacleParams<T>& ob, const T* xbar, T* Cg, T* 
 //   xbar_{k+1} = f_d(xbar_k, warm[k]);  A_k, B_k its Jacobians;  c_k = xbar_{k+1} - A_k xbar_k - B_k warm[k]
 // Layouts: y [4][batch], Uprev / warm [N][2][batch], A [N][16][batch], B [N][8][batch], c [N][4][batch].
 // Optional: obstacle rows Cg [N][9*4][batch], hg [N][9][batch] linearised at xbar_{k+1} (ob != nullptr).
-template <typename T>
-MPC_HD void rti_prepare_body(const BicycleModel<T>& p, T friction, const T* y, const T* Uprev, int first, T* warm,
-                             T* A, T* B, T* c, int N, int64_t bs, int64_t b, const ObstacleParams<T>* ob = nullptr,
-                             T* Cg = nullptr, T* hg = nullptr, T* pack = nullptr) {
+// T = arithmetic type, TIO = element type of the arrays.
+template <typename T, typename TIO>
+MPC_HD void rti_prepare_body(const BicycleModel<T>& p, T friction, const TIO* y, const TIO* Uprev, int first, TIO* warm,
+                             TIO* A, TIO* B, TIO* c, int N, int64_t bs, int64_t b, const ObstacleParams<T>* ob = nullptr,
+                             TIO* Cg = nullptr, TIO* hg = nullptr, TIO* pack = nullptr) {
   T x[4], xn[4], u[2], Ak[16], Bk[8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) x[i] = y[i * bs + b];
+  for (int i = 0; i < 4; ++i) x[i] = (T)y[i * bs + b];
   for (int k = 0; k < N; ++k) {
     const int ks = first ? k : (k + 1 < N ? k + 1 : N - 1);
-    u[0] = Uprev[((int64_t)ks * 2 + 0) * bs + b];
-    u[1] = Uprev[((int64_t)ks * 2 + 1) * bs + b];
-    warm[((int64_t)k * 2 + 0) * bs + b] = u[0];
-    warm[((int64_t)k * 2 + 1) * bs + b] = u[1];
+    const TIO u0 = Uprev[((int64_t)ks * 2 + 0) * bs + b], u1 = Uprev[((int64_t)ks * 2 + 1) * bs + b];
+    u[0] = (T)u0;
+    u[1] = (T)u1;
+    warm[((int64_t)k * 2 + 0) * bs + b] = u0;
+    warm[((int64_t)k * 2 + 1) * bs + b] = u1;
     bicycle_discretize(p, friction, x, u, xn, Ak, Bk);
+    if constexpr (sizeof(TIO) < sizeof(T)) {
+      // the QP sees the stored (rounded) stage matrices: c must close the linearisation with THOSE
+#pragma unroll
+      for (int i = 0; i < 16; ++i) Ak[i] = (T)(TIO)Ak[i];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) Bk[i] = (T)(TIO)Bk[i];
+    }
     T ck[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -278,18 +306,18 @@ MPC_HD void rti_prepare_body(const BicycleModel<T>& p, T friction, const T* y, c
       const T v[kBicyclePack] = {Ak[2], Ak[3], Ak[6], Ak[7], Ak[11], Ak[15], Bk[1], Bk[3], Bk[5], Bk[6],
                                  ck[0], ck[1], ck[2], ck[3]};
 #pragma unroll
-      for (int i = 0; i < kBicyclePack; ++i) pack[((int64_t)k * kBicyclePack + i) * bs + b] = v[i];
+      for (int i = 0; i < kBicyclePack; ++i) pack[((int64_t)k * kBicyclePack + i) * bs + b] = (TIO)v[i];
     } else {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) A[((int64_t)k * 16 + i) * bs + b] = Ak[i];
+      for (int i = 0; i < 16; ++i) A[((int64_t)k * 16 + i) * bs + b] = (TIO)Ak[i];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) B[((int64_t)k * 8 + i) * bs + b] = Bk[i];
+      for (int i = 0; i < 8; ++i) B[((int64_t)k * 8 + i) * bs + b] = (TIO)Bk[i];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) c[((int64_t)k * 4 + i) * bs + b] = ck[i];
+      for (int i = 0; i < 4; ++i) c[((int64_t)k * 4 + i) * bs + b] = (TIO)ck[i];
     }
     if (ob) {
       constexpr int R = kObsCircles * kObsCircles;
-      obstacle_rows<T>(*ob, xn, Cg + (int64_t)k * R * 4 * bs + b, hg + (int64_t)k * R * bs + b, bs);
+      obstacle_rows<T, TIO>(*ob, xn, Cg + (int64_t)k * R * 4 * bs + b, hg + (int64_t)k * R * bs + b, bs);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) x[i] = xn[i];
@@ -297,86 +325,116 @@ MPC_HD void rti_prepare_body(const BicycleModel<T>& p, T friction, const T* y, c
 }
 
 // ---------------------------------------------------------------------------------------------
-// Closed loop (session4_sol.py:443-465 with the RTI controller): per control step
-//   prepare -> LTV box QP (K4) -> apply u_0 -> plant step, with running summaries.
-template <typename T>
+// Closed loop (session4_sol.py:443-465 / main.py:241-271 with the RTI controller): per control step
+//   sqp_iters x (prepare -> LTV QP (K4)) -> apply u_0 -> plant step, with running summaries.
+// sqp_iters = 1 is the real-time iteration (one linearised QP per control step, warm-started by the shifted plan);
+// sqp_iters > 1 re-linearises at the new plan and solves again (full-step SQP towards the converged NLP solution the
+// reference's IPOPT call returns, session4_sol.py:126-130); a round whose plan moves by <= sqp_tol ends the step.
+template <typename T, typename TIO>
 struct RtiLoopArgs {
   BicycleModel<T> model;    // prediction model (friction_model below)
   T friction_model;
-  const T* friction_plant;  // [batch] per-scenario plant friction
-  int plant_substeps;       // 0: Euler plant; > 0: RK4 sub-steps
+  BicycleModel<T> plant;    // plant: its own axle distances and acceleration gain (ts shared)
+  const TIO* friction_plant;  // [batch] per-scenario plant friction
+  int plant_substeps;       // 0: Euler plant; > 0: RK4 sub-steps; < 0: adaptive Dormand-Prince, tol = 10^substeps
   int steps;
-  const T* x0;              // [4][batch]
-  T* xcur;                  // [4][batch] scratch: measured state of the current step
-  T* Acur;                  // [N][16][batch] scratch
-  T* Bcur;                  // [N][8][batch]
-  T* ccur;                  // [N][4][batch]
-  T* warm;                  // [N][2][batch]
-  T* X_cl;                  // [steps+1][4][batch]
-  T* U_cl;                  // [steps][2][batch]
-  T* cost_cl;               // [batch] sum_t x_t'Q x_t + u_t'R u_t
-  T* viol_cl;               // [batch] max state-bound violation of the closed-loop trajectory
+  int sqp_iters;
+  T sqp_tol;
+  int has_obstacle;
+  ObstacleParams<T> ob;
+  const TIO* x0;            // [4][batch]
+  TIO* xcur;                // [4][batch] scratch: measured state of the current step
+  TIO* Acur;                // [N][16][batch] scratch (packed: [N][14][batch])
+  TIO* Bcur;                // [N][8][batch]
+  TIO* ccur;                // [N][4][batch]
+  TIO* warm;                // [N][2][batch]
+  TIO* Cgcur;               // [N][36][batch] (obstacle rows)
+  TIO* hgcur;               // [N][9][batch]
+  TIO* X_cl;                // [steps+1][4][batch]
+  TIO* U_cl;                // [steps][2][batch]
+  TIO* cost_cl;             // [batch] sum_t x_t'Q x_t + u_t'R u_t
+  TIO* viol_cl;             // [batch] max state-bound violation of the closed-loop trajectory
+  TIO* clear_cl;            // optional [batch] smallest obstacle clearance |c_i - o_j|^2 - r2 along the closed loop
   int32_t* n_sat;           // [batch] number of applied inputs on a bound
-  int32_t* n_fail;          // [batch] number of steps whose QP did not reach MPC_SOLVED
+  int32_t* n_fail;          // [batch] number of QPs that did not reach MPC_SOLVED
   int32_t* iters_total;     // [batch]
-  T* X_bundle;              // optional [steps][N+1][4][batch]: the state prediction of every control step
-  T* U_bundle;              // optional [steps][N][2][batch]: the input plan of every control step
-  BoxQpArgs<T> qp;          // ltv = 1; A/B/c = Acur/Bcur/ccur; x0 = xcur; warm_U = warm;
+  TIO* X_bundle;            // optional [steps][N+1][4][batch]: the state prediction of every control step
+  TIO* U_bundle;            // optional [steps][N][2][batch]: the input plan of every control step
+  BoxQpArgs<TIO> qp;        // ltv = 1; A/B/c = Acur/Bcur/ccur; x0 = xcur; warm_U = warm; Cg/hg = Cgcur/hgcur
                             // U = plan buffer: initial plan on entry (zeros = cold start), last plan on exit
 };
 
 // PACKED = the prediction model is forward Euler: stage matrices in the packed 14-value form (a.Acur holds them).
-template <typename T, bool PACKED>
-MPC_HD void rti_closed_loop_body(const RtiLoopArgs<T>& a, const T* sh, int64_t b) {
+// NC = 0 (box constraints) or 9 (obstacle rows).
+template <typename T, typename TIO, bool PACKED, int NC, class ST>
+MPC_HD void rti_closed_loop_body(const RtiLoopArgs<T, TIO>& a, const T* sh, int64_t b) {
   using SH = BoxQpShared<4, 2>;
   const int64_t bs = a.qp.batch;
   const int N = a.qp.N;
   T x[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    x[i] = a.x0[i * bs + b];
-    a.X_cl[i * bs + b] = x[i];
+    x[i] = (T)a.x0[i * bs + b];
+    a.X_cl[i * bs + b] = (TIO)x[i];
   }
-  const T fr_plant = a.friction_plant[b];
-  T cost = T(0), viol = T(0);
+  const T fr_plant = (T)a.friction_plant[b];
+  T cost = T(0), viol = T(0), clear = T(1e300);
   int nsat = 0, nfail = 0, itsum = 0;
   for (int t = 0; t < a.steps; ++t) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) a.xcur[i * bs + b] = x[i];
-    rti_prepare_body<T>(a.model, a.friction_model, a.xcur, a.qp.U, t == 0 ? 1 : 0, a.warm, a.Acur, a.Bcur, a.ccur, N,
-                        bs, b, nullptr, nullptr, nullptr, PACKED ? a.Acur : nullptr);
-    BoxQpIpm<T, 4, 2, 0, PACKED ? 1 : 0> ipm(a.qp, sh, b);
-    ipm.solve();
+    for (int i = 0; i < 4; ++i) a.xcur[i * bs + b] = (TIO)x[i];
+    for (int round = 0; round < a.sqp_iters; ++round) {
+      rti_prepare_body<T, TIO>(a.model, a.friction_model, a.xcur, a.qp.U, (t == 0 || round > 0) ? 1 : 0, a.warm, a.Acur,
+                               a.Bcur, a.ccur, N, bs, b, NC > 0 ? &a.ob : nullptr, a.Cgcur, a.hgcur,
+                               PACKED ? a.Acur : nullptr);
+      BoxQpIpm<T, TIO, 4, 2, NC, PACKED ? 1 : 0, ST> ipm(a.qp, sh, b, b, bs);
+      ipm.solve();
+      if (a.qp.status[b] != MPC_SOLVED) ++nfail;
+      itsum += a.qp.iters[b];
+      if (round + 1 < a.sqp_iters && a.sqp_tol > T(0)) {
+        T du = T(0), un = T(1);
+        for (int i = 0; i < N * 2; ++i) {
+          const T v = (T)a.qp.U[(int64_t)i * bs + b], w = (T)a.warm[(int64_t)i * bs + b];
+          const T d = v > w ? v - w : w - v, av = v < T(0) ? -v : v;
+          du = d > du ? d : du;
+          un = av > un ? av : un;
+        }
+        if (du <= a.sqp_tol * un) break;
+      }
+    }
     if (a.X_bundle) {
-      T* dst = a.X_bundle + (int64_t)t * (N + 1) * 4 * bs;
+      TIO* dst = a.X_bundle + (int64_t)t * (N + 1) * 4 * bs;
       for (int i = 0; i < (N + 1) * 4; ++i) dst[(int64_t)i * bs + b] = a.qp.X[(int64_t)i * bs + b];
     }
     if (a.U_bundle) {
-      T* dst = a.U_bundle + (int64_t)t * N * 2 * bs;
+      TIO* dst = a.U_bundle + (int64_t)t * N * 2 * bs;
       for (int i = 0; i < N * 2; ++i) dst[(int64_t)i * bs + b] = a.qp.U[(int64_t)i * bs + b];
     }
     T u[2];
-    u[0] = a.qp.U[(int64_t)0 * bs + b];
-    u[1] = a.qp.U[(int64_t)1 * bs + b];
-    if (a.qp.status[b] != MPC_SOLVED) ++nfail;
-    itsum += a.qp.iters[b];
+    u[0] = (T)a.qp.U[(int64_t)0 * bs + b];
+    u[1] = (T)a.qp.U[(int64_t)1 * bs + b];
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-      if (u[j] == sh[SH::oLo + j] || u[j] == sh[SH::oHi + j]) ++nsat;
-      a.U_cl[((int64_t)t * 2 + j) * bs + b] = u[j];
+      if (u[j] == (T)(TIO)sh[SH::oLo + j] || u[j] == (T)(TIO)sh[SH::oHi + j]) ++nsat;
+      a.U_cl[((int64_t)t * 2 + j) * bs + b] = (TIO)u[j];
     }
     cost += quad<T, 4>(sh + SH::oQ, x) + quad<T, 2>(sh + SH::oR, u);
-    bicycle_plant<T>(a.model, fr_plant, a.plant_substeps, x, u);
+    bicycle_plant<T>(a.plant, fr_plant, a.plant_substeps, x, u);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      a.X_cl[((int64_t)(t + 1) * 4 + i) * bs + b] = x[i];
+      a.X_cl[((int64_t)(t + 1) * 4 + i) * bs + b] = (TIO)x[i];
       const T lo = sh[SH::oLo + 2 + i], hi = sh[SH::oHi + 2 + i];
       const T v = (lo - x[i]) > (x[i] - hi) ? (lo - x[i]) : (x[i] - hi);
       viol = v > viol ? v : viol;
     }
+    if constexpr (NC > 0) {
+      const T g = obstacle_clearance<T>(a.ob, x);
+      clear = g < clear ? g : clear;
+    }
   }
-  a.cost_cl[b] = cost;
-  a.viol_cl[b] = viol;
+  a.cost_cl[b] = (TIO)cost;
+  a.viol_cl[b] = (TIO)viol;
+  if (a.clear_cl) a.clear_cl[b] = (TIO)(NC > 0 ? clear : T(0));
   a.n_sat[b] = nsat;
   a.n_fail[b] = nfail;
   a.iters_total[b] = itsum;

@@ -593,7 +593,7 @@ __global__ void __launch_bounds__(kCoopWarps * 32, MINB) boxqp_ipm_coop_kernel(B
   const int slot = blockIdx.x * kCoopWarps + warp;
   if (slot >= nslots) return;
   double* wsm = sh + L::shared_total + warp * L::warp_total;
-  double* ws_slot = a.ws + (int64_t)slot * L::slot_elems(a.N);
+  double* ws_slot = static_cast<double*>(a.ws) + (int64_t)slot * L::slot_elems(a.N);
   CoopIpm<NX, NU> ipm(a, sh, wsm, ws_slot, lane);
   for (int64_t b = slot; b < a.batch; b += nslots) ipm.solve(b);
 }

@@ -10,18 +10,34 @@
 // Method: Mehrotra predictor-corrector interior point.  With z_k = (u_k, x_{k+1}), slacks s and
 // multipliers lam for every finite bound, each Newton system (residual form, unknown dz)
 //     dz = argmin 1/2 dz'(H + Sigma) dz - rhs'dz   s.t. dx_{k+1} = A_k dx_k + B_k du_k, dx_0 = 0
-//     Sigma = lam_l/s_l + lam_u/s_u,   rhs = -H z + (sig mu - cc_l)/s_l - Sigma_l r_l - (sig mu - cc_u)/s_u + Sigma_u r_u
+//     Sigma = lam_l/s_l + lam_u/s_u,   rhs = -H z + (tau - cc_l)/s_l - Sigma_l r_l - (tau - cc_u)/s_u + Sigma_u r_u
 // is an unconstrained LQ problem with stage-varying diagonal weight updates, solved by one
-// backward Riccati sweep (factorisation + feed-forward) and one forward rollout; the corrector
-// reuses the stored gains.  The iterate z always satisfies the dynamics exactly (it starts from a
-// rollout and moves along dynamics-consistent directions).  In residual form every term of rhs
-// stays O(lam), so the rounding error of the huge barrier weights (Sigma ~ 1e12) scales with |dz|
+// backward Riccati sweep (factorisation + feed-forward) and one forward rollout.  The iterate z always satisfies
+// the dynamics exactly (it starts from a rollout and moves along dynamics-consistent directions).  In residual form
+// every term of rhs stays O(lam), so the rounding error of the huge barrier weights (Sigma ~ 1e12) scales with |dz|
 // and vanishes at the solution.  A first-order (projected-gradient / ADMM) iteration was evaluated in
 // oracle/boxqp.py (admm_riccati): 600-2000+ iterations for 1e-6 parity on the session-2 data versus
-// ~15 here, so the interior-point iteration is the one that ships.
+// ~11 here, so the interior-point iteration is the one that ships.
 //
 // One thread per scenario.  All per-scenario state lives in a caller-provided workspace laid out
-// [stage][element][batch] (batch-contiguous), so every access of a warp is one coalesced row.
+// [stage][element][lane] (lane-contiguous), so every access of a warp is one coalesced row.  The kernel is bound by
+// the bytes of that workspace it streams per iteration and by the instructions of its per-bound algebra, so one
+// interior-point iteration is organised in FOUR sweeps that touch as little of it as possible (round 1 had five,
+// each reading the whole iterate):
+//   A  backward  apply the previous iteration's step to the iterate (fused: no separate update pass), factorise
+//                (Joseph-form Riccati), feed-forward of the AFFINE right-hand side          -> K, S^-1, d_aff
+//   B  forward   affine direction dz_aff by rollout; per bound the affine step ratio and the second-order term cc;
+//                stores dz_aff and, per element, e = 1/s_l - 1/s_u and g = cc_l/s_l - cc_u/s_u
+//   C  backward  the Newton system is linear in its right-hand side and the corrector's differs from the
+//                predictor's by  tau e - g  only: feed-forward of THAT difference with the stored gains.  Reads e, g,
+//                K, S^-1 -- not the iterate                                                   -> d_aff + d_cor
+//   D  forward   dz by rollout with d_aff + d_cor; per bound ds, dlam, the step ratio and the sums that give the new
+//                barrier parameter; stores dz.  The step itself is applied by the next iteration's sweep A (or by
+//                the output pass after the last iteration).
+// Storage precision is a template policy (BoxQpStore): the float64 product keeps z, the gains and the corrector data
+// and the step dz in float64 and the slacks, multipliers and dz_aff in float32 (relative quantities: they enter through
+// ratios/products only, and every sweep reads the SAME rounded value, so the Newton system stays consistent); the
+// float32 product stores everything in float32.  All arithmetic is float64 in both.
 // The body is __host__ __device__: tests/harness runs it on the CPU against oracle/boxqp.py.
 #pragma once
 
@@ -31,41 +47,73 @@ namespace mpc {
 
 constexpr double kBigBound = 1e19;  // |bound| >= kBigBound means "no bound"
 
-template <typename T>
+// TIO = element type of the caller's arrays (double for MPC_F64, float for MPC_F32)
+template <typename TIO>
 struct BoxQpArgs {
-  const T *A, *B, *c;  // ltv == 0: shared A [n][n], B [n][m], c null
-                       // ltv == 1: A [N][n*n][batch], B [N][n*m][batch], c [N][n][batch]
+  const TIO *A, *B, *c;  // ltv == 0: shared A [n][n], B [n][m], c null
+                         // ltv == 1: A [N][n*n][batch], B [N][n*m][batch], c [N][n][batch]
   int ltv;
-  const T *Q, *R, *Pf;                  // shared
-  const T *u_lo, *u_hi, *x_lo, *x_hi;   // shared [m], [m], [n], [n]
-  const T* x0;                          // [n][batch]
-  const T* warm_U;                      // optional [N][m][batch]
-  T* U;                                 // [N][m][batch]
-  T* X;                                 // [N+1][n][batch]
-  T* cost;                              // [batch]
-  int32_t* status;                      // [batch]
-  int32_t* iters;                       // [batch]
-  int8_t* sat_u;                        // optional [N][m][batch]: -1 lower, +1 upper, 0 free
-  int8_t* sat_x;                        // optional [N][n][batch]
+  const TIO *Q, *R, *Pf;                  // shared
+  const TIO *u_lo, *u_hi, *x_lo, *x_hi;   // shared [m], [m], [n], [n]
+  const TIO* x0;                          // [n][batch]
+  const TIO* warm_U;                      // optional [N][m][batch]
+  TIO* U;                                 // [N][m][batch]
+  TIO* X;                                 // [N+1][n][batch]
+  TIO* cost;                              // [batch]
+  int32_t* status;                        // [batch]
+  int32_t* iters;                         // [batch]
+  int8_t* sat_u;                          // optional [N][m][batch]: -1 lower, +1 upper, 0 free
+  int8_t* sat_x;                          // optional [N][n][batch]
   // optional general stage rows  Cg_k x_{k+1} >= hg_k  (kernels instantiated with NC > 0 only):
-  const T* Cg;                          // [N][NC*n][batch]
-  const T* hg;                          // [N][NC][batch]
-  int8_t* sat_c;                        // optional [N][NC][batch]: -1 = row active
-  T* ws;                                // workspace, boxqp_ws_elems(n, m, N, nc) * batch elements
+  const TIO* Cg;                          // [N][NC*n][batch]
+  const TIO* hg;                          // [N][NC][batch]
+  int8_t* sat_c;                          // optional [N][NC][batch]: -1 = row active
+  void* ws;                               // workspace, boxqp_ws_bytes<ST>(n, m, N, nc, lanes) bytes
   int64_t batch;
   int N;
   int max_iter;
-  T eps;
-  int pf_dist = 0;  // stages of L2 prefetch ahead of each sweep's loads (device only; 0 = off)
+  double eps;
+  int pf_dist = 0;       // stages of L2 prefetch ahead of each sweep's loads (device only; 0 = off)
+  int64_t ws_lanes = 0;  // lanes of the workspace (0 = one per scenario: lane b = scenario b)
 };
 
-// workspace elements per scenario
-inline int64_t boxqp_ws_elems(int n, int m, int N, int nc = 0) {
-  const int d = n + m;
-  return (int64_t)N * (7 * d + m * n + m * m + m + 3 * nc);
+// ---- storage policy: element types of the workspace sections
+template <typename TZ, typename TSL, typename TDA, typename TDZ, typename TEG, typename TGN>
+struct BoxQpStore {
+  using Z = TZ;    // iterate z; carried residuals of general rows
+  using SL = TSL;  // slacks and multipliers
+  using DA = TDA;  // dz_aff (enters the second-order term only)
+  using DZ = TDZ;  // dz (the step the iterate takes: float64 keeps z on the dynamics to float64 accuracy)
+  using EG = TEG;  // corrector right-hand-side ingredients e, g
+  using GN = TGN;  // gains K, S^-1, feed-forward d
+};
+using StoreF64 = BoxQpStore<double, double, double, double, double, double>;  // everything float64
+using StoreMix = BoxQpStore<double, float, float, double, double, double>;    // float64 product
+using StoreF32 = BoxQpStore<float, float, float, float, float, float>;        // float32 product
+
+inline int64_t ws_round16(int64_t bytes) { return (bytes + 15) / 16 * 16; }
+
+// workspace bytes for `lanes` resident scenarios
+template <class ST>
+inline int64_t boxqp_ws_bytes(int n, int m, int N, int nc, int64_t lanes) {
+  const int64_t d = n + m, per = (int64_t)N * lanes;
+  int64_t t = 0;
+  t += ws_round16(per * d * (int64_t)sizeof(typename ST::Z));
+  t += 4 * ws_round16(per * d * (int64_t)sizeof(typename ST::SL));
+  t += ws_round16(per * d * (int64_t)sizeof(typename ST::DA));
+  t += ws_round16(per * d * (int64_t)sizeof(typename ST::DZ));
+  t += 2 * ws_round16(per * d * (int64_t)sizeof(typename ST::EG));
+  t += ws_round16(per * m * n * (int64_t)sizeof(typename ST::GN));
+  t += ws_round16(per * m * m * (int64_t)sizeof(typename ST::GN));
+  t += ws_round16(per * m * (int64_t)sizeof(typename ST::GN));
+  if (nc > 0) {
+    t += 2 * ws_round16(per * nc * (int64_t)sizeof(typename ST::SL));
+    t += ws_round16(per * nc * (int64_t)sizeof(typename ST::Z));
+  }
+  return t;
 }
 
-// shared-parameter block (shared memory on the device)
+// shared-parameter block (shared memory on the device), always in the compute type
 template <int NX, int NU>
 struct BoxQpShared {
   static constexpr int D = NX + NU;
@@ -79,6 +127,21 @@ struct BoxQpShared {
   static constexpr int total = oHi + D;
 };
 
+// fill the shared block from the caller's arrays; element i by the calling thread (host: loop over i)
+template <typename T, typename TIO, int NX, int NU>
+MPC_HD T boxqp_shared_elem(const BoxQpArgs<TIO>& a, int i) {
+  using SH = BoxQpShared<NX, NU>;
+  if (i < SH::oB) return a.ltv ? T(0) : T(a.A[i - SH::oA]);
+  if (i < SH::oQ) return a.ltv ? T(0) : T(a.B[i - SH::oB]);
+  if (i < SH::oR) return T(a.Q[i - SH::oQ]);
+  if (i < SH::oPf) return T(a.R[i - SH::oR]);
+  if (i < SH::oLo) return T(a.Pf[i - SH::oPf]);
+  if (i < SH::oLo + NU) return T(a.u_lo[i - SH::oLo]);
+  if (i < SH::oHi) return T(a.x_lo[i - SH::oLo - NU]);
+  if (i < SH::oHi + NU) return T(a.u_hi[i - SH::oHi]);
+  return T(a.x_hi[i - SH::oHi - NU]);
+}
+
 // MODEL = 0: generic dense model (shared LTI, or per-scenario LTV A [N][n*n][batch], B, c).
 // MODEL = 1: forward-Euler kinematic bicycle (NX = 4, NU = 2), per-scenario LTV in PACKED form: only the 10 entries of
 //            A = I + ts J_x and B = ts J_u that are not structurally 0 or 1, plus c: a.A -> [N][14][batch]
@@ -86,39 +149,67 @@ struct BoxQpShared {
 //            as literals, so the unrolled register algebra drops the corresponding multiplications at compile time.
 constexpr int kBicyclePack = 14;
 
-template <typename T, int NX, int NU, int NC = 0, int MODEL = 0>
+template <typename S, typename T>
+MPC_HD T round_to(T v) {   // the value a later sweep will read back from a section stored as S
+  return (T)(S)v;
+}
+
+template <typename T, typename TIO, int NX, int NU, int NC = 0, int MODEL = 0, class ST = StoreMix>
 struct BoxQpIpm {
   static constexpr int D = NX + NU;
-  // Loads of a stage visit are hidden by resident warps plus an L2 prefetch of the rows a few visits ahead (pf_stage).
-  // Double-buffering the next stage in REGISTERS (an earlier version, for n + m <= 3) cost more than it hid: 168
-  // registers with 245 M local-memory sectors of spill traffic per 65 536 solves (ncu); without it the (2,1) kernel
-  // has no spills at 152 registers and runs 1.2x faster at 4 CTAs/SM.
   using SH = BoxQpShared<NX, NU>;
+  using TZ = typename ST::Z;
+  using TSL = typename ST::SL;
+  using TDA = typename ST::DA;
+  using TDZ = typename ST::DZ;
+  using TEG = typename ST::EG;
+  using TGN = typename ST::GN;
+  static constexpr bool kNarrowSL = sizeof(TSL) < sizeof(T);
+  static constexpr bool kNarrowZ = sizeof(TZ) < sizeof(T);
+  static constexpr bool kNarrowDir = sizeof(TDZ) < sizeof(T);
 
-  const BoxQpArgs<T>& a;
+  const BoxQpArgs<TIO>& a;
   const T* sh;
-  int64_t b, bs;
-  T mu_scale;  // max(1, max|Q|, max|R|): scale of the complementarity tolerance
-  T mu0;       // start value of the barrier parameter, per scenario: max(mu_scale, |H z0|_inf)
-  // workspace sections, each [N][per][batch]
-  T *z, *sl, *su, *ll, *lu, *dza, *dzw, *Kw, *Sw, *dw, *sc, *lc, *rc;  // general rows: slack, multiplier, residual C x - h - s
+  int64_t b, bs;    // scenario and batch stride of the caller's arrays
+  int64_t wb, wbs;  // workspace lane and lane stride
+  T mu_scale;       // max(1, max|Q|, max|R|): scale of the complementarity tolerance
+  T mu0;            // start value of the barrier parameter, per scenario: max(mu_scale, |H z0|_inf)
+  // workspace sections, each [N][per][lanes]
+  TZ* z;
+  TSL *sl, *su, *ll, *lu;
+  TDA* dza;
+  TDZ* dzw;
+  TEG *ew, *gw;
+  TGN *Kw, *Sw, *dw;
+  TSL *sc, *lc;  // general rows: slack, multiplier
+  TZ* rc;        // general rows: residual C x - h - s (carried, see init)
 
-  MPC_HD BoxQpIpm(const BoxQpArgs<T>& args, const T* shared, int64_t scenario)
-      : a(args), sh(shared), b(scenario), bs(args.batch) {
-    const int64_t sec = (int64_t)a.N * D * bs;
-    z = a.ws;
-    sl = z + sec;
-    su = sl + sec;
-    ll = su + sec;
-    lu = ll + sec;
-    dza = lu + sec;   // affine (predictor) direction dz_aff
-    dzw = dza + sec;  // corrector direction dz
-    Kw = dzw + sec;
-    Sw = Kw + (int64_t)a.N * NU * NX * bs;
-    dw = Sw + (int64_t)a.N * NU * NU * bs;
-    sc = dw + (int64_t)a.N * NU * bs;
-    lc = sc + (int64_t)a.N * NC * bs;
-    rc = lc + (int64_t)a.N * NC * bs;
+  template <typename S>
+  MPC_HD static S* take(char*& p, int64_t elems) {
+    S* r = reinterpret_cast<S*>(p);
+    p += (elems * (int64_t)sizeof(S) + 15) / 16 * 16;
+    return r;
+  }
+
+  MPC_HD BoxQpIpm(const BoxQpArgs<TIO>& args, const T* shared, int64_t scenario, int64_t lane, int64_t lanes)
+      : a(args), sh(shared), b(scenario), bs(args.batch), wb(lane), wbs(lanes) {
+    char* p = static_cast<char*>(a.ws);
+    const int64_t per = (int64_t)a.N * wbs;
+    z = take<TZ>(p, per * D);
+    sl = take<TSL>(p, per * D);
+    su = take<TSL>(p, per * D);
+    ll = take<TSL>(p, per * D);
+    lu = take<TSL>(p, per * D);
+    dza = take<TDA>(p, per * D);
+    dzw = take<TDZ>(p, per * D);
+    ew = take<TEG>(p, per * D);
+    gw = take<TEG>(p, per * D);
+    Kw = take<TGN>(p, per * NU * NX);
+    Sw = take<TGN>(p, per * NU * NU);
+    dw = take<TGN>(p, per * NU);
+    sc = take<TSL>(p, per * NC);
+    lc = take<TSL>(p, per * NC);
+    rc = take<TZ>(p, per * NC);
     mu_scale = T(1);
     for (int i = 0; i < NX * NX; ++i) {
       const T v = sh[SH::oQ + i] < T(0) ? -sh[SH::oQ + i] : sh[SH::oQ + i];
@@ -131,11 +222,14 @@ struct BoxQpIpm {
     mu0 = mu_scale;
   }
 
-  MPC_HD int64_t ix(int k, int i, int per) const { return ((int64_t)k * per + i) * bs + b; }
+  MPC_HD int64_t ix(int k, int i, int per) const { return ((int64_t)k * per + i) * bs + b; }     // caller's arrays
+  MPC_HD int64_t wx(int k, int i, int per) const { return ((int64_t)k * per + i) * wbs + wb; }   // workspace
   MPC_HD bool hasl(int i) const { return sh[SH::oLo + i] > T(-kBigBound); }
   MPC_HD bool hasu(int i) const { return sh[SH::oHi + i] < T(kBigBound); }
   MPC_HD T lo(int i) const { return sh[SH::oLo + i]; }
   MPC_HD T hi(int i) const { return sh[SH::oHi + i]; }
+  MPC_HD static T abs_(T v) { return v < T(0) ? -v : v; }
+  MPC_HD static T max_(T x, T y) { return x > y ? x : y; }
 
   // ---- one stage's iterate.  All loads are unconditional and issued together (entries without a
   // bound hold s = 1, lam = 0), so a stage visit costs one memory round trip instead of a chain.
@@ -145,85 +239,108 @@ struct BoxQpIpm {
   MPC_HD void load(int k, Stage& s) const {
 #pragma unroll
     for (int i = 0; i < D; ++i) {
-      const int64_t o = ix(k, i, D);
-      s.z[i] = z[o];
-      s.sl[i] = sl[o];
-      s.su[i] = su[o];
-      s.ll[i] = ll[o];
-      s.lu[i] = lu[o];
+      const int64_t o = wx(k, i, D);
+      s.z[i] = (T)z[o];
+      s.sl[i] = (T)sl[o];
+      s.su[i] = (T)su[o];
+      s.ll[i] = (T)ll[o];
+      s.lu[i] = (T)lu[o];
     }
   }
-  // ---- L2 prefetch of the rows a later stage visit will load.  The workspace is streamed from HBM once per pass
+  MPC_HD void store_stage(int k, const Stage& s) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      const int64_t o = wx(k, i, D);
+      z[o] = (TZ)s.z[i];
+      sl[o] = (TSL)s.sl[i];
+      su[o] = (TSL)s.su[i];
+      ll[o] = (TSL)s.ll[i];
+      lu[o] = (TSL)s.lu[i];
+    }
+  }
+  // the values the next sweeps will read back (identity for float64 storage)
+  MPC_HD static void round_stage(Stage& s) {
+    if constexpr (kNarrowZ || kNarrowSL) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        s.z[i] = round_to<TZ>(s.z[i]);
+        s.sl[i] = round_to<TSL>(s.sl[i]);
+        s.su[i] = round_to<TSL>(s.su[i]);
+        s.ll[i] = round_to<TSL>(s.ll[i]);
+        s.lu[i] = round_to<TSL>(s.lu[i]);
+      }
+    }
+  }
+
+  // ---- L2 prefetch of the rows a later stage visit will load.  The workspace is streamed from HBM once per sweep
   // (it is far larger than L2); a `prefetch.global.L2` per row, issued pf_dist stage visits early, turns the
   // ~1 us DRAM round trip of those loads into an L2 hit without holding registers for the data in flight.  It pays
-  // while a kernel is latency-bound (the (2,1) kernel: pf_dist = 2) and costs once it is bandwidth-bound, because lines
-  // evicted before use are fetched twice (the (4,2) kernels and the fused RTI loop: pf_dist = 0); the launchers decide.
-  MPC_HD static void pf(const T* p) {
+  // while a kernel is latency-bound and costs once it is bandwidth-bound, because lines evicted before use are
+  // fetched twice; the launchers decide (pf_dist = 0: off).
+  template <typename S>
+  MPC_HD static void pf(const S* p) {
 #ifdef __CUDA_ARCH__
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 #else
     (void)p;
 #endif
   }
-  template <int PER>
-  MPC_HD void pf_rows(const T* base, int k) const {
+  template <int PER, typename S>
+  MPC_HD void pf_rows(const S* base, int k) const {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) pf(base + wx(k, i, PER));
+  }
+  template <int PER, typename S>
+  MPC_HD void pf_rows_io(const S* base, int k) const {
 #pragma unroll
     for (int i = 0; i < PER; ++i) pf(base + ix(k, i, PER));
   }
-  // rows every pass reads: the iterate of stage k (+ the per-scenario model)
-  MPC_HD void pf_stage(int k) const {
-#ifdef __CUDA_ARCH__
-    if constexpr (NC > 0) return;     // general rows: measured 6.1e5 QPs/s with, 6.2-6.9e5 without (obstacle workload)
-    if (a.pf_dist <= 0 || k < 0 || k >= a.N) return;
+  MPC_HD void pf_iterate(int k) const {
     pf_rows<D>(z, k);
     pf_rows<D>(sl, k);
     pf_rows<D>(su, k);
     pf_rows<D>(ll, k);
     pf_rows<D>(lu, k);
+  }
+  MPC_HD void pf_model(int k) const {
     if constexpr (MODEL == 1) {
-      pf_rows<kBicyclePack>(a.A, k);
+      pf_rows_io<kBicyclePack>(a.A, k);
     } else if (a.ltv) {
-      pf_rows<NX * NX>(a.A, k);
-      pf_rows<NX * NU>(a.B, k);
-      pf_rows<NX>(a.c, k);
+      pf_rows_io<NX * NX>(a.A, k);
+      pf_rows_io<NX * NU>(a.B, k);
     }
+  }
+  MPC_HD bool pf_on(int k) const {
+#ifdef __CUDA_ARCH__
+    if constexpr (NC > 0) return false;
+    return a.pf_dist > 0 && k >= 0 && k < a.N;
 #else
     (void)k;
-#endif
-  }
-  MPC_HD void pf_extra(int k, bool gains, bool sinv, bool ff, bool aff, bool dir) const {
-#ifdef __CUDA_ARCH__
-    if constexpr (NC > 0) return;
-    if (a.pf_dist <= 0 || k < 0 || k >= a.N) return;
-    if (gains) pf_rows<NU * NX>(Kw, k);
-    if (sinv) pf_rows<NU * NU>(Sw, k);
-    if (ff) pf_rows<NU>(dw, k);
-    if (aff) pf_rows<D>(dza, k);
-    if (dir) pf_rows<D>(dzw, k);
-#else
-    (void)k; (void)gains; (void)sinv; (void)ff; (void)aff; (void)dir;
+    return false;
 #endif
   }
 
-  MPC_HD void load_vec(const T* base, int k, int per, T* v) const {
-    for (int i = 0; i < per; ++i) v[i] = base[ix(k, i, per)];
+  template <int PER, typename S>
+  MPC_HD void loadn(const S* base, int k, T* v) const {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) v[i] = (T)base[wx(k, i, PER)];
+  }
+  template <int PER, typename S>
+  MPC_HD void storen(S* base, int k, const T* v) const {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) base[wx(k, i, PER)] = (S)v[i];
   }
   template <int PER>
-  MPC_HD void loadn(const T* base, int k, T* v) const {
+  MPC_HD void loadn_io(const TIO* base, int k, T* v) const {
 #pragma unroll
-    for (int i = 0; i < PER; ++i) v[i] = base[ix(k, i, PER)];
-  }
-  template <int PER>
-  MPC_HD void storen(T* base, int k, const T* v) const {
-#pragma unroll
-    for (int i = 0; i < PER; ++i) base[ix(k, i, PER)] = v[i];
+    for (int i = 0; i < PER; ++i) v[i] = (T)base[ix(k, i, PER)];
   }
 
   // general row j of stage k: coefficients C[NX] and right-hand side h
   MPC_HD T load_row_c(int k, int j, T* C) const {
 #pragma unroll
-    for (int i = 0; i < NX; ++i) C[i] = a.Cg[ix(k, j * NX + i, NC * NX)];
-    return a.hg[ix(k, j, NC)];
+    for (int i = 0; i < NX; ++i) C[i] = (T)a.Cg[ix(k, j * NX + i, NC * NX)];
+    return (T)a.hg[ix(k, j, NC)];
   }
   MPC_HD static T dotx(const T* C, const T* x) {
     T acc = T(0);
@@ -236,7 +353,7 @@ struct BoxQpIpm {
     if constexpr (MODEL == 1) {
       static_assert(MODEL == 0 || (NX == 4 && NU == 2), "packed bicycle model is 4 x 2");
       T v[kBicyclePack];
-      loadn<kBicyclePack>(a.A, k, v);
+      loadn_io<kBicyclePack>(a.A, k, v);
 #pragma unroll
       for (int i = 0; i < NX * NX; ++i) A[i] = T(0);
 #pragma unroll
@@ -259,9 +376,9 @@ struct BoxQpIpm {
       return;
     }
     if (a.ltv) {
-      loadn<NX * NX>(a.A, k, A);
-      loadn<NX * NU>(a.B, k, B);
-      loadn<NX>(a.c, k, c);
+      loadn_io<NX * NX>(a.A, k, A);
+      loadn_io<NX * NU>(a.B, k, B);
+      loadn_io<NX>(a.c, k, c);
     } else {
 #pragma unroll
       for (int i = 0; i < NX * NX; ++i) A[i] = sh[SH::oA + i];
@@ -288,12 +405,12 @@ struct BoxQpIpm {
     for (int pass = 0; pass < 2; ++pass) {
       T x[NX], xn[NX], u[NU], A[NX * NX], B[NX * NU], c[NX];
 #pragma unroll
-      for (int i = 0; i < NX; ++i) x[i] = a.x0[i * bs + b];
+      for (int i = 0; i < NX; ++i) x[i] = (T)a.x0[i * bs + b];
       for (int k = 0; k < a.N; ++k) {
         load_model(k, A, B, c);
 #pragma unroll
         for (int j = 0; j < NU; ++j) {
-          T v = a.warm_U ? a.warm_U[ix(k, j, NU)] : T(0);
+          T v = a.warm_U ? (T)a.warm_U[ix(k, j, NU)] : T(0);
           v = v < lo(j) ? lo(j) : v;
           v = v > hi(j) ? hi(j) : v;
           u[j] = v;
@@ -306,22 +423,20 @@ struct BoxQpIpm {
             T acc = T(0);
 #pragma unroll
             for (int j = 0; j < NU; ++j) acc = fma_<T>(sh[SH::oR + i * NU + j], u[j], acc);
-            acc = acc < T(0) ? -acc : acc;
-            g0 = acc > g0 ? acc : g0;
+            g0 = max_(abs_(acc), g0);
           }
 #pragma unroll
           for (int i = 0; i < NX; ++i) {
             T acc = T(0);
 #pragma unroll
             for (int j = 0; j < NX; ++j) acc = fma_<T>(Qx[i * NX + j], xn[j], acc);
-            acc = acc < T(0) ? -acc : acc;
-            g0 = acc > g0 ? acc : g0;
+            g0 = max_(abs_(acc), g0);
           }
         } else {
           Stage st;
 #pragma unroll
           for (int i = 0; i < D; ++i) {
-            const T zi = i < NU ? u[i] : xn[i - NU];
+            const T zi = round_to<TZ>(i < NU ? u[i] : xn[i - NU]);
             T s_l = T(1), s_u = T(1), l_l = T(0), l_u = T(0);
             if (hasl(i)) {
               s_l = zi - lo(i);
@@ -346,12 +461,12 @@ struct BoxQpIpm {
               T C[NX];
               const T h = load_row_c(k, j, C);
               const T w = dotx(C, xn) - h;
-              const T s = w > T(1) ? w : T(1);
-              sc[ix(k, j, NC)] = s;
-              lc[ix(k, j, NC)] = mu0 / s;
+              const T s = round_to<TSL>(w > T(1) ? w : T(1));
+              sc[wx(k, j, NC)] = (TSL)s;
+              lc[wx(k, j, NC)] = (TSL)(mu0 / s);
               // the row residual is carried, not recomputed: it decays exactly by (1 - alpha) per step, whereas
               // C x - h - s recomputed from a dot product keeps ~1e-16 of rounding noise that Sigma ~ 1e12 amplifies
-              rc[ix(k, j, NC)] = w - s;
+              rc[wx(k, j, NC)] = (TZ)(w - s);
             }
           }
         }
@@ -362,186 +477,90 @@ struct BoxQpIpm {
     }
   }
 
-  MPC_HD void store_stage(int k, const Stage& s) {
-#pragma unroll
-    for (int i = 0; i < D; ++i) {
-      const int64_t o = ix(k, i, D);
-      z[o] = s.z[i];
-      sl[o] = s.sl[i];
-      su[o] = s.su[i];
-      ll[o] = s.ll[i];
-      lu[o] = s.lu[i];
-    }
-  }
-
   // second-order term cc = ds_aff * dlam_aff of one bound, recomputed from the stored dz_aff
   // (affine direction: ds = +-dz + r, dlam = -lam - Sigma ds with Sigma = lam/s).
-  // Divisions: ONE reciprocal per bound and stage visit, rinv = 1/(s lam); 1/s = rinv lam, 1/lam = rinv s.
   MPC_HD static T cc_of(T dz_signed, T r, T sig, T l) {
     const T ds = dz_signed + r;
     return ds * (-l - sig * ds);
   }
 
-  // ---- backward sweep: (factorisation and) feed-forward terms of the Newton step.
-  // rhs_i = -(H z)_i + (sig_mu - cc_l)/s_l - Sigma_l r_l - (sig_mu - cc_u)/s_u + Sigma_u r_u
-  MPC_HD void backward(const bool FACTOR, T sig_mu) {
-    T Pacc[NX * NX], pacc[NX];
+  // primal residual of a bound as the convergence test sees it: with narrow storage the recomputed residual carries
+  // the storage rounding of z and s (a few ulp of the stored type), which is not an infeasibility
+  MPC_HD static T rp_of(T r, T zi, T bound, T s) {
+    T ar = abs_(r);
+    if constexpr (kNarrowZ || kNarrowSL) {
+      const T ulp = T(2.4e-7);  // 4 ulp of float32
+      T allow = T(0);
+      if constexpr (kNarrowZ) allow += ulp * (abs_(zi) + abs_(bound));
+      if constexpr (kNarrowSL) allow += ulp * s;
+      ar = ar > allow ? ar - allow : T(0);
+    }
+    return ar;
+  }
+
+  // ---- the step of one stage: (z, s, lam) += alpha * direction, slack / multiplier directions recomputed from the
+  // stored dz and dz_aff exactly as sweep D computed them.  Used by sweep A (fused update) and by the output pass.
+  MPC_HD void apply_step(Stage& st, const T* dz, const T* da, T tau, T alpha) const {
 #pragma unroll
-    for (int i = 0; i < NX * NX; ++i) Pacc[i] = sh[SH::oPf + i];
-#pragma unroll
-    for (int i = 0; i < NX; ++i) pacc[i] = T(0);
-    Stage cur;
-    T da[D];
-#pragma unroll
-    for (int i = 0; i < D; ++i) da[i] = T(0);
-    for (int k = a.N - 1; k >= 0; --k) {
-      pf_stage(k - a.pf_dist);
-      pf_extra(k - a.pf_dist, !FACTOR, !FACTOR, false, !FACTOR, false);
-      load(k, cur);
-      if (!FACTOR) loadn<D>(dza, k, da);
-      T A[NX * NX], B[NX * NU], c[NX], K[NU * NX], Sinv[NU * NU];
-      load_model(k, A, B, c);
-      if (!FACTOR) {
-        loadn<NU * NX>(Kw, k, K);
-        loadn<NU * NU>(Sw, k, Sinv);
+    for (int i = 0; i < D; ++i) {
+      const T zi = st.z[i];
+      if (hasl(i)) {
+        const T s = st.sl[i], l = st.ll[i];
+        const T r = zi - lo(i) - s;
+        const T ds = dz[i] + r;
+        const T inv = rcp_(s), sgl = l * inv;
+        const T cc = cc_of(da[i], r, sgl, l);
+        const T dl = (tau - cc) * inv - l - sgl * ds;
+        T sn = s + alpha * ds, ln = l + alpha * dl;
+        if constexpr (kNarrowSL || kNarrowDir) {  // the ratio test ran on unrounded directions: keep the margin
+          sn = max_(sn, T(1e-3) * s);
+          ln = max_(ln, T(1e-3) * l);
+        }
+        st.sl[i] = sn;
+        st.ll[i] = ln;
       }
-      T sig[D], rhs[D];
-      // -(H z): inputs weighted by R, state x_{k+1} by Q (Pf for the last stage)
-      {
-        const T* Qx = sh + (k == a.N - 1 ? SH::oPf : SH::oQ);
-#pragma unroll
-        for (int i = 0; i < NU; ++i) {
-          T acc = T(0);
-#pragma unroll
-          for (int j = 0; j < NU; ++j) acc = fma_<T>(-sh[SH::oR + i * NU + j], cur.z[j], acc);
-          rhs[i] = acc;
+      if (hasu(i)) {
+        const T s = st.su[i], l = st.lu[i];
+        const T r = hi(i) - zi - s;
+        const T ds = -dz[i] + r;
+        const T inv = rcp_(s), sgu = l * inv;
+        const T cc = cc_of(-da[i], r, sgu, l);
+        const T dl = (tau - cc) * inv - l - sgu * ds;
+        T sn = s + alpha * ds, ln = l + alpha * dl;
+        if constexpr (kNarrowSL || kNarrowDir) {
+          sn = max_(sn, T(1e-3) * s);
+          ln = max_(ln, T(1e-3) * l);
         }
-#pragma unroll
-        for (int i = 0; i < NX; ++i) {
-          T acc = T(0);
-#pragma unroll
-          for (int j = 0; j < NX; ++j) acc = fma_<T>(-Qx[i * NX + j], cur.z[NU + j], acc);
-          rhs[NU + i] = acc;
-        }
+        st.su[i] = sn;
+        st.lu[i] = ln;
       }
-#pragma unroll
-      for (int i = 0; i < D; ++i) {
-        T sg = T(0), r = rhs[i];
-        if (hasl(i)) {
-          const T s = cur.sl[i], l = cur.ll[i];
-          const T inv = rcp_(s);
-          const T sgl = l * inv;
-          const T rl = cur.z[i] - lo(i) - s;
-          const T cc = FACTOR ? T(0) : cc_of(da[i], rl, sgl, l);
-          sg += sgl;
-          r += (sig_mu - cc) * inv - sgl * rl;
-        }
-        if (hasu(i)) {
-          const T s = cur.su[i], l = cur.lu[i];
-          const T inv = rcp_(s);
-          const T sgu = l * inv;
-          const T ru = hi(i) - cur.z[i] - s;
-          const T cc = FACTOR ? T(0) : cc_of(-da[i], ru, sgu, l);
-          sg += sgu;
-          r -= (sig_mu - cc) * inv - sgu * ru;
-        }
-        sig[i] = sg;
-        rhs[i] = r;
-      }
-      if constexpr (NC > 0) {
-        // general rows: value w = C x_{k+1}; adds C' Sigma_c C to the stage Hessian and C' rhs_c to the gradient
+      st.z[i] = zi + alpha * dz[i];
+    }
+  }
+  // step of the general rows of stage k (in place in the workspace)
+  MPC_HD void apply_step_rows(int k, const T* dz, const T* da, T tau, T alpha) {
+    if constexpr (NC > 0) {
 #pragma unroll 1
-        for (int j = 0; j < NC; ++j) {
-          T C[NX];
-          const T h = load_row_c(k, j, C);
-          const T s = sc[ix(k, j, NC)], l = lc[ix(k, j, NC)];
-          const T inv = rcp_(s), sgc = l * inv;
-          const T r = rc[ix(k, j, NC)];
-          (void)h;
-          const T cc = FACTOR ? T(0) : cc_of(dotx(C, da + NU), r, sgc, l);
-          const T rhs_c = (sig_mu - cc) * inv - sgc * r;
-#pragma unroll
-          for (int i = 0; i < NX; ++i) rhs[NU + i] = fma_<T>(C[i], rhs_c, rhs[NU + i]);
-          if (FACTOR) {
-#pragma unroll
-            for (int i = 0; i < NX; ++i)
-#pragma unroll
-              for (int i2 = 0; i2 < NX; ++i2) Pacc[i * NX + i2] = fma_<T>(sgc * C[i], C[i2], Pacc[i * NX + i2]);
-          }
+      for (int j = 0; j < NC; ++j) {
+        T C[NX];
+        (void)load_row_c(k, j, C);
+        const T s = (T)sc[wx(k, j, NC)], l = (T)lc[wx(k, j, NC)];
+        const T r = (T)rc[wx(k, j, NC)];
+        const T ds = dotx(C, dz + NU) + r;
+        const T inv = rcp_(s), sgc = l * inv;
+        const T cc = cc_of(dotx(C, da + NU), r, sgc, l);
+        const T dl = (tau - cc) * inv - l - sgc * ds;
+        T sn = s + alpha * ds, ln = l + alpha * dl;
+        if constexpr (kNarrowSL || kNarrowDir) {
+          sn = max_(sn, T(1e-3) * s);
+          ln = max_(ln, T(1e-3) * l);
         }
-      }
-      if (FACTOR) {
-        // P = Pacc + diag(Sigma_x) (+ rows' C' Sigma_c C, added above)
-#pragma unroll
-        for (int i = 0; i < NX; ++i) Pacc[i * NX + i] += sig[NU + i];
-        // Joseph (symmetric) form of the Riccati update:
-        //   PB = P B,  S = Rt + B'PB,  K = -S^-1 (PB)'A,  Acl = A + B K,  Pacc <- Q + Acl' P Acl + K' Rt K
-        // with Rt = R + diag(Sigma_u).  Every term is a positive semidefinite sum: the huge barrier weights inside P
-        // (lam/s ~ 1e12 on active states / rows) meet closed-loop rows Acl_i ~ 1/Sigma and drop out, whereas the short
-        // form Q + A'(PA + PB K) subtracts two O(Sigma) products and loses eps * Sigma of absolute accuracy.
-        T PB[NX * NU], S[NU * NU], Rt[NU * NU];
-        mm<T, NX, NX, NU, false>(Pacc, B, PB);
-#pragma unroll
-        for (int i = 0; i < NU * NU; ++i) Rt[i] = sh[SH::oR + i];
-#pragma unroll
-        for (int i = 0; i < NU; ++i) Rt[i * NU + i] += sig[i];
-#pragma unroll
-        for (int i = 0; i < NU * NU; ++i) S[i] = Rt[i];
-        mtm<T, NU, NX, NU, true>(B, PB, S);
-        sym_inverse(S, Sinv);
-        T G[NU * NX];
-        mtm<T, NU, NX, NX, false>(PB, A, G);  // (PB)'A
-#pragma unroll
-        for (int i = 0; i < NU; ++i)
-#pragma unroll
-          for (int j = 0; j < NX; ++j) {
-            T acc = T(0);
-#pragma unroll
-            for (int l = 0; l < NU; ++l) acc = fma_<T>(Sinv[i * NU + l], G[l * NX + j], acc);
-            K[i * NX + j] = -acc;
-          }
-        T Acl[NX * NX], Tm[NX * NX];
-#pragma unroll
-        for (int i = 0; i < NX * NX; ++i) Acl[i] = A[i];
-        mm<T, NX, NU, NX, true>(B, K, Acl);
-        mm<T, NX, NX, NX, false>(Pacc, Acl, Tm);
-        mm<T, NU, NU, NX, false>(Rt, K, G);  // G <- Rt K
-#pragma unroll
-        for (int i = 0; i < NX; ++i)
-#pragma unroll
-          for (int j = i; j < NX; ++j) {
-            T acc = sh[SH::oQ + i * NX + j];
-#pragma unroll
-            for (int l = 0; l < NX; ++l) acc = fma_<T>(Acl[l * NX + i], Tm[l * NX + j], acc);
-#pragma unroll
-            for (int l = 0; l < NU; ++l) acc = fma_<T>(K[l * NX + i], G[l * NX + j], acc);
-            Pacc[i * NX + j] = acc;
-            Pacc[j * NX + i] = acc;
-          }
-        storen<NU * NX>(Kw, k, K);
-        storen<NU * NU>(Sw, k, Sinv);
-      }
-      // h = -(rhs_x + pacc);  gu = rhs_u - B'h;  dff = Sinv gu;  pacc <- -A'h + K'gu
-      T h[NX], gu[NU], dff[NU];
-#pragma unroll
-      for (int i = 0; i < NX; ++i) h[i] = -(rhs[NU + i] + pacc[i]);
-#pragma unroll
-      for (int j = 0; j < NU; ++j) {
-        T acc = rhs[j];
-#pragma unroll
-        for (int i = 0; i < NX; ++i) acc = fma_<T>(-B[i * NU + j], h[i], acc);
-        gu[j] = acc;
-      }
-      mv<T, NU, NU, false>(Sinv, gu, dff);
-      storen<NU>(dw, k, dff);
-#pragma unroll
-      for (int i = 0; i < NX; ++i) {
-        T acc = T(0);
-#pragma unroll
-        for (int l = 0; l < NX; ++l) acc = fma_<T>(-A[l * NX + i], h[l], acc);
-#pragma unroll
-        for (int j = 0; j < NU; ++j) acc = fma_<T>(K[j * NX + i], gu[j], acc);
-        pacc[i] = acc;
+        // the residual is carried: it must absorb the storage rounding of the slack, or C x - h = s + r drifts by an
+        // ulp of s per iteration (2e-7 on the active rows after ~15 iterations with float32 slacks)
+        const T sr = round_to<TSL>(sn);
+        sc[wx(k, j, NC)] = (TSL)sr;
+        lc[wx(k, j, NC)] = (TSL)ln;
+        rc[wx(k, j, NC)] = (TZ)((T(1) - alpha) * r + (sn - sr));
       }
     }
   }
@@ -587,30 +606,340 @@ struct BoxQpIpm {
     }
   }
 
+  // feed-forward recursion of one stage, shared by sweeps A and C:
+  //   h = -(rhs_x + pacc);  gu = rhs_u - B'h;  d = Sinv gu;  pacc <- -A'h + K'gu
+  MPC_HD static void ff_stage(const T* A, const T* B, const T* K, const T* Sinv, const T* rhs, T* pacc, T* dff) {
+    T h[NX], gu[NU];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) h[i] = -(rhs[NU + i] + pacc[i]);
+#pragma unroll
+    for (int j = 0; j < NU; ++j) {
+      T acc = rhs[j];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) acc = fma_<T>(-B[i * NU + j], h[i], acc);
+      gu[j] = acc;
+    }
+    mv<T, NU, NU, false>(Sinv, gu, dff);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      T acc = T(0);
+#pragma unroll
+      for (int l = 0; l < NX; ++l) acc = fma_<T>(-A[l * NX + i], h[l], acc);
+#pragma unroll
+      for (int j = 0; j < NU; ++j) acc = fma_<T>(K[j * NX + i], gu[j], acc);
+      pacc[i] = acc;
+    }
+  }
+
+  // ---- sweep A (backward): apply the previous step (have_step), factorise, affine feed-forward.
+  // Affine right-hand side: rhs_i = -(H z)_i - Sigma_l r_l + Sigma_u r_u
+  MPC_HD void sweep_a(const bool have_step, T tau, T alpha) {
+    T Pacc[NX * NX], pacc[NX];
+#pragma unroll
+    for (int i = 0; i < NX * NX; ++i) Pacc[i] = sh[SH::oPf + i];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) pacc[i] = T(0);
+    for (int k = a.N - 1; k >= 0; --k) {
+      if (pf_on(k - a.pf_dist)) {
+        pf_iterate(k - a.pf_dist);
+        pf_model(k - a.pf_dist);
+        if (have_step) {
+          pf_rows<D>(dza, k - a.pf_dist);
+          pf_rows<D>(dzw, k - a.pf_dist);
+        }
+      }
+      Stage cur;
+      load(k, cur);
+      T A[NX * NX], B[NX * NU], c[NX];
+      load_model(k, A, B, c);
+      if (have_step) {
+        T dz[D], da[D];
+        loadn<D>(dzw, k, dz);
+        loadn<D>(dza, k, da);
+        apply_step_rows(k, dz, da, tau, alpha);
+        apply_step(cur, dz, da, tau, alpha);
+        round_stage(cur);
+        store_stage(k, cur);
+      }
+      T sig[D], rhs[D];
+      // -(H z): inputs weighted by R, state x_{k+1} by Q (Pf for the last stage)
+      {
+        const T* Qx = sh + (k == a.N - 1 ? SH::oPf : SH::oQ);
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+          T acc = T(0);
+#pragma unroll
+          for (int j = 0; j < NU; ++j) acc = fma_<T>(-sh[SH::oR + i * NU + j], cur.z[j], acc);
+          rhs[i] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+          T acc = T(0);
+#pragma unroll
+          for (int j = 0; j < NX; ++j) acc = fma_<T>(-Qx[i * NX + j], cur.z[NU + j], acc);
+          rhs[NU + i] = acc;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        T sg = T(0), r = rhs[i];
+        if (hasl(i)) {
+          const T s = cur.sl[i], l = cur.ll[i];
+          const T sgl = l * rcp_(s);
+          const T rl = cur.z[i] - lo(i) - s;
+          sg += sgl;
+          r = fma_<T>(-sgl, rl, r);
+        }
+        if (hasu(i)) {
+          const T s = cur.su[i], l = cur.lu[i];
+          const T sgu = l * rcp_(s);
+          const T ru = hi(i) - cur.z[i] - s;
+          sg += sgu;
+          r = fma_<T>(sgu, ru, r);
+        }
+        sig[i] = sg;
+        rhs[i] = r;
+      }
+      if constexpr (NC > 0) {
+        // general rows: value w = C x_{k+1}; adds C' Sigma_c C to the stage Hessian and C' rhs_c to the gradient
+#pragma unroll 1
+        for (int j = 0; j < NC; ++j) {
+          T C[NX];
+          (void)load_row_c(k, j, C);
+          const T s = (T)sc[wx(k, j, NC)], l = (T)lc[wx(k, j, NC)];
+          const T sgc = l * rcp_(s);
+          const T r = (T)rc[wx(k, j, NC)];
+          const T rhs_c = -sgc * r;
+#pragma unroll
+          for (int i = 0; i < NX; ++i) rhs[NU + i] = fma_<T>(C[i], rhs_c, rhs[NU + i]);
+#pragma unroll
+          for (int i = 0; i < NX; ++i)
+#pragma unroll
+            for (int i2 = 0; i2 < NX; ++i2) Pacc[i * NX + i2] = fma_<T>(sgc * C[i], C[i2], Pacc[i * NX + i2]);
+        }
+      }
+      // P = Pacc + diag(Sigma_x) (+ rows' C' Sigma_c C, added above)
+#pragma unroll
+      for (int i = 0; i < NX; ++i) Pacc[i * NX + i] += sig[NU + i];
+      // Joseph (symmetric) form of the Riccati update:
+      //   PB = P B,  S = Rt + B'PB,  K = -S^-1 (PB)'A,  Acl = A + B K,  Pacc <- Q + Acl' P Acl + K' Rt K
+      // with Rt = R + diag(Sigma_u).  Every term is a positive semidefinite sum: the huge barrier weights inside P
+      // (lam/s ~ 1e12 on active states / rows) meet closed-loop rows Acl_i ~ 1/Sigma and drop out, whereas the short
+      // form Q + A'(PA + PB K) subtracts two O(Sigma) products and loses eps * Sigma of absolute accuracy.
+      T K[NU * NX], Sinv[NU * NU];
+      {
+        T PB[NX * NU], S[NU * NU], Rt[NU * NU];
+        mm<T, NX, NX, NU, false>(Pacc, B, PB);
+#pragma unroll
+        for (int i = 0; i < NU * NU; ++i) Rt[i] = sh[SH::oR + i];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) Rt[i * NU + i] += sig[i];
+#pragma unroll
+        for (int i = 0; i < NU * NU; ++i) S[i] = Rt[i];
+        mtm<T, NU, NX, NU, true>(B, PB, S);
+        sym_inverse(S, Sinv);
+        T G[NU * NX];
+        mtm<T, NU, NX, NX, false>(PB, A, G);  // (PB)'A
+#pragma unroll
+        for (int i = 0; i < NU; ++i)
+#pragma unroll
+          for (int j = 0; j < NX; ++j) {
+            T acc = T(0);
+#pragma unroll
+            for (int l = 0; l < NU; ++l) acc = fma_<T>(Sinv[i * NU + l], G[l * NX + j], acc);
+            K[i * NX + j] = -acc;
+          }
+        if constexpr (sizeof(TGN) < sizeof(T)) {  // later sweeps read the stored gains: use the same values here
+#pragma unroll
+          for (int i = 0; i < NU * NX; ++i) K[i] = round_to<TGN>(K[i]);
+#pragma unroll
+          for (int i = 0; i < NU * NU; ++i) Sinv[i] = round_to<TGN>(Sinv[i]);
+        }
+        T Acl[NX * NX], Tm[NX * NX];
+#pragma unroll
+        for (int i = 0; i < NX * NX; ++i) Acl[i] = A[i];
+        mm<T, NX, NU, NX, true>(B, K, Acl);
+        mm<T, NX, NX, NX, false>(Pacc, Acl, Tm);
+        mm<T, NU, NU, NX, false>(Rt, K, G);  // G <- Rt K
+#pragma unroll
+        for (int i = 0; i < NX; ++i)
+#pragma unroll
+          for (int j = i; j < NX; ++j) {
+            T acc = sh[SH::oQ + i * NX + j];
+#pragma unroll
+            for (int l = 0; l < NX; ++l) acc = fma_<T>(Acl[l * NX + i], Tm[l * NX + j], acc);
+#pragma unroll
+            for (int l = 0; l < NU; ++l) acc = fma_<T>(K[l * NX + i], G[l * NX + j], acc);
+            Pacc[i * NX + j] = acc;
+            Pacc[j * NX + i] = acc;
+          }
+        storen<NU * NX>(Kw, k, K);
+        storen<NU * NU>(Sw, k, Sinv);
+      }
+      T dff[NU];
+      ff_stage(A, B, K, Sinv, rhs, pacc, dff);
+      storen<NU>(dw, k, dff);
+    }
+  }
+
   struct Acc {
-    T qmax, s0, s1, s2, dzmax, rp;  // qmax = max_i(-ds_i/s_i, -dlam_i/lam_i): largest feasible step = 1/qmax
+    T qmax, s0, s1, s2, dzmax, rp, zn;  // qmax = max_i(-ds_i/s_i, -dlam_i/lam_i): largest feasible step = 1/qmax
     MPC_HD T amin() const { return qmax > T(0) ? T(1) / qmax : T(1e30); }
   };
 
-  // ---- forward sweep: dz by rollout with the stored gains; per element the slack / multiplier
-  // directions.  AFFINE: stores dz_aff and accumulates the sums that give mu_aff for any step
-  // length.  Otherwise stores dz and accumulates the step ratios / norms.
-  MPC_HD void forward(const bool AFFINE, T sig_mu, Acc& acc) {
+  // ---- sweep B (forward): affine direction by rollout with the stored gains.  For the affine direction
+  // dlam = -lam (1 + ds/s), so per bound the step ratio is max(-t, 1 + t) with t = ds/s, sum(s dlam + lam ds) = -sum(s lam)
+  // and cc = ds dlam; one reciprocal per bound.  Stores dz_aff, e = 1/s_l - 1/s_u, g = cc_l/s_l - cc_u/s_u
+  // (general rows add C'(1/s_c) and C'(cc_c/s_c) to the state part of e and g).
+  MPC_HD void sweep_b(Acc& acc) {
     T x[NX], xn[NX], u[NU];
     acc.qmax = acc.s0 = acc.s1 = acc.s2 = acc.dzmax = acc.rp = T(0);
+    acc.zn = T(1);
 #pragma unroll
     for (int i = 0; i < NX; ++i) x[i] = T(0);  // dx_0 = 0
-    Stage cur;
-    T da[D], K[NU * NX], dff[NU];
-#pragma unroll
-    for (int i = 0; i < D; ++i) da[i] = T(0);
     for (int k = 0; k < a.N; ++k) {
-      pf_stage(k + a.pf_dist);
-      pf_extra(k + a.pf_dist, true, false, true, !AFFINE, false);
+      if (pf_on(k + a.pf_dist)) {
+        pf_iterate(k + a.pf_dist);
+        pf_model(k + a.pf_dist);
+        pf_rows<NU * NX>(Kw, k + a.pf_dist);
+        pf_rows<NU>(dw, k + a.pf_dist);
+      }
+      Stage cur;
       load(k, cur);
+      T K[NU * NX], dff[NU];
       loadn<NU * NX>(Kw, k, K);
       loadn<NU>(dw, k, dff);
-      if (!AFFINE) loadn<D>(dza, k, da);
+      T A[NX * NX], B[NX * NU], c[NX];
+      load_model(k, A, B, c);
+#pragma unroll
+      for (int j = 0; j < NU; ++j) u[j] = dff[j];
+      mv<T, NU, NX, true>(K, x, u);
+      mv<T, NX, NX, false>(A, x, xn);
+      mv<T, NX, NU, true>(B, u, xn);
+      T dzv[D], ev[D], gv[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        const T dz = round_to<TDA>(i < NU ? u[i] : xn[i - NU]);  // cc must use the value sweeps D and A read back
+        dzv[i] = dz;
+        const T zi = cur.z[i];
+        T e = T(0), g = T(0);
+        if (hasl(i)) {
+          const T s = cur.sl[i], l = cur.ll[i];
+          const T r = zi - lo(i) - s;
+          const T ds = dz + r;
+          const T inv = rcp_(s);
+          const T t = ds * inv;
+          const T cc = -ds * l * (T(1) + t);
+          acc.qmax = max_(acc.qmax, max_(-t, T(1) + t));
+          acc.s0 = fma_<T>(s, l, acc.s0);
+          acc.s2 += cc;
+          e += inv;
+          g = fma_<T>(cc, inv, g);
+        }
+        if (hasu(i)) {
+          const T s = cur.su[i], l = cur.lu[i];
+          const T r = hi(i) - zi - s;
+          const T ds = -dz + r;
+          const T inv = rcp_(s);
+          const T t = ds * inv;
+          const T cc = -ds * l * (T(1) + t);
+          acc.qmax = max_(acc.qmax, max_(-t, T(1) + t));
+          acc.s0 = fma_<T>(s, l, acc.s0);
+          acc.s2 += cc;
+          e -= inv;
+          g = fma_<T>(-cc, inv, g);
+        }
+        ev[i] = e;
+        gv[i] = g;
+      }
+      if constexpr (NC > 0) {
+#pragma unroll 1
+        for (int j = 0; j < NC; ++j) {
+          T C[NX];
+          (void)load_row_c(k, j, C);
+          const T s = (T)sc[wx(k, j, NC)], l = (T)lc[wx(k, j, NC)];
+          const T r = (T)rc[wx(k, j, NC)];
+          const T ds = dotx(C, dzv + NU) + r;
+          const T inv = rcp_(s);
+          const T t = ds * inv;
+          const T cc = -ds * l * (T(1) + t);
+          acc.qmax = max_(acc.qmax, max_(-t, T(1) + t));
+          acc.s0 = fma_<T>(s, l, acc.s0);
+          acc.s2 += cc;
+          const T gi = cc * inv;
+#pragma unroll
+          for (int i = 0; i < NX; ++i) {
+            ev[NU + i] = fma_<T>(C[i], inv, ev[NU + i]);
+            gv[NU + i] = fma_<T>(C[i], gi, gv[NU + i]);
+          }
+        }
+      }
+      storen<D>(dza, k, dzv);
+      storen<D>(ew, k, ev);
+      storen<D>(gw, k, gv);
+      // the rollout continues with the UNROUNDED state direction (the stored copy is only used for cc)
+#pragma unroll
+      for (int i = 0; i < NX; ++i) x[i] = xn[i];
+    }
+    acc.s1 = -acc.s0;
+  }
+
+  // ---- sweep C (backward): feed-forward of the corrector's extra right-hand side  tau e - g, added to the affine one
+  MPC_HD void sweep_c(T tau) {
+    T pacc[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) pacc[i] = T(0);
+    for (int k = a.N - 1; k >= 0; --k) {
+      if (pf_on(k - a.pf_dist)) {
+        pf_rows<D>(ew, k - a.pf_dist);
+        pf_rows<D>(gw, k - a.pf_dist);
+        pf_rows<NU * NX>(Kw, k - a.pf_dist);
+        pf_rows<NU * NU>(Sw, k - a.pf_dist);
+        pf_rows<NU>(dw, k - a.pf_dist);
+        pf_model(k - a.pf_dist);
+      }
+      T ev[D], gv[D], K[NU * NX], Sinv[NU * NU];
+      loadn<D>(ew, k, ev);
+      loadn<D>(gw, k, gv);
+      loadn<NU * NX>(Kw, k, K);
+      loadn<NU * NU>(Sw, k, Sinv);
+      T A[NX * NX], B[NX * NU], c[NX];
+      load_model(k, A, B, c);
+      T rhs[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) rhs[i] = fma_<T>(tau, ev[i], -gv[i]);
+      T dff[NU], daff[NU];
+      loadn<NU>(dw, k, daff);
+      ff_stage(A, B, K, Sinv, rhs, pacc, dff);
+#pragma unroll
+      for (int j = 0; j < NU; ++j) dff[j] += daff[j];  // d_aff + d_cor: sweep D rolls the whole direction out at once
+      storen<NU>(dw, k, dff);
+    }
+  }
+
+  // ---- sweep D (forward): dz by rollout with the summed feed-forward (exactly on the linearised dynamics); per bound
+  // the slack / multiplier directions (second-order term from the stored dz_aff), the step ratios and the sums that
+  // give the new barrier parameter for any step length.
+  MPC_HD void sweep_d(T tau, Acc& acc) {
+    T x[NX], xn[NX], u[NU];
+    acc.qmax = acc.s0 = acc.s1 = acc.s2 = acc.dzmax = acc.rp = T(0);
+    acc.zn = T(1);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) x[i] = T(0);
+    for (int k = 0; k < a.N; ++k) {
+      if (pf_on(k + a.pf_dist)) {
+        pf_iterate(k + a.pf_dist);
+        pf_model(k + a.pf_dist);
+        pf_rows<NU * NX>(Kw, k + a.pf_dist);
+        pf_rows<NU>(dw, k + a.pf_dist);
+        pf_rows<D>(dza, k + a.pf_dist);
+      }
+      Stage cur;
+      load(k, cur);
+      T K[NU * NX], dff[NU], da[D];
+      loadn<NU * NX>(Kw, k, K);
+      loadn<NU>(dw, k, dff);
+      loadn<D>(dza, k, da);
       T A[NX * NX], B[NX * NU], c[NX];
       load_model(k, A, B, c);
 #pragma unroll
@@ -621,29 +950,24 @@ struct BoxQpIpm {
       T dzv[D];
 #pragma unroll
       for (int i = 0; i < D; ++i) {
-        const T dz = i < NU ? u[i] : xn[i - NU];
+        const T dz = round_to<TDZ>(i < NU ? u[i] : xn[i - NU]);
         dzv[i] = dz;
         const T zi = cur.z[i];
-        if (!AFFINE) {
-          const T ad = dz < T(0) ? -dz : dz;
-          acc.dzmax = ad > acc.dzmax ? ad : acc.dzmax;
-        }
+        acc.dzmax = max_(acc.dzmax, abs_(dz));
+        acc.zn = max_(acc.zn, abs_(zi));
         if (hasl(i)) {
           const T s = cur.sl[i], l = cur.ll[i];
           const T r = zi - lo(i) - s;
           const T ds = dz + r;
           const T rinv = rcp_(s * l), inv_s = rinv * l, inv_l = rinv * s;
           const T sgl = l * inv_s;
-          const T cc = AFFINE ? T(0) : cc_of(da[i], r, sgl, l);
-          const T dl = (sig_mu - cc) * inv_s - l - sgl * ds;
-          const T qs = -ds * inv_s, ql = -dl * inv_l;  // step is limited to 1 / max(q)
-          acc.qmax = qs > acc.qmax ? qs : acc.qmax;
-          acc.qmax = ql > acc.qmax ? ql : acc.qmax;
-          acc.s0 += s * l;
+          const T cc = cc_of(da[i], r, sgl, l);
+          const T dl = (tau - cc) * inv_s - l - sgl * ds;
+          acc.qmax = max_(acc.qmax, max_(-ds * inv_s, -dl * inv_l));  // step is limited to 1 / max(q)
+          acc.s0 = fma_<T>(s, l, acc.s0);
           acc.s1 += s * dl + l * ds;
-          acc.s2 += ds * dl;
-          const T ar = r < T(0) ? -r : r;
-          acc.rp = ar > acc.rp ? ar : acc.rp;
+          acc.s2 = fma_<T>(ds, dl, acc.s2);
+          acc.rp = max_(acc.rp, rp_of(r, zi, lo(i), s));
         }
         if (hasu(i)) {
           const T s = cur.su[i], l = cur.lu[i];
@@ -651,127 +975,61 @@ struct BoxQpIpm {
           const T ds = -dz + r;
           const T rinv = rcp_(s * l), inv_s = rinv * l, inv_l = rinv * s;
           const T sgu = l * inv_s;
-          const T cc = AFFINE ? T(0) : cc_of(-da[i], r, sgu, l);
-          const T dl = (sig_mu - cc) * inv_s - l - sgu * ds;
-          const T qs = -ds * inv_s, ql = -dl * inv_l;
-          acc.qmax = qs > acc.qmax ? qs : acc.qmax;
-          acc.qmax = ql > acc.qmax ? ql : acc.qmax;
-          acc.s0 += s * l;
+          const T cc = cc_of(-da[i], r, sgu, l);
+          const T dl = (tau - cc) * inv_s - l - sgu * ds;
+          acc.qmax = max_(acc.qmax, max_(-ds * inv_s, -dl * inv_l));
+          acc.s0 = fma_<T>(s, l, acc.s0);
           acc.s1 += s * dl + l * ds;
-          acc.s2 += ds * dl;
-          const T ar = r < T(0) ? -r : r;
-          acc.rp = ar > acc.rp ? ar : acc.rp;
+          acc.s2 = fma_<T>(ds, dl, acc.s2);
+          acc.rp = max_(acc.rp, rp_of(r, zi, hi(i), s));
         }
       }
       if constexpr (NC > 0) {
 #pragma unroll 1
         for (int j = 0; j < NC; ++j) {
           T C[NX];
-          const T h = load_row_c(k, j, C);
-          const T s = sc[ix(k, j, NC)], l = lc[ix(k, j, NC)];
-          const T r = rc[ix(k, j, NC)];
-          (void)h;
-          const T ds = dotx(C, xn) + r;
+          (void)load_row_c(k, j, C);
+          const T s = (T)sc[wx(k, j, NC)], l = (T)lc[wx(k, j, NC)];
+          const T r = (T)rc[wx(k, j, NC)];
+          const T ds = dotx(C, dzv + NU) + r;
           const T rinv = rcp_(s * l), inv_s = rinv * l, inv_l = rinv * s;
           const T sgc = l * inv_s;
-          const T cc = AFFINE ? T(0) : cc_of(dotx(C, da + NU), r, sgc, l);
-          const T dl = (sig_mu - cc) * inv_s - l - sgc * ds;
-          const T qs = -ds * inv_s, ql = -dl * inv_l;
-          acc.qmax = qs > acc.qmax ? qs : acc.qmax;
-          acc.qmax = ql > acc.qmax ? ql : acc.qmax;
-          acc.s0 += s * l;
+          const T cc = cc_of(dotx(C, da + NU), r, sgc, l);
+          const T dl = (tau - cc) * inv_s - l - sgc * ds;
+          acc.qmax = max_(acc.qmax, max_(-ds * inv_s, -dl * inv_l));
+          acc.s0 = fma_<T>(s, l, acc.s0);
           acc.s1 += s * dl + l * ds;
-          acc.s2 += ds * dl;
-          const T ar = r < T(0) ? -r : r;
-          acc.rp = ar > acc.rp ? ar : acc.rp;
+          acc.s2 = fma_<T>(ds, dl, acc.s2);
+          acc.rp = max_(acc.rp, abs_(r));
         }
       }
-      storen<D>(AFFINE ? dza : dzw, k, dzv);
+      storen<D>(dzw, k, dzv);
 #pragma unroll
       for (int i = 0; i < NX; ++i) x[i] = xn[i];
     }
   }
 
-  // ---- step: (z, s, lam) += alpha * direction; returns max |z|.  Stages are independent here.
-  MPC_HD T update(T sig_mu, T alpha, bool second_order) {
-    T zn = T(1);
-    for (int k = 0; k < a.N; ++k) {
-      pf_stage(k + a.pf_dist);
-      pf_extra(k + a.pf_dist, false, false, false, second_order, true);
-      Stage st;
-      T da[D], dz[D];
-      load(k, st);
-      loadn<D>(dzw, k, dz);
-      if (second_order) {
-        loadn<D>(dza, k, da);
-      } else {
-#pragma unroll
-        for (int i = 0; i < D; ++i) da[i] = T(0);
-      }
-      if constexpr (NC > 0) {
-#pragma unroll 1
-        for (int j = 0; j < NC; ++j) {
-          T C[NX];
-          const T h = load_row_c(k, j, C);
-          const T s = sc[ix(k, j, NC)], l = lc[ix(k, j, NC)];
-          const T r = rc[ix(k, j, NC)];
-          (void)h;
-          const T ds = dotx(C, dz + NU) + r;
-          const T inv = rcp_(s), sgc = l * inv;
-          const T cc = second_order ? cc_of(dotx(C, da + NU), r, sgc, l) : T(0);
-          const T dl = (sig_mu - cc) * inv - l - sgc * ds;
-          sc[ix(k, j, NC)] = s + alpha * ds;
-          lc[ix(k, j, NC)] = l + alpha * dl;
-          rc[ix(k, j, NC)] = (T(1) - alpha) * r;
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < D; ++i) {
-        const T zi = st.z[i];
-        if (hasl(i)) {
-          const T s = st.sl[i], l = st.ll[i];
-          const T r = zi - lo(i) - s;
-          const T ds = dz[i] + r;
-          const T inv = rcp_(s), sgl = l * inv;
-          const T cc = second_order ? cc_of(da[i], r, sgl, l) : T(0);
-          const T dl = (sig_mu - cc) * inv - l - sgl * ds;
-          st.sl[i] = s + alpha * ds;
-          st.ll[i] = l + alpha * dl;
-        }
-        if (hasu(i)) {
-          const T s = st.su[i], l = st.lu[i];
-          const T r = hi(i) - zi - s;
-          const T ds = -dz[i] + r;
-          const T inv = rcp_(s), sgu = l * inv;
-          const T cc = second_order ? cc_of(-da[i], r, sgu, l) : T(0);
-          const T dl = (sig_mu - cc) * inv - l - sgu * ds;
-          st.su[i] = s + alpha * ds;
-          st.lu[i] = l + alpha * dl;
-        }
-        const T zn_i = zi + alpha * dz[i];
-        st.z[i] = zn_i;
-        const T az = zn_i < T(0) ? -zn_i : zn_i;
-        zn = az > zn ? az : zn;
-      }
-      store_stage(k, st);
-    }
-    return zn;
-  }
-
-  // ---- output: active set from the complementarity pairs, variables snapped onto active bounds,
-  // states by rollout of the snapped inputs, cost as the reference defines it.
-  MPC_HD void output(int status, int iters) {
+  // ---- output: last step applied on the fly, active set from the complementarity pairs, variables snapped onto
+  // active bounds, states by rollout of the snapped inputs, cost as the reference defines it.
+  MPC_HD void output(int status, int iters, const bool have_step, T tau, T alpha) {
     T x[NX], xn[NX], u[NU], A[NX * NX], B[NX * NU], c[NX];
     T cost = T(0);
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
-      x[i] = a.x0[i * bs + b];
-      a.X[i * bs + b] = x[i];
+      x[i] = (T)a.x0[i * bs + b];
+      a.X[i * bs + b] = (TIO)x[i];
     }
     for (int k = 0; k < a.N; ++k) {
       Stage st;
       load(k, st);
       load_model(k, A, B, c);
+      if (have_step) {
+        T dz[D], da[D];
+        loadn<D>(dzw, k, dz);
+        loadn<D>(dza, k, da);
+        apply_step_rows(k, dz, da, tau, alpha);
+        apply_step(st, dz, da, tau, alpha);
+      }
 #pragma unroll
       for (int i = 0; i < D; ++i) {
         int sat = 0;
@@ -779,7 +1037,8 @@ struct BoxQpIpm {
         if (hasu(i) && st.lu[i] > st.su[i]) sat = 1;
         if (i < NU) {
           u[i] = sat < 0 ? lo(i) : (sat > 0 ? hi(i) : st.z[i]);
-          a.U[ix(k, i, NU)] = u[i];
+          if constexpr (sizeof(TIO) < sizeof(T)) u[i] = (T)(TIO)u[i];  // the rollout uses the input that is returned
+          a.U[ix(k, i, NU)] = (TIO)u[i];
           if (a.sat_u) a.sat_u[ix(k, i, NU)] = (int8_t)sat;
         } else if (a.sat_x) {
           a.sat_x[ix(k, i - NU, NX)] = (int8_t)sat;
@@ -788,7 +1047,8 @@ struct BoxQpIpm {
       if constexpr (NC > 0) {
         if (a.sat_c) {
 #pragma unroll 1
-          for (int j = 0; j < NC; ++j) a.sat_c[ix(k, j, NC)] = lc[ix(k, j, NC)] > sc[ix(k, j, NC)] ? (int8_t)-1 : (int8_t)0;
+          for (int j = 0; j < NC; ++j)
+            a.sat_c[ix(k, j, NC)] = (T)lc[wx(k, j, NC)] > (T)sc[wx(k, j, NC)] ? (int8_t)-1 : (int8_t)0;
         }
       }
       cost += quad<T, NX>(sh + SH::oQ, x) + quad<T, NU>(sh + SH::oR, u);
@@ -796,11 +1056,11 @@ struct BoxQpIpm {
 #pragma unroll
       for (int i = 0; i < NX; ++i) {
         x[i] = xn[i];
-        a.X[ix(k + 1, i, NX)] = x[i];
+        a.X[ix(k + 1, i, NX)] = (TIO)x[i];
       }
     }
     cost += quad<T, NX>(sh + SH::oPf, x);
-    a.cost[b] = cost;
+    a.cost[b] = (TIO)cost;
     a.status[b] = status;
     a.iters[b] = iters;
   }
@@ -812,54 +1072,55 @@ struct BoxQpIpm {
     ncons = (ncons + NC) * a.N;
     init();
     int status = MPC_UNSOLVED, it = 0;
-    T rp = T(0), zn = T(1);
+    T tau = T(0), alpha = T(0);
+    bool have_step = false;
+    const T eps = (T)a.eps;
     // (no finite bound at all: the first iteration below is one exact Newton step onto the LQ optimum -- all barrier
-    // terms vanish, alpha = 1 -- and the loop stops after it.  One call site per pass keeps the kernel's code, which
-    // is far larger than the instruction caches, as small as it can be.)
+    // terms vanish, alpha = 1 -- and the loop stops after it.)
     const T inv_nc = ncons ? T(1) / T(ncons) : T(0);
     while (status == MPC_UNSOLVED && it < a.max_iter) {
       ++it;
       Acc acc;
-      T sig_mu = T(0);
-      // predictor (phase 0: factorise, sigma = 0, no second-order term) and corrector (phase 1) run through the SAME
-      // code: one copy of each sweep in the kernel instead of two
-#pragma unroll 1
-      for (int phase = 0; phase < 2; ++phase) {
-        const bool predictor = (phase == 0);
-        backward(predictor, sig_mu);
-        forward(predictor, sig_mu, acc);
-        if (predictor) {
-          const T mu = acc.s0 * inv_nc;
-          const T am_aff = acc.amin();
-          const T a_aff = am_aff < T(1) ? am_aff : T(1);
-          const T mu_aff = (acc.s0 + a_aff * (acc.s1 + a_aff * acc.s2)) * inv_nc;
-          T ratio = mu_aff / (mu > T(1e-300) ? mu : T(1e-300));
-          T sigma = ratio * ratio * ratio;
-          sigma = sigma < T(1) ? sigma : T(1);
-          // centring target; never below 1e-3 of the complementarity tolerance: driving mu further only inflates
-          // the barrier weights (lam/s ~ lam^2/mu) and with them the rounding noise of the Newton step
-          sig_mu = sigma * mu;
-          const T mu_floor = T(1e-3) * a.eps * mu_scale;
-          sig_mu = sig_mu > mu_floor ? sig_mu : mu_floor;
-        }
+      sweep_a(have_step, tau, alpha);
+      sweep_b(acc);
+      {
+        const T mu = acc.s0 * inv_nc;
+        const T am_aff = acc.amin();
+        const T a_aff = am_aff < T(1) ? am_aff : T(1);
+        const T mu_aff = (acc.s0 + a_aff * (acc.s1 + a_aff * acc.s2)) * inv_nc;
+        T ratio = mu_aff / (mu > T(1e-300) ? mu : T(1e-300));
+        T sigma = ratio * ratio * ratio;
+        sigma = sigma < T(1) ? sigma : T(1);
+        // centring target; never below 1e-3 of the complementarity tolerance: driving mu further only inflates
+        // the barrier weights (lam/s ~ lam^2/mu) and with them the rounding noise of the Newton step
+        tau = sigma * mu;
+        const T mu_floor = T(1e-3) * eps * mu_scale;
+        tau = tau > mu_floor ? tau : mu_floor;
       }
-      T alpha = T(0.995) * acc.amin();
+      sweep_c(tau);
+      sweep_d(tau, acc);
+      alpha = T(0.995) * acc.amin();
       alpha = alpha < T(1) ? alpha : T(1);
-      zn = update(sig_mu, alpha, true);
+      have_step = true;
+      const T zn = acc.zn;
       const T mu_new = (acc.s0 + alpha * (acc.s1 + alpha * acc.s2)) * inv_nc;
-      rp = (T(1) - alpha) * acc.rp;
+      const T rp = (T(1) - alpha) * acc.rp;
       const bool done = (ncons == 0) ||
-                        ((mu_new <= a.eps * mu_scale) && (rp <= a.eps * zn) && (alpha * acc.dzmax <= T(1e-6) * zn));
+                        ((mu_new <= eps * mu_scale) && (rp <= eps * zn) && (alpha * acc.dzmax <= T(1e-6) * zn));
       if (done) {
         status = MPC_SOLVED;
-      } else if (!(alpha >= T(1e-6)) || !(mu_new <= T(100) * mu0)) {
-        // stalled: step length collapsed / barrier parameter grew 100x above its start value.  With a bound residual that
-        // cannot be closed the box and the dynamics do not meet: infeasible.
-        status = (rp <= T(1e-6) * zn) ? MPC_MAX_ITER : MPC_INFEASIBLE;
+      } else {
+        // stalled: step length collapsed / barrier parameter grew 100x above its start value.  With a bound residual
+        // that cannot be closed the box and the dynamics do not meet: infeasible.  Running out of iterations without
+        // that signature is reported as MPC_MAX_ITER unless the barrier parameter has grown above its start value
+        // while the residual is still open (multipliers diverging: the Farkas-type signature of an empty feasible set).
+        const bool stalled = !(alpha >= T(1e-6)) || !(mu_new <= T(100) * mu0);
+        const bool open = !(rp <= T(1e-6) * zn);
+        if (stalled) status = open ? MPC_INFEASIBLE : MPC_MAX_ITER;
+        else if (it >= a.max_iter) status = (open && mu_new > mu0) ? MPC_INFEASIBLE : MPC_MAX_ITER;
       }
     }
-    if (status == MPC_UNSOLVED) status = (rp <= T(1e-6) * zn) ? MPC_MAX_ITER : MPC_INFEASIBLE;
-    output(status, it);
+    output(status, it, have_step, tau, alpha);
   }
 };
 

@@ -54,7 +54,8 @@ class Problem:
 
 @dataclass
 class Problem3(Problem):
-    """Session 3 variant (/root/reference/session_3/problem.py:15,17)."""
+    """Session 3 variant (/root/reference/session_3/problem.py:15,17).  ``problem3.Problem`` is this class under the
+    reference's own name, for code that does ``from problem import Problem`` inside session_3."""
     p_min: float = -120
     v_min: float = -50
 
@@ -69,10 +70,11 @@ class LinearMPC:
     simulator calls every step: returns u_0 and appends the three log entries.
     """
 
-    def __init__(self, problem: Problem, terminal_weight=None, max_iter=60, eps=1e-9):
+    def __init__(self, problem: Problem, terminal_weight=None, max_iter=60, eps=1e-9, dtype=torch.float64):
         self.problem = problem
         self.Pf = problem.Q if terminal_weight is None else terminal_weight
         self.max_iter, self.eps = max_iter, eps
+        self.dtype = dtype   # torch.float64 (reference arithmetic) or torch.float32 arrays (1e-4 tolerance class)
         self._ws = None
 
     def bounds(self):
@@ -81,7 +83,8 @@ class LinearMPC:
 
     def solve(self, x0, warm_U=None):
         p = self.problem
-        x = io.to_dev(x0, torch.float64)
+        dt = self.dtype
+        x = io.to_dev(x0, dt)
         if x.dim() == 1:
             x = x[None, :]
         if x.shape[1] != p.n_state:
@@ -89,11 +92,11 @@ class LinearMPC:
         xT = x.t().contiguous()
         dev = xT.device
         shape = (xT.shape[1], p.n_state, p.n_input, int(p.N))
-        if self._ws is None or self._ws.shape != shape or self._ws.U.device != dev:
-            self._ws = boxqp.BoxQpWorkspace(*shape, dev)
+        if self._ws is None or self._ws.shape != shape or self._ws.U.device != dev or self._ws.dtype != dt:
+            self._ws = boxqp.BoxQpWorkspace(*shape, dev, dtype=dt)
         u_lo, u_hi, x_lo, x_hi = self.bounds()
-        A, B = io.to_dev(p.A, torch.float64), io.to_dev(p.B, torch.float64)
-        Q, R, Pf = (io.to_dev(np.asarray(M, dtype=np.float64) if not io.is_tensor(M) else M, torch.float64)
+        A, B = io.to_dev(p.A, dt, dev), io.to_dev(p.B, dt, dev)
+        Q, R, Pf = (io.to_dev(np.asarray(M, dtype=np.float64) if not io.is_tensor(M) else M, dt, dev)
                     for M in (p.Q, p.R, self.Pf))
         return boxqp.solve(A, B, Q, R, Pf, p.N, xT, u_lo, u_hi, x_lo, x_hi, warm_U=warm_U,
                            max_iter=self.max_iter, eps=self.eps, workspace=self._ws)
@@ -119,14 +122,14 @@ def closed_loop(problem: Problem, x0, n_steps: int, controller: LinearMPC = None
     being simulated with the solver's last (bound-clamped) input and are flagged in ``log``."""
     controller = controller or LinearMPC(problem)
     as_np = not io.is_tensor(x0)
-    x = io.to_dev(x0, torch.float64)
+    x = io.to_dev(x0, controller.dtype)
     if x.dim() == 1:
         x = x[None, :]
-    A, B = io.to_dev(problem.A, torch.float64), io.to_dev(problem.B, torch.float64)
+    A, B = io.to_dev(problem.A, controller.dtype, x.device), io.to_dev(problem.B, controller.dtype, x.device)
     xs, us = [x], []
     for _ in range(int(n_steps)):
         u = controller(xs[-1], log)
-        xn = lq.linear_step(A, B, xs[-1].t().contiguous(), u.t().contiguous()).t()
+        xn = lq.linear_step(A, B, xs[-1].t().contiguous(), u.to(xs[-1].dtype).t().contiguous()).t()
         xs.append(xn)
         us.append(u)
     return io.back(torch.stack(xs, dim=1), as_np), io.back(torch.stack(us, dim=1), as_np)

@@ -32,9 +32,10 @@ _lib.register("mpc_bicycle_rti_prepare", c_int, [c_double] * 5 + [c_int, c_void_
               [c_int64, c_int, c_int, c_void_p])
 _lib.register("mpc_bicycle_plant_step", c_int, [c_double] * 4 + [c_void_p, c_int64, c_int] + [c_void_p] * 3 +
               [c_int64, c_int, c_void_p])
-_lib.register("mpc_rti_workspace_bytes", c_int64, [c_int64, c_int, c_int])
-_lib.register("mpc_rti_closed_loop", c_int, [c_double] * 5 + [c_int, c_void_p, c_int, c_int] + [c_void_p] * 21 +
-              [c_int64, c_int64, c_int, c_int, c_double, c_int, c_void_p])
+_lib.register("mpc_rti_workspace_bytes", c_int64, [c_int64, c_int, c_int, c_int])
+_lib.register("mpc_rti_closed_loop", c_int,
+              [c_double] * 5 + [c_int] + [c_double] * 3 + [c_void_p, c_int, c_int, c_int, c_double] + [c_void_p] * 7 +
+              [c_int, c_double, c_double, c_void_p] + [c_void_p] * 14 + [c_int64, c_int64, c_int, c_int, c_double, c_int, c_void_p])
 
 _lib.register("mpc_bicycle_rti_prepare_obstacle", c_int, [c_double] * 5 + [c_int, c_double, c_double, c_void_p, c_void_p,
               c_void_p, c_int] + [c_void_p] * 6 + [c_int64, c_int, c_int, c_void_p])
@@ -77,7 +78,8 @@ class _Discrete:
     def __call__(self, x, u):
         if self.fusable:
             as_np = not io.any_tensor(x, u)
-            xd, ud = io.to_dev(x, F64), io.to_dev(u, F64)
+            dt = io.pick_dtype(x, u)
+            xd, ud = io.to_dev(x, dt), io.to_dev(u, dt)
             single = xd.dim() == 1
             xT = (xd[None, :] if single else xd).t().contiguous()
             uT = (ud[None, :] if single else ud).t().contiguous()
@@ -122,8 +124,10 @@ def plant_step(params, ts, x, u, friction=None, substeps=4):
     batch = x.shape[1]
     if friction is None:
         friction = params.friction
-    fr = friction if io.is_tensor(friction) else torch.full((1,), float(friction), dtype=F64, device=x.device)
-    fr = fr.to(device=x.device, dtype=F64).contiguous()
+    if u.dtype != x.dtype:
+        raise ValueError("x and u must share one dtype")
+    fr = friction if io.is_tensor(friction) else torch.full((1,), float(friction), dtype=x.dtype, device=x.device)
+    fr = fr.to(device=x.device, dtype=x.dtype).contiguous()
     sfr = 1 if fr.numel() == batch and batch > 1 else (1 if fr.numel() == batch else 0)
     if fr.numel() not in (1, batch):
         raise ValueError("friction must be a scalar or one value per scenario")
@@ -133,7 +137,7 @@ def plant_step(params, ts, x, u, friction=None, substeps=4):
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib().mpc_bicycle_plant_step(params.axis_rear, params.axis_front, params.acceleration, float(ts),
                                                      _lib.ptr(fr), sfr, int(substeps), _lib.ptr(x.contiguous()),
-                                                     _lib.ptr(u.contiguous()), _lib.ptr(xn), batch, _lib.MPC_F64,
+                                                     _lib.ptr(u.contiguous()), _lib.ptr(xn), batch, _lib.dtype_enum(x),
                                                      _lib.stream(x.device)))
     return xn
 
@@ -153,6 +157,7 @@ class RtiClosedLoopResult:
     last_status: torch.Tensor  # [batch]
     X_bundle: torch.Tensor = None  # [steps, N+1, 4, batch] state prediction of every control step (keep_predictions)
     U_bundle: torch.Tensor = None  # [steps, N, 2, batch]
+    clearance: torch.Tensor = None  # [batch] obstacle controller: min |c_i - o_j|^2 - (2r)^2 along the loop
 
     def bundle(self, scenario: int = 0):
         """(time steps x horizon x states) array of one scenario, the layout AnimateParking.bundle takes
@@ -175,16 +180,35 @@ class MPCController:
     template.py:136), R = diag(1, .01); input box as variable bounds and state box on x_1..x_N from
     ``params`` (session4_sol.py:176-181).  ``integrator``: "euler" (session4_sol.py:192) or "rk4"
     (template.py:141).  The controller keeps one input plan per scenario between calls (warm start).
+
+    ``sqp_iters``: linearise-and-solve rounds per call / control step.  1 (default) is the real-time
+    iteration; k > 1 re-linearises at the new plan k - 1 more times (full-step SQP), which converges to the
+    solution of the nonlinear OCP that the reference's IPOPT call returns (session4_sol.py:126-130);
+    ``sqp_tol`` > 0 ends the rounds of a scenario once its plan moves by less than sqp_tol * max(1, |U|).
+    ``swap_state_bounds``: reproduce template.py:132-133, which lists the state bounds in the order
+    [x, y, vel, heading] against the state order [x, y, heading, vel] (default: the corrected order of
+    session4_sol.py:176-177).  ``dtype``: torch.float64 (reference arithmetic) or torch.float32 arrays.
     """
 
+    fusable_loop = True
+    _nc = 0
+
     def __init__(self, N: int, ts: float, *, params: VehicleParameters, integrator: str = "euler",
-                 terminal_scale: float = 10.0, max_iter: int = 60, eps: float = 1e-9):
+                 terminal_scale: float = 10.0, max_iter: int = 60, eps: float = 1e-9, sqp_iters: int = 1,
+                 sqp_tol: float = 0.0, swap_state_bounds: bool = False, dtype=torch.float64):
         if integrator not in ("euler", "rk4"):
             raise ValueError("integrator must be 'euler' or 'rk4'")
+        if int(sqp_iters) < 1 or sqp_tol < 0:
+            raise ValueError("sqp_iters must be >= 1 and sqp_tol >= 0")
+        if dtype not in (torch.float64, torch.float32):
+            raise ValueError("dtype must be torch.float64 or torch.float32")
         self.N, self.ts = int(N), float(ts)
         self.params = params
         self.integrator = integrator
         self.max_iter, self.eps = max_iter, eps
+        self.sqp_iters, self.sqp_tol = int(sqp_iters), float(sqp_tol)
+        self.swap_state_bounds = bool(swap_state_bounds)
+        self.dtype = dtype
         self.Q = np.diag([1.0, 3.0, 0.1, 0.01])
         self.QT = terminal_scale * self.Q
         self.R = np.diag([1.0, 1e-2])
@@ -196,6 +220,8 @@ class MPCController:
     def build_bounds(self, params):
         s_lb = np.array([params.min_pos_x, params.min_pos_y, params.min_heading, params.min_vel])
         s_ub = np.array([params.max_pos_x, params.max_pos_y, params.max_heading, params.max_vel])
+        if self.swap_state_bounds:   # template.py:132-133: [x, y, vel, heading] applied to [x, y, heading, vel]
+            s_lb, s_ub = s_lb[[0, 1, 3, 2]], s_ub[[0, 1, 3, 2]]
         i_lb = np.array([params.min_drive, -params.max_steer])
         i_ub = np.array([params.max_drive, params.max_steer])
         self._boxes = (i_lb, i_ub, s_lb, s_ub)
@@ -209,32 +235,51 @@ class MPCController:
         p = self.params
         return (p.axis_rear, p.axis_front, p.acceleration, float(p.friction), self.ts, 1 if self.integrator == "rk4" else 0)
 
-    def _solve_dev(self, yT):
-        """yT [4, batch] on the device -> BoxQpResult (aliases the controller's workspace)."""
-        batch, N = yT.shape[1], self.N
+    def _obstacle_args(self):
+        return 0, 0.0, 0.0, None
+
+    def _prepare(self, yT, first, bufs):
+        warm, A, B, c = bufs[:4]
         dev = yT.device
-        first = self._plan is None or self._plan.shape[2] != batch or self._plan.device != dev
-        if first:
-            self._plan = torch.zeros((N, 2, batch), dtype=F64, device=dev)
-            self._lin = [torch.empty((N, k, batch), dtype=F64, device=dev) for k in (2, 16, 8, 4)]
-            self._qp_ws = boxqp.BoxQpWorkspace(batch, 4, 2, N, dev)
-        warm, A, B, c = self._lin
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().mpc_bicycle_rti_prepare(*self._model_args(), _lib.ptr(yT), _lib.ptr(self._plan),
                                                           1 if first else 0, _lib.ptr(warm), _lib.ptr(A), _lib.ptr(B),
-                                                          _lib.ptr(c), batch, N, _lib.MPC_F64, _lib.stream(dev)))
+                                                          _lib.ptr(c), yT.shape[1], self.N, _lib.dtype_enum(yT),
+                                                          _lib.stream(dev)))
+        return {}
+
+    _lin_sizes = (2, 16, 8, 4)
+
+    def _solve_dev(self, yT):
+        """yT [4, batch] on the device -> BoxQpResult (aliases the controller's workspace)."""
+        batch, N = yT.shape[1], self.N
+        dev, dt = yT.device, yT.dtype
+        first = (self._plan is None or self._plan.shape[2] != batch or self._plan.device != dev or self._plan.dtype != dt)
+        if first:
+            self._plan = torch.zeros((N, 2, batch), dtype=dt, device=dev)
+            self._lin = [torch.empty((N, k, batch), dtype=dt, device=dev) for k in self._lin_sizes]
+            self._qp_ws = boxqp.BoxQpWorkspace(batch, 4, 2, N, dev, nc=self._nc, dtype=dt)
+        warm, A, B, c = self._lin[:4]
         i_lb, i_ub, s_lb, s_ub = self._boxes
-        Q, R, QT = (torch.as_tensor(M, dtype=F64, device=dev) for M in (self.Q, self.R, self.QT))
-        res = boxqp.solve(A, B, Q, R, QT, N, yT, i_lb, i_ub, s_lb, s_ub, c=c, warm_U=warm, max_iter=self.max_iter,
-                          eps=self.eps, workspace=self._qp_ws)
-        self._plan.copy_(res.U)
+        Q, R, QT = (torch.as_tensor(M, dtype=dt, device=dev) for M in (self.Q, self.R, self.QT))
+        res = None
+        for rnd in range(self.sqp_iters):
+            rows = self._prepare(yT, first or rnd > 0, self._lin)
+            res = boxqp.solve(A, B, Q, R, QT, N, yT, i_lb, i_ub, s_lb, s_ub, c=c, warm_U=warm, max_iter=self.max_iter,
+                              eps=self.eps, workspace=self._qp_ws, **rows)
+            moved = None
+            if self.sqp_tol > 0 and rnd + 1 < self.sqp_iters:
+                moved = float(((res.U - warm).abs().amax(dim=(0, 1)) / res.U.abs().amax(dim=(0, 1)).clamp(min=1.0)).max())
+            self._plan.copy_(res.U)
+            if moved is not None and moved <= self.sqp_tol:
+                break
         return res
 
     def solve(self, x) -> dict:
         """{"x": stacked inputs}: (2N,) for one state, (batch, 2N) for a batch -- the layout of the
         reference's ``sol["x"]`` (u_0, u_1, ... concatenated, session4_sol.py:206)."""
         as_np = not io.is_tensor(x)
-        xd = io.to_dev(x, F64)
+        xd = io.to_dev(x, self.dtype)
         single = xd.dim() == 1
         yT = (xd[None, :] if single else xd).t().contiguous()
         res = self._solve_dev(yT)
@@ -254,45 +299,58 @@ class MPCController:
         u = self.reshape_input(self.solve(y))
         return u[0] if (u.dim() if io.is_tensor(u) else u.ndim) == 2 else u[:, 0]
 
-    # -- fused closed loop: `steps` x (prepare, QP, plant) in one kernel
+    # -- fused closed loop: `steps` x (sqp_iters x (prepare, QP), plant) in one kernel
     def closed_loop(self, x0, n_steps, plant: _Discrete = None, friction_plant=None,
                     keep_predictions: bool = False) -> RtiClosedLoopResult:
-        xd = io.to_dev(x0, F64)
+        """Closed loop of this controller against a bicycle plant in ONE kernel launch.  ``plant``: dynamics from
+        forward_euler / runge_kutta4 / exact_integration over a :class:`KinematicBicycle` (default: RK4 x 4 sub-steps of
+        the controller's own parameters); its axle distances, acceleration gain and friction are the PLANT's, the
+        controller predicts with its own ``params`` (the reference's mismatch study, session4_sol.py:461-465).
+        ``friction_plant`` overrides the plant friction per scenario."""
+        dt = self.dtype
+        xd = io.to_dev(x0, dt)
         if xd.dim() == 1:
             xd = xd[None, :]
         x0T = xd.t().contiguous()
         batch, N, dev = x0T.shape[1], self.N, x0T.device
-        pp = self.params if plant is None or not plant.fusable else plant.f.params
+        if plant is not None and not (isinstance(plant, _Discrete) and plant.fusable):
+            raise ValueError("closed_loop fuses bicycle plants only (forward_euler / runge_kutta4 / exact_integration of a "
+                             "KinematicBicycle); drive other dynamics with simulate(x0, dynamics, n_steps, policy=controller)")
+        pp = self.params if plant is None else plant.f.params
         substeps = 4 if plant is None else (0 if plant.kind == "euler" else (plant.substeps if plant.substeps < 0 else max(plant.substeps, 1)))
         if plant is not None and abs(plant.ts - self.ts) > 1e-15:
             raise ValueError("plant and controller sampling times differ")
         if friction_plant is None:
-            fr = torch.full((batch,), float(pp.friction), dtype=F64, device=dev)
+            fr = torch.full((batch,), float(pp.friction), dtype=dt, device=dev)
         else:
-            fr = io.to_dev(friction_plant, F64).reshape(-1).expand(batch).contiguous() if not io.is_tensor(friction_plant) \
-                else friction_plant.to(device=dev, dtype=F64).reshape(-1).expand(batch).contiguous()
-        plan = torch.zeros((N, 2, batch), dtype=F64, device=dev)
-        Xp = torch.empty((N + 1, 4, batch), dtype=F64, device=dev)
-        Xc = torch.empty((n_steps + 1, 4, batch), dtype=F64, device=dev)
-        Uc = torch.empty((n_steps, 2, batch), dtype=F64, device=dev)
-        cost = torch.empty(batch, dtype=F64, device=dev)
-        viol = torch.empty(batch, dtype=F64, device=dev)
+            fr = io.to_dev(friction_plant, dt).reshape(-1).expand(batch).contiguous() if not io.is_tensor(friction_plant) \
+                else friction_plant.to(device=dev, dtype=dt).reshape(-1).expand(batch).contiguous()
+        plan = torch.zeros((N, 2, batch), dtype=dt, device=dev)
+        Xp = torch.empty((N + 1, 4, batch), dtype=dt, device=dev)
+        Xc = torch.empty((n_steps + 1, 4, batch), dtype=dt, device=dev)
+        Uc = torch.empty((n_steps, 2, batch), dtype=dt, device=dev)
+        cost = torch.empty(batch, dtype=dt, device=dev)
+        viol = torch.empty(batch, dtype=dt, device=dev)
+        nc, length, width, xo = self._obstacle_args()
+        clear = torch.empty(batch, dtype=dt, device=dev) if nc else None
         ints = [torch.empty(batch, dtype=torch.int32, device=dev) for _ in range(4)]
-        Xb = torch.empty((n_steps, N + 1, 4, batch), dtype=F64, device=dev) if keep_predictions else None
-        Ub = torch.empty((n_steps, N, 2, batch), dtype=F64, device=dev) if keep_predictions else None
-        nbytes = _lib.lib().mpc_rti_workspace_bytes(batch, N, _lib.MPC_F64)
-        ws = torch.empty(max(nbytes // 8, 1), dtype=F64, device=dev)
-        i_lb, i_ub, s_lb, s_ub = (torch.as_tensor(v, dtype=F64, device=dev).contiguous() for v in self._boxes)
-        Q, R, QT = (torch.as_tensor(M, dtype=F64, device=dev).contiguous() for M in (self.Q, self.R, self.QT))
+        Xb = torch.empty((n_steps, N + 1, 4, batch), dtype=dt, device=dev) if keep_predictions else None
+        Ub = torch.empty((n_steps, N, 2, batch), dtype=dt, device=dev) if keep_predictions else None
+        en = _lib.MPC_F64 if dt == torch.float64 else _lib.MPC_F32
+        nbytes = _lib.lib().mpc_rti_workspace_bytes(batch, N, nc, en)
+        ws = torch.empty(max(nbytes // 8, 1) + 2, dtype=torch.float64, device=dev)
+        i_lb, i_ub, s_lb, s_ub = (torch.as_tensor(v, dtype=dt, device=dev).contiguous() for v in self._boxes)
+        Q, R, QT = (torch.as_tensor(M, dtype=dt, device=dev).contiguous() for M in (self.Q, self.R, self.QT))
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().mpc_rti_closed_loop(
-                *self._model_args(), _lib.ptr(fr), int(substeps), int(n_steps), _lib.ptr(Q), _lib.ptr(R), _lib.ptr(QT),
-                _lib.ptr(i_lb), _lib.ptr(i_ub), _lib.ptr(s_lb), _lib.ptr(s_ub), _lib.ptr(x0T), _lib.ptr(plan), _lib.ptr(Xp),
-                _lib.ptr(Xc), _lib.ptr(Uc), _lib.ptr(cost), _lib.ptr(viol), *[_lib.ptr(t) for t in ints], _lib.ptr(Xb), _lib.ptr(Ub),
-                _lib.ptr(ws),
-                nbytes, batch, N, int(self.max_iter), float(self.eps), _lib.MPC_F64, _lib.stream(dev)))
+                *self._model_args(), float(pp.axis_rear), float(pp.axis_front), float(pp.acceleration), _lib.ptr(fr),
+                int(substeps), int(n_steps), self.sqp_iters, self.sqp_tol, _lib.ptr(Q), _lib.ptr(R), _lib.ptr(QT),
+                _lib.ptr(i_lb), _lib.ptr(i_ub), _lib.ptr(s_lb), _lib.ptr(s_ub), nc, length, width, xo, _lib.ptr(x0T),
+                _lib.ptr(plan), _lib.ptr(Xp), _lib.ptr(Xc), _lib.ptr(Uc), _lib.ptr(cost), _lib.ptr(viol), _lib.ptr(clear),
+                *[_lib.ptr(t) for t in ints], _lib.ptr(Xb), _lib.ptr(Ub), _lib.ptr(ws), nbytes, batch, N, int(self.max_iter),
+                float(self.eps), en, _lib.stream(dev)))
         self._plan = plan
-        return RtiClosedLoopResult(Xc, Uc, cost, viol, ints[0], ints[1], ints[2], ints[3], Xb, Ub)
+        return RtiClosedLoopResult(Xc, Uc, cost, viol, ints[0], ints[1], ints[2], ints[3], Xb, Ub, clear)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -318,13 +376,19 @@ class ObstacleMPCController(MPCController):
     (:76), input box, state box, and the nine collision constraints between the three covering
     circles of the vehicle and of the obstacle parked at ``x_obs`` (:49-56, :95-104).  Every control
     step linearises the collision constraints along the rolled-out plan and solves ONE QP with
-    polytopic stage constraints on the GPU (K4 with general rows)."""
+    polytopic stage constraints on the GPU (K4 with general rows); ``closed_loop`` /
+    ``simulate(x0, exact_integration(bicycle, ts), n_steps, policy=controller)`` (main.py:269-271) run the
+    whole loop in one kernel."""
+
+    _nc = 9
+    _lin_sizes = (2, 16, 8, 4, 36, 9)
 
     def __init__(self, N: int, ts: float, params: VehicleParameters, model=None, x_obs=None, max_iter: int = 60,
-                 eps: float = 1e-9):
+                 eps: float = 1e-9, sqp_iters: int = 1, sqp_tol: float = 0.0, dtype=torch.float64):
         if x_obs is None:
             raise ValueError("x_obs (pose of the parked obstacle) is required")
-        super().__init__(N, ts, params=params, integrator="euler", max_iter=max_iter, eps=eps)
+        super().__init__(N, ts, params=params, integrator="euler", max_iter=max_iter, eps=eps, sqp_iters=sqp_iters,
+                         sqp_tol=sqp_tol, dtype=dtype)
         self.model = model
         self.x_obs = np.asarray(x_obs, dtype=np.float64).reshape(-1)
         self.Q = np.diag([1.0, 6.0, 0.2, 0.05])
@@ -338,59 +402,84 @@ class ObstacleMPCController(MPCController):
         _, r = create_cover_circles(self.params.length, self.params.width, 3)
         return float((2 * r) ** 2)
 
-    def _solve_dev(self, yT):
-        batch, N = yT.shape[1], self.N
-        dev = yT.device
-        first = self._plan is None or self._plan.shape[2] != batch or self._plan.device != dev
-        if first:
-            self._plan = torch.zeros((N, 2, batch), dtype=F64, device=dev)
-            self._lin = [torch.empty((N, k, batch), dtype=F64, device=dev) for k in (2, 16, 8, 4, 36, 9)]
-            self._qp_ws = boxqp.BoxQpWorkspace(batch, 4, 2, N, dev, nc=9)
-        warm, A, B, c, Cg, hg = self._lin
-        from ctypes import POINTER
-        xo = (c_double * 4)(*[float(v) for v in self.x_obs[:4]])
+    def _obstacle_args(self):
         p = self.params
+        return 9, float(p.length), float(p.width), (c_double * 4)(*[float(v) for v in self.x_obs[:4]])
+
+    def _prepare(self, yT, first, bufs):
+        warm, A, B, c, Cg, hg = bufs
+        dev = yT.device
+        _, length, width, xo = self._obstacle_args()
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().mpc_bicycle_rti_prepare_obstacle(
-                *self._model_args(), float(p.length), float(p.width), xo, _lib.ptr(yT), _lib.ptr(self._plan),
-                1 if first else 0, _lib.ptr(warm), _lib.ptr(A), _lib.ptr(B), _lib.ptr(c), _lib.ptr(Cg), _lib.ptr(hg), batch, N,
-                _lib.MPC_F64, _lib.stream(dev)))
-        i_lb, i_ub, s_lb, s_ub = self._boxes
-        Q, R, QT = (torch.as_tensor(M, dtype=F64, device=dev) for M in (self.Q, self.R, self.QT))
-        res = boxqp.solve(A, B, Q, R, QT, N, yT, i_lb, i_ub, s_lb, s_ub, c=c, warm_U=warm, max_iter=self.max_iter,
-                          eps=self.eps, workspace=self._qp_ws, Cg=Cg, hg=hg)
-        self._plan.copy_(res.U)
-        return res
-
-    def closed_loop(self, *args, **kwargs):
-        raise NotImplementedError("the fused closed-loop kernel covers the box-constrained controller; drive this "
-                                  "controller step by step (simulate(x0, dynamics, n_steps, policy=controller))")
+                *self._model_args(), length, width, xo, _lib.ptr(yT), _lib.ptr(self._plan),
+                1 if first else 0, _lib.ptr(warm), _lib.ptr(A), _lib.ptr(B), _lib.ptr(c), _lib.ptr(Cg), _lib.ptr(hg),
+                yT.shape[1], self.N, _lib.dtype_enum(yT), _lib.stream(dev)))
+        return {"Cg": Cg, "hg": hg}
 
 
 # ------------------------------------------------------------------------------------------------
 # closed-loop driver (the reference imports it from rcracers.simulator)
 # ------------------------------------------------------------------------------------------------
-def simulate(x0, dynamics: Callable, n_steps: int, policy=None, friction_plant=None):
-    """States of the closed loop: (n_steps+1, 4) for one x0, (batch, n_steps+1, 4) for a batch.
+def _policy_caller(policy):
+    """How the course simulator (rcracers.simulator.simulate; call sites session4_sol.py:361,366,407,416,458,465,
+    template.py:391,396, main.py:270) hands arguments to a policy: by PARAMETER NAME.  A policy may name any of ``y``
+    (the measured state), ``t`` (the step index) and ``log`` (the controller log of sessions 2/3,
+    session_2/log.py:8-12) and receives exactly those: ``open_loop_policy(t)`` (session4_sol.py:353-354) gets the step
+    index, ``lambda y, t:`` (:61) both, ``MPCController.__call__(y)`` (:222) the state, a sessions-2/3 controller
+    ``__call__(y, log)`` the state and the log.  Parameters with other names are filled positionally from
+    (y, t) so that ``lambda x: ...`` and ``lambda x, k: ...`` keep working."""
+    import inspect
+    try:
+        params = [q for q in inspect.signature(policy).parameters.values()
+                  if q.kind in (q.POSITIONAL_ONLY, q.POSITIONAL_OR_KEYWORD, q.KEYWORD_ONLY)]
+    except (TypeError, ValueError):   # builtins / C callables: call with the measurement only
+        return lambda y, t, log: policy(y)
+    names = [q.name for q in params]
+    known = {"y", "t", "log"}
+    if names and all(nm in known for nm in names):
+        def call(y, t, log):
+            kw = {"y": y, "t": t, "log": log}
+            return policy(**{nm: kw[nm] for nm in names})
+        return call
+    # unknown names: (state, step index) in order; a parameter called `log` still receives the log
+    free = [q for q in params if q.name != "log" and q.kind != q.KEYWORD_ONLY and q.default is q.empty]
+    takes_log = "log" in names
+
+    def call(y, t, log):
+        args = (y, t)[:max(1, min(2, len(free)))]
+        return policy(*args, log=log) if takes_log else policy(*args)
+    return call
+
+
+def _same_bicycle(p, q):
+    return all(float(getattr(p, k)) == float(getattr(q, k)) for k in ("axis_rear", "axis_front", "acceleration"))
+
+
+def simulate(x0, dynamics: Callable, n_steps: int, policy=None, friction_plant=None, log=None):
+    """States of the closed loop: (n_steps+1, n) for one x0, (batch, n_steps+1, n) for a batch -- the call
+    ``simulate(x0, dynamics, n_steps, policy=..., log=...)`` the reference imports from rcracers.
     With an :class:`MPCController` policy and bicycle dynamics from one of the integrator factories
-    the whole loop is one fused kernel; any other callables run step by step.  The policy is called
-    as ``policy(y)`` or ``policy(y, t)`` depending on its signature, as the course simulator does."""
+    the whole loop is one fused kernel (prediction model = the controller's parameters, plant = the
+    dynamics' parameters); any other callables run step by step.  The policy receives ``y`` / ``t`` /
+    ``log`` according to its parameter NAMES (see :func:`_policy_caller`)."""
     as_np = not io.is_tensor(x0)
-    if (isinstance(policy, MPCController) and not isinstance(policy, ObstacleMPCController)
+    if (isinstance(policy, MPCController) and policy.fusable_loop and log is None
             and isinstance(dynamics, _Discrete) and dynamics.fusable):
         policy.reset()
         res = policy.closed_loop(x0, int(n_steps), plant=dynamics, friction_plant=friction_plant)
         X = res.states
         single = (np.ndim(x0) if as_np else x0.dim()) == 1
         return io.back(X[0] if single else X, as_np)
-    import inspect
+    if policy is None:
+        raise ValueError("simulate needs a policy")
     if isinstance(policy, MPCController):
         policy.reset()
-    takes_t = policy is not None and len(inspect.signature(policy).parameters) >= 2
+    call = _policy_caller(policy)
     x = x0
     xs = [x]
     for t in range(int(n_steps)):
-        u = policy(x, t) if takes_t else policy(x)
+        u = call(x, t, log)
         x = dynamics(x, u)
         xs.append(x)
     if as_np:

@@ -175,37 +175,54 @@ def rti_prepare(y, U_prev, ts, par, friction, method="euler", first=False):
 
 
 def closed_loop(x0, n_steps, N=50, ts=0.05, par=None, friction_model=None, friction_plant=None, ocp_method="euler",
-                plant_method="rk4", substeps=4, variant="sol", qp="port", max_iter=60):
+                plant_method="rk4", substeps=4, variant="sol", qp="port", max_iter=60, sqp_iters=1, sqp_tol=0.0,
+                plant_par=None, keep_plans=False):
     """Batched RTI closed loop.  x0 [batch,4].  qp = "port" (numpy restatement of the GPU interior
     point method, batched) or "exact" (HiGHS active set + KKT refinement, one scenario at a time).
+    sqp_iters > 1: re-linearise at the new plan and solve again (full-step SQP), per control step; a scenario whose
+    plan moved by <= sqp_tol * max(1, |U|) stops early.  plant_par: parameters of the plant (default: the model's).
     Returns dict(X [steps+1,batch,4], U [steps,batch,2], status [steps,batch], cost [batch], viol [batch])."""
     par = par or VehicleParameters()
+    pp = plant_par or par
     x = np.atleast_2d(np.asarray(x0, float))
     batch = x.shape[0]
     fm = par.friction if friction_model is None else friction_model
-    fp = np.full(batch, par.friction, float) if friction_plant is None else np.broadcast_to(np.asarray(friction_plant, float), (batch,))
+    fp = np.full(batch, pp.friction, float) if friction_plant is None else np.broadcast_to(np.asarray(friction_plant, float), (batch,))
     Q, QT, R = weights(variant)
     ulo, uhi, xlo, xhi = bounds(par)
     U_prev = np.zeros((N, batch, 2))
-    Xs, Us, Ss = [x], [], []
+    Xs, Us, Ss, Ps = [x], [], [], []
     cost = np.zeros(batch); viol = np.zeros(batch)
     for t in range(n_steps):
-        Ubar, A, B, c, _ = rti_prepare(x, U_prev, ts, par, fm, ocp_method, first=(t == 0))
-        if qp == "port":
-            r = bq.ipm_riccati(list(A), list(B), Q, R, QT, N, x, ulo, uhi, xlo, xhi, c=list(c), warm_U=Ubar, max_iter=max_iter)
-            U, status = r["U"], r["status"]
-        else:
-            U = np.zeros((N, batch, 2)); status = np.zeros(batch, dtype=np.int32)
-            for b in range(batch):
-                e = bq.solve_exact(A[:, b], B[:, b], Q, R, QT, N, x[b], ulo, uhi, xlo, xhi, c=c[:, b])
-                U[:, b], status[b] = e["U"], e["status"]
+        live = np.ones(batch, dtype=bool)
+        for rnd in range(sqp_iters):
+            Ubar, A, B, c, _ = rti_prepare(x, U_prev, ts, par, fm, ocp_method, first=(t == 0 or rnd > 0))
+            if qp == "port":
+                r = bq.ipm_riccati(list(A), list(B), Q, R, QT, N, x, ulo, uhi, xlo, xhi, c=list(c), warm_U=Ubar, max_iter=max_iter)
+                U, status = r["U"], r["status"]
+            else:
+                U = np.zeros((N, batch, 2)); status = np.zeros(batch, dtype=np.int32)
+                for b in range(batch):
+                    e = bq.solve_exact(A[:, b], B[:, b], Q, R, QT, N, x[b], ulo, uhi, xlo, xhi, c=c[:, b])
+                    U[:, b], status[b] = e["U"], e["status"]
+            U = np.where(live[None, :, None], U, U_prev)   # scenarios that already met sqp_tol keep their plan
+            if rnd + 1 < sqp_iters and sqp_tol > 0:
+                du = np.abs(U - Ubar).max(axis=(0, 2)); un = np.maximum(1.0, np.abs(U).max(axis=(0, 2)))
+                live = live & ~(du <= sqp_tol * un)
+            U_prev = U
+            if not live.any():
+                break
         u0 = U[0]
         cost += np.einsum("bi,ij,bj->b", x, Q, x) + np.einsum("bi,ij,bj->b", u0, R, u0)
-        x = _plant(x, u0, ts, par, fp, plant_method, substeps)
+        x = _plant(x, u0, ts, pp, fp, plant_method, substeps)
         viol = np.maximum(viol, np.maximum(xlo - x, x - xhi).max(axis=1).clip(min=0))
-        U_prev = U
         Xs.append(x); Us.append(u0); Ss.append(status)
-    return {"X": np.array(Xs), "U": np.array(Us), "status": np.array(Ss), "cost": cost, "viol": viol}
+        if keep_plans:
+            Ps.append(U.copy())
+    out = {"X": np.array(Xs), "U": np.array(Us), "status": np.array(Ss), "cost": cost, "viol": viol}
+    if keep_plans:
+        out["plans"] = np.array(Ps)
+    return out
 
 
 def _plant(x, u, ts, par, friction, method, substeps):

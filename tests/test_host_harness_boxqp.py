@@ -18,7 +18,7 @@ def c_(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
-def run_harness(hh, A, B, c, ltv, Q, R, Pf, ulo, uhi, xlo, xhi, x0, N, warm=None, max_iter=60, eps=1e-9):
+def run_harness(hh, A, B, c, ltv, Q, R, Pf, ulo, uhi, xlo, xhi, x0, N, warm=None, max_iter=60, eps=1e-9, store=1):
     """x0 [batch, n] -> dict with U [N, batch, m], X [N+1, batch, n] (oracle layout)."""
     batch, n = x0.shape
     m = len(ulo)
@@ -31,7 +31,7 @@ def run_harness(hh, A, B, c, ltv, Q, R, Pf, ulo, uhi, xlo, xhi, x0, N, warm=None
                            p(c_(ulo)), p(c_(uhi)), p(c_(xlo)), p(c_(xhi)), p(x0T), p(warmT), p(U), p(X), p(cost),
                            status.ctypes.data_as(C.POINTER(C.c_int32)), iters.ctypes.data_as(C.POINTER(C.c_int32)),
                            su.ctypes.data_as(C.POINTER(C.c_int8)), sx.ctypes.data_as(C.POINTER(C.c_int8)),
-                           C.c_int64(batch), n, m, N, max_iter, C.c_double(eps))
+                           C.c_int64(batch), n, m, N, max_iter, C.c_double(eps), store)
     assert rc == 0
     return {"U": U.transpose(0, 2, 1), "X": X.transpose(0, 2, 1), "cost": cost, "status": status, "iters": iters,
             "sat_u": su.transpose(0, 2, 1), "sat_x": sx.transpose(0, 2, 1)}
@@ -41,15 +41,16 @@ def session_x0(rng, batch):
     return np.stack([rng.uniform(-100, 0, batch), rng.uniform(-10, 15, batch)], 1)
 
 
+@pytest.mark.parametrize("store", [0, 1])
 @pytest.mark.parametrize("make,N", [(bq.Problem, 5), (bq.Problem, 30), (bq.session3_problem, 30)])
-def test_session23_problem_matches_numpy_port_and_exact(hh, make, N):
+def test_session23_problem_matches_numpy_port_and_exact(hh, make, N, store):
     prob = make(N=N)
     ulo, uhi, xlo, xhi = bq.problem_bounds(prob)
     rng = np.random.default_rng(N)
     x0 = session_x0(rng, 48)
     x0[0] = [-100.0, 0.0]  # U* = [10,10,10,10,-20] at N = 5
     x0[1] = [-1.0, 14.0]   # cannot brake in time: infeasible
-    got = run_harness(hh, prob.A, prob.B, None, 0, prob.Q, prob.R, prob.Q, ulo, uhi, xlo, xhi, x0, N)
+    got = run_harness(hh, prob.A, prob.B, None, 0, prob.Q, prob.R, prob.Q, ulo, uhi, xlo, xhi, x0, N, store=store)
     port = bq.ipm_riccati(prob.A, prob.B, prob.Q, prob.R, prob.Q, N, x0, ulo, uhi, xlo, xhi)
     np.testing.assert_array_equal(got["status"], port["status"])
     np.testing.assert_array_equal(got["iters"], port["iters"])
@@ -87,8 +88,9 @@ def random_ltv(rng, batch, N, n, m):
     return A, B, c
 
 
+@pytest.mark.parametrize("store", [0, 1])
 @pytest.mark.parametrize("n,m", [(2, 1), (4, 1), (4, 2)])
-def test_ltv_per_scenario_models(hh, n, m):
+def test_ltv_per_scenario_models(hh, n, m, store):
     rng = np.random.default_rng(n * 10 + m)
     batch, N = 12, 15
     A, B, c = random_ltv(rng, batch, N, n, m)
@@ -101,7 +103,7 @@ def test_ltv_per_scenario_models(hh, n, m):
     # harness layout: A [N][n*n][batch]
     Ah = A.reshape(N, batch, n * n).transpose(0, 2, 1); Bh = B.reshape(N, batch, n * m).transpose(0, 2, 1)
     ch = c.transpose(0, 2, 1)
-    got = run_harness(hh, Ah, Bh, ch, 1, Q, R, Pf, ulo, uhi, xlo, xhi, x0, N, warm=warm)
+    got = run_harness(hh, Ah, Bh, ch, 1, Q, R, Pf, ulo, uhi, xlo, xhi, x0, N, warm=warm, store=store)
     port = bq.ipm_riccati(list(A), list(B), Q, R, Pf, N, x0, ulo, uhi, xlo, xhi, c=list(c), warm_U=warm)
     np.testing.assert_array_equal(got["status"], port["status"])
     ok = got["status"] == bq.SOLVED
@@ -144,8 +146,9 @@ def rows_problem(rng, batch, N, nc, n=4, m=2):
     return A, B, c, Q, R, Pf, ulo, uhi, xlo, xhi, x0, Cg, hg
 
 
+@pytest.mark.parametrize("store", [0, 1])
 @pytest.mark.parametrize("nc", [3, 9])
-def test_general_stage_rows(hh, nc):
+def test_general_stage_rows(hh, nc, store):
     """Polytopic stage constraints Cg x >= hg (the linearised collision constraints of
     session_4/main.py:95-104 have this form) against the numpy restatement and the exact oracle."""
     rng = np.random.default_rng(40 + nc)
@@ -161,7 +164,7 @@ def test_general_stage_rows(hh, nc):
                                 p(c_(xhi)), p(c_(Cg.reshape(N, batch, nc * n).transpose(0, 2, 1))), p(c_(hg.transpose(0, 2, 1))), nc,
                                 p(c_(x0.T)), None, p(U), p(X), p(cost), status.ctypes.data_as(I32), iters.ctypes.data_as(I32),
                                 su.ctypes.data_as(I8), sx.ctypes.data_as(I8), scn.ctypes.data_as(I8), C.c_int64(batch), n, m, N,
-                                60, C.c_double(1e-9))
+                                60, C.c_double(1e-9), store)
     assert rc == 0
     port = bq.ipm_riccati(list(A), list(B), Q, R, Pf, N, x0, ulo, uhi, xlo, xhi, c=list(c), Cg=Cg, hg=hg)
     np.testing.assert_array_equal(status, port["status"])

@@ -74,31 +74,40 @@ def test_plant_step_body(hh, substeps):
     np.testing.assert_allclose(xn.T, ref, rtol=1e-12, atol=1e-14)
 
 
-def run_loop(hh, x0, fr, steps, N, rk4=0, substeps=4, ts=0.05, variant="sol"):
+def run_loop(hh, x0, fr, steps, N, rk4=0, substeps=4, ts=0.05, variant="sol", store=1, sqp_iters=1, sqp_tol=0.0,
+             plant_par=None, x_obs=None):
     par = bc.VehicleParameters()
+    pp = plant_par or par
     batch = x0.shape[0]
     Q, QT, R = bc.weights(variant)
     ulo, uhi, xlo, xhi = bc.bounds(par)
     U_plan = np.zeros((N, 2, batch)); X_pred = np.zeros((N + 1, 4, batch))
     X_cl = np.zeros((steps + 1, 4, batch)); U_cl = np.zeros((steps, 2, batch))
-    cost = np.zeros(batch); viol = np.zeros(batch)
+    cost = np.zeros(batch); viol = np.zeros(batch); clear = np.zeros(batch)
     ints = [np.zeros(batch, dtype=np.int32) for _ in range(4)]
+    nc = 0 if x_obs is None else 9
+    xo = None if x_obs is None else c_(x_obs)
     rc = hh.hh_rti_closed_loop(C.c_double(par.axis_rear), C.c_double(par.axis_front), C.c_double(par.acceleration),
-                               C.c_double(par.friction), C.c_double(ts), rk4, p(c_(fr)), substeps, steps, p(c_(Q)), p(c_(R)),
-                               p(c_(QT)), p(c_(ulo)), p(c_(uhi)), p(c_(xlo)), p(c_(xhi)), p(c_(x0.T)), p(U_plan), p(X_pred),
-                               p(X_cl), p(U_cl), p(cost), p(viol), *[a.ctypes.data_as(P32) for a in ints],
-                               C.c_int64(batch), N, 60, C.c_double(1e-9))
+                               C.c_double(par.friction), C.c_double(ts), rk4, C.c_double(pp.axis_rear),
+                               C.c_double(pp.axis_front), C.c_double(pp.acceleration), p(c_(fr)), substeps, steps,
+                               sqp_iters, C.c_double(sqp_tol), p(c_(Q)), p(c_(R)),
+                               p(c_(QT)), p(c_(ulo)), p(c_(uhi)), p(c_(xlo)), p(c_(xhi)), nc, C.c_double(0.17),
+                               C.c_double(0.08), p(xo), p(c_(x0.T)), p(U_plan), p(X_pred),
+                               p(X_cl), p(U_cl), p(cost), p(viol), p(clear), *[a.ctypes.data_as(P32) for a in ints],
+                               C.c_int64(batch), N, 60, C.c_double(1e-9), store)
     assert rc == 0
     return {"X": X_cl.transpose(0, 2, 1), "U": U_cl.transpose(0, 2, 1), "cost": cost, "viol": viol, "n_sat": ints[0],
-            "n_fail": ints[1], "iters": ints[2], "last_status": ints[3], "U_plan": U_plan.transpose(0, 2, 1)}
+            "n_fail": ints[1], "iters": ints[2], "last_status": ints[3], "U_plan": U_plan.transpose(0, 2, 1),
+            "X_pred": X_pred.transpose(0, 2, 1), "clear": clear}
 
 
+@pytest.mark.parametrize("store", [0, 1])
 @pytest.mark.parametrize("rk4", [0, 1])
-def test_closed_loop_matches_numpy_restatement(hh, rk4):
+def test_closed_loop_matches_numpy_restatement(hh, rk4, store):
     rng = np.random.default_rng(3)
     x0, fr = scenarios(rng, 6)
     steps, N = 25, 20
-    got = run_loop(hh, x0, fr, steps, N, rk4=rk4)
+    got = run_loop(hh, x0, fr, steps, N, rk4=rk4, store=store)
     ref = bc.closed_loop(x0, steps, N=N, friction_plant=fr, ocp_method="rk4" if rk4 else "euler", qp="port")
     assert np.all(got["n_fail"] == 0) and np.all(ref["status"] == 1)
     np.testing.assert_allclose(got["X"], ref["X"], rtol=0, atol=1e-6 * np.abs(ref["X"]).max())
