@@ -111,25 +111,58 @@ def krylov_path_fraction(A, B, cond_max=1e3):
 # CPU arms (oracle = restated reference; the only place bench.py executes oracle/)
 # ------------------------------------------------------------------------------------------------
 def _cpu_worker(args):
-    seed, count = args
-    from oracle import lq as olq
+    """One worker of the CPU arm: `count` cfg-2b scenarios, one finite-horizon solve each, in a Python loop.
+    kind == "reference": the reference's OWN functions, unmodified (FHC.ricatti_recursion, FHC.py:51-61; the open-loop
+    plan by AutoCruising.pred through LinearSystem.prediction exactly as FHC.py:87-88 calls it; V = x0'P_0 x0, :123-124),
+    imported from /root/reference or its staged copy oracle/_ref (oracle/ref_loader.py).
+    kind == "port": the oracle restatement of the same loop (when the reference files are not available)."""
+    seed, count, kind = args
     A, B, Q, R, Pf, x0 = cfg2b_inputs_numpy(count, seed)
-    t0 = time.perf_counter()
     acc = 0.0
+    if kind == "reference":
+        from oracle import ref_loader
+        FHC, _, _ = ref_loader.load_session1()
+        t0 = time.perf_counter()
+        for b in range(count):
+            P, K = FHC.ricatti_recursion(A[b], B[b], Q[b], R[b], Pf[b], 20)
+            sys_ = FHC.AutoCruising(A[b], B[b])
+            sys_.set_opti_gain(K)
+            xb = x0[b][:, None]
+            sys_.prediction(xb, sys_.pred, 20)
+            acc += float(xb.T @ P[0] @ xb)
+        return time.perf_counter() - t0, count, acc
+    from oracle import lq as olq
+    t0 = time.perf_counter()
     for b in range(count):  # the reference as shipped: one ricatti_recursion + rollout per scenario
         X, U, V, _, _ = olq.lq_open_loop(A[b], B[b], Q[b], R[b], Pf[b], x0[b], 20)
         acc += V
     return time.perf_counter() - t0, count, acc
 
 
-def cpu_reference_rate(total_scenarios, cores):
-    """Solves/s of the oracle port of FHC.ricatti_recursion + rollout, one Python loop per core."""
+def cpu_arm_kind():
+    """ "reference" when the reference's session-1 files are mounted or staged (oracle/_ref, built by
+    __graft_entry__.build()), else "port"."""
+    try:
+        from oracle import ref_loader
+        return "reference" if ref_loader.session1_root() is not None else "port"
+    except Exception:
+        return "port"
+
+
+CPU_SAMPLE = {"reference": "python loop of the reference's own FHC.ricatti_recursion + AutoCruising.pred / LinearSystem.prediction "
+                           "+ x0'P_0x0 per scenario (unmodified session_1 files), one process per core",
+              "port": "python loop of the oracle port of FHC.ricatti_recursion + rollout, one process per core"}
+
+
+def cpu_reference_rate(total_scenarios, cores, kind=None):
+    """Solves/s of the CPU arm, one Python loop per core."""
     import multiprocessing as mp
+    kind = kind or cpu_arm_kind()
     per = max(1, total_scenarios // cores)
     ctx = mp.get_context("spawn")
     t0 = time.perf_counter()
     with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, [(9000 + i, per) for i in range(cores)])
+        res = pool.map(_cpu_worker, [(9000 + i, per, kind) for i in range(cores)])
     wall = time.perf_counter() - t0
     inner = max(r[0] for r in res)
     done = sum(r[1] for r in res)
@@ -148,20 +181,21 @@ def run_reference_arm(args):
     if rank != 0:
         return
     cores = host_cores()
-    per_step = 1500 * cores  # ~1-2 s of CPU work per step on every core
+    kind = cpu_arm_kind()
+    per_step = (700 if kind == "reference" else 1500) * cores  # ~1-2 s of CPU work per step on every core
     rates = []
     for i in range(args.warmup + args.steps):
-        rate, done, wall = cpu_reference_rate(per_step, cores)
+        rate, done, wall = cpu_reference_rate(per_step, cores, kind)
         if i >= args.warmup:
             rates.append((rate, done))
     value = sum(r for r, _ in rates) / len(rates)
-    sample = f"{rates[0][1]} scenarios/step of cfg2b (nx=4,nu=1,N=20), python loop of the oracle port of FHC.ricatti_recursion + rollout, one process per core"
+    sample = f"{rates[0][1]} scenarios/step of cfg2b (nx=4,nu=1,N=20), {CPU_SAMPLE[kind]}"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * rates[0][1] / value,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "cfg2b: FHC Riccati LQ, nx=4 nu=1 N=20, per-scenario model + x0 (bounded CPU sample)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -229,6 +263,124 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
+# process context: one process per GPU (torchrun), NUMA placement, host-link probe
+# ------------------------------------------------------------------------------------------------
+def gpu_numa_cpus(index):
+    """(numa_node, cpu set) of the PCIe root the GPU hangs off (sysfs), or (None, None)."""
+    try:
+        bus = subprocess.run(["nvidia-smi", f"--id={index}", "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        if not bus:
+            return None, None
+        dom, rest = bus.split(":", 1)
+        path = f"/sys/bus/pci/devices/{dom[-4:]}:{rest}"
+        with open(path + "/numa_node") as fh:
+            node = int(fh.read().strip())
+        with open(path + "/local_cpulist") as fh:
+            cpus = set()
+            for part in fh.read().strip().split(","):
+                if "-" in part:
+                    lo, hi = part.split("-")
+                    cpus.update(range(int(lo), int(hi) + 1))
+                elif part:
+                    cpus.add(int(part))
+        return node, cpus
+    except Exception:
+        return None, None
+
+
+class Ctx:
+    """One rank of the bench: device, process group, barrier and the max-over-ranks reduction of a timing."""
+
+    def __init__(self, bind_numa=True):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+        self.affinity0 = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+        self.numa = None
+        if bind_numa and self.affinity0 is not None:
+            # pinned host buffers are allocated on the node of the thread that allocates them: run next to the GPU
+            node, cpus = gpu_numa_cpus(self.local)
+            if cpus:
+                use = cpus & self.affinity0
+                if use:
+                    os.sched_setaffinity(0, use)
+                    self.numa = {"node": node, "cpus": len(use)}
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier(device_ids=[self.local])
+        self.torch.cuda.synchronize()
+
+    def allmax(self, value):
+        t = self.torch.tensor([value], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(self, value):
+        t = self.torch.tensor([value], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def restore_affinity(self):
+        if self.affinity0 is not None:
+            os.sched_setaffinity(0, self.affinity0)
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def host_link_probe(ctx, mbytes=256, reps=6):
+    """Ceiling of the host link under the e2e protocol: plain pinned cudaMemcpyAsync, one call per buffer, all ranks
+    at the same time.  Returns GB/s per GPU for H2D alone, D2H alone and both directions concurrently (the e2e
+    pipeline runs full duplex), each the MIN over ranks (the slowest link bounds the max-over-ranks timing)."""
+    torch = ctx.torch
+    n = mbytes * (1 << 20) // 8
+    h_in = torch.empty(n, dtype=torch.float64, pin_memory=True).fill_(1.0)
+    h_out = torch.empty(n, dtype=torch.float64, pin_memory=True)
+    d_in = torch.empty(n, dtype=torch.float64, device=ctx.dev)
+    d_out = torch.ones(n, dtype=torch.float64, device=ctx.dev)
+    s1, s2 = torch.cuda.Stream(ctx.dev), torch.cuda.Stream(ctx.dev)
+
+    def timed(do_h2d, do_d2h):
+        ctx.barrier()
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        e[0].record(s1); e[2].record(s2)
+        for _ in range(reps):
+            if do_h2d:
+                with torch.cuda.stream(s1):
+                    d_in.copy_(h_in, non_blocking=True)
+            if do_d2h:
+                with torch.cuda.stream(s2):
+                    h_out.copy_(d_out, non_blocking=True)
+        e[1].record(s1); e[3].record(s2)
+        s1.synchronize(); s2.synchronize()
+        ms = max(e[0].elapsed_time(e[1]) if do_h2d else 0.0, e[2].elapsed_time(e[3]) if do_d2h else 0.0)
+        return ctx.allmax(ms)
+
+    timed(True, True)
+    nbytes = reps * n * 8
+    out = {"h2d_gbs": nbytes / (timed(True, False) * 1e-3) / 1e9, "d2h_gbs": nbytes / (timed(False, True) * 1e-3) / 1e9}
+    out["duplex_gbs_each"] = nbytes / (timed(True, True) * 1e-3) / 1e9
+    out["note"] = (f"pinned cudaMemcpyAsync of {mbytes} MiB x {reps}, one call per buffer, all {ctx.world} rank(s) concurrently, "
+                   "slowest rank; duplex = H2D and D2H at the same time on two streams (GB/s per direction per GPU)")
+    del h_in, h_out, d_in, d_out
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def load_peaks():
@@ -253,20 +405,69 @@ def load_traffic(key, solves_per_launch=None):
     return ent["bytes"] / ent["solves"] * solves_per_launch
 
 
+def time_e2e(ctx, pipe, host_in, steps):
+    """solves/s through LqHostPipeline.submit with pinned host buffers (H2D of every input and D2H of the selected
+    outputs inside the timed region), max over ranks."""
+    torch = ctx.torch
+    for _ in range(3):
+        host_res = pipe.submit(*host_in)
+    pipe.wait()
+    ctx.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(pipe.s_in)
+    for _ in range(steps):
+        host_res = pipe.submit(*host_in)
+    e1.record(pipe.s_out)
+    pipe.wait()
+    ctx.barrier()
+    ms = ctx.allmax(e0.elapsed_time(e1))
+    return ctx.world * pipe.batch * steps / (ms * 1e-3), host_res
+
+
+def k1_riccati_block(ctx, args, peak):
+    """a1's literal contract (FHC.ricatti_recursion returns EVERY P_k and K_k, FHC.py:61): mpc_riccati on per-scenario
+    models with all gains and all cost-to-go matrices written.  HBM-bound: 3n^2+nm+m^2 values read, N m n + (N+1) n^2 written."""
+    torch = ctx.torch
+    from model_predictive_control_b200 import lq
+    n, m, N = 4, 1, 20
+    batch = args.batch or (1 << 20)
+    A, B, Q, R, Pf, _ = cfg2b_inputs_torch(batch, 1234 + 2 + 1000 * ctx.rank, ctx.dev, torch.float64)
+
+    def step():
+        return lq.riccati(A, B, Q, R, Pf, N, all_P=True)
+
+    for _ in range(3):
+        step()
+    ctx.barrier()
+    steps = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        K, P = step()
+    e1.record()
+    ctx.barrier()
+    ms = ctx.allmax(e0.elapsed_time(e1)) / steps
+    bytes_solve = 8 * (3 * n * n + n * m + m * m) + 8 * (N * m * n + (N + 1) * n * n)
+    f_ric = 4 * n**3 + 6 * n * n * m + 4 * n * m * m + 2 * m**3 + 2 * n * n + m * m
+    achieved = bytes_solve * batch / (ms * 1e-3) / 1e9
+    fp_peak = lq.fma_peak(torch.float64)
+    del K, P
+    return {"value": ctx.world * batch / (ms * 1e-3), "unit": "recursions/s", "ms_per_step": ms, "steps": steps,
+            "config": {"workload": f"k1: FHC.ricatti_recursion (FHC.py:51-61) with every K_k and P_k returned, nx=4 nu=1 N=20, "
+                                   f"{batch} per-scenario models per GPU", "batch_per_gpu": batch,
+                       "l2": f"{bytes_solve * batch / 1e6:.0f} MB written/read per step > 126 MB L2"},
+            "roofline": {"bound": "hbm", "kernel": "riccati_reg_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "bytes_per_solve": bytes_solve, "traffic": load_traffic("riccati_reg_kernel_f64", batch),
+                         "fp_pipe": {"flops_per_solve": N * f_ric, "frac": N * f_ric * batch / (ms * 1e-3) / fp_peak}},
+            "gpu_launches": steps}
+
+
 def run_ours(args):
-    import torch
-    import torch.distributed as dist
+    ctx = Ctx()
+    torch, dist = ctx.torch, ctx.dist
     from model_predictive_control_b200 import lq
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    world, rank, local, dev = ctx.world, ctx.rank, ctx.local, ctx.dev
     dtype = torch.float64 if args.dtype == "f64" else torch.float32
     w = 8 if args.dtype == "f64" else 4
     shp = cfg2_shapes()
@@ -278,11 +479,7 @@ def run_ours(args):
     def step():
         lq.lq_solve(A, B, Q, R, Pf, x0, N, out=out)
 
-    def barrier():
-        if world > 1:
-            dist.barrier(device_ids=[local])
-        torch.cuda.synchronize()
-
+    barrier = ctx.barrier
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
@@ -303,36 +500,28 @@ def run_ours(args):
     total_ms = evs[0].elapsed_time(evs[-1])
     per_launch = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
+    total_ms = ctx.allmax(total_ms)
     ms_per_step = total_ms / args.steps
     value = world * batch * args.steps / (total_ms * 1e-3)
 
     # ---- end-to-end through the public API with HOST buffers (pinned): every step copies all of its
-    # inputs host->device and its results X, U, V device->host inside the timed region.  The public
+    # inputs host->device and its results device->host inside the timed region.  The public
     # call is lq.LqHostPipeline.submit, which overlaps the copies of consecutive steps (PCIe full duplex).
+    # Two output sets: the full one (X, U, V: 840 B per solve) is the headline; (U, V) -- the plan and its cost, the
+    # states being a function of inputs and plan -- is 168 B per solve.
     host_in = [torch.empty(t_.shape, dtype=t_.dtype, pin_memory=True).copy_(t_) for t_ in (A, B, Q, R, Pf, x0)]
     pipe = lq.LqHostPipeline(batch, n, m, N, dtype, dev)
     h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
     e2e_steps = max(4, min(args.steps, 8))
-    for _ in range(3):
-        host_res = pipe.submit(*host_in)
-    pipe.wait()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(pipe.s_in)
-    for _ in range(e2e_steps):
-        host_res = pipe.submit(*host_in)
-    e1.record(pipe.s_out)
-    pipe.wait()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * batch * e2e_steps / (float(t.item()) * 1e-3)
+    e2e_value, host_res = time_e2e(ctx, pipe, host_in, e2e_steps)
     e2e_check = bool(torch.equal(host_res[2], out.V.cpu()))   # the host result is the device result
+    del pipe
+    pipe_uv = lq.LqHostPipeline(batch, n, m, N, dtype, dev, outputs=("U", "V"))
+    d2h_uv = pipe_uv.d2h_bytes
+    e2e_uv, host_uv = time_e2e(ctx, pipe_uv, host_in, e2e_steps)
+    e2e_uv_check = bool(torch.equal(host_uv[1], out.V.cpu()))
+    del pipe_uv
+    link = host_link_probe(ctx)
 
     # ---- the other reading of configs[1] (cfg 2a: ONE shared model, random initial states): Riccati recursion once per
     # step (a single CTA) + the K2 rollout kernel for every scenario.  Reported beside the headline, not instead of it.
@@ -355,10 +544,31 @@ def run_ours(args):
         step2a()
     eb.record()
     barrier()
-    t = torch.tensor([ea.elapsed_time(eb)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms2a = float(t.item()) / args.steps
+    ms2a = ctx.allmax(ea.elapsed_time(eb)) / args.steps
+
+    # ---- the Krylov guard under divergence: the same launch on models spread 4x wider (sigma = 0.2), where ~15 % of
+    # the scenarios take the dense recursion inside the launch and most warps execute both bodies
+    guard = None
+    if dtype == torch.float64 and not args.quick:
+        gsd = torch.Generator(device=dev); gsd.manual_seed(77 + rank)
+        Aw = A + 0.15 * torch.randn(A.shape, generator=gsd, device=dev, dtype=dtype)
+        Bw = B + 0.15 * torch.randn(B.shape, generator=gsd, device=dev, dtype=dtype)
+        for _ in range(3):
+            lq.lq_solve(Aw, Bw, Q, R, Pf, x0, N, out=out)
+        barrier()
+        eg0, eg1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        eg0.record()
+        for _ in range(5):
+            lq.lq_solve(Aw, Bw, Q, R, Pf, x0, N, out=out)
+        eg1.record()
+        barrier()
+        msg = ctx.allmax(eg0.elapsed_time(eg1)) / 5
+        guard = {"value": world * batch / (msg * 1e-3), "unit": UNIT, "ms_per_step": msg,
+                 "krylov_path_fraction": krylov_path_fraction(Aw, Bw, float(os.environ.get("MPC_LQ_KRYLOV_COND", "1e3"))),
+                 "note": "same kernel and shapes, per-scenario models perturbed with sigma ~ 0.2 instead of 0.05: the "
+                         "conditioning guard sends part of every warp through the dense recursion (divergent warps)"}
+        del Aw, Bw
+        step()  # restore the headline outputs for the summary below
 
     # ---- device copy bandwidth under the SAME protocol as the timed loop (0.3 s of back-to-back launches first, then
     # 10 timed ones): what a pure streaming kernel sustains on this board once the power cap has set the clocks.
@@ -397,20 +607,34 @@ def run_ours(args):
         summ_all = torch.stack(gathered)
     else:
         summ_all = summ[None]
+    peak, peak_src = load_peaks()
+    kernel = lq.lq_solve_kernel_name(n, m, dtype)
+    kfrac = (krylov_path_fraction(A, B, float(os.environ.get("MPC_LQ_KRYLOV_COND", "1e3")))
+             if kernel == "lq_solve_krylov_kernel" else 0.0)
+    del A, B, Q, R, Pf, host_in, out
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs and a1's literal outputs, each a short block of its own (every rank runs them;
+    # cfg 5 at 2^20 scenarios per GPU is the named 1/2/4/8-GPU sweep)
+    secondary = {}
+    if not args.quick:
+        secondary["k1_riccati"] = k1_riccati_block(ctx, args, peak)
+        for wl, st in (("cfg3", 5), ("cfg4", 2), ("cfg5", 2)):
+            line_w = secondary_line(ctx, wl, steps=st, warmup=3 if wl == "cfg3" else 1, cpu=False)
+            if rank == 0:
+                secondary[wl] = {k: line_w[k] for k in ("value", "unit", "ms_per_step", "steps", "config", "roofline", "e2e",
+                                                        "gpu_launches", "summary", "solved_only") if k in line_w}
 
     if rank == 0:
-        peak, peak_src = load_peaks()
         bytes_solve = cfg2b_bytes_per_solve(w, n, m, N)
-        kernel = lq.lq_solve_kernel_name(n, m, dtype)
         if kernel == "lq_solve_krylov_kernel":
-            kfrac = krylov_path_fraction(A, B, float(os.environ.get("MPC_LQ_KRYLOV_COND", "1e3")))
             flops_solve = kfrac * cfg2b_flops_per_solve_krylov(n, N) + (1 - kfrac) * cfg2b_flops_per_solve(n, m, N)
         else:
-            kfrac = 0.0
             flops_solve = cfg2b_flops_per_solve(n, m, N)
         kern_ms = sum(per_launch) / len(per_launch)
         achieved = bytes_solve * batch / (kern_ms * 1e-3) / 1e9
         fp_peak = lq.fma_peak(dtype)
+        per_gpu = lambda v: v / world / batch
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -418,6 +642,7 @@ def run_ours(args):
             "config": {"workload": "cfg2b: FHC Riccati LQ solve (backward recursion + optimal plan + cost), nx=4 nu=1 N=20, "
                                    f"{batch} scenarios per GPU, per-scenario model and initial state",
                        "batch_per_gpu": batch, "nx": n, "nu": m, "horizon": N, "parallelism": f"scenario-shard x{world}",
+                       "numa": ctx.numa,
                        "l2": (f"inputs+outputs {bytes_solve * batch / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)"
                               if bytes_solve * batch > 126e6 else
                               f"inputs+outputs {bytes_solve * batch / 1e6:.0f} MB per step FIT in the 126 MB L2: not a valid "
@@ -437,12 +662,24 @@ def run_ours(args):
                          "peak_source": peak_src, "bytes_per_solve": bytes_solve, "kernel_ms": kern_ms,
                          "fp_pipe": {"flops_per_solve": flops_solve, "achieved_tflops": flops_solve * batch / (kern_ms * 1e-3) / 1e12,
                                      "measured_fma_peak_tflops": fp_peak / 1e12,
-                                     "frac": flops_solve * batch / (kern_ms * 1e-3) / fp_peak}},
+                                     "frac": flops_solve * batch / (kern_ms * 1e-3) / fp_peak},
+                         "guard_divergence": guard},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "d2h_gbs_per_gpu": d2h * (e2e_value / world / batch) / 1e9, "h2d_gbs_per_gpu": h2d * (e2e_value / world / batch) / 1e9,
-                    "note": "lq.LqHostPipeline: pinned host buffers, all model/x0 inputs H2D and X/U/V D2H every step, "
-                            "copies of consecutive steps overlapped on separate streams (full duplex); the D2H stream "
-                            "(840 B per solve) runs at the PCIe link rate, which bounds this figure", "result_matches_device": e2e_check},
+                    "d2h_gbs_per_gpu": d2h * per_gpu(e2e_value) / 1e9, "h2d_gbs_per_gpu": h2d * per_gpu(e2e_value) / 1e9,
+                    "host_link": link,
+                    "frac_of_host_link": d2h * per_gpu(e2e_value) / 1e9 / link["duplex_gbs_each"],
+                    "plan_only": {"value": e2e_uv, "unit": UNIT, "outputs": ["U", "V"], "h2d_bytes_per_step": h2d,
+                                  "d2h_bytes_per_step": d2h_uv, "h2d_gbs_per_gpu": h2d * per_gpu(e2e_uv) / 1e9,
+                                  "frac_of_host_link": h2d * per_gpu(e2e_uv) / 1e9 / link["duplex_gbs_each"],
+                                  "result_matches_device": e2e_uv_check,
+                                  "note": "same call with outputs=('U','V'): the plan and its cost travel back, the predicted "
+                                          "states (a function of inputs and plan) stay on the device; now the H2D stream of the "
+                                          "per-scenario models (456 B per solve) is the bound"},
+                    "note": "lq.LqHostPipeline: pinned host buffers (allocated on the GPU's NUMA node), all model/x0 inputs H2D and "
+                            "X/U/V D2H every step, copies of consecutive steps overlapped on separate streams (full duplex); "
+                            "the D2H stream (840 B per solve) runs at the host-link rate, which bounds this figure: "
+                            "frac_of_host_link = D2H GB/s of this run / the duplex ceiling measured by host_link",
+                    "result_matches_device": e2e_check},
             "gpu_launches": args.steps, "clocks": clocks,
             "cfg2a_shared_model": {"value": world * batch / (ms2a * 1e-3), "unit": UNIT, "ms_per_step": ms2a,
                                    "kernels": "riccati_reg_kernel (1 CTA) + rollout_shared_kernel",
@@ -451,15 +688,17 @@ def run_ours(args):
                                    "note": "same shapes with ONE shared model: Riccati recursion once per step, optimal plan X, U, cost per scenario"},
             "summary": {"sum_cost": float(summ_all[:, 0].sum()), "max_abs_u0": float(summ_all[:, 1].max()),
                         "scenarios": int(summ_all[:, 2].sum())},
+            "secondary": secondary,
         }
         if world == 1 and not args.no_cpu:
+            ctx.restore_affinity()
             cores = host_cores()
-            rate, done, wall = cpu_reference_rate(25000 * cores, cores)  # ~15-20 s of CPU work per core
-            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{done} scenarios of cfg2b, python loop of the oracle port of FHC.ricatti_recursion + rollout, one process per core ({wall:.1f} s wall)"}
+            kind = cpu_arm_kind()
+            rate, done, wall = cpu_reference_rate((8000 if kind == "reference" else 25000) * cores, cores, kind)  # ~10-20 s per core
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
+                                    "sample": f"{done} scenarios of cfg2b, {CPU_SAMPLE[kind]} ({wall:.1f} s wall)"}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    ctx.close()
 
 
 def run_cfg2a(args):
@@ -606,31 +845,44 @@ def cpu_baseline_secondary(workload, cores):
             "sample": f"{nb} scenarios x {nsteps} control steps of cfg4, numpy restatement of the RTI loop and of the interior-point QP solver (oracle/bicycle.py, batched numpy, one process); restatement, not reference code"}
 
 
-def run_secondary(args):
-    """cfg3 / cfg4 bench lines (same JSON schema; the headline line is cfg2b)."""
-    import torch
-    import torch.distributed as dist
+def ipm_workspace_bytes_v2(n, m, N, model_elems, narrow=True, elem=8):
+    """HBM bytes one interior-point iteration of the round-2 kernels moves BY DESIGN (csrc/boxqp_core.cuh, four sweeps;
+    `narrow` = the float64 product's mixed workspace: slacks, multipliers and dz_aff in float32):
+      A reads z, s, lam (4 d), dz, dz_aff (+ model) and writes z, s, lam, K, S^-1, d;  B reads z, s, lam, K, d (+ model) and
+      writes dz_aff, e, g;  C reads e, g, K, S^-1, d (+ model) and writes d;  D reads z, s, lam, dz_aff, K, d (+ model), writes dz."""
+    d = n + m
+    z, sl, da = elem * d, (4 if narrow else elem) * 4 * d, (4 if narrow else elem) * d
+    dz, eg = elem * d, 2 * elem * d
+    K, S, ff, mod = elem * m * n, elem * m * m, elem * m, elem * model_elems
+    a = (z + sl + dz + da + mod) + (z + sl + K + S + ff)
+    b = (z + sl + K + ff + mod) + (da + eg)
+    c = (eg + K + S + ff + mod) + ff
+    dd = (z + sl + da + K + ff + mod) + dz
+    return N * (a + b + c + dd)
+
+
+def secondary_line(ctx, workload, steps, warmup, batch=0, horizon=0, cpu=False, dtype="f64"):
+    """One bench line (same JSON schema as the headline) for cfg3 / cfg4 / cfg5.  Collective: every rank calls it."""
+    torch, dist = ctx.torch, ctx.dist
     from model_predictive_control_b200 import boxqp, distributed as D, lq, problem, session4
 
-    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    g = torch.Generator(device=dev); g.manual_seed(1234 + int(args.workload[-1]) + 1000 * rank)
+    world, rank, local, dev = ctx.world, ctx.rank, ctx.local, ctx.dev
+    tdt = torch.float64 if dtype == "f64" else torch.float32
+    es = 8 if dtype == "f64" else 4
+    g = torch.Generator(device=dev); g.manual_seed(1234 + int(workload[-1]) + 1000 * rank)
     rnd = lambda *shape: torch.rand(*shape, generator=g, device=dev, dtype=torch.float64)
-    if args.workload == "cfg3":
-        batch = args.batch or (1 << 18)
-        N = args.horizon or 30
+    make_step_on = None
+    if workload == "cfg3":
+        batch = batch or (1 << 18)
+        N = horizon or 30
         prob = problem.Problem(N=N)
         n, m = 2, 1
         x0 = torch.stack([rnd(batch) * 100 - 100, rnd(batch) * 25 - 10], dim=1)
         mpc = problem.LinearMPC(prob)
-        x0T = x0.t().contiguous()
-        ws = boxqp.BoxQpWorkspace(batch, n, m, N, dev)
-        A, B = (torch.tensor(M, dtype=torch.float64, device=dev) for M in (prob.A, prob.B))
-        Q, R = (torch.tensor(M.astype(float), device=dev) for M in (prob.Q, prob.R))
+        x0T = x0.t().contiguous().to(tdt)
+        ws = boxqp.BoxQpWorkspace(batch, n, m, N, dev, dtype=tdt)
+        A, B = (torch.tensor(M, dtype=tdt, device=dev) for M in (prob.A, prob.B))
+        Q, R = (torch.tensor(M.astype(float), dtype=tdt, device=dev) for M in (prob.Q, prob.R))
         u_lo, u_hi, x_lo, x_hi = mpc.bounds()
 
         def step():
@@ -638,11 +890,12 @@ def run_secondary(args):
 
         solves_per_step = batch
         name = f"cfg3: session-2 Problem box-QP (input + state bounds), nx=2 nu=1 N={N}, {batch} scenarios per GPU"
-        io_bytes = 8 * (n + N * m + (N + 1) * n + 1) + 8 + N * (n + m)
+        io_bytes = es * (n + N * m + (N + 1) * n + 1) + 8 + N * (n + m)
         host_in, host_out = [x0T], lambda r: [r.U, r.X, r.cost, r.status]
-    elif args.workload == "cfg5":
+        kname, model_elems = "boxqp_ipm_refill_kernel", 0
+    elif workload == "cfg5":
         import numpy as np
-        batch = args.batch or (1 << 20)
+        batch = batch or (1 << 20)
         n, m, N = 12, 4, 50
         rng = np.random.default_rng(1234 + 5)      # the shared model is the same on every rank
         Ts = 0.1
@@ -656,53 +909,54 @@ def run_secondary(args):
         def step():
             return boxqp.solve(A, B, Q, R, Q, N, x0T, -1.0, 1.0, -5.0, 5.0, workspace=ws)
 
+        def make_step_on(x_sub):
+            ws_sub = boxqp.BoxQpWorkspace(x_sub.shape[1], n, m, N, dev, sat=False)
+            return lambda: boxqp.solve(A, B, Q, R, Q, N, x_sub, -1.0, 1.0, -5.0, 5.0, workspace=ws_sub)
+
         solves_per_step = batch
         name = (f"cfg5: box-QP nx=12 nu=4 N=50 (four coupled triple integrators, |u|<=1, |x|<=5, x0~U[-2,2]^12), "
                 f"{batch} scenarios per GPU")
         io_bytes = 8 * (n + N * m + (N + 1) * n + 1) + 8
         host_in, host_out = [x0T], lambda r: [r.U, r.X, r.cost, r.status]
-    else:
-        batch = args.batch or (1 << 16)
+        kname, model_elems = "boxqp_ipm_coop_kernel", 0
+    elif workload == "cfg4":
+        batch = batch or (1 << 16)
         n, m, N, steps_cl = 4, 2, 50, 200
         par = session4.VehicleParameters()
         scale = torch.tensor([1, 1, 0.5, 0.2], device=dev, dtype=torch.float64)
-        x0 = torch.tensor([0.6, -0.25, 0, 0], device=dev, dtype=torch.float64) + (rnd(batch, 4) * 0.4 - 0.2) * scale
-        fr = rnd(batch) * 0.3 + 0.7
-        ctrl = session4.MPCController(N=N, ts=0.05, params=par)
+        x0 = (torch.tensor([0.6, -0.25, 0, 0], device=dev, dtype=torch.float64) + (rnd(batch, 4) * 0.4 - 0.2) * scale).to(tdt)
+        fr = (rnd(batch) * 0.3 + 0.7).to(tdt)
+        ctrl = session4.MPCController(N=N, ts=0.05, params=par, dtype=tdt)
 
         def step():
             return ctrl.closed_loop(x0, steps_cl, friction_plant=fr)
 
         solves_per_step = batch * steps_cl
         name = f"cfg4: session-4 bicycle RTI closed loop, nx=4 nu=2 N=50, {batch} scenarios x {steps_cl} control steps per GPU"
-        io_bytes = 8 * (4 + 1) / steps_cl + 8 * 6  # per solve: x0 + friction amortised, X_cl/U_cl rows written
+        io_bytes = es * (4 + 1) / steps_cl + es * 6  # per solve: x0 + friction amortised, X_cl/U_cl rows written
         host_in, host_out = [x0, fr], lambda r: [r.X, r.U, r.cost, r.violation]
+        kname, model_elems = "rti_closed_loop_kernel", 14
+    else:
+        raise SystemExit(f"unknown workload {workload}")
 
-    def barrier():
-        if world > 1:
-            dist.barrier(device_ids=[local])
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
+    barrier = ctx.barrier
+    for _ in range(max(warmup, 1)):
         res = step()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
     evs[0].record()
-    for i in range(args.steps):
+    for i in range(steps):
         res = step()
         evs[i + 1].record()
     barrier()
     total_ms = evs[0].elapsed_time(evs[-1])
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    value = world * solves_per_step * args.steps / (total_ms * 1e-3)
-    kern_ms = total_ms / args.steps
+    total_ms = ctx.allmax(total_ms)
+    value = world * solves_per_step * steps / (total_ms * 1e-3)
+    kern_ms = total_ms / steps
     # e2e: host x0 in, predictions / closed-loop trajectories out (pinned buffers)
     pin_in = [torch.empty(t_.shape, dtype=t_.dtype, pin_memory=True).copy_(t_) for t_ in host_in]
     outs = host_out(res)
@@ -715,58 +969,98 @@ def run_secondary(args):
         for h_, d_ in zip(pin_out, host_out(r)):
             h_.copy_(d_, non_blocking=True)
 
+    e2e_n = 2 if kern_ms > 500 else 3
     e2e_step(); barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(3):
+    for _ in range(e2e_n):
         e2e_step()
     e1.record(); barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * solves_per_step * 3 / (float(t.item()) * 1e-3)
-    if args.workload in ("cfg3", "cfg5"):
-        summ = D.local_summary(cost=res.cost, status=res.status, iters=res.iters)
+    e2e_value = world * solves_per_step * e2e_n / (ctx.allmax(e0.elapsed_time(e1)) * 1e-3)
+    if workload in ("cfg3", "cfg5"):
+        nsat = (res.sat_u != 0).sum(dim=(0, 1)).to(torch.int32).contiguous() if res.sat_u is not None else None
+        summ = D.local_summary(cost=res.cost.double(), status=res.status, iters=res.iters, n_saturated=nsat)
+        solved = res.status == 1
+        it_s = float(res.iters[solved].double().mean()) if bool(solved.any()) else 0.0
+        it_f = float(res.iters[~solved].double().mean()) if bool((~solved).any()) else 0.0
     else:
-        summ = D.local_summary(cost=res.cost, violation=res.violation, n_saturated=res.n_saturated, iters=res.iters)
+        summ = D.local_summary(cost=res.cost.double(), violation=res.violation.double(), n_saturated=res.n_saturated, iters=res.iters)
+        solved, it_s, it_f = None, None, None
     merged = D.gather_summaries(summ)
+    # solved-only rate: the same launch on the feasible scenarios alone (infeasible ones leave early through the stall
+    # test and would flatter the rate) -- measured, not derived
+    solved_only = None
+    if make_step_on is not None:
+        idx = torch.nonzero(solved).flatten()
+        x_sub = x0T[:, idx].contiguous()
+        step_sub = make_step_on(x_sub)
+        step_sub(); barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        r_sub = step_sub()
+        s1.record(); barrier()
+        ms_sub = ctx.allmax(s0.elapsed_time(s1))
+        n_sub = ctx.allsum(float(idx.numel()))
+        solved_only = {"value": n_sub / (ms_sub * 1e-3), "unit": UNIT, "scenarios": n_sub, "ms": ms_sub,
+                       "all_solved": bool((r_sub.status == 1).all()), "mean_iters": float(r_sub.iters.double().mean()),
+                       "note": "the feasible scenarios of the batch alone, one more launch"}
+    line = None
     if rank == 0:
         peak, peak_src = load_peaks()
         fp_peak = lq.fma_peak(torch.float64)
         iters_total = merged["sum_iters"] / world  # per rank (ranks run the same distribution)
         flops = iters_total * ipm_flops_per_iter(n, m, N)
         achieved = io_bytes * solves_per_step / (kern_ms * 1e-3) / 1e9
-        kname = {"cfg3": "boxqp_ipm_kernel", "cfg4": "rti_closed_loop_kernel", "cfg5": "boxqp_ipm_coop_kernel"}[args.workload]
+        traffic = load_traffic(kname + ("_" + workload), solves_per_step)
+        wsb = None
+        if workload != "cfg5":
+            wb = ipm_workspace_bytes_v2(n, m, N, model_elems, narrow=(dtype == "f64"), elem=es)
+            wsb = {"bytes_per_iter": wb, "achieved": wb * iters_total / (kern_ms * 1e-3) / 1e9,
+                   "frac": wb * iters_total / (kern_ms * 1e-3) / 1e9 / peak,
+                   "dram_bytes_per_solve_ncu": (traffic / solves_per_step) if traffic else None,
+                   "note": "HBM bytes the kernel moves by design (solver workspace streamed once per sweep, "
+                           "ipm_workspace_bytes_v2) x iterations performed; self-inflicted traffic, reported for "
+                           "transparency -- no roofline credit is claimed for it"}
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": kern_ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": max(warmup, 1), "ms_per_step": kern_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": dtype, "data": "synthetic",
             "config": {"workload": name, "batch_per_gpu": batch, "nx": n, "nu": m, "horizon": N,
                        "parallelism": f"scenario-shard x{world}",
-                       "l2": "solver state is a per-scenario workspace streamed through L2/HBM every iteration (> 126 MB)"},
+                       "l2": "solver state is a per-lane workspace streamed through L2/HBM every iteration (> 126 MB)"},
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": load_traffic(kname, solves_per_step), "peak_source": peak_src,
-                         "note": "algorithmic I/O only; the kernel is bound by the FP64 pipe and its workspace traffic, see fp_pipe",
-                         "kernel_ms": kern_ms,
-                         "workspace_stream": (None if args.workload == "cfg5" else (lambda wb: {
-                             "bytes_per_iter": wb, "achieved": wb * iters_total / (kern_ms * 1e-3) / 1e9,
-                             "frac": wb * iters_total / (kern_ms * 1e-3) / 1e9 / peak,
-                             "note": "HBM bytes the kernel moves by design (solver workspace streamed once per pass, "
-                                     "ipm_workspace_bytes_per_iter) x iterations performed: the roofline this kernel actually "
-                                     "runs against"})(ipm_workspace_bytes_per_iter(n, m, N, 14 if args.workload == "cfg4" else 0))),
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "note": "algorithmic I/O only; the kernel is bound by its FP64 instruction stream and its workspace "
+                                 "traffic, see fp_pipe / workspace_stream",
+                         "kernel_ms": kern_ms, "workspace_stream": wsb,
                          "fp_pipe": {"mean_iters_per_solve": iters_total / solves_per_step,
+                                     "mean_iters_solved": it_s, "mean_iters_not_solved": it_f,
                                      "flops_per_iter": ipm_flops_per_iter(n, m, N),
                                      "achieved_tflops": flops / (kern_ms * 1e-3) / 1e12,
                                      "measured_fma_peak_tflops": fp_peak / 1e12, "frac": flops / (kern_ms * 1e-3) / fp_peak}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": sum(t_.numel() * t_.element_size() for t_ in pin_in),
                     "d2h_bytes_per_step": sum(t_.numel() * t_.element_size() for t_ in pin_out)},
-            "gpu_launches": args.steps, "clocks": clocks, "summary": merged,
+            "gpu_launches": steps, "clocks": clocks, "summary": merged,
         }
-        if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline_secondary(args.workload, host_cores())
+        if solved_only is not None:
+            line["solved_only"] = solved_only
+        if world == 1 and cpu:
+            ctx.restore_affinity()
+            line["cpu_baseline"] = cpu_baseline_secondary(workload, host_cores())
+    res = ws = ctrl = None
+    torch.cuda.empty_cache()
+    return line
+
+
+def run_secondary(args):
+    """--workload cfg3 | cfg4 | cfg5: one bench line of that config (same JSON schema; the default line is cfg2b with
+    these as `secondary` blocks)."""
+    ctx = Ctx()
+    line = secondary_line(ctx, args.workload, args.steps, max(args.warmup, 3), batch=args.batch, horizon=args.horizon,
+                          cpu=not args.no_cpu, dtype=args.dtype)
+    if ctx.rank == 0:
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    ctx.close()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -999,6 +1293,8 @@ def main():
     ap.add_argument("--horizon", type=int, default=0, help="cfg3 only: horizon N (default 30, the BASELINE config; the north star's "
                                                           "throughput target is quoted at N = 20)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--quick", action="store_true", help="cfg2b headline only: skip the secondary blocks (cfg3/4/5, k1) "
+                                                         "and the guard-divergence leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -253,6 +253,15 @@ int mpc_rti_closed_loop(double lr, double lf, double accel, double friction_mode
                         mpc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Exact stability test of a linear closed loop: rho[b] = spectral radius of A_b + B_b K_b (stable iff < 1).
+ * The reference only flags |x| > 100 while simulating and leaves the exact test as an exercise
+ * (session_1/session1_sol.py:86-89, :114-116).  A [*,n,n], B [*,n,m], K [*,m,n] (batch stride s?, 0 = shared),
+ * rho [batch].  (n, m) in {(2,1), (4,1), (4,2)}.
+ */
+int mpc_spectral_radius(const void* A, int64_t sA, const void* B, int64_t sB, const void* K, int64_t sK, void* rho,
+                        int64_t batch, int n, int m, int dtype, mpc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Device FP pipe probe: runs a register-resident FMA chain kernel and reports achieved
  * FLOP/s (2 flops per FMA).  Used by bench.py as the measured FP64 / FP32 vector-pipe roofline
  * denominator (MEASURED_PEAKS.json only carries HBM and bf16 tensor peaks).  Synchronises.

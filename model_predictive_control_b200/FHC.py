@@ -104,13 +104,17 @@ def terminal_cost_sweep(A, B, Q, R, P_f, x0, horizons=range(1, 10)):
     return V, float(np.squeeze(x0n.T @ P_inf @ x0n))
 
 
-def infinite_horizon(A, B, Q, R, tol=1e-13, max_horizon=1 << 16):
+def infinite_horizon(A, B, Q, R, tol=None, max_horizon=1 << 16):
     """(P_inf, K_inf) of the reference's infinite-horizon comparison (FHC.py:97-98,126), computed on
     the GPU by running the Riccati recursion (K1) with doubling horizons until P stops changing --
     the fixed point of the recursion is the stabilising DARE solution the reference gets from
-    scipy.linalg.solve_discrete_are.  K_inf = -(R + B'P B)^-1 B'P A is the converged first-stage gain."""
+    scipy.linalg.solve_discrete_are.  K_inf = -(R + B'P B)^-1 B'P A is the converged first-stage gain.
+    ``tol``: relative change of P that counts as converged (default 1e-13 in float64, 1e-5 in float32: what the
+    arithmetic can resolve); a RuntimeWarning is issued when ``max_horizon`` is reached first."""
     as_np = not io.any_tensor(A, B, Q, R)
     dt = io.pick_dtype(A, B, Q, R)
+    if tol is None:
+        tol = 1e-13 if dt == torch.float64 else 1e-5
     Ad, Bd, Qd = (io.to_dev(M, dt) for M in (A, B, Q))
     Rd = _prep_R(R, Bd.shape[-1], dt)
     P, N = Qd, 64
@@ -119,7 +123,13 @@ def infinite_horizon(A, B, Q, R, tol=1e-13, max_horizon=1 << 16):
         P_new = Pn[0] if Ad.dim() == 2 else Pn
         done = bool((P_new - P).abs().max() <= tol * P_new.abs().max())
         P = P_new
-        if done or N >= max_horizon:
+        if done:
+            break
+        if N >= max_horizon:
+            import warnings
+            warnings.warn(f"infinite_horizon: P still changes by more than {tol:g} (relative) at horizon {N}; "
+                          "returning the last iterate (unstabilisable model, or tol below the arithmetic's resolution)",
+                          RuntimeWarning, stacklevel=2)
             break
         N *= 2
     K0 = K[0, 0] if Ad.dim() == 2 else K[0]
@@ -147,6 +157,18 @@ def closed_loop_with_predictions(A, B, Q, R, P_f, x0, N, n_steps=30, gains=None)
     bundle = pred.reshape(n, n_steps, batch, pred.shape[-1])
     bundle = bundle.permute(1, 0, 2, 3) if io.is_tensor(bundle) else np.transpose(bundle, (1, 0, 2, 3))
     return gains, x, bundle
+
+
+def closed_loop_spectral_radius(A, B, K):
+    """rho(A + B K): the exact stability test of the receding-horizon closed loop u = gains[0] x that the reference
+    hints at (session_1/session1_sol.py:114-116) -- stable iff < 1.  ``K`` is ``gains[0]`` (or any (m, n) gain);
+    A, B, K may carry a leading batch axis.  numpy in -> numpy out."""
+    as_np = not io.any_tensor(A, B, K)
+    dt = io.pick_dtype(A, B, K)
+    rho = lq.spectral_radius(io.to_dev(A, dt), io.to_dev(B, dt), io.to_dev(K, dt))
+    batched = any(np.ndim(M) == 3 if not io.is_tensor(M) else M.dim() == 3 for M in (A, B, K))
+    out = rho if batched else rho[0]
+    return io.back(out, as_np) if batched else (float(out.item()) if as_np else out)
 
 
 def run_and_plot_traj(A, B, Q, R, P_f, x0):

@@ -71,5 +71,40 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(name: str, defines, only=("boxqp.cu", "rti.cu")) -> str:
+    """Ablation build: the library with extra -D macros (csrc/boxqp_core.cuh: MPC_VAR_*), as lib/variants/<name>.so.
+    Sources not in ``only`` reuse the objects of the main build.  Load it with MPC_B200_LIB=<path>."""
+    build_library()
+    vdir = os.path.join(BUILD, "variants", name)
+    os.makedirs(vdir, exist_ok=True)
+    os.makedirs(os.path.join(LIBDIR, "variants"), exist_ok=True)
+    objs = []
+
+    def one(src):
+        base = os.path.basename(src)
+        if base not in only:
+            return os.path.join(BUILD, base[:-3] + ".o")
+        obj = os.path.join(vdir, base[:-3] + ".o")
+        res = subprocess.run([nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", src, "-o", obj],
+                             capture_output=True, text=True)
+        with open(obj[:-2] + ".ptxas.log", "w") as fh:
+            fh.write(res.stderr)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed for %s:\n%s" % (src, res.stderr[-8000:]))
+        return obj
+    with cf.ThreadPoolExecutor(max_workers=4) as ex:
+        objs = list(ex.map(one, sources()))
+    out = os.path.join(LIBDIR, "variants", name + ".so")
+    res = subprocess.run([nvcc(), "-shared", "-o", out, *objs, "-gencode", "arch=compute_100a,code=sm_100a"],
+                         capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("link failed:\n" + res.stderr[-4000:])
+    return out
+
+
 if __name__ == "__main__":
-    build_library(force="--force" in sys.argv, verbose=True)
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print("built", build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        build_library(force="--force" in sys.argv, verbose=True)

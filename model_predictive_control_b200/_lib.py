@@ -11,7 +11,8 @@ import os
 from ctypes import c_char_p, c_double, c_int, c_int64, c_void_p, POINTER
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "lib", "libmpc_b200.so")
+# MPC_B200_LIB: load another build of the same library (ablation builds under lib/variants, tools/prof)
+LIB_PATH = os.environ.get("MPC_B200_LIB") or os.path.join(PKG, "lib", "libmpc_b200.so")
 
 MPC_F64, MPC_F32 = 0, 1
 MPC_SOLVED, MPC_MAX_ITER, MPC_INFEASIBLE, MPC_UNSOLVED = 1, 2, 3, 0
@@ -70,7 +71,12 @@ def lib():
                 "(needs nvcc).  There is no CPU fallback.")
         L = ctypes.CDLL(LIB_PATH)
         for name, (restype, argtypes) in SIGNATURES.items():
-            fn = getattr(L, name)
+            try:
+                fn = getattr(L, name)
+            except AttributeError:
+                if os.environ.get("MPC_B200_LIB"):   # an older ablation build may lack newer entry points
+                    continue
+                raise
             fn.restype, fn.argtypes = restype, argtypes
         _lib = L
     return _lib

@@ -177,9 +177,15 @@ _lib.register("mpc_condense", c_int, [c_void_p, c_int64] * 5 + [c_void_p] * 4 + 
 def condense(A, B, Q, R, Pf, N):
     """Condensed prediction matrices (K3).  Models shared ([n,n], ...) or batched ([batch,n,n], ...).
     Returns Phi [.., N n, n], Gamma [.., N n, N m], H [.., N m, N m], F [.., N m, n] with
-    H = Gamma' Qbar Gamma + Rbar, F = Gamma' Qbar Phi, so J(U) = U'HU + 2 x0'F'U + const."""
-    from .lq import _common_batch, _model
+    H = Gamma' Qbar Gamma + Rbar, F = Gamma' Qbar Phi, so J(U) = U'HU + 2 x0'F'U + const.  Q and Pf must be symmetric
+    (as every weight of the reference is); a non-symmetric weight raises."""
+    from .lq import _common_batch, _model, _same_kind
     _lib.require_cuda(A, B, Q, R, Pf)
+    _same_kind(A, B=B, Q=Q, R=R, Pf=Pf)
+    # the kernel contracts (Q Gamma) with Phi, i.e. it forms Gamma' Qbar' Phi: F = Gamma' Qbar Phi needs symmetric weights
+    for name, M in (("Q", Q), ("Pf", Pf)):
+        if float((M - M.transpose(-1, -2)).abs().max()) > 1e-12 * max(1.0, float(M.abs().max())):
+            raise ValueError(f"{name} must be symmetric (F = Gamma' Qbar Phi is formed from Q Gamma)")
     n, m = A.shape[-1], B.shape[-1]
     A, bA, sA = _model(A, n, n, "A")
     B, bB, sB = _model(B, n, m, "B")

@@ -324,6 +324,18 @@ MPC_HD void rti_prepare_body(const BicycleModel<T>& p, T friction, const TIO* y,
   }
 }
 
+// out-of-line copies for the fused loop (see MPC_HD_COLD)
+template <typename T, typename TIO>
+MPC_HD_COLD void rti_prepare_cold(const BicycleModel<T>& p, T friction, const TIO* y, const TIO* Uprev, int first,
+                                  TIO* warm, TIO* A, TIO* B, TIO* c, int N, int64_t bs, int64_t b,
+                                  const ObstacleParams<T>* ob, TIO* Cg, TIO* hg, TIO* pack) {
+  rti_prepare_body<T, TIO>(p, friction, y, Uprev, first, warm, A, B, c, N, bs, b, ob, Cg, hg, pack);
+}
+template <typename T>
+MPC_HD_COLD void bicycle_plant_cold(const BicycleModel<T>& p, T friction, int substeps, T* x, const T* u) {
+  bicycle_plant<T>(p, friction, substeps, x, u);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Closed loop (session4_sol.py:443-465 / main.py:241-271 with the RTI controller): per control step
 //   sqp_iters x (prepare -> LTV QP (K4)) -> apply u_0 -> plant step, with running summaries.
@@ -364,6 +376,55 @@ struct RtiLoopArgs {
                             // U = plan buffer: initial plan on entry (zeros = cold start), last plan on exit
 };
 
+// l1 merit of the NONLINEAR OCP at the plan  warm + beta (U - warm):  cost of the nonlinear rollout from xcur plus
+// rho times the summed violations of the state box (and of the collision constraints |c_i - o_j|^2 >= r2).  The
+// globalisation of the SQP rounds (sqp_iters > 1): full Gauss-Newton steps cycle on this OCP (the steering weight is
+// 0.01 and the curvature of the dynamics is not in the QP Hessian: the plan flips between the steering bounds), a
+// backtracking line search on this merit makes every round a descent step.
+constexpr double kSqpMeritRho = 100.0;
+constexpr int kSqpMaxHalvings = 10;
+template <typename T, typename TIO, int NC>
+MPC_HD_COLD T rti_merit(const RtiLoopArgs<T, TIO>& a, const T* sh, int64_t b, T beta) {
+  using SH = BoxQpShared<4, 2>;
+  const int64_t bs = a.qp.batch;
+  const int N = a.qp.N;
+  T x[4], u[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) x[i] = (T)a.xcur[i * bs + b];
+  T cost = T(0), viol = T(0);
+  for (int k = 0; k < N; ++k) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const T w = (T)a.warm[((int64_t)k * 2 + j) * bs + b], q = (T)a.qp.U[((int64_t)k * 2 + j) * bs + b];
+      u[j] = fma_<T>(beta, q - w, w);
+    }
+    cost += quad<T, 4>(sh + SH::oQ, x) + quad<T, 2>(sh + SH::oR, u);
+    bicycle_plant<T>(a.model, a.friction_model, a.model.rk4 ? 1 : 0, x, u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const T lo = sh[SH::oLo + 2 + i], hi = sh[SH::oHi + 2 + i];
+      const T v = (lo - x[i]) > (x[i] - hi) ? (lo - x[i]) : (x[i] - hi);
+      viol += v > T(0) ? v : T(0);
+    }
+    if constexpr (NC > 0) {
+      T sp, cp;
+      sincos(x[2], &sp, &cp);
+#pragma unroll
+      for (int i = 0; i < kObsCircles; ++i) {
+        const T cx = x[0] + a.ob.a[i] * cp, cy = x[1] + a.ob.a[i] * sp;
+#pragma unroll
+        for (int j = 0; j < kObsCircles; ++j) {
+          const T dx = cx - a.ob.ox[j], dy = cy - a.ob.oy[j];
+          const T g = a.ob.r2 - (dx * dx + dy * dy);
+          viol += g > T(0) ? g : T(0);
+        }
+      }
+    }
+  }
+  cost += quad<T, 4>(sh + SH::oPf, x);
+  return cost + T(kSqpMeritRho) * viol;
+}
+
 // PACKED = the prediction model is forward Euler: stage matrices in the packed 14-value form (a.Acur holds them).
 // NC = 0 (box constraints) or 9 (obstacle rows).
 template <typename T, typename TIO, bool PACKED, int NC, class ST>
@@ -384,22 +445,36 @@ MPC_HD void rti_closed_loop_body(const RtiLoopArgs<T, TIO>& a, const T* sh, int6
 #pragma unroll
     for (int i = 0; i < 4; ++i) a.xcur[i * bs + b] = (TIO)x[i];
     for (int round = 0; round < a.sqp_iters; ++round) {
-      rti_prepare_body<T, TIO>(a.model, a.friction_model, a.xcur, a.qp.U, (t == 0 || round > 0) ? 1 : 0, a.warm, a.Acur,
+      rti_prepare_cold<T, TIO>(a.model, a.friction_model, a.xcur, a.qp.U, (t == 0 || round > 0) ? 1 : 0, a.warm, a.Acur,
                                a.Bcur, a.ccur, N, bs, b, NC > 0 ? &a.ob : nullptr, a.Cgcur, a.hgcur,
                                PACKED ? a.Acur : nullptr);
-      BoxQpIpm<T, TIO, 4, 2, NC, PACKED ? 1 : 0, ST> ipm(a.qp, sh, b, b, bs);
+      BoxQpIpm<T, TIO, 4, 2, NC, PACKED ? 1 : 0, ST, true> ipm(a.qp, sh, b, b, bs);
       ipm.solve();
-      if (a.qp.status[b] != MPC_SOLVED) ++nfail;
+      const bool solved = a.qp.status[b] == MPC_SOLVED;
+      if (!solved) ++nfail;
       itsum += a.qp.iters[b];
-      if (round + 1 < a.sqp_iters && a.sqp_tol > T(0)) {
+      if (a.sqp_iters > 1) {
+        // globalised SQP round: backtrack on the l1 merit of the nonlinear OCP, plan <- warm + beta (U_qp - warm)
+        T beta = T(1);
+        if (solved) {
+          const T m0 = rti_merit<T, TIO, NC>(a, sh, b, T(0));
+          int h = 0;
+          while (h <= kSqpMaxHalvings && !(rti_merit<T, TIO, NC>(a, sh, b, beta) < m0)) {
+            beta *= T(0.5);
+            ++h;
+          }
+          if (h > kSqpMaxHalvings) beta = T(0);
+        }
         T du = T(0), un = T(1);
         for (int i = 0; i < N * 2; ++i) {
-          const T v = (T)a.qp.U[(int64_t)i * bs + b], w = (T)a.warm[(int64_t)i * bs + b];
+          const T q = (T)a.qp.U[(int64_t)i * bs + b], w = (T)a.warm[(int64_t)i * bs + b];
+          const T v = fma_<T>(beta, q - w, w);
+          if (beta != T(1)) a.qp.U[(int64_t)i * bs + b] = (TIO)v;
           const T d = v > w ? v - w : w - v, av = v < T(0) ? -v : v;
           du = d > du ? d : du;
           un = av > un ? av : un;
         }
-        if (du <= a.sqp_tol * un) break;
+        if (du <= a.sqp_tol * un) break;   // converged (sqp_tol = 0: only an exactly stationary plan ends the rounds)
       }
     }
     if (a.X_bundle) {
@@ -419,7 +494,7 @@ MPC_HD void rti_closed_loop_body(const RtiLoopArgs<T, TIO>& a, const T* sh, int6
       a.U_cl[((int64_t)t * 2 + j) * bs + b] = (TIO)u[j];
     }
     cost += quad<T, 4>(sh + SH::oQ, x) + quad<T, 2>(sh + SH::oR, u);
-    bicycle_plant<T>(a.plant, fr_plant, a.plant_substeps, x, u);
+    bicycle_plant_cold<T>(a.plant, fr_plant, a.plant_substeps, x, u);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       a.X_cl[((int64_t)(t + 1) * 4 + i) * bs + b] = (TIO)x[i];

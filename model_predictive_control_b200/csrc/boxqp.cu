@@ -12,6 +12,9 @@ bool coop_supported(int n, int m, int ltv);
 int launch_boxqp_coop(const BoxQpArgs<double>& a, int n, int m, cudaStream_t st);
 
 constexpr int kQpThreads = 128;
+// the first bytes of the caller's workspace hold the scenario queue of the refill kernel; a full 256 bytes, so that every
+// workspace row stays aligned to the 128-byte lines a warp reads and writes
+constexpr int64_t kWsHeader = 256;
 
 // MINB = resident CTAs per SM the register allocation must allow (latency hiding for the streamed
 // workspace matters more than a few spills).  NC > 0: general stage rows (polytopic constraints), same body.
@@ -23,8 +26,87 @@ __global__ void __launch_bounds__(kQpThreads, MINB) boxqp_ipm_kernel(BoxQpArgs<T
   __syncthreads();
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= a.batch) return;
-  BoxQpIpm<double, TIO, NX, NU, NC, 0, ST> ipm(a, sh, b, b, a.batch);
+  // a.batch is padded to a multiple of 4 lanes by the launcher (ws_lanes == batch rounded up): lane = scenario
+  BoxQpIpm<double, TIO, NX, NU, NC, 0, ST, true> ipm(a, sh, b, b, a.batch);
   ipm.solve();
+}
+
+// the same with lane = scenario and ONE stride (batch % 4 == 0): the variant every full-size launch takes
+template <typename TIO, class ST, int NX, int NU, int NC, int MINB>
+__global__ void __launch_bounds__(kQpThreads, MINB) boxqp_ipm_kernel_s(BoxQpArgs<TIO> a) {
+  using SH = BoxQpShared<NX, NU>;
+  __shared__ double sh[SH::total];
+  for (int i = threadIdx.x; i < SH::total; i += blockDim.x) sh[i] = boxqp_shared_elem<double, TIO, NX, NU>(a, i);
+  __syncthreads();
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.batch) return;
+  BoxQpIpm<double, TIO, NX, NU, NC, 0, ST, false> ipm(a, sh, b, b, a.batch);
+  ipm.solve();
+}
+
+// (2,1) only: CTAs of 96 threads with the register count pinned to 136, so that five of them are resident (480 threads
+// per SM).  __launch_bounds__(128, 4) leaves ptxas 128 registers, which it overshoots by ~100 bytes of spills since the
+// fused sweep A; (128, 3) gives 168 registers but only 384 threads.
+template <typename TIO, class ST, int NX, int NU>
+__global__ void __maxnreg__(136) boxqp_ipm_kernel_s96(BoxQpArgs<TIO> a) {
+  using SH = BoxQpShared<NX, NU>;
+  __shared__ double sh[SH::total];
+  for (int i = threadIdx.x; i < SH::total; i += blockDim.x) sh[i] = boxqp_shared_elem<double, TIO, NX, NU>(a, i);
+  __syncthreads();
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.batch) return;
+  BoxQpIpm<double, TIO, NX, NU, 0, 0, ST, false> ipm(a, sh, b, b, a.batch);
+  ipm.solve();
+}
+
+// Persistent variant with LANE REFILL.  Interior-point iteration counts differ between scenarios (cfg 3: mean 10.8,
+// max 22), and a warp of the kernel above runs until its slowest lane has converged: 21 of 32 lanes were active on
+// average (ncu, round 1), and because a 32-byte sector is moved whole, the idle lanes' share of every workspace row
+// still crossed HBM.  Here the grid is the resident set, every thread owns ONE workspace lane and pulls scenarios from
+// a global queue: when a lane's scenario has converged it is parked, and as soon as `refill_min` lanes of the warp
+// are parked (or the queue is empty) they write their outputs and start their next scenarios together -- the
+// divergent output/init section then serves several lanes at once.  The workspace is one lane per resident thread,
+// independent of the batch.
+template <typename TIO, class ST, int NX, int NU, int MINB>
+__global__ void __launch_bounds__(kQpThreads, MINB) boxqp_ipm_refill_kernel(BoxQpArgs<TIO> a, unsigned long long* queue,
+                                                                            int refill_min) {
+  using SH = BoxQpShared<NX, NU>;
+  __shared__ double sh[SH::total];
+  for (int i = threadIdx.x; i < SH::total; i += blockDim.x) sh[i] = boxqp_shared_elem<double, TIO, NX, NU>(a, i);
+  __syncthreads();
+  const int64_t lane = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool has_lane = lane < a.ws_lanes;
+  BoxQpIpm<double, TIO, NX, NU, 0, 0, ST, true> ipm(a, sh, 0, has_lane ? lane : 0, a.ws_lanes);
+  auto fetch = [&]() -> int64_t {
+    if (!has_lane) return -1;
+    const unsigned long long t = atomicAdd(queue, 1ULL);
+    return t < (unsigned long long)a.batch ? (int64_t)t : -1;
+  };
+  int64_t scn = fetch();
+  if (scn >= 0) ipm.begin(scn);
+  bool parked = false;      // converged, output not written yet
+  bool drained = false;     // this warp has seen the end of the queue
+  while (true) {
+    const bool running = scn >= 0 && !parked;
+    if (running) parked = ipm.iterate();
+    const unsigned m_parked = __ballot_sync(0xffffffffu, parked);
+    const unsigned m_idle = __ballot_sync(0xffffffffu, scn < 0);
+    const int n_parked = __popc(m_parked), n_idle = __popc(m_idle);
+    if (n_parked == 0) {
+      if (n_idle == 32) break;
+      continue;
+    }
+    // refill when enough lanes wait (parked or out of work), when nothing else runs in this warp, or at the tail
+    if (n_parked + n_idle >= refill_min || drained || n_parked + n_idle == 32) {
+      if (parked) {
+        ipm.finish();
+        parked = false;
+        scn = fetch();
+        if (scn >= 0) ipm.begin(scn);
+      }
+      drained = drained || __any_sync(0xffffffffu, scn < 0 && has_lane);
+    }
+  }
 }
 
 // which storage policy the float64 product uses: "mix" (default; slacks, multipliers and dz_aff in float32) or
@@ -34,24 +116,71 @@ static bool store_all_f64() {
   return env && strcmp(env, "f64") == 0;
 }
 
+// lanes of the refill kernel: the resident threads (occupancy query), capped by the batch
+template <typename K>
+static int64_t resident_threads(K kern) {
+  int dev = 0, sms = kNumSMs, occ = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kQpThreads, 0) != cudaSuccess || occ < 1) occ = 1;
+  return (int64_t)sms * occ * kQpThreads;
+}
+
+template <typename TIO, class ST, int NX, int NU, int MINB>
+static int launch_refill(BoxQpArgs<TIO> a, int refill_min, cudaStream_t st) {
+  auto kern = boxqp_ipm_refill_kernel<TIO, ST, NX, NU, MINB>;
+  int64_t lanes = resident_threads(kern);
+  if (lanes > a.batch) lanes = a.batch;
+  a.ws_lanes = lanes;
+  // the queue counter lives in the header of the caller's workspace
+  unsigned long long* queue = static_cast<unsigned long long*>(a.ws);
+  a.ws = static_cast<char*>(a.ws) + kWsHeader;
+  cudaError_t e = cudaMemsetAsync(queue, 0, 16, st);  // (the header is kWsHeader bytes; the counter uses the first 8)
+  if (e != cudaSuccess) return fail((int)e, "mpc_boxqp_solve: %s", cudaGetErrorString(e));
+  const unsigned grid = (unsigned)((lanes + kQpThreads - 1) / kQpThreads);
+  kern<<<grid, kQpThreads, 0, st>>>(a, queue, refill_min);
+  return check_launch("boxqp_ipm_refill_kernel");
+}
+
 template <typename TIO, class ST, int NX, int NU, int NC>
 static int launch_boxqp_st(const BoxQpArgs<TIO>& a_in, cudaStream_t st) {
   const unsigned grid = (unsigned)((a_in.batch + kQpThreads - 1) / kQpThreads);
   BoxQpArgs<TIO> a = a_in;
   a.ws_lanes = a.batch;
+  // lane refill (persistent kernel): lanes of a warp waiting before they restart together; 0 (default) = one thread
+  // per scenario, no refill.  Measured on B200 at cfg 3 (tools/prof/r2_gpu6.sh, 2^18 scenarios): 17.7 ms without,
+  // 18.1-20.2 ms with refill thresholds 16 / 8 / 4 -- the divergent output + start section and the per-lane iteration
+  // state cost more than the recovered lanes bring, so it stays an opt-in experiment.
+  int refill = 0;
+  if (const char* env = getenv("MPC_QP_REFILL")) refill = atoi(env);
   if constexpr (NC > 0) {
+    a.ws = static_cast<char*>(a.ws) + kWsHeader;
     boxqp_ipm_kernel<TIO, ST, NX, NU, NC, 2><<<grid, kQpThreads, 0, st>>>(a);
     return check_launch("boxqp_ipm_rows_kernel");
   } else if constexpr (NX + NU <= 3) {
     // (2,1): residency against registers, measured on B200 (tools/prof/exp_q3.sh); default 4 CTAs/SM
     int minb = 4;
     if (const char* env = getenv("MPC_QP_MINB")) minb = atoi(env);
-    if (!getenv("MPC_QP_PREFETCH")) a.pf_dist = 2;
-    if (minb >= 6) boxqp_ipm_kernel<TIO, ST, NX, NU, 0, 6><<<grid, kQpThreads, 0, st>>>(a);
-    else if (minb >= 4) boxqp_ipm_kernel<TIO, ST, NX, NU, 0, 4><<<grid, kQpThreads, 0, st>>>(a);
-    else boxqp_ipm_kernel<TIO, ST, NX, NU, 0, 3><<<grid, kQpThreads, 0, st>>>(a);
+    if (!getenv("MPC_QP_PREFETCH")) a.pf_dist = 1;
+    if (refill > 0 && a.batch > 4096) {
+      if (minb >= 4) return launch_refill<TIO, ST, NX, NU, 4>(a, refill, st);
+      return launch_refill<TIO, ST, NX, NU, 3>(a, refill, st);
+    }
+    a.ws = static_cast<char*>(a.ws) + kWsHeader;
+    if (a.batch % 4 == 0) {
+      // 5 CTAs of 96 threads (136 registers, no spills, 480 threads per SM) against 4 of 128 (128 registers: ptxas
+      // spills ~100 bytes there since the fused sweep A) and 3 of 128 (168 registers, 384 threads)
+      if (minb >= 5) boxqp_ipm_kernel_s96<TIO, ST, NX, NU><<<(unsigned)((a.batch + 95) / 96), 96, 0, st>>>(a);
+      else if (minb >= 4) boxqp_ipm_kernel_s<TIO, ST, NX, NU, 0, 4><<<grid, kQpThreads, 0, st>>>(a);
+      else boxqp_ipm_kernel_s<TIO, ST, NX, NU, 0, 3><<<grid, kQpThreads, 0, st>>>(a);
+    } else {
+      boxqp_ipm_kernel<TIO, ST, NX, NU, 0, 3><<<grid, kQpThreads, 0, st>>>(a);
+    }
   } else {
-    boxqp_ipm_kernel<TIO, ST, NX, NU, 0, 2><<<grid, kQpThreads, 0, st>>>(a);
+    if (refill > 0 && a.batch > 4096) return launch_refill<TIO, ST, NX, NU, 2>(a, refill, st);
+    a.ws = static_cast<char*>(a.ws) + kWsHeader;
+    if (a.batch % 4 == 0) boxqp_ipm_kernel_s<TIO, ST, NX, NU, 0, 2><<<grid, kQpThreads, 0, st>>>(a);
+    else boxqp_ipm_kernel<TIO, ST, NX, NU, 0, 2><<<grid, kQpThreads, 0, st>>>(a);
   }
   return check_launch("boxqp_ipm_kernel");
 }
@@ -68,8 +197,10 @@ using namespace mpc;
 
 extern "C" int64_t mpc_boxqp_rows_workspace_bytes(int64_t batch, int n, int m, int N, int nc, int dtype) {
   if (batch < 0 || n < 1 || m < 1 || N < 1 || nc < 0) return 0;
-  // MPC_F64: the size of the all-float64 layout (the default mixed layout is smaller; MPC_QP_STORE=f64 needs this)
-  return dtype == MPC_F32 ? boxqp_ws_bytes<StoreF32>(n, m, N, nc, batch) : boxqp_ws_bytes<StoreF64>(n, m, N, nc, batch);
+  // kWsHeader bytes for the scenario queue of the refill kernel + one lane per scenario (the refill kernel uses one per
+  // resident thread only).  MPC_F64: the size of the all-float64 layout (the default mixed layout is smaller;
+  // MPC_QP_STORE=f64 needs this)
+  return kWsHeader + (dtype == MPC_F32 ? boxqp_ws_bytes<StoreF32>(n, m, N, nc, batch) : boxqp_ws_bytes<StoreF64>(n, m, N, nc, batch));
 }
 
 extern "C" int64_t mpc_boxqp_workspace_bytes(int64_t batch, int n, int m, int N, int dtype) {

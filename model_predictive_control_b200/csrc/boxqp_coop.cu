@@ -87,7 +87,43 @@ __device__ __forceinline__ void wmm(const double* __restrict__ A, const double* 
   }
 }
 
-template <int NX, int NU>
+// D[M x Nn] = Cin + op(A) B on the FP64 TENSOR pipe: warp-wide DMMA m8n8k4 (mma.sync, f64), operands in shared memory,
+// zero-padded to the 8 x 8 x 4 tile.  Element (i, k) of op(A) is A[i * sai + k * sak], element (k, j) of B is
+// B[k * sbk + j * sbj]; Cin (row-major, ldc; nullptr = 0) may alias D: a lane reads and writes the same two entries.
+// Fragment layout (PTX ISA, mma.m8n8k4 f64): A: row = lane / 4, col = lane % 4;  B: row = lane % 4, col = lane / 4;
+// C / D: row = lane / 4, cols = 2 (lane % 4) + {0, 1}.
+// Per 8 x 8 x 4 tile step a lane issues 2 shared loads and 1 DMMA (512 FMAs warp-wide), where the scalar form needs
+// 16 DFMAs and ~16 loads: the 12 x 12 products of the factorisation are no longer what the kernel waits for.
+template <int M, int K, int Nn>
+__device__ __forceinline__ void dmma_mm(const double* __restrict__ A, int sai, int sak, const double* __restrict__ B, int sbk,
+                                        int sbj, const double* Cin, double* D, int ldc, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int mt = 0; mt < (M + 7) / 8; ++mt) {
+#pragma unroll
+    for (int nt = 0; nt < (Nn + 7) / 8; ++nt) {
+      const int ci = mt * 8 + g, cj = nt * 8 + 2 * t;
+      const bool ok0 = ci < M && cj < Nn, ok1 = ci < M && cj + 1 < Nn;
+      double c0 = (Cin && ok0) ? Cin[ci * ldc + cj] : 0.0;
+      double c1 = (Cin && ok1) ? Cin[ci * ldc + cj + 1] : 0.0;
+#pragma unroll
+      for (int kt = 0; kt < (K + 3) / 4; ++kt) {
+        const int ak = kt * 4 + t;           // A fragment: (row g, col t)
+        const int bj = nt * 8 + g;           // B fragment: (row t, col g)
+        const double av = (ci < M && ak < K) ? A[ci * sai + ak * sak] : 0.0;
+        const double bv = (ak < K && bj < Nn) ? B[ak * sbk + bj * sbj] : 0.0;
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c0), "+d"(c1)
+                     : "d"(av), "d"(bv));
+      }
+      if (ok0) D[ci * ldc + cj] = c0;
+      if (ok1) D[ci * ldc + cj + 1] = c1;
+    }
+  }
+}
+
+// env MPC_COOP_DMMA=0 selects the scalar (lane-parallel DFMA) products, for A/B measurements
+template <int NX, int NU, bool DMMA = true>
 struct CoopIpm {
   using L = CoopLayout<NX, NU>;
   static constexpr int D = NX + NU;
@@ -251,7 +287,8 @@ struct CoopIpm {
         __syncwarp();
         // Joseph form (see BoxQpIpm::backward): PB = P B, S = Rt + B'PB, K = -S^-1 (PB)'A, Acl = A + B K,
         // Pacc <- Q + Acl' P Acl + K' Rt K with Rt = R + diag(Sigma_u)
-        wmm<NX, NX, NU, false, false>(w + L::wP, sh + L::oB, w + L::wPB, lane);  // PB = P B
+        if constexpr (DMMA) dmma_mm<NX, NX, NU>(w + L::wP, NX, 1, sh + L::oB, NU, 1, nullptr, w + L::wPB, NU, lane);
+        else wmm<NX, NX, NU, false, false>(w + L::wP, sh + L::oB, w + L::wPB, lane);  // PB = P B
         __syncwarp();
         // augmented [S | I], S = Rt + B'PB ;  G = (PB)'A
         for (int e = lane; e < NU * NU; e += 32) {
@@ -262,7 +299,8 @@ struct CoopIpm {
           w[L::wAug + i * 2 * NU + j] = acc;
           w[L::wAug + i * 2 * NU + NU + j] = (i == j) ? 1.0 : 0.0;
         }
-        wmm<NU, NX, NX, true, false>(w + L::wPB, sh + L::oA, w + L::wG, lane);
+        if constexpr (DMMA) dmma_mm<NU, NX, NX>(w + L::wPB, 1, NU, sh + L::oA, NX, 1, nullptr, w + L::wG, NX, lane);  // (PB)'A
+        else wmm<NU, NX, NX, true, false>(w + L::wPB, sh + L::oA, w + L::wG, lane);
         __syncwarp();
         // Gauss-Jordan without pivoting (S is symmetric positive definite); lanes over [NU][2 NU]
         for (int p = 0; p < NU; ++p) {
@@ -290,12 +328,16 @@ struct CoopIpm {
         }
         __syncwarp();
         // Acl = A + B K (into wAcl = the PB.. no: its own buffer wW2), G <- Rt K
-        for (int e = lane; e < NX * NX; e += 32) {
-          const int i = e / NX, j = e % NX;
-          double acc = sh[L::oA + e];
+        if constexpr (DMMA) {
+          dmma_mm<NX, NU, NX>(sh + L::oB, NU, 1, w + L::wK, NX, 1, sh + L::oA, w + L::wAcl, NX, lane);
+        } else {
+          for (int e = lane; e < NX * NX; e += 32) {
+            const int i = e / NX, j = e % NX;
+            double acc = sh[L::oA + e];
 #pragma unroll
-          for (int l = 0; l < NU; ++l) acc = fma(sh[L::oB + i * NU + l], w[L::wK + l * NX + j], acc);
-          w[L::wAcl + e] = acc;
+            for (int l = 0; l < NU; ++l) acc = fma(sh[L::oB + i * NU + l], w[L::wK + l * NX + j], acc);
+            w[L::wAcl + e] = acc;
+          }
         }
         for (int e = lane; e < NU * NX; e += 32) {
           const int i = e / NX, j = e % NX;
@@ -305,8 +347,21 @@ struct CoopIpm {
           w[L::wG + e] = acc;
         }
         __syncwarp();
-        wmm<NX, NX, NX, false, false>(w + L::wP, w + L::wAcl, w + L::wW, lane);  // T = P Acl
+        if constexpr (DMMA) dmma_mm<NX, NX, NX>(w + L::wP, NX, 1, w + L::wAcl, NX, 1, nullptr, w + L::wW, NX, lane);
+        else wmm<NX, NX, NX, false, false>(w + L::wP, w + L::wAcl, w + L::wW, lane);  // T = P Acl
         __syncwarp();
+        if constexpr (DMMA) {
+          // Pacc <- Q + Acl'T + K'(Rt K): two accumulating tile products, then the upper triangle mirrored so that P
+          // stays exactly symmetric (as the scalar form, which only computes that triangle)
+          dmma_mm<NX, NX, NX>(w + L::wAcl, 1, NX, w + L::wW, NX, 1, sh + L::oQ, w + L::wP, NX, lane);
+          __syncwarp();
+          dmma_mm<NX, NU, NX>(w + L::wK, 1, NX, w + L::wG, NX, 1, w + L::wP, w + L::wP, NX, lane);
+          __syncwarp();
+          for (int e = lane; e < NX * NX; e += 32) {
+            const int i = e / NX, j = e % NX;
+            if (i > j) w[L::wP + e] = w[L::wP + j * NX + i];
+          }
+        } else
         // Pacc <- Q + Acl'T + K'(Rt K) on the upper triangle (NX (NX+1)/2 entries over the lanes), mirrored
         for (int e = lane; e < NX * (NX + 1) / 2; e += 32) {
           int i = 0, rem = e;
@@ -570,7 +625,7 @@ struct CoopIpm {
   }
 };
 
-template <int NX, int NU, int MINB>
+template <int NX, int NU, int MINB, bool DMMA>
 __global__ void __launch_bounds__(kCoopWarps * 32, MINB) boxqp_ipm_coop_kernel(BoxQpArgs<double> a, int nslots) {
   using L = CoopLayout<NX, NU>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -594,7 +649,7 @@ __global__ void __launch_bounds__(kCoopWarps * 32, MINB) boxqp_ipm_coop_kernel(B
   if (slot >= nslots) return;
   double* wsm = sh + L::shared_total + warp * L::warp_total;
   double* ws_slot = static_cast<double*>(a.ws) + (int64_t)slot * L::slot_elems(a.N);
-  CoopIpm<NX, NU> ipm(a, sh, wsm, ws_slot, lane);
+  CoopIpm<NX, NU, DMMA> ipm(a, sh, wsm, ws_slot, lane);
   for (int64_t b = slot; b < a.batch; b += nslots) ipm.solve(b);
 }
 
@@ -605,11 +660,11 @@ int64_t coop_ws_elems(int n, int m, int N, int64_t batch) {
 
 bool coop_supported(int n, int m, int ltv) { return n == 12 && m == 4 && !ltv; }
 
-template <int NX, int NU, int MINB>
+template <int NX, int NU, int MINB, bool DMMA>
 static int launch_coop_variant(const BoxQpArgs<double>& a, cudaStream_t st) {
   using L = CoopLayout<NX, NU>;
   const size_t smem = sizeof(double) * (size_t)(L::shared_total + kCoopWarps * L::warp_total);
-  auto kern = boxqp_ipm_coop_kernel<NX, NU, MINB>;
+  auto kern = boxqp_ipm_coop_kernel<NX, NU, MINB, DMMA>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail((int)e, "mpc_boxqp_solve: %s", cudaGetErrorString(e));
   // persistent grid: exactly the CTAs that are resident at once (one workspace slot per warp)
@@ -630,9 +685,15 @@ int launch_boxqp_coop(const BoxQpArgs<double>& a, int n, int m, cudaStream_t st)
   if (n == 12 && m == 4) {
     int minb = 4;  // measured on B200: 4 CTAs/SM (64 registers) is marginally the fastest
     if (const char* env = getenv("MPC_COOP_MINB")) minb = atoi(env);
-    if (minb >= 4) return launch_coop_variant<12, 4, 4>(a, st);
-    if (minb == 3) return launch_coop_variant<12, 4, 3>(a, st);
-    return launch_coop_variant<12, 4, 2>(a, st);
+    bool dmma = true;  // products of the factorisation on the FP64 tensor pipe (DMMA); 0 = lane-parallel DFMA
+    if (const char* env = getenv("MPC_COOP_DMMA")) dmma = atoi(env) != 0;
+    if (!dmma) {
+      if (minb >= 4) return launch_coop_variant<12, 4, 4, false>(a, st);
+      return launch_coop_variant<12, 4, 2, false>(a, st);
+    }
+    if (minb >= 4) return launch_coop_variant<12, 4, 4, true>(a, st);
+    if (minb == 3) return launch_coop_variant<12, 4, 3, true>(a, st);
+    return launch_coop_variant<12, 4, 2, true>(a, st);
   }
   return fail(MPC_ERR_UNSUPPORTED, "mpc_boxqp_solve: no cooperative kernel for n=%d m=%d", n, m);
 }

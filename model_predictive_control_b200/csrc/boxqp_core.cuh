@@ -41,6 +41,8 @@
 // The body is __host__ __device__: tests/harness runs it on the CPU against oracle/boxqp.py.
 #pragma once
 
+#include <type_traits>
+
 #include "smallmat.cuh"
 
 namespace mpc {
@@ -92,25 +94,22 @@ using StoreMix = BoxQpStore<double, float, float, double, double, double>;    //
 using StoreF32 = BoxQpStore<float, float, float, float, float, float>;        // float32 product
 
 inline int64_t ws_round16(int64_t bytes) { return (bytes + 15) / 16 * 16; }
+inline int64_t ws_lanes_padded(int64_t lanes) { return (lanes + 3) / 4 * 4; }  // keeps every section 16-byte aligned
+
+// bytes per (stage x lane) of the workspace: sections are laid out back to back, each [N][per][lanes]
+template <class ST>
+constexpr int64_t boxqp_ws_bytes_per_cell(int n, int m, int nc) {
+  const int64_t d = n + m;
+  return d * (int64_t)(sizeof(typename ST::Z) + 4 * sizeof(typename ST::SL) + sizeof(typename ST::DA) +
+                       sizeof(typename ST::DZ) + 2 * sizeof(typename ST::EG)) +
+         (int64_t)(m * n + m * m + m) * (int64_t)sizeof(typename ST::GN) +
+         (int64_t)nc * (int64_t)(2 * sizeof(typename ST::SL) + sizeof(typename ST::Z));
+}
 
 // workspace bytes for `lanes` resident scenarios
 template <class ST>
 inline int64_t boxqp_ws_bytes(int n, int m, int N, int nc, int64_t lanes) {
-  const int64_t d = n + m, per = (int64_t)N * lanes;
-  int64_t t = 0;
-  t += ws_round16(per * d * (int64_t)sizeof(typename ST::Z));
-  t += 4 * ws_round16(per * d * (int64_t)sizeof(typename ST::SL));
-  t += ws_round16(per * d * (int64_t)sizeof(typename ST::DA));
-  t += ws_round16(per * d * (int64_t)sizeof(typename ST::DZ));
-  t += 2 * ws_round16(per * d * (int64_t)sizeof(typename ST::EG));
-  t += ws_round16(per * m * n * (int64_t)sizeof(typename ST::GN));
-  t += ws_round16(per * m * m * (int64_t)sizeof(typename ST::GN));
-  t += ws_round16(per * m * (int64_t)sizeof(typename ST::GN));
-  if (nc > 0) {
-    t += 2 * ws_round16(per * nc * (int64_t)sizeof(typename ST::SL));
-    t += ws_round16(per * nc * (int64_t)sizeof(typename ST::Z));
-  }
-  return t;
+  return (int64_t)N * ws_lanes_padded(lanes) * boxqp_ws_bytes_per_cell<ST>(n, m, nc);
 }
 
 // shared-parameter block (shared memory on the device), always in the compute type
@@ -154,7 +153,10 @@ MPC_HD T round_to(T v) {   // the value a later sweep will read back from a sect
   return (T)(S)v;
 }
 
-template <typename T, typename TIO, int NX, int NU, int NC = 0, int MODEL = 0, class ST = StoreMix>
+// LANES = true: the workspace has its own lane index and stride (persistent refill kernel: one lane per resident thread).
+// LANES = false: lane b = scenario b and both share the stride `batch` (which must then be a multiple of 4): one index
+// computation and four registers less in the kernels that run at their register limit.
+template <typename T, typename TIO, int NX, int NU, int NC = 0, int MODEL = 0, class ST = StoreMix, bool LANES = false>
 struct BoxQpIpm {
   static constexpr int D = NX + NU;
   using SH = BoxQpShared<NX, NU>;
@@ -174,42 +176,66 @@ struct BoxQpIpm {
   int64_t wb, wbs;  // workspace lane and lane stride
   T mu_scale;       // max(1, max|Q|, max|R|): scale of the complementarity tolerance
   T mu0;            // start value of the barrier parameter, per scenario: max(mu_scale, |H z0|_inf)
-  // workspace sections, each [N][per][lanes]
-  TZ* z;
-  TSL *sl, *su, *ll, *lu;
-  TDA* dza;
-  TDZ* dzw;
-  TEG *ew, *gw;
-  TGN *Kw, *Sw, *dw;
-  TSL *sc, *lc;  // general rows: slack, multiplier
-  TZ* rc;        // general rows: residual C x - h - s (carried, see init)
-
-  template <typename S>
-  MPC_HD static S* take(char*& p, int64_t elems) {
-    S* r = reinterpret_cast<S*>(p);
-    p += (elems * (int64_t)sizeof(S) + 15) / 16 * 16;
-    return r;
-  }
+  // Workspace layout [stage][row][lane]: ALL rows of one stage are adjacent (z, slacks, multipliers, directions, e, g,
+  // gains ...), every row lane-contiguous, so a stage visit touches one contiguous region and the address of row
+  // (section offset OFF, element i) of stage k is
+  //     base + ((k * kCell + OFF + i * sizeof(S)) * lanes + lane * sizeof(S))
+  // with kCell, OFF compile-time constants: one base pointer and the lane stride stay in registers, an access costs one
+  // integer multiply-add.  (Round 2 first laid the sections out back to back, [section][stage][row][lane], with
+  // fifteen section pointers -- thirty registers, spills in the (4,2) and RTI kernels -- and then with per-access
+  // base + stride * offset arithmetic -- +54 % integer multiply-adds in the (2,1) kernel, measured -12 %.)
+  char* wsb;
+  static constexpr int64_t oZ = 0;
+  static constexpr int64_t oSl = oZ + D * (int64_t)sizeof(TZ);
+  static constexpr int64_t oSu = oSl + D * (int64_t)sizeof(TSL);
+  static constexpr int64_t oLl = oSu + D * (int64_t)sizeof(TSL);
+  static constexpr int64_t oLu = oLl + D * (int64_t)sizeof(TSL);
+  static constexpr int64_t oDa = oLu + D * (int64_t)sizeof(TSL);
+  static constexpr int64_t oDz = oDa + D * (int64_t)sizeof(TDA);
+  static constexpr int64_t oE = oDz + D * (int64_t)sizeof(TDZ);
+  static constexpr int64_t oG = oE + D * (int64_t)sizeof(TEG);
+  static constexpr int64_t oK = oG + D * (int64_t)sizeof(TEG);
+  static constexpr int64_t oS = oK + NU * NX * (int64_t)sizeof(TGN);
+  static constexpr int64_t oD = oS + NU * NU * (int64_t)sizeof(TGN);
+  static constexpr int64_t oSc = oD + NU * (int64_t)sizeof(TGN);
+  static constexpr int64_t oLc = oSc + NC * (int64_t)sizeof(TSL);
+  static constexpr int64_t oRc = oLc + NC * (int64_t)sizeof(TSL);
+  static constexpr int64_t kCell = oRc + NC * (int64_t)sizeof(TZ);   // bytes per stage and lane
+  struct Idx {
+    int k, i;
+  };
+  MPC_HD int64_t lane_stride() const { return LANES ? wbs : bs; }
+  MPC_HD int64_t lane_index() const { return LANES ? wb : b; }
+  template <typename S, int64_t OFF>
+  struct Sec {
+    const BoxQpIpm* p;
+    MPC_HD S& operator[](Idx o) const {
+      return *reinterpret_cast<S*>(p->wsb + ((int64_t)o.k * kCell + OFF + (int64_t)o.i * (int64_t)sizeof(S)) * p->lane_stride() +
+                                   p->lane_index() * (int64_t)sizeof(S));
+    }
+  };
+#define MPC_WS_SECTION(name, type, off) \
+  MPC_HD Sec<type, off> name##_() const { return Sec<type, off>{this}; }
+  MPC_WS_SECTION(z, TZ, oZ)
+  MPC_WS_SECTION(sl, TSL, oSl)
+  MPC_WS_SECTION(su, TSL, oSu)
+  MPC_WS_SECTION(ll, TSL, oLl)
+  MPC_WS_SECTION(lu, TSL, oLu)
+  MPC_WS_SECTION(dza, TDA, oDa)
+  MPC_WS_SECTION(dzw, TDZ, oDz)
+  MPC_WS_SECTION(ew, TEG, oE)
+  MPC_WS_SECTION(gw, TEG, oG)
+  MPC_WS_SECTION(Kw, TGN, oK)
+  MPC_WS_SECTION(Sw, TGN, oS)
+  MPC_WS_SECTION(dw, TGN, oD)
+  MPC_WS_SECTION(sc, TSL, oSc)
+  MPC_WS_SECTION(lc, TSL, oLc)
+  MPC_WS_SECTION(rc, TZ, oRc)
+#undef MPC_WS_SECTION
 
   MPC_HD BoxQpIpm(const BoxQpArgs<TIO>& args, const T* shared, int64_t scenario, int64_t lane, int64_t lanes)
-      : a(args), sh(shared), b(scenario), bs(args.batch), wb(lane), wbs(lanes) {
-    char* p = static_cast<char*>(a.ws);
-    const int64_t per = (int64_t)a.N * wbs;
-    z = take<TZ>(p, per * D);
-    sl = take<TSL>(p, per * D);
-    su = take<TSL>(p, per * D);
-    ll = take<TSL>(p, per * D);
-    lu = take<TSL>(p, per * D);
-    dza = take<TDA>(p, per * D);
-    dzw = take<TDZ>(p, per * D);
-    ew = take<TEG>(p, per * D);
-    gw = take<TEG>(p, per * D);
-    Kw = take<TGN>(p, per * NU * NX);
-    Sw = take<TGN>(p, per * NU * NU);
-    dw = take<TGN>(p, per * NU);
-    sc = take<TSL>(p, per * NC);
-    lc = take<TSL>(p, per * NC);
-    rc = take<TZ>(p, per * NC);
+      : a(args), sh(shared), b(scenario), bs(args.batch), wb(lane), wbs((lanes + 3) / 4 * 4) {
+    wsb = static_cast<char*>(a.ws);
     mu_scale = T(1);
     for (int i = 0; i < NX * NX; ++i) {
       const T v = sh[SH::oQ + i] < T(0) ? -sh[SH::oQ + i] : sh[SH::oQ + i];
@@ -223,7 +249,7 @@ struct BoxQpIpm {
   }
 
   MPC_HD int64_t ix(int k, int i, int per) const { return ((int64_t)k * per + i) * bs + b; }     // caller's arrays
-  MPC_HD int64_t wx(int k, int i, int per) const { return ((int64_t)k * per + i) * wbs + wb; }   // workspace
+  MPC_HD static Idx wx(int k, int i, int /*per*/) { return Idx{k, i}; }                         // workspace
   MPC_HD bool hasl(int i) const { return sh[SH::oLo + i] > T(-kBigBound); }
   MPC_HD bool hasu(int i) const { return sh[SH::oHi + i] < T(kBigBound); }
   MPC_HD T lo(int i) const { return sh[SH::oLo + i]; }
@@ -239,23 +265,23 @@ struct BoxQpIpm {
   MPC_HD void load(int k, Stage& s) const {
 #pragma unroll
     for (int i = 0; i < D; ++i) {
-      const int64_t o = wx(k, i, D);
-      s.z[i] = (T)z[o];
-      s.sl[i] = (T)sl[o];
-      s.su[i] = (T)su[o];
-      s.ll[i] = (T)ll[o];
-      s.lu[i] = (T)lu[o];
+      const Idx o = wx(k, i, D);
+      s.z[i] = (T)z_()[o];
+      s.sl[i] = (T)sl_()[o];
+      s.su[i] = (T)su_()[o];
+      s.ll[i] = (T)ll_()[o];
+      s.lu[i] = (T)lu_()[o];
     }
   }
   MPC_HD void store_stage(int k, const Stage& s) {
 #pragma unroll
     for (int i = 0; i < D; ++i) {
-      const int64_t o = wx(k, i, D);
-      z[o] = (TZ)s.z[i];
-      sl[o] = (TSL)s.sl[i];
-      su[o] = (TSL)s.su[i];
-      ll[o] = (TSL)s.ll[i];
-      lu[o] = (TSL)s.lu[i];
+      const Idx o = wx(k, i, D);
+      z_()[o] = (TZ)s.z[i];
+      sl_()[o] = (TSL)s.sl[i];
+      su_()[o] = (TSL)s.su[i];
+      ll_()[o] = (TSL)s.ll[i];
+      lu_()[o] = (TSL)s.lu[i];
     }
   }
   // the values the next sweeps will read back (identity for float64 storage)
@@ -285,10 +311,10 @@ struct BoxQpIpm {
     (void)p;
 #endif
   }
-  template <int PER, typename S>
-  MPC_HD void pf_rows(const S* base, int k) const {
+  template <int PER, class SEC>
+  MPC_HD void pf_rows(SEC base, int k) const {
 #pragma unroll
-    for (int i = 0; i < PER; ++i) pf(base + wx(k, i, PER));
+    for (int i = 0; i < PER; ++i) pf(&base[wx(k, i, PER)]);
   }
   template <int PER, typename S>
   MPC_HD void pf_rows_io(const S* base, int k) const {
@@ -296,11 +322,11 @@ struct BoxQpIpm {
     for (int i = 0; i < PER; ++i) pf(base + ix(k, i, PER));
   }
   MPC_HD void pf_iterate(int k) const {
-    pf_rows<D>(z, k);
-    pf_rows<D>(sl, k);
-    pf_rows<D>(su, k);
-    pf_rows<D>(ll, k);
-    pf_rows<D>(lu, k);
+    pf_rows<D>(z_(), k);
+    pf_rows<D>(sl_(), k);
+    pf_rows<D>(su_(), k);
+    pf_rows<D>(ll_(), k);
+    pf_rows<D>(lu_(), k);
   }
   MPC_HD void pf_model(int k) const {
     if constexpr (MODEL == 1) {
@@ -320,15 +346,18 @@ struct BoxQpIpm {
 #endif
   }
 
-  template <int PER, typename S>
-  MPC_HD void loadn(const S* base, int k, T* v) const {
+  template <int PER, class SEC>
+  MPC_HD void loadn(SEC base, int k, T* v) const {
 #pragma unroll
     for (int i = 0; i < PER; ++i) v[i] = (T)base[wx(k, i, PER)];
   }
-  template <int PER, typename S>
-  MPC_HD void storen(S* base, int k, const T* v) const {
+  template <int PER, class SEC>
+  MPC_HD void storen(SEC base, int k, const T* v) const {
 #pragma unroll
-    for (int i = 0; i < PER; ++i) base[wx(k, i, PER)] = (S)v[i];
+    for (int i = 0; i < PER; ++i) {
+      auto& slot = base[wx(k, i, PER)];
+      slot = (typename std::remove_reference<decltype(slot)>::type)v[i];
+    }
   }
   template <int PER>
   MPC_HD void loadn_io(const TIO* base, int k, T* v) const {
@@ -462,11 +491,11 @@ struct BoxQpIpm {
               const T h = load_row_c(k, j, C);
               const T w = dotx(C, xn) - h;
               const T s = round_to<TSL>(w > T(1) ? w : T(1));
-              sc[wx(k, j, NC)] = (TSL)s;
-              lc[wx(k, j, NC)] = (TSL)(mu0 / s);
+              sc_()[wx(k, j, NC)] = (TSL)s;
+              lc_()[wx(k, j, NC)] = (TSL)(mu0 / s);
               // the row residual is carried, not recomputed: it decays exactly by (1 - alpha) per step, whereas
               // C x - h - s recomputed from a dot product keeps ~1e-16 of rounding noise that Sigma ~ 1e12 amplifies
-              rc[wx(k, j, NC)] = (TZ)(w - s);
+              rc_()[wx(k, j, NC)] = (TZ)(w - s);
             }
           }
         }
@@ -498,43 +527,31 @@ struct BoxQpIpm {
     return ar;
   }
 
+  // step of one bound: (s, lam) += alpha * (ds, dlam), rounded to the stored type.  r = residual of the bound at the
+  // OLD iterate, dzs / das = the signed direction (+dz for a lower bound, -dz for an upper one)
+  MPC_HD static void step_bound(T& s, T& l, T r, T dzs, T das, T tau, T alpha) {
+    const T ds = dzs + r;
+    const T inv = rcp_(s), sg = l * inv;
+    const T cc = cc_of(das, r, sg, l);
+    const T dl = (tau - cc) * inv - l - sg * ds;
+    T sn = s + alpha * ds, ln = l + alpha * dl;
+    if constexpr (kNarrowSL || kNarrowDir) {  // the ratio test ran on unrounded values: keep the margin
+      sn = max_(sn, T(1e-3) * s);
+      ln = max_(ln, T(1e-3) * l);
+    }
+    s = round_to<TSL>(sn);
+    l = round_to<TSL>(ln);
+  }
+
   // ---- the step of one stage: (z, s, lam) += alpha * direction, slack / multiplier directions recomputed from the
   // stored dz and dz_aff exactly as sweep D computed them.  Used by sweep A (fused update) and by the output pass.
   MPC_HD void apply_step(Stage& st, const T* dz, const T* da, T tau, T alpha) const {
 #pragma unroll
     for (int i = 0; i < D; ++i) {
       const T zi = st.z[i];
-      if (hasl(i)) {
-        const T s = st.sl[i], l = st.ll[i];
-        const T r = zi - lo(i) - s;
-        const T ds = dz[i] + r;
-        const T inv = rcp_(s), sgl = l * inv;
-        const T cc = cc_of(da[i], r, sgl, l);
-        const T dl = (tau - cc) * inv - l - sgl * ds;
-        T sn = s + alpha * ds, ln = l + alpha * dl;
-        if constexpr (kNarrowSL || kNarrowDir) {  // the ratio test ran on unrounded directions: keep the margin
-          sn = max_(sn, T(1e-3) * s);
-          ln = max_(ln, T(1e-3) * l);
-        }
-        st.sl[i] = sn;
-        st.ll[i] = ln;
-      }
-      if (hasu(i)) {
-        const T s = st.su[i], l = st.lu[i];
-        const T r = hi(i) - zi - s;
-        const T ds = -dz[i] + r;
-        const T inv = rcp_(s), sgu = l * inv;
-        const T cc = cc_of(-da[i], r, sgu, l);
-        const T dl = (tau - cc) * inv - l - sgu * ds;
-        T sn = s + alpha * ds, ln = l + alpha * dl;
-        if constexpr (kNarrowSL || kNarrowDir) {
-          sn = max_(sn, T(1e-3) * s);
-          ln = max_(ln, T(1e-3) * l);
-        }
-        st.su[i] = sn;
-        st.lu[i] = ln;
-      }
-      st.z[i] = zi + alpha * dz[i];
+      if (hasl(i)) step_bound(st.sl[i], st.ll[i], zi - lo(i) - st.sl[i], dz[i], da[i], tau, alpha);
+      if (hasu(i)) step_bound(st.su[i], st.lu[i], hi(i) - zi - st.su[i], -dz[i], -da[i], tau, alpha);
+      st.z[i] = round_to<TZ>(zi + alpha * dz[i]);
     }
   }
   // step of the general rows of stage k (in place in the workspace)
@@ -544,8 +561,8 @@ struct BoxQpIpm {
       for (int j = 0; j < NC; ++j) {
         T C[NX];
         (void)load_row_c(k, j, C);
-        const T s = (T)sc[wx(k, j, NC)], l = (T)lc[wx(k, j, NC)];
-        const T r = (T)rc[wx(k, j, NC)];
+        const T s = (T)sc_()[wx(k, j, NC)], l = (T)lc_()[wx(k, j, NC)];
+        const T r = (T)rc_()[wx(k, j, NC)];
         const T ds = dotx(C, dz + NU) + r;
         const T inv = rcp_(s), sgc = l * inv;
         const T cc = cc_of(dotx(C, da + NU), r, sgc, l);
@@ -558,9 +575,9 @@ struct BoxQpIpm {
         // the residual is carried: it must absorb the storage rounding of the slack, or C x - h = s + r drifts by an
         // ulp of s per iteration (2e-7 on the active rows after ~15 iterations with float32 slacks)
         const T sr = round_to<TSL>(sn);
-        sc[wx(k, j, NC)] = (TSL)sr;
-        lc[wx(k, j, NC)] = (TSL)ln;
-        rc[wx(k, j, NC)] = (TZ)((T(1) - alpha) * r + (sn - sr));
+        sc_()[wx(k, j, NC)] = (TSL)sr;
+        lc_()[wx(k, j, NC)] = (TSL)ln;
+        rc_()[wx(k, j, NC)] = (TZ)((T(1) - alpha) * r + (sn - sr));
       }
     }
   }
@@ -644,61 +661,118 @@ struct BoxQpIpm {
         pf_iterate(k - a.pf_dist);
         pf_model(k - a.pf_dist);
         if (have_step) {
-          pf_rows<D>(dza, k - a.pf_dist);
-          pf_rows<D>(dzw, k - a.pf_dist);
+          pf_rows<D>(dza_(), k - a.pf_dist);
+          pf_rows<D>(dzw_(), k - a.pf_dist);
         }
       }
+#if MPC_VAR_SWEEPA_STAGE
       Stage cur;
       load(k, cur);
       T A[NX * NX], B[NX * NU], c[NX];
       load_model(k, A, B, c);
+      T znew[D], sig[D], rhs[D];
       if (have_step) {
         T dz[D], da[D];
-        loadn<D>(dzw, k, dz);
-        loadn<D>(dza, k, da);
+        loadn<D>(dzw_(), k, dz);
+        loadn<D>(dza_(), k, da);
         apply_step_rows(k, dz, da, tau, alpha);
         apply_step(cur, dz, da, tau, alpha);
-        round_stage(cur);
         store_stage(k, cur);
       }
-      T sig[D], rhs[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        T sg = T(0), r = T(0);
+        if (hasl(i)) {
+          const T s = cur.sl[i], l = cur.ll[i];
+          const T sgl = l * rcp_(s);
+          sg += sgl;
+          r = fma_<T>(-sgl, cur.z[i] - lo(i) - s, r);
+        }
+        if (hasu(i)) {
+          const T s = cur.su[i], l = cur.lu[i];
+          const T sgu = l * rcp_(s);
+          sg += sgu;
+          r = fma_<T>(sgu, hi(i) - cur.z[i] - s, r);
+        }
+        znew[i] = cur.z[i];
+        sig[i] = sg;
+        rhs[i] = r;
+      }
+#else
+      // ALL loads of the stage visit are issued first (one memory round trip; the stores below would otherwise fence
+      // the later loads, the compiler cannot prove that the sections do not alias); slacks and multipliers stay in
+      // their stored type until they are used, which keeps the (4,2) instantiation inside the register file.
+      TZ zr[D];
+      TSL slr[D], sur[D], llr[D], lur[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        const Idx o = wx(k, i, D);
+        zr[i] = z_()[o];
+        slr[i] = sl_()[o];
+        sur[i] = su_()[o];
+        llr[i] = ll_()[o];
+        lur[i] = lu_()[o];
+      }
+      T znew[D], sig[D], rhs[D], dz[D], da[D];
+      if (have_step) {
+        loadn<D>(dzw_(), k, dz);
+        loadn<D>(dza_(), k, da);
+      }
+      T A[NX * NX], B[NX * NU], c[NX];
+      load_model(k, A, B, c);
+      if (have_step) apply_step_rows(k, dz, da, tau, alpha);
+      // per element: (previous step applied,) Sigma and the bound part of the affine right-hand side
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        const Idx o = wx(k, i, D);
+        const T zi = (T)zr[i];
+        const T zn = have_step ? round_to<TZ>(zi + alpha * dz[i]) : zi;
+        T sg = T(0), r = T(0);
+        if (hasl(i)) {
+          T s = (T)slr[i], l = (T)llr[i];
+          if (have_step) {
+            step_bound(s, l, zi - lo(i) - s, dz[i], da[i], tau, alpha);
+            sl_()[o] = (TSL)s;
+            ll_()[o] = (TSL)l;
+          }
+          const T sgl = l * rcp_(s);
+          sg += sgl;
+          r = fma_<T>(-sgl, zn - lo(i) - s, r);
+        }
+        if (hasu(i)) {
+          T s = (T)sur[i], l = (T)lur[i];
+          if (have_step) {
+            step_bound(s, l, hi(i) - zi - s, -dz[i], -da[i], tau, alpha);
+            su_()[o] = (TSL)s;
+            lu_()[o] = (TSL)l;
+          }
+          const T sgu = l * rcp_(s);
+          sg += sgu;
+          r = fma_<T>(sgu, hi(i) - zn - s, r);
+        }
+        if (have_step) z_()[o] = (TZ)zn;
+        znew[i] = zn;
+        sig[i] = sg;
+        rhs[i] = r;
+      }
+#endif
       // -(H z): inputs weighted by R, state x_{k+1} by Q (Pf for the last stage)
       {
         const T* Qx = sh + (k == a.N - 1 ? SH::oPf : SH::oQ);
 #pragma unroll
         for (int i = 0; i < NU; ++i) {
-          T acc = T(0);
+          T acc = rhs[i];
 #pragma unroll
-          for (int j = 0; j < NU; ++j) acc = fma_<T>(-sh[SH::oR + i * NU + j], cur.z[j], acc);
+          for (int j = 0; j < NU; ++j) acc = fma_<T>(-sh[SH::oR + i * NU + j], znew[j], acc);
           rhs[i] = acc;
         }
 #pragma unroll
         for (int i = 0; i < NX; ++i) {
-          T acc = T(0);
+          T acc = rhs[NU + i];
 #pragma unroll
-          for (int j = 0; j < NX; ++j) acc = fma_<T>(-Qx[i * NX + j], cur.z[NU + j], acc);
+          for (int j = 0; j < NX; ++j) acc = fma_<T>(-Qx[i * NX + j], znew[NU + j], acc);
           rhs[NU + i] = acc;
         }
-      }
-#pragma unroll
-      for (int i = 0; i < D; ++i) {
-        T sg = T(0), r = rhs[i];
-        if (hasl(i)) {
-          const T s = cur.sl[i], l = cur.ll[i];
-          const T sgl = l * rcp_(s);
-          const T rl = cur.z[i] - lo(i) - s;
-          sg += sgl;
-          r = fma_<T>(-sgl, rl, r);
-        }
-        if (hasu(i)) {
-          const T s = cur.su[i], l = cur.lu[i];
-          const T sgu = l * rcp_(s);
-          const T ru = hi(i) - cur.z[i] - s;
-          sg += sgu;
-          r = fma_<T>(sgu, ru, r);
-        }
-        sig[i] = sg;
-        rhs[i] = r;
       }
       if constexpr (NC > 0) {
         // general rows: value w = C x_{k+1}; adds C' Sigma_c C to the stage Hessian and C' rhs_c to the gradient
@@ -706,9 +780,9 @@ struct BoxQpIpm {
         for (int j = 0; j < NC; ++j) {
           T C[NX];
           (void)load_row_c(k, j, C);
-          const T s = (T)sc[wx(k, j, NC)], l = (T)lc[wx(k, j, NC)];
+          const T s = (T)sc_()[wx(k, j, NC)], l = (T)lc_()[wx(k, j, NC)];
           const T sgc = l * rcp_(s);
-          const T r = (T)rc[wx(k, j, NC)];
+          const T r = (T)rc_()[wx(k, j, NC)];
           const T rhs_c = -sgc * r;
 #pragma unroll
           for (int i = 0; i < NX; ++i) rhs[NU + i] = fma_<T>(C[i], rhs_c, rhs[NU + i]);
@@ -773,12 +847,12 @@ struct BoxQpIpm {
             Pacc[i * NX + j] = acc;
             Pacc[j * NX + i] = acc;
           }
-        storen<NU * NX>(Kw, k, K);
-        storen<NU * NU>(Sw, k, Sinv);
+        storen<NU * NX>(Kw_(), k, K);
+        storen<NU * NU>(Sw_(), k, Sinv);
       }
       T dff[NU];
       ff_stage(A, B, K, Sinv, rhs, pacc, dff);
-      storen<NU>(dw, k, dff);
+      storen<NU>(dw_(), k, dff);
     }
   }
 
@@ -801,14 +875,14 @@ struct BoxQpIpm {
       if (pf_on(k + a.pf_dist)) {
         pf_iterate(k + a.pf_dist);
         pf_model(k + a.pf_dist);
-        pf_rows<NU * NX>(Kw, k + a.pf_dist);
-        pf_rows<NU>(dw, k + a.pf_dist);
+        pf_rows<NU * NX>(Kw_(), k + a.pf_dist);
+        pf_rows<NU>(dw_(), k + a.pf_dist);
       }
       Stage cur;
       load(k, cur);
       T K[NU * NX], dff[NU];
-      loadn<NU * NX>(Kw, k, K);
-      loadn<NU>(dw, k, dff);
+      loadn<NU * NX>(Kw_(), k, K);
+      loadn<NU>(dw_(), k, dff);
       T A[NX * NX], B[NX * NU], c[NX];
       load_model(k, A, B, c);
 #pragma unroll
@@ -857,8 +931,8 @@ struct BoxQpIpm {
         for (int j = 0; j < NC; ++j) {
           T C[NX];
           (void)load_row_c(k, j, C);
-          const T s = (T)sc[wx(k, j, NC)], l = (T)lc[wx(k, j, NC)];
-          const T r = (T)rc[wx(k, j, NC)];
+          const T s = (T)sc_()[wx(k, j, NC)], l = (T)lc_()[wx(k, j, NC)];
+          const T r = (T)rc_()[wx(k, j, NC)];
           const T ds = dotx(C, dzv + NU) + r;
           const T inv = rcp_(s);
           const T t = ds * inv;
@@ -874,9 +948,9 @@ struct BoxQpIpm {
           }
         }
       }
-      storen<D>(dza, k, dzv);
-      storen<D>(ew, k, ev);
-      storen<D>(gw, k, gv);
+      storen<D>(dza_(), k, dzv);
+      storen<D>(ew_(), k, ev);
+      storen<D>(gw_(), k, gv);
       // the rollout continues with the UNROUNDED state direction (the stored copy is only used for cc)
 #pragma unroll
       for (int i = 0; i < NX; ++i) x[i] = xn[i];
@@ -891,29 +965,29 @@ struct BoxQpIpm {
     for (int i = 0; i < NX; ++i) pacc[i] = T(0);
     for (int k = a.N - 1; k >= 0; --k) {
       if (pf_on(k - a.pf_dist)) {
-        pf_rows<D>(ew, k - a.pf_dist);
-        pf_rows<D>(gw, k - a.pf_dist);
-        pf_rows<NU * NX>(Kw, k - a.pf_dist);
-        pf_rows<NU * NU>(Sw, k - a.pf_dist);
-        pf_rows<NU>(dw, k - a.pf_dist);
+        pf_rows<D>(ew_(), k - a.pf_dist);
+        pf_rows<D>(gw_(), k - a.pf_dist);
+        pf_rows<NU * NX>(Kw_(), k - a.pf_dist);
+        pf_rows<NU * NU>(Sw_(), k - a.pf_dist);
+        pf_rows<NU>(dw_(), k - a.pf_dist);
         pf_model(k - a.pf_dist);
       }
       T ev[D], gv[D], K[NU * NX], Sinv[NU * NU];
-      loadn<D>(ew, k, ev);
-      loadn<D>(gw, k, gv);
-      loadn<NU * NX>(Kw, k, K);
-      loadn<NU * NU>(Sw, k, Sinv);
+      loadn<D>(ew_(), k, ev);
+      loadn<D>(gw_(), k, gv);
+      loadn<NU * NX>(Kw_(), k, K);
+      loadn<NU * NU>(Sw_(), k, Sinv);
       T A[NX * NX], B[NX * NU], c[NX];
       load_model(k, A, B, c);
       T rhs[D];
 #pragma unroll
       for (int i = 0; i < D; ++i) rhs[i] = fma_<T>(tau, ev[i], -gv[i]);
       T dff[NU], daff[NU];
-      loadn<NU>(dw, k, daff);
+      loadn<NU>(dw_(), k, daff);
       ff_stage(A, B, K, Sinv, rhs, pacc, dff);
 #pragma unroll
       for (int j = 0; j < NU; ++j) dff[j] += daff[j];  // d_aff + d_cor: sweep D rolls the whole direction out at once
-      storen<NU>(dw, k, dff);
+      storen<NU>(dw_(), k, dff);
     }
   }
 
@@ -930,16 +1004,16 @@ struct BoxQpIpm {
       if (pf_on(k + a.pf_dist)) {
         pf_iterate(k + a.pf_dist);
         pf_model(k + a.pf_dist);
-        pf_rows<NU * NX>(Kw, k + a.pf_dist);
-        pf_rows<NU>(dw, k + a.pf_dist);
-        pf_rows<D>(dza, k + a.pf_dist);
+        pf_rows<NU * NX>(Kw_(), k + a.pf_dist);
+        pf_rows<NU>(dw_(), k + a.pf_dist);
+        pf_rows<D>(dza_(), k + a.pf_dist);
       }
       Stage cur;
       load(k, cur);
       T K[NU * NX], dff[NU], da[D];
-      loadn<NU * NX>(Kw, k, K);
-      loadn<NU>(dw, k, dff);
-      loadn<D>(dza, k, da);
+      loadn<NU * NX>(Kw_(), k, K);
+      loadn<NU>(dw_(), k, dff);
+      loadn<D>(dza_(), k, da);
       T A[NX * NX], B[NX * NU], c[NX];
       load_model(k, A, B, c);
 #pragma unroll
@@ -989,8 +1063,8 @@ struct BoxQpIpm {
         for (int j = 0; j < NC; ++j) {
           T C[NX];
           (void)load_row_c(k, j, C);
-          const T s = (T)sc[wx(k, j, NC)], l = (T)lc[wx(k, j, NC)];
-          const T r = (T)rc[wx(k, j, NC)];
+          const T s = (T)sc_()[wx(k, j, NC)], l = (T)lc_()[wx(k, j, NC)];
+          const T r = (T)rc_()[wx(k, j, NC)];
           const T ds = dotx(C, dzv + NU) + r;
           const T rinv = rcp_(s * l), inv_s = rinv * l, inv_l = rinv * s;
           const T sgc = l * inv_s;
@@ -1003,7 +1077,7 @@ struct BoxQpIpm {
           acc.rp = max_(acc.rp, abs_(r));
         }
       }
-      storen<D>(dzw, k, dzv);
+      storen<D>(dzw_(), k, dzv);
 #pragma unroll
       for (int i = 0; i < NX; ++i) x[i] = xn[i];
     }
@@ -1025,8 +1099,8 @@ struct BoxQpIpm {
       load_model(k, A, B, c);
       if (have_step) {
         T dz[D], da[D];
-        loadn<D>(dzw, k, dz);
-        loadn<D>(dza, k, da);
+        loadn<D>(dzw_(), k, dz);
+        loadn<D>(dza_(), k, da);
         apply_step_rows(k, dz, da, tau, alpha);
         apply_step(st, dz, da, tau, alpha);
       }
@@ -1048,7 +1122,7 @@ struct BoxQpIpm {
         if (a.sat_c) {
 #pragma unroll 1
           for (int j = 0; j < NC; ++j)
-            a.sat_c[ix(k, j, NC)] = (T)lc[wx(k, j, NC)] > (T)sc[wx(k, j, NC)] ? (int8_t)-1 : (int8_t)0;
+            a.sat_c[ix(k, j, NC)] = (T)lc_()[wx(k, j, NC)] > (T)sc_()[wx(k, j, NC)] ? (int8_t)-1 : (int8_t)0;
         }
       }
       cost += quad<T, NX>(sh + SH::oQ, x) + quad<T, NU>(sh + SH::oR, u);
@@ -1065,63 +1139,94 @@ struct BoxQpIpm {
     a.iters[b] = iters;
   }
 
-  MPC_HD void solve() {
-    int ncons = 0;
+  // number of slack / multiplier pairs of one scenario
+  MPC_HD int count_constraints() const {
+    int nc = 0;
 #pragma unroll
-    for (int i = 0; i < D; ++i) ncons += (hasl(i) ? 1 : 0) + (hasu(i) ? 1 : 0);
-    ncons = (ncons + NC) * a.N;
+    for (int i = 0; i < D; ++i) nc += (hasl(i) ? 1 : 0) + (hasu(i) ? 1 : 0);
+    return (nc + NC) * a.N;
+  }
+
+  // ---- one interior-point iteration on the caller's iteration state; true when the scenario is finished (status set)
+  MPC_HD bool iterate_on(int ncons, T inv_nc, int& it, int& status, T& tau, T& alpha, bool& have_step) {
+    ++it;
+    const T eps = (T)a.eps;
+    Acc acc;
+    sweep_a(have_step, tau, alpha);
+    sweep_b(acc);
+    {
+      const T mu = acc.s0 * inv_nc;
+      const T am_aff = acc.amin();
+      const T a_aff = am_aff < T(1) ? am_aff : T(1);
+      const T mu_aff = (acc.s0 + a_aff * (acc.s1 + a_aff * acc.s2)) * inv_nc;
+      T ratio = mu_aff / (mu > T(1e-300) ? mu : T(1e-300));
+      T sigma = ratio * ratio * ratio;
+      sigma = sigma < T(1) ? sigma : T(1);
+      // centring target; never below 1e-3 of the complementarity tolerance: driving mu further only inflates
+      // the barrier weights (lam/s ~ lam^2/mu) and with them the rounding noise of the Newton step
+      tau = sigma * mu;
+      const T mu_floor = T(1e-3) * eps * mu_scale;
+      tau = tau > mu_floor ? tau : mu_floor;
+    }
+    sweep_c(tau);
+    sweep_d(tau, acc);
+    alpha = T(0.995) * acc.amin();
+    alpha = alpha < T(1) ? alpha : T(1);
+    have_step = true;
+    const T zn = acc.zn;
+    const T mu_new = (acc.s0 + alpha * (acc.s1 + alpha * acc.s2)) * inv_nc;
+    const T rp = (T(1) - alpha) * acc.rp;
+    const bool done = (ncons == 0) ||
+                      ((mu_new <= eps * mu_scale) && (rp <= eps * zn) && (alpha * acc.dzmax <= T(1e-6) * zn));
+    if (done) {
+      status = MPC_SOLVED;
+    } else {
+      // stalled: step length collapsed / barrier parameter grew 100x above its start value.  With a bound residual
+      // that cannot be closed the box and the dynamics do not meet: infeasible.  Running out of iterations without
+      // that signature is reported as MPC_MAX_ITER unless the barrier parameter has grown above its start value
+      // while the residual is still open (multipliers diverging: the Farkas-type signature of an empty feasible set).
+      const bool stalled = !(alpha >= T(1e-6)) || !(mu_new <= T(100) * mu0);
+      const bool open = !(rp <= T(1e-6) * zn);
+      if (stalled) status = open ? MPC_INFEASIBLE : MPC_MAX_ITER;
+      else if (it >= a.max_iter) status = (open && mu_new > mu0) ? MPC_INFEASIBLE : MPC_MAX_ITER;
+    }
+    return status != MPC_UNSOLVED;
+  }
+
+  // ---- one scenario, start to end: the iteration state lives in locals (registers).
+  // (no finite bound at all: the first iteration is one exact Newton step onto the LQ optimum -- all barrier
+  // terms vanish, alpha = 1 -- and the loop stops after it.)
+  MPC_HD void solve() {
+    const int ncons = count_constraints();
+    const T inv_nc = ncons ? T(1) / T(ncons) : T(0);
     init();
     int status = MPC_UNSOLVED, it = 0;
     T tau = T(0), alpha = T(0);
     bool have_step = false;
-    const T eps = (T)a.eps;
-    // (no finite bound at all: the first iteration below is one exact Newton step onto the LQ optimum -- all barrier
-    // terms vanish, alpha = 1 -- and the loop stops after it.)
-    const T inv_nc = ncons ? T(1) / T(ncons) : T(0);
-    while (status == MPC_UNSOLVED && it < a.max_iter) {
-      ++it;
-      Acc acc;
-      sweep_a(have_step, tau, alpha);
-      sweep_b(acc);
-      {
-        const T mu = acc.s0 * inv_nc;
-        const T am_aff = acc.amin();
-        const T a_aff = am_aff < T(1) ? am_aff : T(1);
-        const T mu_aff = (acc.s0 + a_aff * (acc.s1 + a_aff * acc.s2)) * inv_nc;
-        T ratio = mu_aff / (mu > T(1e-300) ? mu : T(1e-300));
-        T sigma = ratio * ratio * ratio;
-        sigma = sigma < T(1) ? sigma : T(1);
-        // centring target; never below 1e-3 of the complementarity tolerance: driving mu further only inflates
-        // the barrier weights (lam/s ~ lam^2/mu) and with them the rounding noise of the Newton step
-        tau = sigma * mu;
-        const T mu_floor = T(1e-3) * eps * mu_scale;
-        tau = tau > mu_floor ? tau : mu_floor;
-      }
-      sweep_c(tau);
-      sweep_d(tau, acc);
-      alpha = T(0.995) * acc.amin();
-      alpha = alpha < T(1) ? alpha : T(1);
-      have_step = true;
-      const T zn = acc.zn;
-      const T mu_new = (acc.s0 + alpha * (acc.s1 + alpha * acc.s2)) * inv_nc;
-      const T rp = (T(1) - alpha) * acc.rp;
-      const bool done = (ncons == 0) ||
-                        ((mu_new <= eps * mu_scale) && (rp <= eps * zn) && (alpha * acc.dzmax <= T(1e-6) * zn));
-      if (done) {
-        status = MPC_SOLVED;
-      } else {
-        // stalled: step length collapsed / barrier parameter grew 100x above its start value.  With a bound residual
-        // that cannot be closed the box and the dynamics do not meet: infeasible.  Running out of iterations without
-        // that signature is reported as MPC_MAX_ITER unless the barrier parameter has grown above its start value
-        // while the residual is still open (multipliers diverging: the Farkas-type signature of an empty feasible set).
-        const bool stalled = !(alpha >= T(1e-6)) || !(mu_new <= T(100) * mu0);
-        const bool open = !(rp <= T(1e-6) * zn);
-        if (stalled) status = open ? MPC_INFEASIBLE : MPC_MAX_ITER;
-        else if (it >= a.max_iter) status = (open && mu_new > mu0) ? MPC_INFEASIBLE : MPC_MAX_ITER;
-      }
+    while (!iterate_on(ncons, inv_nc, it, status, tau, alpha, have_step)) {
     }
     output(status, it, have_step, tau, alpha);
   }
+
+  // ---- the same, split for a persistent kernel that refills a lane with the next scenario as soon as its current one
+  // has converged (csrc/boxqp.cu, boxqp_ipm_refill_kernel): begin(); while (!iterate()) {}; finish();
+  int ncons_m = 0, status_m = MPC_UNSOLVED, it_m = 0;
+  T tau_m = T(0), alpha_m = T(0), inv_nc_m = T(0);
+  bool have_step_m = false;
+
+  MPC_HD void begin(int64_t scenario) {
+    b = scenario;
+    ncons_m = count_constraints();
+    inv_nc_m = ncons_m ? T(1) / T(ncons_m) : T(0);
+    mu0 = mu_scale;
+    init();
+    status_m = MPC_UNSOLVED;
+    it_m = 0;
+    tau_m = alpha_m = T(0);
+    have_step_m = false;
+  }
+  MPC_HD bool iterate() { return iterate_on(ncons_m, inv_nc_m, it_m, status_m, tau_m, alpha_m, have_step_m); }
+  MPC_HD void finish() { output(status_m, it_m, have_step_m, tau_m, alpha_m); }
 };
 
 }  // namespace mpc

@@ -12,6 +12,9 @@
 #endif
 
 #define MPC_HD __host__ __device__ __forceinline__
+// per-step (not per-stage-visit) pieces of the fused loops: kept out of line so that their register needs do not
+// spill the interior-point sweeps they sit next to
+#define MPC_HD_COLD __host__ __device__ __noinline__
 
 namespace mpc {
 

@@ -1,5 +1,6 @@
 // K5 kernels + C ABI: bicycle RTI preparation, plant step and the fused closed loop (session 4).
 #include <stdlib.h>
+#include <string.h>
 
 #include "bicycle_core.cuh"
 
@@ -282,6 +283,13 @@ extern "C" int mpc_rti_closed_loop(double lr, double lf, double accel, double fr
                                           sqp_tol, Q, R, Pf, u_lo, u_hi, x_lo, x_hi, nc, nc > 0 ? &ob : nullptr, x0, U_plan,
                                           X_pred, X_cl, U_cl, cost_cl, viol_cl, clear_cl, n_sat, n_fail, iters_total,
                                           last_status, X_bundle, U_bundle, ws, batch, N, max_iter, eps, st);
+  if (const char* env = getenv("MPC_QP_STORE")) {   // "f64": all-float64 workspace (A/B measurements, as mpc_boxqp_solve)
+    if (strcmp(env, "f64") == 0)
+      return rti_loop_impl<double, StoreF64>(model, friction_model, plant, friction_plant, plant_substeps, steps, sqp_iters,
+                                             sqp_tol, Q, R, Pf, u_lo, u_hi, x_lo, x_hi, nc, nc > 0 ? &ob : nullptr, x0,
+                                             U_plan, X_pred, X_cl, U_cl, cost_cl, viol_cl, clear_cl, n_sat, n_fail,
+                                             iters_total, last_status, X_bundle, U_bundle, ws, batch, N, max_iter, eps, st);
+  }
   return rti_loop_impl<double, StoreMix>(model, friction_model, plant, friction_plant, plant_substeps, steps, sqp_iters,
                                          sqp_tol, Q, R, Pf, u_lo, u_hi, x_lo, x_hi, nc, nc > 0 ? &ob : nullptr, x0, U_plan,
                                          X_pred, X_cl, U_cl, cost_cl, viol_cl, clear_cl, n_sat, n_fail, iters_total,

@@ -9,6 +9,8 @@ from __future__ import annotations
 
 import torch
 
+from ctypes import c_int, c_int64, c_void_p
+
 from . import _lib
 
 
@@ -21,6 +23,15 @@ def _model(t, rows, cols, name):
     if t.dim() == 3 and tuple(t.shape[1:]) == (rows, cols):
         return t.contiguous(), t.shape[0], rows * cols
     raise ValueError(f"{name} must be ({rows},{cols}) or (batch,{rows},{cols}), got {tuple(t.shape)}")
+
+
+def _same_kind(ref, **named):
+    """Every operand shares dtype and device with ``ref`` -- the kernels reinterpret raw pointers, so a float32 matrix
+    next to a float64 state would be read as garbage without this check."""
+    for name, t in named.items():
+        if t is not None and (t.dtype != ref.dtype or t.device != ref.device):
+            raise ValueError(f"{name} must share dtype and device with the other operands "
+                             f"({ref.dtype}, {ref.device}); got {t.dtype}, {t.device}")
 
 
 def _common_batch(bs, extra=None):
@@ -37,6 +48,7 @@ def riccati(A, B, Q, R, Pf, N, all_P=True):
     (or [batch, n, n] = P_0 when ``all_P`` is false).  batch = 1 when every matrix is shared.
     Replaces reference session_1/FHC.py:51-61."""
     _lib.require_cuda(A, B, Q, R, Pf)
+    _same_kind(A, B=B, Q=Q, R=R, P_f=Pf)
     n, m = A.shape[-1], B.shape[-1]
     A, bA, sA = _model(A, n, n, "A")
     B, bB, sB = _model(B, n, m, "B")
@@ -66,6 +78,7 @@ def lq_rollout(A, B, K, x0, T, gain_offset=0, gain_step=0, Q=None, R=None, Pf=No
     unstable [batch] (uint8).  Transition i uses gain ``gain_offset + gain_step * i``.
     Replaces reference session_1/LinearSystem.py:20-35 + FHC.py:25-29."""
     _lib.require_cuda(A, B, K, x0)
+    _same_kind(x0, A=A, B=B, K=K, Q=Q if want_cost else None, R=R if want_cost else None, Pf=Pf if want_cost else None)
     n, m = A.shape[-1], B.shape[-1]
     if x0.dim() != 2 or x0.shape[0] != n:
         raise ValueError(f"x0 must be (n={n}, batch), got {tuple(x0.shape)}")
@@ -112,6 +125,7 @@ def lq_rollout(A, B, K, x0, T, gain_offset=0, gain_step=0, Q=None, R=None, Pf=No
 def linear_step(A, B, x, u):
     """x+ = A x + B u for x [n, batch], u [m, batch] (reference LinearSystem.py:16-18)."""
     _lib.require_cuda(A, B, x, u)
+    _same_kind(x, A=A, B=B, u=u)
     n, m = A.shape[-1], B.shape[-1]
     x, u = x.contiguous(), u.contiguous()
     if x.shape[0] != n or u.shape[0] != m or x.shape[1] != u.shape[1]:
@@ -134,6 +148,19 @@ class LqSolveBuffers:
         self.K = torch.empty((N, batch, m, n), dtype=dtype, device=device) if want_K else None
         self.P0 = torch.empty((batch, n, n), dtype=dtype, device=device) if want_P0 else None
 
+    def check(self, batch, n, m, N, dtype, device, want_K, want_P0):
+        """A caller-supplied buffer set must match the call it is used for (the kernel writes through raw pointers)."""
+        want = {"X": (N + 1, batch, n), "U": (N, batch, m), "V": (batch,), "K": (N, batch, m, n), "P0": (batch, n, n)}
+        for name, shape in want.items():
+            t = getattr(self, name)
+            if t is None:
+                if name in ("X", "U", "V") or (name == "K" and want_K) or (name == "P0" and want_P0):
+                    raise ValueError(f"out.{name} is missing (build the buffers with want_K / want_P0 as the call needs)")
+                continue
+            if tuple(t.shape) != shape or t.dtype != dtype or t.device != torch.device(device) or not t.is_contiguous():
+                raise ValueError(f"out.{name} must be a contiguous {shape} {dtype} tensor on {device}; "
+                                 f"got {tuple(t.shape)}, {t.dtype}, {t.device}")
+
 
 def lq_solve(A, B, Q, R, Pf, x0, N, want_K=False, want_P0=False, out=None):
     """Fused per-scenario finite-horizon LQ solve (K1+K2): x0 [batch, n] ->
@@ -144,6 +171,7 @@ def lq_solve(A, B, Q, R, Pf, x0, N, want_K=False, want_P0=False, out=None):
     same plan as the dense recursion within ~1e-10 of each scenario's scale on well-conditioned
     models, with a per-scenario fallback to the dense recursion otherwise."""
     _lib.require_cuda(A, B, Q, R, Pf, x0)
+    _same_kind(x0, A=A, B=B, Q=Q, R=R, P_f=Pf)
     n, m = A.shape[-1], B.shape[-1]
     if x0.dim() != 2 or x0.shape[1] != n:
         raise ValueError(f"x0 must be (batch, n={n}), got {tuple(x0.shape)}")
@@ -158,7 +186,11 @@ def lq_solve(A, B, Q, R, Pf, x0, N, want_K=False, want_P0=False, out=None):
     N = int(N)
     if out is None:
         out = LqSolveBuffers(batch, n, m, N, x0.dtype, x0.device, want_K, want_P0)
-    if (n, m) not in FUSED_SHAPES:
+    else:
+        out.check(batch, n, m, N, x0.dtype, x0.device, want_K, want_P0)
+    # the fused kernels keep the gains on chip (N m n elements per thread of shared memory): longer horizons and the
+    # shapes without a register-resident kernel take the two-launch path
+    if (n, m) not in FUSED_SHAPES or N * m * n * x0.element_size() > FUSED_GAIN_BYTES:
         return _lq_solve_composed(A, B, Q, R, Pf, x0, N, out)
     with torch.cuda.device(x0.device):
         _lib.check(_lib.lib().mpc_lq_solve(
@@ -169,6 +201,7 @@ def lq_solve(A, B, Q, R, Pf, x0, N, want_K=False, want_P0=False, out=None):
 
 
 FUSED_SHAPES = {(2, 1), (4, 1), (4, 2)}   # (n, m) with a register-resident fused kernel behind mpc_lq_solve
+FUSED_GAIN_BYTES = 220 * 1024 // 32        # on-chip gains per thread: a 32-thread CTA's slice must fit 220 KB (csrc/lq.cu)
 
 
 def _lq_solve_composed(A, B, Q, R, Pf, x0, N, out):
@@ -201,21 +234,29 @@ class LqHostPipeline:
     """End-to-end fused LQ solves for callers whose data lives in HOST memory.
 
     ``submit(A, B, Q, R, Pf, x0)`` takes pinned host tensors of one batch and returns pinned host
-    tensors ``(X, U, V)``.  Consecutive submissions are software-pipelined over three CUDA streams
+    tensors, one per entry of ``outputs`` (default ``(X, U, V)``).  Consecutive submissions are software-pipelined over three CUDA streams
     with double-buffered device storage: the H2D copy of batch i+1 overlaps the kernel and the D2H
     copy of batch i (PCIe is full duplex), so the steady-state cost per batch is
     max(H2D, D2H, kernel) rather than their sum.  ``wait()`` blocks until everything submitted has
     landed in the returned host buffers.
     """
 
-    def __init__(self, batch, n, m, N, dtype=torch.float64, device=None, per_scenario_model=True):
+    def __init__(self, batch, n, m, N, dtype=torch.float64, device=None, per_scenario_model=True,
+                 outputs=("X", "U", "V")):
+        """``outputs``: which results travel back to the host, in this order -- any of "X" (predicted states,
+        (N+1) n values per solve), "U" (the optimal plan, N m) and "V" (the optimal cost).  The states are a function of
+        the inputs and the plan (x+ = A x + B u), so a caller that only applies / logs the plan can leave X on the
+        device: ("U", "V") is 168 B instead of 840 B of D2H per solve at cfg 2b."""
+        if not outputs or any(o not in ("X", "U", "V") for o in outputs):
+            raise ValueError('outputs must be a non-empty selection of "X", "U", "V"')
+        self.outputs = tuple(outputs)
         self.dev = device or torch.device("cuda", torch.cuda.current_device())
         self.batch, self.n, self.m, self.N, self.dtype = batch, n, m, N, dtype
         mb = (batch,) if per_scenario_model else ()
         shapes = [mb + (n, n), mb + (n, m), mb + (n, n), mb + (m, m), mb + (n, n), (batch, n)]
         self.dev_in = [[torch.empty(sh, dtype=dtype, device=self.dev) for sh in shapes] for _ in range(2)]
         self.dev_out = [LqSolveBuffers(batch, n, m, N, dtype, self.dev) for _ in range(2)]
-        self.host_out = [[torch.empty(t.shape, dtype=dtype, pin_memory=True) for t in (o.X, o.U, o.V)]
+        self.host_out = [[torch.empty(getattr(o, name).shape, dtype=dtype, pin_memory=True) for name in self.outputs]
                          for o in self.dev_out]
         self.s_in, self.s_c, self.s_out = (torch.cuda.Stream(self.dev) for _ in range(3))
         self.ev_in = [torch.cuda.Event() for _ in range(2)]
@@ -243,8 +284,8 @@ class LqHostPipeline:
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(self.ev_c[s])
             o = self.dev_out[s]
-            for h, d in zip(self.host_out[s], (o.X, o.U, o.V)):
-                h.copy_(d, non_blocking=True)
+            for h, name in zip(self.host_out[s], self.outputs):
+                h.copy_(getattr(o, name), non_blocking=True)
             self.ev_out[s].record(self.s_out)
         self.count += 1
         return self.host_out[s]
@@ -252,6 +293,28 @@ class LqHostPipeline:
     def wait(self):
         for st in (self.s_in, self.s_c, self.s_out):
             st.synchronize()
+
+
+_lib.register("mpc_spectral_radius", c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
+                                             c_int, c_int, c_int, c_void_p])
+
+
+def spectral_radius(A, B, K):
+    """rho(A + B K) per scenario: the exact stability test of the linear closed loop under u = K x that the
+    reference leaves as an exercise (session_1/session1_sol.py:114-116).  A, B, K shared ([n,n], [n,m], [m,n]) or
+    batched with a leading axis.  Returns a tensor [batch] (batch = 1 when everything is shared)."""
+    _lib.require_cuda(A, B, K)
+    _same_kind(A, B=B, K=K)
+    n, m = A.shape[-1], B.shape[-1]
+    A, bA, sA = _model(A, n, n, "A")
+    B, bB, sB = _model(B, n, m, "B")
+    K, bK, sK = _model(K, m, n, "K")
+    batch = _common_batch([bA, bB, bK]) or 1
+    rho = torch.empty((batch,), dtype=A.dtype, device=A.device)
+    with torch.cuda.device(A.device):
+        _lib.check(_lib.lib().mpc_spectral_radius(_lib.ptr(A), sA, _lib.ptr(B), sB, _lib.ptr(K), sK, _lib.ptr(rho),
+                                                  batch, n, m, _lib.dtype_enum(A), _lib.stream(A.device)))
+    return rho
 
 
 def fma_peak(dtype=torch.float64):

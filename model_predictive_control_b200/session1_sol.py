@@ -77,6 +77,15 @@ def simulate(x0, f: Callable, policy: Callable, steps: int) -> Tuple[np.ndarray,
     return np.array(x), instability_occured
 
 
+def is_stable(A, B, gains) -> bool:
+    """The exact test the reference's ``plot_ex4`` leaves as an exercise (session1_sol.py:114-116): the receding-horizon
+    closed loop x+ = (A + B gains[0]) x is stable iff its spectral radius is below one."""
+    from .FHC import closed_loop_spectral_radius
+    K0 = gains[0] if isinstance(gains, (list, tuple)) else gains
+    rho = closed_loop_spectral_radius(A, B, K0)
+    return bool(rho < 1.0) if np.ndim(rho) == 0 else rho < 1.0
+
+
 def setup():
     """Problem data of the exercise (reference session1_sol.py:136-144)."""
     ts = 0.5

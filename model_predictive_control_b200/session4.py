@@ -35,7 +35,7 @@ _lib.register("mpc_bicycle_plant_step", c_int, [c_double] * 4 + [c_void_p, c_int
 _lib.register("mpc_rti_workspace_bytes", c_int64, [c_int64, c_int, c_int, c_int])
 _lib.register("mpc_rti_closed_loop", c_int,
               [c_double] * 5 + [c_int] + [c_double] * 3 + [c_void_p, c_int, c_int, c_int, c_double] + [c_void_p] * 7 +
-              [c_int, c_double, c_double, c_void_p] + [c_void_p] * 14 + [c_int64, c_int64, c_int, c_int, c_double, c_int, c_void_p])
+              [c_int, c_double, c_double, c_void_p] + [c_void_p] * 15 + [c_int64, c_int64, c_int, c_int, c_double, c_int, c_void_p])
 
 _lib.register("mpc_bicycle_rti_prepare_obstacle", c_int, [c_double] * 5 + [c_int, c_double, c_double, c_void_p, c_void_p,
               c_void_p, c_int] + [c_void_p] * 6 + [c_int64, c_int, c_int, c_void_p])

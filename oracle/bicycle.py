@@ -205,8 +205,22 @@ def closed_loop(x0, n_steps, N=50, ts=0.05, par=None, friction_model=None, frict
                 for b in range(batch):
                     e = bq.solve_exact(A[:, b], B[:, b], Q, R, QT, N, x[b], ulo, uhi, xlo, xhi, c=c[:, b])
                     U[:, b], status[b] = e["U"], e["status"]
+            if sqp_iters > 1:
+                # globalised SQP round (csrc/bicycle_core.cuh, rti_merit): backtracking on the l1 merit of the
+                # nonlinear OCP along Ubar -> U_qp, beta = 1, 1/2, .., 2^-10, else 0; failed QPs keep the full step
+                for b in range(batch):
+                    if not live[b] or status[b] != bq.SOLVED:
+                        continue
+                    m0 = _merit(x[b], Ubar[:, b], ts, par, fm, ocp_method, Q, QT, R, xlo, xhi)
+                    beta, h = 1.0, 0
+                    while h <= 10 and not (_merit(x[b], Ubar[:, b] + beta * (U[:, b] - Ubar[:, b]), ts, par, fm, ocp_method,
+                                                  Q, QT, R, xlo, xhi) < m0):
+                        beta *= 0.5; h += 1
+                    if h > 10:
+                        beta = 0.0
+                    U[:, b] = Ubar[:, b] + beta * (U[:, b] - Ubar[:, b])
             U = np.where(live[None, :, None], U, U_prev)   # scenarios that already met sqp_tol keep their plan
-            if rnd + 1 < sqp_iters and sqp_tol > 0:
+            if sqp_iters > 1:
                 du = np.abs(U - Ubar).max(axis=(0, 2)); un = np.maximum(1.0, np.abs(U).max(axis=(0, 2)))
                 live = live & ~(du <= sqp_tol * un)
             U_prev = U
@@ -223,6 +237,30 @@ def closed_loop(x0, n_steps, N=50, ts=0.05, par=None, friction_model=None, frict
     if keep_plans:
         out["plans"] = np.array(Ps)
     return out
+
+
+SQP_MERIT_RHO = 100.0
+
+
+def _merit(x0, U, ts, par, friction, method, Q, QT, R, xlo, xhi, x_obs=None, length=0.17, width=0.08):
+    """l1 merit of the nonlinear OCP for one scenario: rollout cost + rho * summed state-box (and collision) violations."""
+    x = np.asarray(x0, float); cost = 0.0; viol = 0.0
+    lr, lf, acc = par.axis_rear, par.axis_front, par.acceleration
+    f = lambda xx, uu: bicycle_f(xx, uu, lr, lf, friction, acc)
+    step = forward_euler(f, ts) if method == "euler" else runge_kutta4(f, ts)
+    if x_obs is not None:
+        a, r = create_cover_circles(length, width, 3)
+        r2 = (2 * r) ** 2
+        ox = x_obs[0] + a * np.cos(x_obs[2]); oy = x_obs[1] + a * np.sin(x_obs[2])
+    for k in range(U.shape[0]):
+        cost += x @ Q @ x + U[k] @ R @ U[k]
+        x = step(x, U[k])
+        viol += np.maximum(0.0, np.maximum(xlo - x, x - xhi)).sum()
+        if x_obs is not None:
+            cx = x[0] + a * np.cos(x[2]); cy = x[1] + a * np.sin(x[2])
+            g = r2 - ((cx[:, None] - ox[None]) ** 2 + (cy[:, None] - oy[None]) ** 2)
+            viol += np.maximum(0.0, g).sum()
+    return cost + x @ QT @ x + SQP_MERIT_RHO * viol
 
 
 def _plant(x, u, ts, par, friction, method, substeps):
@@ -316,3 +354,93 @@ def min_clearance(X, x_obs, length=0.17, width=0.08, n_c=3):
     cx = X[..., 0, None] + a * np.cos(X[..., 2, None]); cy = X[..., 1, None] + a * np.sin(X[..., 2, None])
     dist = np.sqrt((cx[..., :, None] - ox) ** 2 + (cy[..., :, None] - oy) ** 2)
     return float(dist.min() - 2 * r)
+
+
+# ------------------------------------------------------------------------------------------------
+# converged solution of the nonlinear OCP (what the reference's IPOPT call returns, session4_sol.py:126-130)
+# ------------------------------------------------------------------------------------------------
+def ocp_functions(x0, N, ts=0.05, par=None, friction=None, method="euler", variant="sol"):
+    """The single-shooting NLP of session4_sol.MPCController.build_ocp (:132-217) for one x0 [4]:
+    decision U [N,2]; cost f(U) = sum_{k<N} x_k'Qx_k + u_k'Ru_k + x_N'Q_T x_N; constraint vector g(U) = (x_1..x_N)
+    (state box); variable bounds = input box.  Returns (fun, con) with fun(U) -> (f, df/dU [2N]) and
+    con(U) -> (g [4N], dg/dU [4N, 2N]), derivatives by the exact chain rule through the rollout.
+    tests/test_oracle_golden_s234.py pins f and g to the reference's own build_ocp evaluated numerically."""
+    par = par or VehicleParameters()
+    fr = par.friction if friction is None else friction
+    Q, QT, R = weights(variant)
+    x0 = np.asarray(x0, float).reshape(4)
+
+    def rollout(U):
+        U = np.asarray(U, float).reshape(N, 2)
+        X = [x0]; As = []; Bs = []
+        for k in range(N):
+            xn, A, B = discretize(X[-1][None], U[k][None], ts, par, fr, method)
+            X.append(xn[0]); As.append(A[0]); Bs.append(B[0])
+        return U, np.array(X), As, Bs
+
+    def sens(As, Bs):
+        """S[k] = d x_{k+1} / dU  [4, 2N]"""
+        S = np.zeros((N, 4, 2 * N)); cur = np.zeros((4, 2 * N))
+        for k in range(N):
+            cur = As[k] @ cur
+            cur[:, 2 * k:2 * k + 2] += Bs[k]
+            S[k] = cur
+        return S
+
+    def fun(Uf):
+        U, X, As, Bs = rollout(Uf)
+        f = float(sum(X[k] @ Q @ X[k] + U[k] @ R @ U[k] for k in range(N)) + X[N] @ QT @ X[N])
+        S = sens(As, Bs)
+        grad = (2 * U @ R).reshape(-1).copy()
+        for k in range(1, N):
+            grad += 2 * (Q @ X[k]) @ S[k - 1]
+        grad += 2 * (QT @ X[N]) @ S[N - 1]
+        return f, grad
+
+    def con(Uf):
+        U, X, As, Bs = rollout(Uf)
+        return X[1:].reshape(-1), sens(As, Bs).reshape(4 * N, 2 * N)
+
+    return fun, con
+
+
+def nlp_solve(x0, N=50, ts=0.05, par=None, friction=None, method="euler", variant="sol", U_init=None, tol=1e-13,
+              maxiter=500):
+    """Converged local solution of the OCP by scipy SLSQP (exact derivatives), from U_init (default: zeros, the
+    reference's cold start).  Returns dict(U [N,2], X [N+1,4], f, success, nit, kkt) with kkt = max-norm of the
+    projected gradient of the Lagrangian."""
+    from scipy.optimize import minimize
+    par = par or VehicleParameters()
+    fun, con = ocp_functions(x0, N, ts, par, friction, method, variant)
+    ulo, uhi, xlo, xhi = bounds(par)
+    lbg, ubg = np.tile(xlo, N), np.tile(xhi, N)
+    cons = [{"type": "ineq", "fun": lambda U: con(U)[0] - lbg, "jac": lambda U: con(U)[1]},
+            {"type": "ineq", "fun": lambda U: ubg - con(U)[0], "jac": lambda U: -con(U)[1]}]
+    U0 = np.zeros(2 * N) if U_init is None else np.asarray(U_init, float).reshape(-1)
+    bnds = list(zip(np.tile(ulo, N), np.tile(uhi, N)))
+    res = minimize(lambda U: fun(U), np.clip(U0, np.tile(ulo, N), np.tile(uhi, N)), jac=True, bounds=bnds, constraints=cons,
+                   method="SLSQP", options={"ftol": tol, "maxiter": maxiter})
+    U = res.x.reshape(N, 2)
+    g, _ = con(res.x)
+    return {"U": U, "X": np.vstack([np.asarray(x0, float)[None], g.reshape(N, 4)]), "f": float(res.fun),
+            "success": bool(res.success), "nit": int(res.nit), "message": str(res.message)}
+
+
+def closed_loop_converged(x0, n_steps, N=50, ts=0.05, par=None, friction_plant=None, plant_method="euler", substeps=4,
+                          warm=True):
+    """Closed loop of ONE scenario with the OCP solved to convergence at every step (the reference's exercise5,
+    session4_sol.py:443-465; the reference cold-starts IPOPT, here SLSQP starts from the shifted previous plan when
+    ``warm`` -- the OCP is smooth and both reach the same local solution on this task)."""
+    par = par or VehicleParameters()
+    fp = par.friction if friction_plant is None else friction_plant
+    x = np.asarray(x0, float).reshape(4)
+    Xs, Us, plans = [x], [], []
+    U_prev = None
+    for t in range(n_steps):
+        init = None if (U_prev is None or not warm) else np.vstack([U_prev[1:], U_prev[-1:]])
+        r = nlp_solve(x, N, ts, par, U_init=init)
+        U_prev = r["U"]
+        u0 = U_prev[0]
+        x = _plant(x[None], u0[None], ts, par, np.array([fp]), plant_method, substeps)[0]
+        Xs.append(x); Us.append(u0); plans.append(U_prev.copy())
+    return {"X": np.array(Xs), "U": np.array(Us), "plans": np.array(plans)}

@@ -659,3 +659,23 @@ def ipm_riccati(A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi, c=None, warm_U=No
     sat = act_u.astype(np.int8) - act_l.astype(np.int8)
     return {"U": U, "X": X, "cost": cost, "status": status, "iters": iters, "sat_u": sat[:, :, :m],
             "sat_x": sat[:, :, m:], "sat_c": (lc > sc).astype(np.int8) * -1}
+
+
+# ------------------------------------------------------------------------------------------------
+# exact solves of many scenarios on all host cores (tests of the full-size configurations)
+# ------------------------------------------------------------------------------------------------
+def _exact_worker(args):
+    A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi = args
+    return solve_exact(A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi)
+
+
+def solve_exact_many(A, B, Q, R, Pf, N, X0, u_lo, u_hi, x_lo, x_hi, processes=None):
+    """solve_exact for every row of X0 [count, n] (shared LTI model), one process per host core."""
+    import multiprocessing as mp
+    import os
+    procs = processes or max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    jobs = [(A, B, Q, R, Pf, N, np.asarray(x, float), u_lo, u_hi, x_lo, x_hi) for x in X0]
+    if procs == 1 or len(jobs) < 4:
+        return [_exact_worker(j) for j in jobs]
+    with mp.get_context("spawn").Pool(min(procs, len(jobs))) as pool:
+        return pool.map(_exact_worker, jobs, chunksize=1)

@@ -1,6 +1,9 @@
 """Import the reference's own session-1 modules (oracle, test infra).
 
-Only works where /root/reference is mounted (this container; never the GPU box).
+Works where /root/reference is mounted (this container) or where ``stage_reference()`` has staged
+the three session-1 files into the git-ignored ``oracle/_ref/session_1`` (the staging runs in
+``__graft_entry__.build()`` here; ``oracle/_ref`` is not gpurun-ignored, so the staged files travel to the
+GPU box and ``bench.py --impl reference`` times the reference's OWN code there).
 ``FHC.py`` imports casadi, rcracers and matplotlib at module top
 (/root/reference/session_1/FHC.py:1-17) and ``session1_sol.py`` exits without
 matplotlib (:4-8); none of them is used by the numeric functions, so they are
@@ -14,6 +17,8 @@ import sys
 from unittest import mock
 
 REFERENCE_ROOT = "/root/reference"
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+_SESSION1_FILES = ("FHC.py", "LinearSystem.py", "session1_sol.py")
 _STUBS = ("matplotlib", "matplotlib.pyplot", "matplotlib.patches", "casadi", "rcracers")
 
 
@@ -21,14 +26,41 @@ def available() -> bool:
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "session_1", "FHC.py"))
 
 
+def staged() -> bool:
+    return all(os.path.isfile(os.path.join(STAGED_ROOT, "session_1", f)) for f in _SESSION1_FILES)
+
+
+def stage_reference() -> bool:
+    """Stage the reference's session-1 files, byte for byte, into oracle/_ref/session_1 (git-ignored: never part of
+    the history; shipped to the GPU box by gpurun).  No-op without /root/reference.  Returns whether a staged copy
+    exists afterwards."""
+    if available():
+        import shutil
+        dst = os.path.join(STAGED_ROOT, "session_1")
+        os.makedirs(dst, exist_ok=True)
+        for f in _SESSION1_FILES:
+            shutil.copyfile(os.path.join(REFERENCE_ROOT, "session_1", f), os.path.join(dst, f))
+    return staged()
+
+
+def session1_root():
+    """Directory the reference's session-1 modules are imported from: the mounted reference, else the staged copy."""
+    if available():
+        return REFERENCE_ROOT
+    if staged():
+        return STAGED_ROOT
+    return None
+
+
 def load_session1():
     """Return (FHC, LinearSystem, session1_sol) modules of the unmodified reference."""
-    if not available():
-        raise RuntimeError("reference not mounted at " + REFERENCE_ROOT)
+    root = session1_root()
+    if root is None:
+        raise RuntimeError("reference neither mounted at " + REFERENCE_ROOT + " nor staged in " + STAGED_ROOT)
     for name in _STUBS:
         if name not in sys.modules:
             sys.modules[name] = mock.MagicMock(name=name)
-    path = os.path.join(REFERENCE_ROOT, "session_1")
+    path = os.path.join(root, "session_1")
     # the reference's module names (FHC, LinearSystem) collide with nothing of ours:
     # the product lives in the model_predictive_control_b200 package.
     sys.path.insert(0, path)
@@ -40,7 +72,7 @@ def load_session1():
     finally:
         sys.path.remove(path)
     for mod in mods:
-        if not mod.__file__.startswith(REFERENCE_ROOT):
+        if not mod.__file__.startswith(root):
             raise RuntimeError(f"{mod.__name__} resolved to {mod.__file__}, not the reference")
     return mods
 

@@ -27,7 +27,7 @@ def test_reference_arm_line():
     assert d["value"] > 0 and d["unit"] == "solves/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
     assert "workload" in d["config"] and d["gpu_launches"] == 0
     # other ranks of a torchrun launch print nothing and exit 0
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
