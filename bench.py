@@ -667,10 +667,11 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "d2h_gbs_per_gpu": d2h * per_gpu(e2e_value) / 1e9, "h2d_gbs_per_gpu": h2d * per_gpu(e2e_value) / 1e9,
                     "host_link": link,
-                    "frac_of_host_link": d2h * per_gpu(e2e_value) / 1e9 / link["duplex_gbs_each"],
+                    "frac_of_host_link": d2h * per_gpu(e2e_value) / 1e9 / link["d2h_gbs"],
+                    "frac_of_host_link_duplex": d2h * per_gpu(e2e_value) / 1e9 / link["duplex_gbs_each"],
                     "plan_only": {"value": e2e_uv, "unit": UNIT, "outputs": ["U", "V"], "h2d_bytes_per_step": h2d,
                                   "d2h_bytes_per_step": d2h_uv, "h2d_gbs_per_gpu": h2d * per_gpu(e2e_uv) / 1e9,
-                                  "frac_of_host_link": h2d * per_gpu(e2e_uv) / 1e9 / link["duplex_gbs_each"],
+                                  "frac_of_host_link": h2d * per_gpu(e2e_uv) / 1e9 / link["h2d_gbs"],
                                   "result_matches_device": e2e_uv_check,
                                   "note": "same call with outputs=('U','V'): the plan and its cost travel back, the predicted "
                                           "states (a function of inputs and plan) stay on the device; now the H2D stream of the "
@@ -678,7 +679,8 @@ def run_ours(args):
                     "note": "lq.LqHostPipeline: pinned host buffers (allocated on the GPU's NUMA node), all model/x0 inputs H2D and "
                             "X/U/V D2H every step, copies of consecutive steps overlapped on separate streams (full duplex); "
                             "the D2H stream (840 B per solve) runs at the host-link rate, which bounds this figure: "
-                            "frac_of_host_link = D2H GB/s of this run / the duplex ceiling measured by host_link",
+                            "frac_of_host_link = D2H GB/s of this run / the D2H ceiling measured by host_link (all ranks "
+                            "concurrently); _duplex = against the ceiling with both directions fully loaded",
                     "result_matches_device": e2e_check},
             "gpu_launches": args.steps, "clocks": clocks,
             "cfg2a_shared_model": {"value": world * batch / (ms2a * 1e-3), "unit": UNIT, "ms_per_step": ms2a,
@@ -892,7 +894,7 @@ def secondary_line(ctx, workload, steps, warmup, batch=0, horizon=0, cpu=False, 
         name = f"cfg3: session-2 Problem box-QP (input + state bounds), nx=2 nu=1 N={N}, {batch} scenarios per GPU"
         io_bytes = es * (n + N * m + (N + 1) * n + 1) + 8 + N * (n + m)
         host_in, host_out = [x0T], lambda r: [r.U, r.X, r.cost, r.status]
-        kname, model_elems = "boxqp_ipm_refill_kernel", 0
+        kname, model_elems = "boxqp_ipm_kernel", 0
     elif workload == "cfg5":
         import numpy as np
         batch = batch or (1 << 20)
@@ -1014,7 +1016,9 @@ def secondary_line(ctx, workload, steps, warmup, batch=0, horizon=0, cpu=False, 
         traffic = load_traffic(kname + ("_" + workload), solves_per_step)
         wsb = None
         if workload != "cfg5":
-            wb = ipm_workspace_bytes_v2(n, m, N, model_elems, narrow=(dtype == "f64"), elem=es)
+            narrow = dtype == "f64" and not (workload == "cfg4" and os.environ.get("MPC_QP_STORE") != "mix") \
+                and os.environ.get("MPC_QP_STORE") != "f64"
+            wb = ipm_workspace_bytes_v2(n, m, N, model_elems, narrow=narrow, elem=es)
             wsb = {"bytes_per_iter": wb, "achieved": wb * iters_total / (kern_ms * 1e-3) / 1e9,
                    "frac": wb * iters_total / (kern_ms * 1e-3) / 1e9 / peak,
                    "dram_bytes_per_solve_ncu": (traffic / solves_per_step) if traffic else None,

@@ -241,6 +241,15 @@ int mpc_bicycle_rti_prepare_obstacle(double lr, double lf, double accel, double 
 int mpc_bicycle_plant_step(double lr, double lf, double accel, double ts, const void* friction,
                            int64_t s_friction, int substeps, const void* x, const void* u, void* xn,
                            int64_t batch, int dtype, mpc_stream_t stream);
+/* One globalised SQP round of the step-wise controller path (MPCController.solve / __call__ with sqp_iters > 1): after
+ * mpc_bicycle_rti_prepare + mpc_boxqp_solve, backtrack on the l1 merit of the NONLINEAR OCP (cost of the nonlinear
+ * rollout from y + 100 x summed state-box / collision violations) along warm_U -> U:  U <- warm_U + beta (U - warm_U),
+ * beta = 1, 1/2, .., 2^-10, else 0; scenarios with status != MPC_SOLVED keep the full step.  beta optional [batch].
+ * The fused loop (mpc_rti_closed_loop) runs the same rule inside its kernel. */
+int mpc_bicycle_sqp_linesearch(double lr, double lf, double accel, double friction, double ts, int rk4, const void* Q,
+                               const void* R, const void* Pf, const void* x_lo, const void* x_hi, int nc, double length,
+                               double width, const double* x_obs, const void* y, const void* warm_U, void* U,
+                               const int32_t* status, void* beta, int64_t batch, int N, int dtype, mpc_stream_t stream);
 int64_t mpc_rti_workspace_bytes(int64_t batch, int N, int nc, int dtype);
 int mpc_rti_closed_loop(double lr, double lf, double accel, double friction_model, double ts, int rk4,
                         double plant_lr, double plant_lf, double plant_accel, const void* friction_plant,

@@ -448,7 +448,7 @@ MPC_HD void rti_closed_loop_body(const RtiLoopArgs<T, TIO>& a, const T* sh, int6
       rti_prepare_cold<T, TIO>(a.model, a.friction_model, a.xcur, a.qp.U, (t == 0 || round > 0) ? 1 : 0, a.warm, a.Acur,
                                a.Bcur, a.ccur, N, bs, b, NC > 0 ? &a.ob : nullptr, a.Cgcur, a.hgcur,
                                PACKED ? a.Acur : nullptr);
-      BoxQpIpm<T, TIO, 4, 2, NC, PACKED ? 1 : 0, ST, true> ipm(a.qp, sh, b, b, bs);
+      BoxQpIpm<T, TIO, 4, 2, NC, PACKED ? 1 : 0, ST> ipm(a.qp, sh, b, b, bs);
       ipm.solve();
       const bool solved = a.qp.status[b] == MPC_SOLVED;
       if (!solved) ++nfail;

@@ -26,36 +26,7 @@ __global__ void __launch_bounds__(kQpThreads, MINB) boxqp_ipm_kernel(BoxQpArgs<T
   __syncthreads();
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= a.batch) return;
-  // a.batch is padded to a multiple of 4 lanes by the launcher (ws_lanes == batch rounded up): lane = scenario
-  BoxQpIpm<double, TIO, NX, NU, NC, 0, ST, true> ipm(a, sh, b, b, a.batch);
-  ipm.solve();
-}
-
-// the same with lane = scenario and ONE stride (batch % 4 == 0): the variant every full-size launch takes
-template <typename TIO, class ST, int NX, int NU, int NC, int MINB>
-__global__ void __launch_bounds__(kQpThreads, MINB) boxqp_ipm_kernel_s(BoxQpArgs<TIO> a) {
-  using SH = BoxQpShared<NX, NU>;
-  __shared__ double sh[SH::total];
-  for (int i = threadIdx.x; i < SH::total; i += blockDim.x) sh[i] = boxqp_shared_elem<double, TIO, NX, NU>(a, i);
-  __syncthreads();
-  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= a.batch) return;
-  BoxQpIpm<double, TIO, NX, NU, NC, 0, ST, false> ipm(a, sh, b, b, a.batch);
-  ipm.solve();
-}
-
-// (2,1) only: CTAs of 96 threads with the register count pinned to 136, so that five of them are resident (480 threads
-// per SM).  __launch_bounds__(128, 4) leaves ptxas 128 registers, which it overshoots by ~100 bytes of spills since the
-// fused sweep A; (128, 3) gives 168 registers but only 384 threads.
-template <typename TIO, class ST, int NX, int NU>
-__global__ void __maxnreg__(136) boxqp_ipm_kernel_s96(BoxQpArgs<TIO> a) {
-  using SH = BoxQpShared<NX, NU>;
-  __shared__ double sh[SH::total];
-  for (int i = threadIdx.x; i < SH::total; i += blockDim.x) sh[i] = boxqp_shared_elem<double, TIO, NX, NU>(a, i);
-  __syncthreads();
-  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= a.batch) return;
-  BoxQpIpm<double, TIO, NX, NU, 0, 0, ST, false> ipm(a, sh, b, b, a.batch);
+  BoxQpIpm<double, TIO, NX, NU, NC, 0, ST> ipm(a, sh, b, b, a.batch);
   ipm.solve();
 }
 
@@ -167,20 +138,12 @@ static int launch_boxqp_st(const BoxQpArgs<TIO>& a_in, cudaStream_t st) {
       return launch_refill<TIO, ST, NX, NU, 3>(a, refill, st);
     }
     a.ws = static_cast<char*>(a.ws) + kWsHeader;
-    if (a.batch % 4 == 0) {
-      // 5 CTAs of 96 threads (136 registers, no spills, 480 threads per SM) against 4 of 128 (128 registers: ptxas
-      // spills ~100 bytes there since the fused sweep A) and 3 of 128 (168 registers, 384 threads)
-      if (minb >= 5) boxqp_ipm_kernel_s96<TIO, ST, NX, NU><<<(unsigned)((a.batch + 95) / 96), 96, 0, st>>>(a);
-      else if (minb >= 4) boxqp_ipm_kernel_s<TIO, ST, NX, NU, 0, 4><<<grid, kQpThreads, 0, st>>>(a);
-      else boxqp_ipm_kernel_s<TIO, ST, NX, NU, 0, 3><<<grid, kQpThreads, 0, st>>>(a);
-    } else {
-      boxqp_ipm_kernel<TIO, ST, NX, NU, 0, 3><<<grid, kQpThreads, 0, st>>>(a);
-    }
+    if (minb >= 4) boxqp_ipm_kernel<TIO, ST, NX, NU, 0, 4><<<grid, kQpThreads, 0, st>>>(a);
+    else boxqp_ipm_kernel<TIO, ST, NX, NU, 0, 3><<<grid, kQpThreads, 0, st>>>(a);
   } else {
     if (refill > 0 && a.batch > 4096) return launch_refill<TIO, ST, NX, NU, 2>(a, refill, st);
     a.ws = static_cast<char*>(a.ws) + kWsHeader;
-    if (a.batch % 4 == 0) boxqp_ipm_kernel_s<TIO, ST, NX, NU, 0, 2><<<grid, kQpThreads, 0, st>>>(a);
-    else boxqp_ipm_kernel<TIO, ST, NX, NU, 0, 2><<<grid, kQpThreads, 0, st>>>(a);
+    boxqp_ipm_kernel<TIO, ST, NX, NU, 0, 2><<<grid, kQpThreads, 0, st>>>(a);
   }
   return check_launch("boxqp_ipm_kernel");
 }

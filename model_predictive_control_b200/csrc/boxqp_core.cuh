@@ -41,8 +41,6 @@
 // The body is __host__ __device__: tests/harness runs it on the CPU against oracle/boxqp.py.
 #pragma once
 
-#include <type_traits>
-
 #include "smallmat.cuh"
 
 namespace mpc {
@@ -94,22 +92,25 @@ using StoreMix = BoxQpStore<double, float, float, double, double, double>;    //
 using StoreF32 = BoxQpStore<float, float, float, float, float, float>;        // float32 product
 
 inline int64_t ws_round16(int64_t bytes) { return (bytes + 15) / 16 * 16; }
-inline int64_t ws_lanes_padded(int64_t lanes) { return (lanes + 3) / 4 * 4; }  // keeps every section 16-byte aligned
-
-// bytes per (stage x lane) of the workspace: sections are laid out back to back, each [N][per][lanes]
-template <class ST>
-constexpr int64_t boxqp_ws_bytes_per_cell(int n, int m, int nc) {
-  const int64_t d = n + m;
-  return d * (int64_t)(sizeof(typename ST::Z) + 4 * sizeof(typename ST::SL) + sizeof(typename ST::DA) +
-                       sizeof(typename ST::DZ) + 2 * sizeof(typename ST::EG)) +
-         (int64_t)(m * n + m * m + m) * (int64_t)sizeof(typename ST::GN) +
-         (int64_t)nc * (int64_t)(2 * sizeof(typename ST::SL) + sizeof(typename ST::Z));
-}
 
 // workspace bytes for `lanes` resident scenarios
 template <class ST>
 inline int64_t boxqp_ws_bytes(int n, int m, int N, int nc, int64_t lanes) {
-  return (int64_t)N * ws_lanes_padded(lanes) * boxqp_ws_bytes_per_cell<ST>(n, m, nc);
+  const int64_t d = n + m, per = (int64_t)N * lanes;
+  int64_t t = 0;
+  t += ws_round16(per * d * (int64_t)sizeof(typename ST::Z));
+  t += 4 * ws_round16(per * d * (int64_t)sizeof(typename ST::SL));
+  t += ws_round16(per * d * (int64_t)sizeof(typename ST::DA));
+  t += ws_round16(per * d * (int64_t)sizeof(typename ST::DZ));
+  t += 2 * ws_round16(per * d * (int64_t)sizeof(typename ST::EG));
+  t += ws_round16(per * m * n * (int64_t)sizeof(typename ST::GN));
+  t += ws_round16(per * m * m * (int64_t)sizeof(typename ST::GN));
+  t += ws_round16(per * m * (int64_t)sizeof(typename ST::GN));
+  if (nc > 0) {
+    t += 2 * ws_round16(per * nc * (int64_t)sizeof(typename ST::SL));
+    t += ws_round16(per * nc * (int64_t)sizeof(typename ST::Z));
+  }
+  return t;
 }
 
 // shared-parameter block (shared memory on the device), always in the compute type
@@ -153,10 +154,7 @@ MPC_HD T round_to(T v) {   // the value a later sweep will read back from a sect
   return (T)(S)v;
 }
 
-// LANES = true: the workspace has its own lane index and stride (persistent refill kernel: one lane per resident thread).
-// LANES = false: lane b = scenario b and both share the stride `batch` (which must then be a multiple of 4): one index
-// computation and four registers less in the kernels that run at their register limit.
-template <typename T, typename TIO, int NX, int NU, int NC = 0, int MODEL = 0, class ST = StoreMix, bool LANES = false>
+template <typename T, typename TIO, int NX, int NU, int NC = 0, int MODEL = 0, class ST = StoreMix, bool LANES = true>
 struct BoxQpIpm {
   static constexpr int D = NX + NU;
   using SH = BoxQpShared<NX, NU>;
@@ -176,66 +174,42 @@ struct BoxQpIpm {
   int64_t wb, wbs;  // workspace lane and lane stride
   T mu_scale;       // max(1, max|Q|, max|R|): scale of the complementarity tolerance
   T mu0;            // start value of the barrier parameter, per scenario: max(mu_scale, |H z0|_inf)
-  // Workspace layout [stage][row][lane]: ALL rows of one stage are adjacent (z, slacks, multipliers, directions, e, g,
-  // gains ...), every row lane-contiguous, so a stage visit touches one contiguous region and the address of row
-  // (section offset OFF, element i) of stage k is
-  //     base + ((k * kCell + OFF + i * sizeof(S)) * lanes + lane * sizeof(S))
-  // with kCell, OFF compile-time constants: one base pointer and the lane stride stay in registers, an access costs one
-  // integer multiply-add.  (Round 2 first laid the sections out back to back, [section][stage][row][lane], with
-  // fifteen section pointers -- thirty registers, spills in the (4,2) and RTI kernels -- and then with per-access
-  // base + stride * offset arithmetic -- +54 % integer multiply-adds in the (2,1) kernel, measured -12 %.)
-  char* wsb;
-  static constexpr int64_t oZ = 0;
-  static constexpr int64_t oSl = oZ + D * (int64_t)sizeof(TZ);
-  static constexpr int64_t oSu = oSl + D * (int64_t)sizeof(TSL);
-  static constexpr int64_t oLl = oSu + D * (int64_t)sizeof(TSL);
-  static constexpr int64_t oLu = oLl + D * (int64_t)sizeof(TSL);
-  static constexpr int64_t oDa = oLu + D * (int64_t)sizeof(TSL);
-  static constexpr int64_t oDz = oDa + D * (int64_t)sizeof(TDA);
-  static constexpr int64_t oE = oDz + D * (int64_t)sizeof(TDZ);
-  static constexpr int64_t oG = oE + D * (int64_t)sizeof(TEG);
-  static constexpr int64_t oK = oG + D * (int64_t)sizeof(TEG);
-  static constexpr int64_t oS = oK + NU * NX * (int64_t)sizeof(TGN);
-  static constexpr int64_t oD = oS + NU * NU * (int64_t)sizeof(TGN);
-  static constexpr int64_t oSc = oD + NU * (int64_t)sizeof(TGN);
-  static constexpr int64_t oLc = oSc + NC * (int64_t)sizeof(TSL);
-  static constexpr int64_t oRc = oLc + NC * (int64_t)sizeof(TSL);
-  static constexpr int64_t kCell = oRc + NC * (int64_t)sizeof(TZ);   // bytes per stage and lane
-  struct Idx {
-    int k, i;
-  };
-  MPC_HD int64_t lane_stride() const { return LANES ? wbs : bs; }
-  MPC_HD int64_t lane_index() const { return LANES ? wb : b; }
-  template <typename S, int64_t OFF>
-  struct Sec {
-    const BoxQpIpm* p;
-    MPC_HD S& operator[](Idx o) const {
-      return *reinterpret_cast<S*>(p->wsb + ((int64_t)o.k * kCell + OFF + (int64_t)o.i * (int64_t)sizeof(S)) * p->lane_stride() +
-                                   p->lane_index() * (int64_t)sizeof(S));
-    }
-  };
-#define MPC_WS_SECTION(name, type, off) \
-  MPC_HD Sec<type, off> name##_() const { return Sec<type, off>{this}; }
-  MPC_WS_SECTION(z, TZ, oZ)
-  MPC_WS_SECTION(sl, TSL, oSl)
-  MPC_WS_SECTION(su, TSL, oSu)
-  MPC_WS_SECTION(ll, TSL, oLl)
-  MPC_WS_SECTION(lu, TSL, oLu)
-  MPC_WS_SECTION(dza, TDA, oDa)
-  MPC_WS_SECTION(dzw, TDZ, oDz)
-  MPC_WS_SECTION(ew, TEG, oE)
-  MPC_WS_SECTION(gw, TEG, oG)
-  MPC_WS_SECTION(Kw, TGN, oK)
-  MPC_WS_SECTION(Sw, TGN, oS)
-  MPC_WS_SECTION(dw, TGN, oD)
-  MPC_WS_SECTION(sc, TSL, oSc)
-  MPC_WS_SECTION(lc, TSL, oLc)
-  MPC_WS_SECTION(rc, TZ, oRc)
-#undef MPC_WS_SECTION
+  // workspace sections, each [N][per][lanes]
+  TZ* z;
+  TSL *sl, *su, *ll, *lu;
+  TDA* dza;
+  TDZ* dzw;
+  TEG *ew, *gw;
+  TGN *Kw, *Sw, *dw;
+  TSL *sc, *lc;  // general rows: slack, multiplier
+  TZ* rc;        // general rows: residual C x - h - s (carried, see init)
+
+  template <typename S>
+  MPC_HD static S* take(char*& p, int64_t elems) {
+    S* r = reinterpret_cast<S*>(p);
+    p += (elems * (int64_t)sizeof(S) + 15) / 16 * 16;
+    return r;
+  }
 
   MPC_HD BoxQpIpm(const BoxQpArgs<TIO>& args, const T* shared, int64_t scenario, int64_t lane, int64_t lanes)
-      : a(args), sh(shared), b(scenario), bs(args.batch), wb(lane), wbs((lanes + 3) / 4 * 4) {
-    wsb = static_cast<char*>(a.ws);
+      : a(args), sh(shared), b(scenario), bs(args.batch), wb(lane), wbs(lanes) {
+    char* p = static_cast<char*>(a.ws);
+    const int64_t per = (int64_t)a.N * wbs;
+    z = take<TZ>(p, per * D);
+    sl = take<TSL>(p, per * D);
+    su = take<TSL>(p, per * D);
+    ll = take<TSL>(p, per * D);
+    lu = take<TSL>(p, per * D);
+    dza = take<TDA>(p, per * D);
+    dzw = take<TDZ>(p, per * D);
+    ew = take<TEG>(p, per * D);
+    gw = take<TEG>(p, per * D);
+    Kw = take<TGN>(p, per * NU * NX);
+    Sw = take<TGN>(p, per * NU * NU);
+    dw = take<TGN>(p, per * NU);
+    sc = take<TSL>(p, per * NC);
+    lc = take<TSL>(p, per * NC);
+    rc = take<TZ>(p, per * NC);
     mu_scale = T(1);
     for (int i = 0; i < NX * NX; ++i) {
       const T v = sh[SH::oQ + i] < T(0) ? -sh[SH::oQ + i] : sh[SH::oQ + i];
@@ -249,7 +223,7 @@ struct BoxQpIpm {
   }
 
   MPC_HD int64_t ix(int k, int i, int per) const { return ((int64_t)k * per + i) * bs + b; }     // caller's arrays
-  MPC_HD static Idx wx(int k, int i, int /*per*/) { return Idx{k, i}; }                         // workspace
+  MPC_HD int64_t wx(int k, int i, int per) const { return ((int64_t)k * per + i) * wbs + wb; }   // workspace
   MPC_HD bool hasl(int i) const { return sh[SH::oLo + i] > T(-kBigBound); }
   MPC_HD bool hasu(int i) const { return sh[SH::oHi + i] < T(kBigBound); }
   MPC_HD T lo(int i) const { return sh[SH::oLo + i]; }
@@ -265,23 +239,23 @@ struct BoxQpIpm {
   MPC_HD void load(int k, Stage& s) const {
 #pragma unroll
     for (int i = 0; i < D; ++i) {
-      const Idx o = wx(k, i, D);
-      s.z[i] = (T)z_()[o];
-      s.sl[i] = (T)sl_()[o];
-      s.su[i] = (T)su_()[o];
-      s.ll[i] = (T)ll_()[o];
-      s.lu[i] = (T)lu_()[o];
+      const int64_t o = wx(k, i, D);
+      s.z[i] = (T)z[o];
+      s.sl[i] = (T)sl[o];
+      s.su[i] = (T)su[o];
+      s.ll[i] = (T)ll[o];
+      s.lu[i] = (T)lu[o];
     }
   }
   MPC_HD void store_stage(int k, const Stage& s) {
 #pragma unroll
     for (int i = 0; i < D; ++i) {
-      const Idx o = wx(k, i, D);
-      z_()[o] = (TZ)s.z[i];
-      sl_()[o] = (TSL)s.sl[i];
-      su_()[o] = (TSL)s.su[i];
-      ll_()[o] = (TSL)s.ll[i];
-      lu_()[o] = (TSL)s.lu[i];
+      const int64_t o = wx(k, i, D);
+      z[o] = (TZ)s.z[i];
+      sl[o] = (TSL)s.sl[i];
+      su[o] = (TSL)s.su[i];
+      ll[o] = (TSL)s.ll[i];
+      lu[o] = (TSL)s.lu[i];
     }
   }
   // the values the next sweeps will read back (identity for float64 storage)
@@ -311,10 +285,10 @@ struct BoxQpIpm {
     (void)p;
 #endif
   }
-  template <int PER, class SEC>
-  MPC_HD void pf_rows(SEC base, int k) const {
+  template <int PER, typename S>
+  MPC_HD void pf_rows(const S* base, int k) const {
 #pragma unroll
-    for (int i = 0; i < PER; ++i) pf(&base[wx(k, i, PER)]);
+    for (int i = 0; i < PER; ++i) pf(base + wx(k, i, PER));
   }
   template <int PER, typename S>
   MPC_HD void pf_rows_io(const S* base, int k) const {
@@ -322,11 +296,11 @@ struct BoxQpIpm {
     for (int i = 0; i < PER; ++i) pf(base + ix(k, i, PER));
   }
   MPC_HD void pf_iterate(int k) const {
-    pf_rows<D>(z_(), k);
-    pf_rows<D>(sl_(), k);
-    pf_rows<D>(su_(), k);
-    pf_rows<D>(ll_(), k);
-    pf_rows<D>(lu_(), k);
+    pf_rows<D>(z, k);
+    pf_rows<D>(sl, k);
+    pf_rows<D>(su, k);
+    pf_rows<D>(ll, k);
+    pf_rows<D>(lu, k);
   }
   MPC_HD void pf_model(int k) const {
     if constexpr (MODEL == 1) {
@@ -346,18 +320,15 @@ struct BoxQpIpm {
 #endif
   }
 
-  template <int PER, class SEC>
-  MPC_HD void loadn(SEC base, int k, T* v) const {
+  template <int PER, typename S>
+  MPC_HD void loadn(const S* base, int k, T* v) const {
 #pragma unroll
     for (int i = 0; i < PER; ++i) v[i] = (T)base[wx(k, i, PER)];
   }
-  template <int PER, class SEC>
-  MPC_HD void storen(SEC base, int k, const T* v) const {
+  template <int PER, typename S>
+  MPC_HD void storen(S* base, int k, const T* v) const {
 #pragma unroll
-    for (int i = 0; i < PER; ++i) {
-      auto& slot = base[wx(k, i, PER)];
-      slot = (typename std::remove_reference<decltype(slot)>::type)v[i];
-    }
+    for (int i = 0; i < PER; ++i) base[wx(k, i, PER)] = (S)v[i];
   }
   template <int PER>
   MPC_HD void loadn_io(const TIO* base, int k, T* v) const {
@@ -491,11 +462,11 @@ struct BoxQpIpm {
               const T h = load_row_c(k, j, C);
               const T w = dotx(C, xn) - h;
               const T s = round_to<TSL>(w > T(1) ? w : T(1));
-              sc_()[wx(k, j, NC)] = (TSL)s;
-              lc_()[wx(k, j, NC)] = (TSL)(mu0 / s);
+              sc[wx(k, j, NC)] = (TSL)s;
+              lc[wx(k, j, NC)] = (TSL)(mu0 / s);
               // the row residual is carried, not recomputed: it decays exactly by (1 - alpha) per step, whereas
               // C x - h - s recomputed from a dot product keeps ~1e-16 of rounding noise that Sigma ~ 1e12 amplifies
-              rc_()[wx(k, j, NC)] = (TZ)(w - s);
+              rc[wx(k, j, NC)] = (TZ)(w - s);
             }
           }
         }
@@ -561,8 +532,8 @@ struct BoxQpIpm {
       for (int j = 0; j < NC; ++j) {
         T C[NX];
         (void)load_row_c(k, j, C);
-        const T s = (T)sc_()[wx(k, j, NC)], l = (T)lc_()[wx(k, j, NC)];
-        const T r = (T)rc_()[wx(k, j, NC)];
+        const T s = (T)sc[wx(k, j, NC)], l = (T)lc[wx(k, j, NC)];
+        const T r = (T)rc[wx(k, j, NC)];
         const T ds = dotx(C, dz + NU) + r;
         const T inv = rcp_(s), sgc = l * inv;
         const T cc = cc_of(dotx(C, da + NU), r, sgc, l);
@@ -575,9 +546,9 @@ struct BoxQpIpm {
         // the residual is carried: it must absorb the storage rounding of the slack, or C x - h = s + r drifts by an
         // ulp of s per iteration (2e-7 on the active rows after ~15 iterations with float32 slacks)
         const T sr = round_to<TSL>(sn);
-        sc_()[wx(k, j, NC)] = (TSL)sr;
-        lc_()[wx(k, j, NC)] = (TSL)ln;
-        rc_()[wx(k, j, NC)] = (TZ)((T(1) - alpha) * r + (sn - sr));
+        sc[wx(k, j, NC)] = (TSL)sr;
+        lc[wx(k, j, NC)] = (TSL)ln;
+        rc[wx(k, j, NC)] = (TZ)((T(1) - alpha) * r + (sn - sr));
       }
     }
   }
@@ -661,101 +632,102 @@ struct BoxQpIpm {
         pf_iterate(k - a.pf_dist);
         pf_model(k - a.pf_dist);
         if (have_step) {
-          pf_rows<D>(dza_(), k - a.pf_dist);
-          pf_rows<D>(dzw_(), k - a.pf_dist);
+          pf_rows<D>(dza, k - a.pf_dist);
+          pf_rows<D>(dzw, k - a.pf_dist);
         }
       }
-#if MPC_VAR_SWEEPA_STAGE
-      Stage cur;
-      load(k, cur);
-      T A[NX * NX], B[NX * NU], c[NX];
-      load_model(k, A, B, c);
       T znew[D], sig[D], rhs[D];
-      if (have_step) {
-        T dz[D], da[D];
-        loadn<D>(dzw_(), k, dz);
-        loadn<D>(dza_(), k, da);
-        apply_step_rows(k, dz, da, tau, alpha);
-        apply_step(cur, dz, da, tau, alpha);
-        store_stage(k, cur);
-      }
-#pragma unroll
-      for (int i = 0; i < D; ++i) {
-        T sg = T(0), r = T(0);
-        if (hasl(i)) {
-          const T s = cur.sl[i], l = cur.ll[i];
-          const T sgl = l * rcp_(s);
-          sg += sgl;
-          r = fma_<T>(-sgl, cur.z[i] - lo(i) - s, r);
-        }
-        if (hasu(i)) {
-          const T s = cur.su[i], l = cur.lu[i];
-          const T sgu = l * rcp_(s);
-          sg += sgu;
-          r = fma_<T>(sgu, hi(i) - cur.z[i] - s, r);
-        }
-        znew[i] = cur.z[i];
-        sig[i] = sg;
-        rhs[i] = r;
-      }
-#else
-      // ALL loads of the stage visit are issued first (one memory round trip; the stores below would otherwise fence
-      // the later loads, the compiler cannot prove that the sections do not alias); slacks and multipliers stay in
-      // their stored type until they are used, which keeps the (4,2) instantiation inside the register file.
-      TZ zr[D];
-      TSL slr[D], sur[D], llr[D], lur[D];
-#pragma unroll
-      for (int i = 0; i < D; ++i) {
-        const Idx o = wx(k, i, D);
-        zr[i] = z_()[o];
-        slr[i] = sl_()[o];
-        sur[i] = su_()[o];
-        llr[i] = ll_()[o];
-        lur[i] = lu_()[o];
-      }
-      T znew[D], sig[D], rhs[D], dz[D], da[D];
-      if (have_step) {
-        loadn<D>(dzw_(), k, dz);
-        loadn<D>(dza_(), k, da);
-      }
       T A[NX * NX], B[NX * NU], c[NX];
-      load_model(k, A, B, c);
-      if (have_step) apply_step_rows(k, dz, da, tau, alpha);
-      // per element: (previous step applied,) Sigma and the bound part of the affine right-hand side
+      if constexpr (D <= 3) {
+        // (2,1): the whole iterate in double registers, one step / store, then the bound terms (the variant ptxas fits
+        // into 128 registers without spills; the element-wise form below costs ~100 bytes of spills there)
+        Stage cur;
+        load(k, cur);
+        load_model(k, A, B, c);
+        if (have_step) {
+          T dz[D], da[D];
+          loadn<D>(dzw, k, dz);
+          loadn<D>(dza, k, da);
+          apply_step_rows(k, dz, da, tau, alpha);
+          apply_step(cur, dz, da, tau, alpha);
+          store_stage(k, cur);
+        }
 #pragma unroll
-      for (int i = 0; i < D; ++i) {
-        const Idx o = wx(k, i, D);
-        const T zi = (T)zr[i];
-        const T zn = have_step ? round_to<TZ>(zi + alpha * dz[i]) : zi;
-        T sg = T(0), r = T(0);
-        if (hasl(i)) {
-          T s = (T)slr[i], l = (T)llr[i];
-          if (have_step) {
-            step_bound(s, l, zi - lo(i) - s, dz[i], da[i], tau, alpha);
-            sl_()[o] = (TSL)s;
-            ll_()[o] = (TSL)l;
+        for (int i = 0; i < D; ++i) {
+          T sg = T(0), r = T(0);
+          if (hasl(i)) {
+            const T s = cur.sl[i], l = cur.ll[i];
+            const T sgl = l * rcp_(s);
+            sg += sgl;
+            r = fma_<T>(-sgl, cur.z[i] - lo(i) - s, r);
           }
-          const T sgl = l * rcp_(s);
-          sg += sgl;
-          r = fma_<T>(-sgl, zn - lo(i) - s, r);
-        }
-        if (hasu(i)) {
-          T s = (T)sur[i], l = (T)lur[i];
-          if (have_step) {
-            step_bound(s, l, hi(i) - zi - s, -dz[i], -da[i], tau, alpha);
-            su_()[o] = (TSL)s;
-            lu_()[o] = (TSL)l;
+          if (hasu(i)) {
+            const T s = cur.su[i], l = cur.lu[i];
+            const T sgu = l * rcp_(s);
+            sg += sgu;
+            r = fma_<T>(sgu, hi(i) - cur.z[i] - s, r);
           }
-          const T sgu = l * rcp_(s);
-          sg += sgu;
-          r = fma_<T>(sgu, hi(i) - zn - s, r);
+          znew[i] = cur.z[i];
+          sig[i] = sg;
+          rhs[i] = r;
         }
-        if (have_step) z_()[o] = (TZ)zn;
-        znew[i] = zn;
-        sig[i] = sg;
-        rhs[i] = r;
+      } else {
+        // ALL loads of the stage visit are issued first (one memory round trip; the stores below would otherwise fence
+        // the later loads, the compiler cannot prove that the sections do not alias); slacks and multipliers stay in
+        // their stored type until they are used, which keeps the (4,2) instantiation inside the register file.
+        TZ zr[D];
+        TSL slr[D], sur[D], llr[D], lur[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          const int64_t o = wx(k, i, D);
+          zr[i] = z[o];
+          slr[i] = sl[o];
+          sur[i] = su[o];
+          llr[i] = ll[o];
+          lur[i] = lu[o];
+        }
+        T dz[D], da[D];
+        if (have_step) {
+          loadn<D>(dzw, k, dz);
+          loadn<D>(dza, k, da);
+        }
+        load_model(k, A, B, c);
+        if (have_step) apply_step_rows(k, dz, da, tau, alpha);
+        // per element: (previous step applied,) Sigma and the bound part of the affine right-hand side
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          const int64_t o = wx(k, i, D);
+          const T zi = (T)zr[i];
+          const T zn = have_step ? round_to<TZ>(zi + alpha * dz[i]) : zi;
+          T sg = T(0), r = T(0);
+          if (hasl(i)) {
+            T s = (T)slr[i], l = (T)llr[i];
+            if (have_step) {
+              step_bound(s, l, zi - lo(i) - s, dz[i], da[i], tau, alpha);
+              sl[o] = (TSL)s;
+              ll[o] = (TSL)l;
+            }
+            const T sgl = l * rcp_(s);
+            sg += sgl;
+            r = fma_<T>(-sgl, zn - lo(i) - s, r);
+          }
+          if (hasu(i)) {
+            T s = (T)sur[i], l = (T)lur[i];
+            if (have_step) {
+              step_bound(s, l, hi(i) - zi - s, -dz[i], -da[i], tau, alpha);
+              su[o] = (TSL)s;
+              lu[o] = (TSL)l;
+            }
+            const T sgu = l * rcp_(s);
+            sg += sgu;
+            r = fma_<T>(sgu, hi(i) - zn - s, r);
+          }
+          if (have_step) z[o] = (TZ)zn;
+          znew[i] = zn;
+          sig[i] = sg;
+          rhs[i] = r;
+        }
       }
-#endif
       // -(H z): inputs weighted by R, state x_{k+1} by Q (Pf for the last stage)
       {
         const T* Qx = sh + (k == a.N - 1 ? SH::oPf : SH::oQ);
@@ -780,9 +752,9 @@ struct BoxQpIpm {
         for (int j = 0; j < NC; ++j) {
           T C[NX];
           (void)load_row_c(k, j, C);
-          const T s = (T)sc_()[wx(k, j, NC)], l = (T)lc_()[wx(k, j, NC)];
+          const T s = (T)sc[wx(k, j, NC)], l = (T)lc[wx(k, j, NC)];
           const T sgc = l * rcp_(s);
-          const T r = (T)rc_()[wx(k, j, NC)];
+          const T r = (T)rc[wx(k, j, NC)];
           const T rhs_c = -sgc * r;
 #pragma unroll
           for (int i = 0; i < NX; ++i) rhs[NU + i] = fma_<T>(C[i], rhs_c, rhs[NU + i]);
@@ -847,12 +819,12 @@ struct BoxQpIpm {
             Pacc[i * NX + j] = acc;
             Pacc[j * NX + i] = acc;
           }
-        storen<NU * NX>(Kw_(), k, K);
-        storen<NU * NU>(Sw_(), k, Sinv);
+        storen<NU * NX>(Kw, k, K);
+        storen<NU * NU>(Sw, k, Sinv);
       }
       T dff[NU];
       ff_stage(A, B, K, Sinv, rhs, pacc, dff);
-      storen<NU>(dw_(), k, dff);
+      storen<NU>(dw, k, dff);
     }
   }
 
@@ -875,14 +847,14 @@ struct BoxQpIpm {
       if (pf_on(k + a.pf_dist)) {
         pf_iterate(k + a.pf_dist);
         pf_model(k + a.pf_dist);
-        pf_rows<NU * NX>(Kw_(), k + a.pf_dist);
-        pf_rows<NU>(dw_(), k + a.pf_dist);
+        pf_rows<NU * NX>(Kw, k + a.pf_dist);
+        pf_rows<NU>(dw, k + a.pf_dist);
       }
       Stage cur;
       load(k, cur);
       T K[NU * NX], dff[NU];
-      loadn<NU * NX>(Kw_(), k, K);
-      loadn<NU>(dw_(), k, dff);
+      loadn<NU * NX>(Kw, k, K);
+      loadn<NU>(dw, k, dff);
       T A[NX * NX], B[NX * NU], c[NX];
       load_model(k, A, B, c);
 #pragma unroll
@@ -931,8 +903,8 @@ struct BoxQpIpm {
         for (int j = 0; j < NC; ++j) {
           T C[NX];
           (void)load_row_c(k, j, C);
-          const T s = (T)sc_()[wx(k, j, NC)], l = (T)lc_()[wx(k, j, NC)];
-          const T r = (T)rc_()[wx(k, j, NC)];
+          const T s = (T)sc[wx(k, j, NC)], l = (T)lc[wx(k, j, NC)];
+          const T r = (T)rc[wx(k, j, NC)];
           const T ds = dotx(C, dzv + NU) + r;
           const T inv = rcp_(s);
           const T t = ds * inv;
@@ -948,9 +920,9 @@ struct BoxQpIpm {
           }
         }
       }
-      storen<D>(dza_(), k, dzv);
-      storen<D>(ew_(), k, ev);
-      storen<D>(gw_(), k, gv);
+      storen<D>(dza, k, dzv);
+      storen<D>(ew, k, ev);
+      storen<D>(gw, k, gv);
       // the rollout continues with the UNROUNDED state direction (the stored copy is only used for cc)
 #pragma unroll
       for (int i = 0; i < NX; ++i) x[i] = xn[i];
@@ -965,29 +937,29 @@ struct BoxQpIpm {
     for (int i = 0; i < NX; ++i) pacc[i] = T(0);
     for (int k = a.N - 1; k >= 0; --k) {
       if (pf_on(k - a.pf_dist)) {
-        pf_rows<D>(ew_(), k - a.pf_dist);
-        pf_rows<D>(gw_(), k - a.pf_dist);
-        pf_rows<NU * NX>(Kw_(), k - a.pf_dist);
-        pf_rows<NU * NU>(Sw_(), k - a.pf_dist);
-        pf_rows<NU>(dw_(), k - a.pf_dist);
+        pf_rows<D>(ew, k - a.pf_dist);
+        pf_rows<D>(gw, k - a.pf_dist);
+        pf_rows<NU * NX>(Kw, k - a.pf_dist);
+        pf_rows<NU * NU>(Sw, k - a.pf_dist);
+        pf_rows<NU>(dw, k - a.pf_dist);
         pf_model(k - a.pf_dist);
       }
       T ev[D], gv[D], K[NU * NX], Sinv[NU * NU];
-      loadn<D>(ew_(), k, ev);
-      loadn<D>(gw_(), k, gv);
-      loadn<NU * NX>(Kw_(), k, K);
-      loadn<NU * NU>(Sw_(), k, Sinv);
+      loadn<D>(ew, k, ev);
+      loadn<D>(gw, k, gv);
+      loadn<NU * NX>(Kw, k, K);
+      loadn<NU * NU>(Sw, k, Sinv);
       T A[NX * NX], B[NX * NU], c[NX];
       load_model(k, A, B, c);
       T rhs[D];
 #pragma unroll
       for (int i = 0; i < D; ++i) rhs[i] = fma_<T>(tau, ev[i], -gv[i]);
       T dff[NU], daff[NU];
-      loadn<NU>(dw_(), k, daff);
+      loadn<NU>(dw, k, daff);
       ff_stage(A, B, K, Sinv, rhs, pacc, dff);
 #pragma unroll
       for (int j = 0; j < NU; ++j) dff[j] += daff[j];  // d_aff + d_cor: sweep D rolls the whole direction out at once
-      storen<NU>(dw_(), k, dff);
+      storen<NU>(dw, k, dff);
     }
   }
 
@@ -1004,16 +976,16 @@ struct BoxQpIpm {
       if (pf_on(k + a.pf_dist)) {
         pf_iterate(k + a.pf_dist);
         pf_model(k + a.pf_dist);
-        pf_rows<NU * NX>(Kw_(), k + a.pf_dist);
-        pf_rows<NU>(dw_(), k + a.pf_dist);
-        pf_rows<D>(dza_(), k + a.pf_dist);
+        pf_rows<NU * NX>(Kw, k + a.pf_dist);
+        pf_rows<NU>(dw, k + a.pf_dist);
+        pf_rows<D>(dza, k + a.pf_dist);
       }
       Stage cur;
       load(k, cur);
       T K[NU * NX], dff[NU], da[D];
-      loadn<NU * NX>(Kw_(), k, K);
-      loadn<NU>(dw_(), k, dff);
-      loadn<D>(dza_(), k, da);
+      loadn<NU * NX>(Kw, k, K);
+      loadn<NU>(dw, k, dff);
+      loadn<D>(dza, k, da);
       T A[NX * NX], B[NX * NU], c[NX];
       load_model(k, A, B, c);
 #pragma unroll
@@ -1063,8 +1035,8 @@ struct BoxQpIpm {
         for (int j = 0; j < NC; ++j) {
           T C[NX];
           (void)load_row_c(k, j, C);
-          const T s = (T)sc_()[wx(k, j, NC)], l = (T)lc_()[wx(k, j, NC)];
-          const T r = (T)rc_()[wx(k, j, NC)];
+          const T s = (T)sc[wx(k, j, NC)], l = (T)lc[wx(k, j, NC)];
+          const T r = (T)rc[wx(k, j, NC)];
           const T ds = dotx(C, dzv + NU) + r;
           const T rinv = rcp_(s * l), inv_s = rinv * l, inv_l = rinv * s;
           const T sgc = l * inv_s;
@@ -1077,7 +1049,7 @@ struct BoxQpIpm {
           acc.rp = max_(acc.rp, abs_(r));
         }
       }
-      storen<D>(dzw_(), k, dzv);
+      storen<D>(dzw, k, dzv);
 #pragma unroll
       for (int i = 0; i < NX; ++i) x[i] = xn[i];
     }
@@ -1099,8 +1071,8 @@ struct BoxQpIpm {
       load_model(k, A, B, c);
       if (have_step) {
         T dz[D], da[D];
-        loadn<D>(dzw_(), k, dz);
-        loadn<D>(dza_(), k, da);
+        loadn<D>(dzw, k, dz);
+        loadn<D>(dza, k, da);
         apply_step_rows(k, dz, da, tau, alpha);
         apply_step(st, dz, da, tau, alpha);
       }
@@ -1122,7 +1094,7 @@ struct BoxQpIpm {
         if (a.sat_c) {
 #pragma unroll 1
           for (int j = 0; j < NC; ++j)
-            a.sat_c[ix(k, j, NC)] = (T)lc_()[wx(k, j, NC)] > (T)sc_()[wx(k, j, NC)] ? (int8_t)-1 : (int8_t)0;
+            a.sat_c[ix(k, j, NC)] = (T)lc[wx(k, j, NC)] > (T)sc[wx(k, j, NC)] ? (int8_t)-1 : (int8_t)0;
         }
       }
       cost += quad<T, NX>(sh + SH::oQ, x) + quad<T, NU>(sh + SH::oR, u);

@@ -52,6 +52,36 @@ __global__ void __launch_bounds__(kRtiThreads, MINB) rti_closed_loop_kernel(RtiL
   if (b < a.qp.batch) rti_closed_loop_body<double, TIO, PACKED, NC, ST>(a, sh, b);
 }
 
+// one globalised SQP round of the step-wise controller path: backtracking on the l1 merit (rti_merit) along
+// warm -> U_qp, plan <- warm + beta (U_qp - warm); scenarios whose QP did not solve keep the full step
+template <typename TIO, int NC>
+__global__ void __launch_bounds__(kRtiThreads) sqp_linesearch_kernel(RtiLoopArgs<double, TIO> a, TIO* beta_out) {
+  using SH = BoxQpShared<4, 2>;
+  __shared__ double sh[SH::total];
+  for (int i = threadIdx.x; i < SH::total; i += blockDim.x) sh[i] = boxqp_shared_elem<double, TIO, 4, 2>(a.qp, i);
+  __syncthreads();
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.qp.batch) return;
+  const int64_t bs = a.qp.batch;
+  double beta = 1.0;
+  if (a.qp.status[b] == MPC_SOLVED) {
+    const double m0 = rti_merit<double, TIO, NC>(a, sh, b, 0.0);
+    int h = 0;
+    while (h <= kSqpMaxHalvings && !(rti_merit<double, TIO, NC>(a, sh, b, beta) < m0)) {
+      beta *= 0.5;
+      ++h;
+    }
+    if (h > kSqpMaxHalvings) beta = 0.0;
+  }
+  if (beta != 1.0) {
+    for (int i = 0; i < a.qp.N * 2; ++i) {
+      const double q = (double)a.qp.U[(int64_t)i * bs + b], w = (double)a.warm[(int64_t)i * bs + b];
+      a.qp.U[(int64_t)i * bs + b] = (TIO)fma(beta, q - w, w);
+    }
+  }
+  if (beta_out) beta_out[b] = (TIO)beta;
+}
+
 // covering circles of vehicle and obstacle (reference session_4/main.py:49-56,191-200); x_obs is a HOST pointer to
 // the obstacle pose [p_x, p_y, psi, ...]
 static ObstacleParams<double> make_obstacle(double length, double width, const double* x_obs) {
@@ -283,15 +313,64 @@ extern "C" int mpc_rti_closed_loop(double lr, double lf, double accel, double fr
                                           sqp_tol, Q, R, Pf, u_lo, u_hi, x_lo, x_hi, nc, nc > 0 ? &ob : nullptr, x0, U_plan,
                                           X_pred, X_cl, U_cl, cost_cl, viol_cl, clear_cl, n_sat, n_fail, iters_total,
                                           last_status, X_bundle, U_bundle, ws, batch, N, max_iter, eps, st);
-  if (const char* env = getenv("MPC_QP_STORE")) {   // "f64": all-float64 workspace (A/B measurements, as mpc_boxqp_solve)
-    if (strcmp(env, "f64") == 0)
-      return rti_loop_impl<double, StoreF64>(model, friction_model, plant, friction_plant, plant_substeps, steps, sqp_iters,
-                                             sqp_tol, Q, R, Pf, u_lo, u_hi, x_lo, x_hi, nc, nc > 0 ? &ob : nullptr, x0,
-                                             U_plan, X_pred, X_cl, U_cl, cost_cl, viol_cl, clear_cl, n_sat, n_fail,
-                                             iters_total, last_status, X_bundle, U_bundle, ws, batch, N, max_iter, eps, st);
-  }
-  return rti_loop_impl<double, StoreMix>(model, friction_model, plant, friction_plant, plant_substeps, steps, sqp_iters,
+  // float64 product: the all-float64 workspace is the default HERE (the (4,2) stages at 8 warps per SM are bound by
+  // latency and instruction issue, not by bytes: measured at cfg 4 (tools/prof/r2_gpu10.sh) 2.91 s per 13.1 M QPs with
+  // it against 3.15 s with the mixed float32/float64 workspace of mpc_boxqp_solve, whose conversions sit on every
+  // load-to-use chain); MPC_QP_STORE=mix selects the mixed one (0.6x the DRAM bytes)
+  const char* env = getenv("MPC_QP_STORE");
+  if (env && strcmp(env, "mix") == 0)
+    return rti_loop_impl<double, StoreMix>(model, friction_model, plant, friction_plant, plant_substeps, steps, sqp_iters,
+                                           sqp_tol, Q, R, Pf, u_lo, u_hi, x_lo, x_hi, nc, nc > 0 ? &ob : nullptr, x0,
+                                           U_plan, X_pred, X_cl, U_cl, cost_cl, viol_cl, clear_cl, n_sat, n_fail,
+                                           iters_total, last_status, X_bundle, U_bundle, ws, batch, N, max_iter, eps, st);
+  return rti_loop_impl<double, StoreF64>(model, friction_model, plant, friction_plant, plant_substeps, steps, sqp_iters,
                                          sqp_tol, Q, R, Pf, u_lo, u_hi, x_lo, x_hi, nc, nc > 0 ? &ob : nullptr, x0, U_plan,
                                          X_pred, X_cl, U_cl, cost_cl, viol_cl, clear_cl, n_sat, n_fail, iters_total,
                                          last_status, X_bundle, U_bundle, ws, batch, N, max_iter, eps, st);
+}
+
+extern "C" int mpc_bicycle_sqp_linesearch(double lr, double lf, double accel, double friction, double ts, int rk4,
+                                          const void* Q, const void* R, const void* Pf, const void* x_lo,
+                                          const void* x_hi, int nc, double length, double width, const double* x_obs,
+                                          const void* y, const void* warm_U, void* U, const int32_t* status,
+                                          void* beta, int64_t batch, int N, int dtype, mpc_stream_t stream) {
+  MPC_REQUIRE(dtype == MPC_F64 || dtype == MPC_F32, MPC_ERR_DTYPE, "mpc_bicycle_sqp_linesearch: unknown dtype %d", dtype);
+  if (batch == 0) return MPC_OK;
+  MPC_REQUIRE(Q && R && Pf && x_lo && x_hi && y && warm_U && U && status, MPC_ERR_NULL,
+              "mpc_bicycle_sqp_linesearch: null pointer");
+  MPC_REQUIRE(N >= 1 && batch >= 0 && lr > 0 && ts > 0, MPC_ERR_SHAPE, "mpc_bicycle_sqp_linesearch: bad argument");
+  MPC_REQUIRE(nc == 0 || (nc == kObsCircles * kObsCircles && x_obs && length > 0 && width > 0), MPC_ERR_UNSUPPORTED,
+              "mpc_bicycle_sqp_linesearch: nc must be 0 or 9 (with x_obs, length, width)");
+  MPC_REQUIRE(al(dtype == MPC_F32 ? 4 : 8, {Q, R, Pf, x_lo, x_hi, y, warm_U, U, beta}), MPC_ERR_ALIGN,
+              "mpc_bicycle_sqp_linesearch: misaligned pointer");
+  const unsigned grid = (unsigned)((batch + kRtiThreads - 1) / kRtiThreads);
+  cudaStream_t st = (cudaStream_t)stream;
+  auto launch = [&](auto tag) {
+    using TIO = decltype(tag);
+    RtiLoopArgs<double, TIO> a{};
+    a.model = BicycleModel<double>{lr, lf, accel, ts, rk4 ? 1 : 0};
+    a.friction_model = friction;
+    if (nc > 0) a.ob = make_obstacle(length, width, x_obs);
+    a.xcur = (TIO*)y;
+    a.warm = (TIO*)warm_U;
+    a.qp = BoxQpArgs<TIO>{};
+    a.qp.ltv = 1;
+    a.qp.Q = (const TIO*)Q;
+    a.qp.R = (const TIO*)R;
+    a.qp.Pf = (const TIO*)Pf;
+    // the input box is not needed by the merit (the QP solution and the warm plan are inside it): reuse the state box
+    a.qp.u_lo = (const TIO*)x_lo;
+    a.qp.u_hi = (const TIO*)x_hi;
+    a.qp.x_lo = (const TIO*)x_lo;
+    a.qp.x_hi = (const TIO*)x_hi;
+    a.qp.U = (TIO*)U;
+    a.qp.status = const_cast<int32_t*>(status);
+    a.qp.batch = batch;
+    a.qp.N = N;
+    if (nc > 0) sqp_linesearch_kernel<TIO, 9><<<grid, kRtiThreads, 0, st>>>(a, (TIO*)beta);
+    else sqp_linesearch_kernel<TIO, 0><<<grid, kRtiThreads, 0, st>>>(a, (TIO*)beta);
+  };
+  if (dtype == MPC_F32) launch(float{});
+  else launch(double{});
+  return check_launch("sqp_linesearch_kernel");
 }

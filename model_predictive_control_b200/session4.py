@@ -37,6 +37,8 @@ _lib.register("mpc_rti_closed_loop", c_int,
               [c_double] * 5 + [c_int] + [c_double] * 3 + [c_void_p, c_int, c_int, c_int, c_double] + [c_void_p] * 7 +
               [c_int, c_double, c_double, c_void_p] + [c_void_p] * 15 + [c_int64, c_int64, c_int, c_int, c_double, c_int, c_void_p])
 
+_lib.register("mpc_bicycle_sqp_linesearch", c_int, [c_double] * 5 + [c_int] + [c_void_p] * 5 + [c_int, c_double, c_double] +
+              [c_void_p] * 6 + [c_int64, c_int, c_int, c_void_p])
 _lib.register("mpc_bicycle_rti_prepare_obstacle", c_int, [c_double] * 5 + [c_int, c_double, c_double, c_void_p, c_void_p,
               c_void_p, c_int] + [c_void_p] * 6 + [c_int64, c_int, c_int, c_void_p])
 
@@ -267,8 +269,18 @@ class MPCController:
             rows = self._prepare(yT, first or rnd > 0, self._lin)
             res = boxqp.solve(A, B, Q, R, QT, N, yT, i_lb, i_ub, s_lb, s_ub, c=c, warm_U=warm, max_iter=self.max_iter,
                               eps=self.eps, workspace=self._qp_ws, **rows)
+            if self.sqp_iters > 1:
+                # globalised round: backtracking on the l1 merit of the nonlinear OCP (the fused loop does the same
+                # inside its kernel); full Gauss-Newton steps cycle on this OCP
+                nc, length, width, xo = self._obstacle_args()
+                xlo, xhi = (torch.as_tensor(v, dtype=dt, device=dev).contiguous() for v in (s_lb, s_ub))
+                with torch.cuda.device(dev):
+                    _lib.check(_lib.lib().mpc_bicycle_sqp_linesearch(
+                        *self._model_args(), _lib.ptr(Q), _lib.ptr(R), _lib.ptr(QT), _lib.ptr(xlo), _lib.ptr(xhi), nc, length,
+                        width, xo, _lib.ptr(yT), _lib.ptr(warm), _lib.ptr(res.U), _lib.ptr(res.status), None, batch, N,
+                        _lib.dtype_enum(yT), _lib.stream(dev)))
             moved = None
-            if self.sqp_tol > 0 and rnd + 1 < self.sqp_iters:
+            if self.sqp_iters > 1 and rnd + 1 < self.sqp_iters:
                 moved = float(((res.U - warm).abs().amax(dim=(0, 1)) / res.U.abs().amax(dim=(0, 1)).clamp(min=1.0)).max())
             self._plan.copy_(res.U)
             if moved is not None and moved <= self.sqp_tol:

@@ -127,7 +127,7 @@ static void boxqp_loop_st(BoxQpArgs<double> a) {
   a.ws_lanes = a.batch;
   const std::vector<double> sh = shared_block<double, NX, NU>(a);
   for (int64_t b = 0; b < a.batch; ++b) {
-    BoxQpIpm<double, double, NX, NU, NC, 0, ST, true> ipm(a, sh.data(), b, b, a.batch);
+    BoxQpIpm<double, double, NX, NU, NC, 0, ST> ipm(a, sh.data(), b, b, a.batch);
     ipm.solve();
   }
 }
@@ -170,7 +170,7 @@ extern "C" int hh_boxqp_solve_f32(const float* A, const float* B, const float* c
   a.ws_lanes = batch;
   const std::vector<double> sh = shared_block<float, 2, 1>(a);
   for (int64_t b = 0; b < batch; ++b) {
-    BoxQpIpm<double, float, 2, 1, 0, 0, StoreF32, true> ipm(a, sh.data(), b, b, batch);
+    BoxQpIpm<double, float, 2, 1, 0, 0, StoreF32> ipm(a, sh.data(), b, b, batch);
     ipm.solve();
   }
   return 0;
