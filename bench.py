@@ -1095,7 +1095,7 @@ def run_next(args):
     cpu = None
     if w == "obstacle":
         batch = args.batch or (1 << 16)
-        N, ts, steps_cl = 30, 0.08, 10
+        N, ts, steps_cl = 30, 0.08, 100     # reference protocol: 100 closed-loop steps (session_4/main.py:241-271)
         par = session4.VehicleParameters()
         x_obs = np.array([0.25, 0.0, 0.0, 0.0])
         x0 = torch.tensor([0.3, -0.1, 0.0, 0.0], device=dev, dtype=torch.float64) + (rnd(batch, 4) * 0.1 - 0.05) * \
@@ -1107,10 +1107,10 @@ def run_next(args):
             return session4.simulate(x0, plant, n_steps=steps_cl, policy=ctrl)
 
         units, n, m = batch * steps_cl, 4, 2
-        launches = 3 * steps_cl   # rti_prepare_obstacle_kernel + boxqp_ipm_rows_kernel + bicycle_plant_kernel per control step
+        launches = 1              # the whole closed loop is ONE rti_closed_loop_kernel launch (round 1: three per control step)
         name = (f"8(f).1 obstacle-avoidance RTI closed loop (session_4/main.py controller, 9 linearised collision rows per stage), "
-                f"nx=4 nu=2 N={N}, {batch} scenarios x {steps_cl} control steps per GPU, step-wise driver")
-        kname, io_bytes = "boxqp_ipm_rows_kernel", 8 * 6
+                f"nx=4 nu=2 N={N}, {batch} scenarios x {steps_cl} control steps per GPU, fused closed loop")
+        kname, io_bytes = "rti_closed_loop_kernel", 8 * 6
         host_in, host_out = [x0], lambda r: [r]
 
         def cpu_fn():
