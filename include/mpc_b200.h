@@ -180,6 +180,24 @@ int mpc_boxqp_solve(const void* A, const void* B, const void* c, int ltv, const 
                     int64_t ws_bytes, int64_t batch, int n, int m, int N, int max_iter, double eps,
                     int dtype, mpc_stream_t stream);
 
+/* Difficulty-sorted batches for the thread-per-scenario kernels.  Interior-point iteration counts differ between
+ * scenarios (cfg 3: mean 10.8, max 22) and a warp runs until its slowest lane has converged.  Neighbouring initial
+ * states have similar active sets and iteration counts, so:
+ *   mpc_state_order_keys  writes keys[b] = Morton (Z-order) code of x0[:, b] (8 bits per coordinate, scaled by
+ *                         lohi = [min_0..min_{n-1}, max_0..max_{n-1}] on the device); the caller sorts them (any stable
+ *                         device sort) into order [batch] (int32);
+ *   mpc_boxqp_solve_ordered = mpc_boxqp_solve where lane b of the workspace solves scenario order[b].  Every scenario's
+ *                         arithmetic is independent of its lane: results are bitwise those of mpc_boxqp_solve and are
+ *                         written at the scenario's own index. */
+int mpc_state_order_keys(const void* x0, const void* lohi, int32_t* keys, int64_t batch, int n, int dtype,
+                         mpc_stream_t stream);
+int mpc_boxqp_solve_ordered(const void* A, const void* B, const void* c, int ltv, const void* Q, const void* R,
+                            const void* Pf, const void* u_lo, const void* u_hi, const void* x_lo, const void* x_hi,
+                            const void* x0, const void* warm_U, void* U, void* X, void* cost, int32_t* status,
+                            int32_t* iters, int8_t* sat_u, int8_t* sat_x, const int32_t* order, void* ws,
+                            int64_t ws_bytes, int64_t batch, int n, int m, int N, int max_iter, double eps, int dtype,
+                            mpc_stream_t stream);
+
 /* K4 with general stage rows (polytopic constraints):  additionally  Cg_k x_{k+1} >= hg_k,  k < N.
  * Replaces, after linearisation, the collision constraints of the obstacle-avoidance controller
  * (session_4/main.py:95-104: nine squared-distance constraints per stage).

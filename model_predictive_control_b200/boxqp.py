@@ -22,6 +22,10 @@ _lib.register("mpc_boxqp_solve", c_int,
               [c_void_p] * 3 + [c_int] + [c_void_p] * 16 + [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int,
                                                            c_double, c_int, c_void_p])
 
+_lib.register("mpc_state_order_keys", c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p])
+_lib.register("mpc_boxqp_solve_ordered", c_int,
+              [c_void_p] * 3 + [c_int] + [c_void_p] * 17 + [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int,
+                                                           c_double, c_int, c_void_p])
 _lib.register("mpc_boxqp_rows_workspace_bytes", c_int64, [c_int64, c_int, c_int, c_int, c_int, c_int])
 _lib.register("mpc_boxqp_solve_rows", c_int,
               [c_void_p] * 3 + [c_int] + [c_void_p] * 9 + [c_int] + [c_void_p] * 11 + [c_int64, c_int64, c_int, c_int, c_int, c_int,
@@ -92,8 +96,25 @@ def _vec(v, k, device, name, dtype=torch.float64):
     return t.to(dtype).contiguous()
 
 
+ORDER_MIN_BATCH = 8192   # below this a launch is one partial wave: ordering the scenarios buys nothing
+
+
+def state_order(x0):
+    """Permutation that sorts the scenarios along the Morton (Z-order) curve of their initial states x0 [n, batch]:
+    neighbouring initial states -- similar active sets, similar iteration counts -- land in the same warp
+    (``mpc_state_order_keys`` + a device sort).  int32 [batch]."""
+    n, batch = x0.shape
+    lo, hi = torch.aminmax(x0, dim=1)
+    lohi = torch.cat([lo, hi]).contiguous()
+    keys = torch.empty(batch, dtype=torch.int32, device=x0.device)
+    with torch.cuda.device(x0.device):
+        _lib.check(_lib.lib().mpc_state_order_keys(_lib.ptr(x0), _lib.ptr(lohi), _lib.ptr(keys), batch, n,
+                                                   _lib.dtype_enum(x0), _lib.stream(x0.device)))
+    return torch.argsort(keys).to(torch.int32)
+
+
 def solve(A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi, c=None, warm_U=None, max_iter=60, eps=1e-9,
-          workspace=None, Cg=None, hg=None):
+          workspace=None, Cg=None, hg=None, order="auto"):
     """Solve ``batch`` QPs.  x0 [n, batch] (CUDA; float64 = the reference's arithmetic, or float32: float32 arrays
     and solver workspace, float64 arithmetic inside the kernel -- the north star's 1e-4 tolerance class).
 
@@ -101,6 +122,10 @@ def solve(A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi, c=None, warm_U=None, ma
     LTV: A [N, n*n, batch], B [N, n*m, batch], c [N, n, batch] per scenario and stage.
     Bounds are per coordinate, shared by all stages and scenarios; +-inf = unbounded.
     Optional general stage rows  Cg_k x_{k+1} >= hg_k:  Cg [N, nc*n, batch] (row-major rows), hg [N, nc, batch].
+    ``order``: which workspace lane solves which scenario.  "auto" (default): shared-model problems of at least
+    ORDER_MIN_BATCH scenarios on the thread-per-scenario kernels are solved in the order of :func:`state_order`
+    (difficulty-sorted warps; results are bitwise independent of the order and land at each scenario's own index);
+    None: lane b solves scenario b; or an int32 permutation of range(batch).
     """
     _lib.require_cuda(A, B, Q, R, Pf, x0)
     dt = x0.dtype
@@ -152,6 +177,22 @@ def solve(A, B, Q, R, Pf, N, x0, u_lo, u_hi, x_lo, x_hi, c=None, warm_U=None, ma
     if w.shape != (batch, n, m, N) or getattr(w, "nc", 0) != nc or w.dtype != dt or w.U.device != dev:
         raise ValueError(f"workspace was built for {w.shape} (nc={getattr(w, 'nc', 0)}, {w.dtype}, {w.U.device}), "
                          f"need {(batch, n, m, N)} (nc={nc}, {dt}, {dev})")
+    if isinstance(order, str):
+        if order != "auto":
+            raise ValueError('order must be "auto", None or an int32 permutation')
+        order = state_order(x0) if (not ltv and not nc and n <= 4 and batch >= ORDER_MIN_BATCH) else None
+    if order is not None:
+        if nc or order.dtype != torch.int32 or tuple(order.shape) != (batch,) or order.device != dev:
+            raise ValueError("order must be an int32 permutation [batch] on the device of x0 (not available with rows)")
+        order = order.contiguous()
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().mpc_boxqp_solve_ordered(
+                _lib.ptr(A), _lib.ptr(B), _lib.ptr(c), 1 if ltv else 0, _lib.ptr(Q), _lib.ptr(R), _lib.ptr(Pf),
+                _lib.ptr(ulo), _lib.ptr(uhi), _lib.ptr(xlo), _lib.ptr(xhi), _lib.ptr(x0), _lib.ptr(warm_U),
+                _lib.ptr(w.U), _lib.ptr(w.X), _lib.ptr(w.cost), _lib.ptr(w.status), _lib.ptr(w.iters),
+                _lib.ptr(w.sat_u), _lib.ptr(w.sat_x), _lib.ptr(order), _lib.ptr(w.ws), w.nbytes, batch, n, m, N,
+                int(max_iter), float(eps), en, _lib.stream(dev)))
+        return BoxQpResult(w.U, w.X, w.cost, w.status, w.iters, w.sat_u, w.sat_x)
     if nc:
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().mpc_boxqp_solve_rows(

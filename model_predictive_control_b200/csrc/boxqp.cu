@@ -26,8 +26,31 @@ __global__ void __launch_bounds__(kQpThreads, MINB) boxqp_ipm_kernel(BoxQpArgs<T
   __syncthreads();
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= a.batch) return;
-  BoxQpIpm<double, TIO, NX, NU, NC, 0, ST> ipm(a, sh, b, b, a.batch);
+  // lane b of the workspace solves scenario order[b] (or b): with scenarios ordered along a space-filling curve of
+  // their initial states, the lanes of a warp see similar active sets and finish after similar iteration counts
+  const int64_t scn = a.order ? (int64_t)a.order[b] : b;
+  BoxQpIpm<double, TIO, NX, NU, NC, 0, ST> ipm(a, sh, scn, b, a.batch);
   ipm.solve();
+}
+
+// Morton (Z-order) key of the initial state: 8 bits per coordinate, coordinates scaled by the batch's own range
+// (lohi = [min_0..min_{n-1}, max_0..max_{n-1}] on the device).  Sorting the scenarios by this key puts neighbouring
+// initial states -- similar active sets, similar interior-point iteration counts -- into the same warp.
+template <typename TIO>
+__global__ void __launch_bounds__(256) state_order_key_kernel(const TIO* x0, const TIO* lohi, int n, int64_t batch,
+                                                              int32_t* keys) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  unsigned key = 0;
+  const int bits = n <= 4 ? 8 : 2;
+  for (int j = 0; j < n && j < 16; ++j) {
+    const double lo = (double)lohi[j], hi = (double)lohi[n + j];
+    const double t = hi > lo ? ((double)x0[(int64_t)j * batch + b] - lo) / (hi - lo) : 0.0;
+    int q = (int)(t * (double)((1 << bits) - 1) + 0.5);
+    q = q < 0 ? 0 : (q > (1 << bits) - 1 ? (1 << bits) - 1 : q);
+    for (int k = 0; k < bits; ++k) key |= (unsigned)((q >> k) & 1) << (k * n + j);
+  }
+  keys[b] = (int32_t)(key & 0x7fffffffu);
 }
 
 // Persistent variant with LANE REFILL.  Interior-point iteration counts differ between scenarios (cfg 3: mean 10.8,
@@ -113,9 +136,20 @@ static int launch_refill(BoxQpArgs<TIO> a, int refill_min, cudaStream_t st) {
   return check_launch("boxqp_ipm_refill_kernel");
 }
 
+// threads per CTA of the thread-per-scenario kernels (env MPC_QP_THREADS: 32, 64 or 128).  A CTA holds its registers
+// until its slowest warp has converged; smaller CTAs return them earlier (same resident warps per SM).
+static int qp_threads(int dflt) {
+  if (const char* env = getenv("MPC_QP_THREADS")) {
+    const int t = atoi(env);
+    if (t == 32 || t == 64 || t == 128) return t;
+  }
+  return dflt;
+}
+
 template <typename TIO, class ST, int NX, int NU, int NC>
 static int launch_boxqp_st(const BoxQpArgs<TIO>& a_in, cudaStream_t st) {
-  const unsigned grid = (unsigned)((a_in.batch + kQpThreads - 1) / kQpThreads);
+  const int kQpThreadsRt = qp_threads(kQpThreads);
+  const unsigned grid = (unsigned)((a_in.batch + kQpThreadsRt - 1) / kQpThreadsRt);
   BoxQpArgs<TIO> a = a_in;
   a.ws_lanes = a.batch;
   // lane refill (persistent kernel): lanes of a warp waiting before they restart together; 0 (default) = one thread
@@ -126,7 +160,7 @@ static int launch_boxqp_st(const BoxQpArgs<TIO>& a_in, cudaStream_t st) {
   if (const char* env = getenv("MPC_QP_REFILL")) refill = atoi(env);
   if constexpr (NC > 0) {
     a.ws = static_cast<char*>(a.ws) + kWsHeader;
-    boxqp_ipm_kernel<TIO, ST, NX, NU, NC, 2><<<grid, kQpThreads, 0, st>>>(a);
+    boxqp_ipm_kernel<TIO, ST, NX, NU, NC, 2><<<grid, kQpThreadsRt, 0, st>>>(a);
     return check_launch("boxqp_ipm_rows_kernel");
   } else if constexpr (NX + NU <= 3) {
     // (2,1): residency against registers, measured on B200 (tools/prof/exp_q3.sh); default 4 CTAs/SM
@@ -138,12 +172,12 @@ static int launch_boxqp_st(const BoxQpArgs<TIO>& a_in, cudaStream_t st) {
       return launch_refill<TIO, ST, NX, NU, 3>(a, refill, st);
     }
     a.ws = static_cast<char*>(a.ws) + kWsHeader;
-    if (minb >= 4) boxqp_ipm_kernel<TIO, ST, NX, NU, 0, 4><<<grid, kQpThreads, 0, st>>>(a);
-    else boxqp_ipm_kernel<TIO, ST, NX, NU, 0, 3><<<grid, kQpThreads, 0, st>>>(a);
+    if (minb >= 4) boxqp_ipm_kernel<TIO, ST, NX, NU, 0, 4><<<grid, kQpThreadsRt, 0, st>>>(a);
+    else boxqp_ipm_kernel<TIO, ST, NX, NU, 0, 3><<<grid, kQpThreadsRt, 0, st>>>(a);
   } else {
     if (refill > 0 && a.batch > 4096) return launch_refill<TIO, ST, NX, NU, 2>(a, refill, st);
     a.ws = static_cast<char*>(a.ws) + kWsHeader;
-    boxqp_ipm_kernel<TIO, ST, NX, NU, 0, 2><<<grid, kQpThreads, 0, st>>>(a);
+    boxqp_ipm_kernel<TIO, ST, NX, NU, 0, 2><<<grid, kQpThreadsRt, 0, st>>>(a);
   }
   return check_launch("boxqp_ipm_kernel");
 }
@@ -192,7 +226,7 @@ static int boxqp_solve_impl(const void* A, const void* B, const void* c, int ltv
                                void* U, void* X, void* cost, int32_t* status, int32_t* iters,
                                int8_t* sat_u, int8_t* sat_x, const void* Cg, const void* hg, int nc, int8_t* sat_c,
                                void* ws, int64_t ws_bytes, int64_t batch, int n, int m, int N, int max_iter,
-                               double eps, int dtype, mpc_stream_t stream) {
+                               double eps, int dtype, mpc_stream_t stream, const int32_t* order = nullptr) {
   MPC_REQUIRE(dtype == MPC_F64 || dtype == MPC_F32, MPC_ERR_DTYPE, "mpc_boxqp_solve: unknown dtype %d", dtype);
   MPC_REQUIRE(n >= 1 && n <= MPC_MAX_NX && m >= 1 && m <= MPC_MAX_NU, MPC_ERR_SHAPE, "mpc_boxqp_solve: bad (n=%d, m=%d)", n, m);
   MPC_REQUIRE(N >= 1 && batch >= 0 && max_iter >= 1, MPC_ERR_SHAPE, "mpc_boxqp_solve: bad N / batch / max_iter");
@@ -217,6 +251,7 @@ static int boxqp_solve_impl(const void* A, const void* B, const void* c, int ltv
     BoxQpArgs<float> a = make_args<float>(A, B, c, ltv, Q, R, Pf, u_lo, u_hi, x_lo, x_hi, x0, warm_U, U, X, cost, status,
                                           iters, sat_u, sat_x, Cg, hg, sat_c, ws, batch, N, max_iter, eps);
     a.pf_dist = pf_dist;
+    a.order = order;
     if (nc > 0) {
       if (n == 4 && m == 2 && nc == 9) return launch_boxqp_st<float, StoreF32, 4, 2, 9>(a, st);
       return fail(MPC_ERR_UNSUPPORTED, "mpc_boxqp_solve_rows: no float32 kernel instantiated for n=%d m=%d nc=%d", n, m, nc);
@@ -229,6 +264,9 @@ static int boxqp_solve_impl(const void* A, const void* B, const void* c, int ltv
   BoxQpArgs<double> a = make_args<double>(A, B, c, ltv, Q, R, Pf, u_lo, u_hi, x_lo, x_hi, x0, warm_U, U, X, cost, status,
                                           iters, sat_u, sat_x, Cg, hg, sat_c, ws, batch, N, max_iter, eps);
   a.pf_dist = pf_dist;
+  a.order = order;
+  MPC_REQUIRE(!order || !coop_supported(n, m, ltv) || n <= 4, MPC_ERR_UNSUPPORTED,
+              "mpc_boxqp_solve_ordered: the warp-per-scenario kernel takes no order (its lanes share one scenario)");
   if (nc > 0) {
     if (n == 4 && m == 2 && nc == 9) return launch_boxqp<4, 2, 9>(a, st);
     if (n == 4 && m == 2 && nc == 3) return launch_boxqp<4, 2, 3>(a, st);
@@ -248,6 +286,31 @@ extern "C" int mpc_boxqp_solve(const void* A, const void* B, const void* c, int 
                                int n, int m, int N, int max_iter, double eps, int dtype, mpc_stream_t stream) {
   return boxqp_solve_impl(A, B, c, ltv, Q, R, Pf, u_lo, u_hi, x_lo, x_hi, x0, warm_U, U, X, cost, status, iters, sat_u,
                           sat_x, nullptr, nullptr, 0, nullptr, ws, ws_bytes, batch, n, m, N, max_iter, eps, dtype, stream);
+}
+
+extern "C" int mpc_state_order_keys(const void* x0, const void* lohi, int32_t* keys, int64_t batch, int n, int dtype,
+                                    mpc_stream_t stream) {
+  MPC_REQUIRE(dtype == MPC_F64 || dtype == MPC_F32, MPC_ERR_DTYPE, "mpc_state_order_keys: unknown dtype %d", dtype);
+  if (batch == 0) return MPC_OK;
+  MPC_REQUIRE(x0 && lohi && keys, MPC_ERR_NULL, "mpc_state_order_keys: null pointer");
+  MPC_REQUIRE(n >= 1 && n <= 16 && batch >= 0, MPC_ERR_SHAPE, "mpc_state_order_keys: bad (n=%d)", n);
+  const unsigned grid = (unsigned)((batch + 255) / 256);
+  if (dtype == MPC_F32)
+    state_order_key_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x0, (const float*)lohi, n, batch, keys);
+  else
+    state_order_key_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)x0, (const double*)lohi, n, batch, keys);
+  return check_launch("state_order_key_kernel");
+}
+
+extern "C" int mpc_boxqp_solve_ordered(const void* A, const void* B, const void* c, int ltv, const void* Q, const void* R,
+                                       const void* Pf, const void* u_lo, const void* u_hi, const void* x_lo,
+                                       const void* x_hi, const void* x0, const void* warm_U, void* U, void* X, void* cost,
+                                       int32_t* status, int32_t* iters, int8_t* sat_u, int8_t* sat_x, const int32_t* order,
+                                       void* ws, int64_t ws_bytes, int64_t batch, int n, int m, int N, int max_iter,
+                                       double eps, int dtype, mpc_stream_t stream) {
+  return boxqp_solve_impl(A, B, c, ltv, Q, R, Pf, u_lo, u_hi, x_lo, x_hi, x0, warm_U, U, X, cost, status, iters, sat_u,
+                          sat_x, nullptr, nullptr, 0, nullptr, ws, ws_bytes, batch, n, m, N, max_iter, eps, dtype, stream,
+                          order);
 }
 
 extern "C" int mpc_boxqp_solve_rows(const void* A, const void* B, const void* c, int ltv, const void* Q, const void* R,

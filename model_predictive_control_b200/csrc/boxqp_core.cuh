@@ -73,6 +73,7 @@ struct BoxQpArgs {
   int N;
   int max_iter;
   double eps;
+  const int32_t* order = nullptr;  // optional [batch]: lane b solves scenario order[b] (difficulty-sorted batches)
   int pf_dist = 0;       // stages of L2 prefetch ahead of each sweep's loads (device only; 0 = off)
   int64_t ws_lanes = 0;  // lanes of the workspace (0 = one per scenario: lane b = scenario b)
 };

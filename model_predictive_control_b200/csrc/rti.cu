@@ -264,16 +264,21 @@ static int rti_loop_impl(const BicycleModel<double>& model, double friction_mode
   a.qp.pf_dist = 0;
   a.qp.ws_lanes = batch;
   if (const char* env = getenv("MPC_QP_PREFETCH")) a.qp.pf_dist = atoi(env);
-  const unsigned grid = (unsigned)((batch + kRtiThreads - 1) / kRtiThreads);
+  int threads = kRtiThreads;   // env MPC_RTI_THREADS: 32 / 64 / 128 threads per CTA (same resident warps)
+  if (const char* env = getenv("MPC_RTI_THREADS")) {
+    const int t = atoi(env);
+    if (t == 32 || t == 64 || t == 128) threads = t;
+  }
+  const unsigned grid = (unsigned)((batch + threads - 1) / threads);
   // MINB = resident CTAs per SM the register allocation must allow: 2 (255 registers).  Measured at cfg 4 in round 1
   // (tools/prof/exp_rti_minb.sh): 2 CTAs/SM 2.74 s per 13.1 M QPs, 4 CTAs/SM (128 registers, spills) 3.15 s, 3: 3.96 s.
   if (nc > 0) {
     if (model.rk4) return fail(MPC_ERR_UNSUPPORTED, "mpc_rti_closed_loop: obstacle rows need the forward-Euler prediction model");
-    rti_closed_loop_kernel<TIO, true, 9, ST, 2><<<grid, kRtiThreads, 0, st>>>(a);
+    rti_closed_loop_kernel<TIO, true, 9, ST, 2><<<grid, threads, 0, st>>>(a);
   } else if (model.rk4) {
-    rti_closed_loop_kernel<TIO, false, 0, ST, 2><<<grid, kRtiThreads, 0, st>>>(a);
+    rti_closed_loop_kernel<TIO, false, 0, ST, 2><<<grid, threads, 0, st>>>(a);
   } else {  // forward-Euler prediction model: packed sparse stage matrices
-    rti_closed_loop_kernel<TIO, true, 0, ST, 2><<<grid, kRtiThreads, 0, st>>>(a);
+    rti_closed_loop_kernel<TIO, true, 0, ST, 2><<<grid, threads, 0, st>>>(a);
   }
   return check_launch("rti_closed_loop_kernel");
 }

@@ -313,12 +313,13 @@ class MPCController:
 
     # -- fused closed loop: `steps` x (sqp_iters x (prepare, QP), plant) in one kernel
     def closed_loop(self, x0, n_steps, plant: _Discrete = None, friction_plant=None,
-                    keep_predictions: bool = False) -> RtiClosedLoopResult:
+                    keep_predictions: bool = False, order="auto") -> RtiClosedLoopResult:
         """Closed loop of this controller against a bicycle plant in ONE kernel launch.  ``plant``: dynamics from
         forward_euler / runge_kutta4 / exact_integration over a :class:`KinematicBicycle` (default: RK4 x 4 sub-steps of
         the controller's own parameters); its axle distances, acceleration gain and friction are the PLANT's, the
         controller predicts with its own ``params`` (the reference's mismatch study, session4_sol.py:461-465).
-        ``friction_plant`` overrides the plant friction per scenario."""
+        ``friction_plant`` overrides the plant friction per scenario.  ``order``: "auto" (batches of at least
+        ``boxqp.ORDER_MIN_BATCH`` scenarios run in Morton order of their initial states), None, or an int32 permutation."""
         dt = self.dtype
         xd = io.to_dev(x0, dt)
         if xd.dim() == 1:
@@ -337,6 +338,17 @@ class MPCController:
         else:
             fr = io.to_dev(friction_plant, dt).reshape(-1).expand(batch).contiguous() if not io.is_tensor(friction_plant) \
                 else friction_plant.to(device=dev, dtype=dt).reshape(-1).expand(batch).contiguous()
+        # scenarios ordered along the Morton curve of their initial states: neighbours stay neighbours along the closed
+        # loop, so the lanes of a warp need similar iteration counts at every control step (results do not depend on
+        # the order; they are returned in the caller's order)
+        inv = None
+        if order == "auto":
+            order = boxqp.state_order(x0T) if batch >= boxqp.ORDER_MIN_BATCH else None
+        if order is not None:
+            ol = order.long()
+            x0T, fr = x0T[:, ol].contiguous(), fr[ol].contiguous()
+            inv = torch.empty_like(ol)
+            inv[ol] = torch.arange(batch, device=dev)
         plan = torch.zeros((N, 2, batch), dtype=dt, device=dev)
         Xp = torch.empty((N + 1, 4, batch), dtype=dt, device=dev)
         Xc = torch.empty((n_steps + 1, 4, batch), dtype=dt, device=dev)
@@ -361,6 +373,10 @@ class MPCController:
                 _lib.ptr(plan), _lib.ptr(Xp), _lib.ptr(Xc), _lib.ptr(Uc), _lib.ptr(cost), _lib.ptr(viol), _lib.ptr(clear),
                 *[_lib.ptr(t) for t in ints], _lib.ptr(Xb), _lib.ptr(Ub), _lib.ptr(ws), nbytes, batch, N, int(self.max_iter),
                 float(self.eps), en, _lib.stream(dev)))
+        if inv is not None:
+            back = lambda t: None if t is None else t.index_select(t.dim() - 1, inv)
+            plan, Xc, Uc, cost, viol, clear, Xb, Ub = (back(t) for t in (plan, Xc, Uc, cost, viol, clear, Xb, Ub))
+            ints = [back(t) for t in ints]
         self._plan = plan
         return RtiClosedLoopResult(Xc, Uc, cost, viol, ints[0], ints[1], ints[2], ints[3], Xb, Ub, clear)
 

@@ -360,3 +360,36 @@ def test_cfg5_full_size_against_exact_oracle(mods):
             assert e["status"] == bq.INFEASIBLE, (j, e["status"])     # HiGHS: kInfeasible
             n_i += 1
     assert n_s >= 64 and n_i >= 64
+
+
+def test_state_ordered_batches_are_bitwise_identical(mods):
+    """Difficulty-sorted batches (mpc_state_order_keys + mpc_boxqp_solve_ordered): lane b solves scenario order[b];
+    every scenario's arithmetic is independent of its lane, so all outputs are bitwise those of the unordered launch."""
+    torch, boxqp, problem = mods["torch"], mods["boxqp"], mods["problem"]
+    prob = problem.Problem(N=30)
+    batch = 20000
+    g = torch.Generator(device="cuda"); g.manual_seed(9)
+    x0T = torch.stack([torch.rand(batch, generator=g, device="cuda", dtype=torch.float64) * 100 - 100,
+                       torch.rand(batch, generator=g, device="cuda", dtype=torch.float64) * 25 - 10], 0).contiguous()
+    dev = lambda M: torch.tensor(np.asarray(M, dtype=np.float64), device="cuda")
+    A, B, Q, R = dev(prob.A), dev(prob.B), dev(prob.Q), dev(prob.R)
+    bounds = ([prob.u_min], [prob.u_max], [prob.p_min, prob.v_min], [prob.p_max, prob.v_max])
+    order = boxqp.state_order(x0T)
+    assert order.dtype == torch.int32 and torch.equal(torch.sort(order.long()).values, torch.arange(batch, device="cuda"))
+    # neighbours in the order are neighbours in state space: mean jump far below that of a random order
+    xs = x0T[:, order.long()]
+    jump = (xs[:, 1:] - xs[:, :-1]).abs().mean(dim=1)
+    rand = (x0T[:, 1:] - x0T[:, :-1]).abs().mean(dim=1)
+    assert bool((jump < 0.2 * rand).all())
+    plain = boxqp.solve(A, B, Q, R, Q, 30, x0T, *bounds, order=None)
+    keep = [t.clone() for t in (plain.U, plain.X, plain.cost, plain.status, plain.iters, plain.sat_u, plain.sat_x)]
+    for how in ("auto", order, torch.randperm(batch, device="cuda", generator=g).to(torch.int32)):
+        res = boxqp.solve(A, B, Q, R, Q, 30, x0T, *bounds, order=how)
+        for a_, b_ in zip(keep, (res.U, res.X, res.cost, res.status, res.iters, res.sat_u, res.sat_x)):
+            assert torch.equal(a_, b_)
+    # warps of the ordered launch are more homogeneous than those of the caller's order
+    it = keep[4].double()
+    wmax = lambda v: v[: batch // 32 * 32].reshape(-1, 32).max(dim=1).values.mean()
+    assert float(wmax(it[order.long()])) < 0.9 * float(wmax(it))
+    with pytest.raises(ValueError):
+        boxqp.solve(A, B, Q, R, Q, 30, x0T, *bounds, order=order.long())
