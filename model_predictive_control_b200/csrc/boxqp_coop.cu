@@ -162,30 +162,9 @@ struct CoopIpm {
     hu = lane < D && hi < kBigBound;
   }
 
-  // L2 prefetch of the workspace rows stage k's visit will load (the slot is streamed from HBM once per pass: 72 KB per
-  // warp x ~4 700 resident warps is far beyond L2); each section's stage row is one 128-byte line, so seven lanes (+ the
-  // gain rows) cover a visit.  DRAM is 13 % busy in this kernel (ncu): the prefetches cost nothing that is scarce.
-  __device__ __forceinline__ void prefetch_stage(int k, bool gains) const {
-    if (k < 0 || k >= a.N) return;
-    const double* p = nullptr;
-    const int64_t o = (int64_t)k * D;
-    switch (lane) {
-      case 0: p = z + o; break;
-      case 1: p = sl + o; break;
-      case 2: p = su + o; break;
-      case 3: p = ll + o; break;
-      case 4: p = lu + o; break;
-      case 5: p = dza + o; break;
-      case 6: p = dzw + o; break;
-      case 7: p = dw + (int64_t)k * NU; break;
-      case 8: p = gains ? Sw + (int64_t)k * NU * NU : nullptr; break;
-      default:
-        if (gains && lane < 9 + (NU * NX + 15) / 16) p = Kw + (int64_t)k * NU * NX + (lane - 9) * 16;
-        break;
-    }
-    if (p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-  }
-
+  // (An L2 prefetch of the next stage's workspace rows -- one lane per section, `prefetch.global.L2` -- was measured
+  // here in round 2: 4.23 s instead of 3.53 s per 2^20 cfg-5 solves.  The long-scoreboard stalls of this kernel are not
+  // DRAM latency that a prefetch could hide cheaply; not kept.)
   // x+ = A x + B u (lanes < NX), from / to the warp's vectors
   __device__ void step_vec(const double* x, const double* u, double* xn) {
     if (lane < NX) {
@@ -271,7 +250,6 @@ struct CoopIpm {
     if (lane < NX) w[L::wPacc + lane] = 0.0;
     __syncwarp();
     for (int k = a.N - 1; k >= 0; --k) {
-      prefetch_stage(k - 1, !FACTOR);
       const int64_t o = (int64_t)k * D + lane;
       double zi = 0.0, s_l = 1.0, s_u = 1.0, l_l = 0.0, l_u = 0.0, da = 0.0;
       if (lane < D) {
@@ -446,7 +424,6 @@ struct CoopIpm {
     if (lane < NX) w[L::wX + lane] = 0.0;  // dx_0 = 0
     __syncwarp();
     for (int k = 0; k < a.N; ++k) {
-      prefetch_stage(k + 1, true);
       const int64_t o = (int64_t)k * D + lane;
       double zi = 0.0, s_l = 1.0, s_u = 1.0, l_l = 0.0, l_u = 0.0, da = 0.0;
       if (lane < D) {
