@@ -19,8 +19,9 @@
 // oracle/boxqp.py (admm_riccati): 600-2000+ iterations for 1e-6 parity on the session-2 data versus
 // ~11 here, so the interior-point iteration is the one that ships.
 //
-// One thread per scenario.  All per-scenario state lives in a caller-provided workspace laid out
-// [stage][element][lane] (lane-contiguous), so every access of a warp is one coalesced row.  The kernel is bound by
+// One thread per scenario.  All per-scenario state lives in a caller-provided workspace laid out in tiles of 32 lanes,
+// [tile][stage][section row][lane] (lane-contiguous), so every access of a warp is one coalesced row at a compile-time
+// offset from the thread's stage pointer.  The kernel is bound by
 // the bytes of that workspace it streams per iteration and by the instructions of its per-bound algebra, so one
 // interior-point iteration is organised in FOUR sweeps that touch as little of it as possible (round 1 had five,
 // each reading the whole iterate):
@@ -94,24 +95,17 @@ using StoreF32 = BoxQpStore<float, float, float, float, float, float>;        //
 
 inline int64_t ws_round16(int64_t bytes) { return (bytes + 15) / 16 * 16; }
 
-// workspace bytes for `lanes` resident scenarios
+// workspace bytes for `lanes` resident scenarios: tiles of 32 lanes, each [N stages][section rows][32 lanes]
+// (BoxQpIpm: kStage bytes per stage and tile)
 template <class ST>
 inline int64_t boxqp_ws_bytes(int n, int m, int N, int nc, int64_t lanes) {
-  const int64_t d = n + m, per = (int64_t)N * lanes;
-  int64_t t = 0;
-  t += ws_round16(per * d * (int64_t)sizeof(typename ST::Z));
-  t += 4 * ws_round16(per * d * (int64_t)sizeof(typename ST::SL));
-  t += ws_round16(per * d * (int64_t)sizeof(typename ST::DA));
-  t += ws_round16(per * d * (int64_t)sizeof(typename ST::DZ));
-  t += 2 * ws_round16(per * d * (int64_t)sizeof(typename ST::EG));
-  t += ws_round16(per * m * n * (int64_t)sizeof(typename ST::GN));
-  t += ws_round16(per * m * m * (int64_t)sizeof(typename ST::GN));
-  t += ws_round16(per * m * (int64_t)sizeof(typename ST::GN));
-  if (nc > 0) {
-    t += 2 * ws_round16(per * nc * (int64_t)sizeof(typename ST::SL));
-    t += ws_round16(per * nc * (int64_t)sizeof(typename ST::Z));
-  }
-  return t;
+  const int64_t d = n + m;
+  int64_t per_lane = d * (int64_t)(sizeof(typename ST::Z) + 4 * sizeof(typename ST::SL) + sizeof(typename ST::DA) +
+                                   sizeof(typename ST::DZ) + 2 * sizeof(typename ST::EG));
+  per_lane += (int64_t)(m * n + m * m + m) * (int64_t)sizeof(typename ST::GN);
+  per_lane += (int64_t)nc * (int64_t)(2 * sizeof(typename ST::SL) + sizeof(typename ST::Z));
+  const int64_t tiles = (lanes + 31) / 32;
+  return tiles * N * per_lane * 32;
 }
 
 // shared-parameter block (shared memory on the device), always in the compute type
@@ -143,7 +137,9 @@ MPC_HD T boxqp_shared_elem(const BoxQpArgs<TIO>& a, int i) {
   return T(a.x_hi[i - SH::oHi - NU]);
 }
 
-// MODEL = 0: generic dense model (shared LTI, or per-scenario LTV A [N][n*n][batch], B, c).
+// MODEL = 0: generic dense model (shared LTI, or per-scenario LTV A [N][n*n][batch], B, c), chosen by a.ltv at run time;
+// MODEL = 2 / 3: the same with the choice made at compile time (2 = shared LTI, 3 = LTV): the kernels instantiate
+//            these, so the body of the other case is not in their instruction stream.
 // MODEL = 1: forward-Euler kinematic bicycle (NX = 4, NU = 2), per-scenario LTV in PACKED form: only the 10 entries of
 //            A = I + ts J_x and B = ts J_u that are not structurally 0 or 1, plus c: a.A -> [N][14][batch]
 //            {a02, a03, a12, a13, a23, a33, b01, b11, b21, b30, c0..c3}.  The structural zeros and ones are written
@@ -172,45 +168,53 @@ struct BoxQpIpm {
   const BoxQpArgs<TIO>& a;
   const T* sh;
   int64_t b, bs;    // scenario and batch stride of the caller's arrays
-  int64_t wb, wbs;  // workspace lane and lane stride
   T mu_scale;       // max(1, max|Q|, max|R|): scale of the complementarity tolerance
   T mu0;            // start value of the barrier parameter, per scenario: max(mu_scale, |H z0|_inf)
-  // workspace sections, each [N][per][lanes]
-  TZ* z;
-  TSL *sl, *su, *ll, *lu;
-  TDA* dza;
-  TDZ* dzw;
-  TEG *ew, *gw;
-  TGN *Kw, *Sw, *dw;
-  TSL *sc, *lc;  // general rows: slack, multiplier
-  TZ* rc;        // general rows: residual C x - h - s (carried, see init)
 
-  template <typename S>
-  MPC_HD static S* take(char*& p, int64_t elems) {
-    S* r = reinterpret_cast<S*>(p);
-    p += (elems * (int64_t)sizeof(S) + 15) / 16 * 16;
-    return r;
+  // ---- workspace: TILES of kTile = 32 lanes (one warp).  A tile holds [stage][section row][32 lanes]; one stage of a
+  // tile is kStage bytes with every section row at a COMPILE-TIME byte offset, so each access of a stage visit is
+  // [per-thread base + stage * kStage + immediate]: two base pointers per thread (8- and 4-byte rows) instead of
+  // fifteen section pointers and a 64-bit multiply-add per access (a third of the executed instructions with the
+  // [stage][row][batch] layout of round 1, whose lane stride is a runtime value).  Every row of a warp is one
+  // contiguous 256- or 128-byte segment, as before.
+  static constexpr int kTile = 32;
+  template <typename S, int OFF>
+  struct Sec {
+    using type = S;
+    static constexpr int off = OFF;
+    static constexpr int rowb = kTile * (int)sizeof(S);
+  };
+  using Zs = Sec<TZ, 0>;                                 // iterate z
+  using SLs = Sec<TSL, Zs::off + D * Zs::rowb>;          // slacks, multipliers
+  using SUs = Sec<TSL, SLs::off + D * SLs::rowb>;
+  using LLs = Sec<TSL, SUs::off + D * SUs::rowb>;
+  using LUs = Sec<TSL, LLs::off + D * LLs::rowb>;
+  using DAs = Sec<TDA, LUs::off + D * LUs::rowb>;        // dz_aff
+  using DZs = Sec<TDZ, DAs::off + D * DAs::rowb>;        // dz
+  using Es = Sec<TEG, DZs::off + D * DZs::rowb>;         // corrector data e, g
+  using Gs = Sec<TEG, Es::off + D * Es::rowb>;
+  using Ks = Sec<TGN, Gs::off + D * Gs::rowb>;           // gains K, S^-1, feed-forward d
+  using Ss = Sec<TGN, Ks::off + NU * NX * Ks::rowb>;
+  using Ds = Sec<TGN, Ss::off + NU * NU * Ss::rowb>;
+  using SCs = Sec<TSL, Ds::off + NU * Ds::rowb>;         // general rows: slack, multiplier
+  using LCs = Sec<TSL, SCs::off + NC * SCs::rowb>;
+  using RCs = Sec<TZ, LCs::off + NC * LCs::rowb>;        // general rows: residual C x - h - s (carried, see init)
+  static constexpr int kStage = RCs::off + NC * RCs::rowb;
+  char *t8, *t4;    // tile base + lane * 8 / lane * 4
+
+  template <class SEC>
+  MPC_HD typename SEC::type* row(int k, int i) const {
+    char* base = sizeof(typename SEC::type) == 8 ? t8 : t4;
+    return reinterpret_cast<typename SEC::type*>(base + (int64_t)k * kStage + (SEC::off + i * SEC::rowb));
   }
 
-  MPC_HD BoxQpIpm(const BoxQpArgs<TIO>& args, const T* shared, int64_t scenario, int64_t lane, int64_t lanes)
-      : a(args), sh(shared), b(scenario), bs(args.batch), wb(lane), wbs(lanes) {
-    char* p = static_cast<char*>(a.ws);
-    const int64_t per = (int64_t)a.N * wbs;
-    z = take<TZ>(p, per * D);
-    sl = take<TSL>(p, per * D);
-    su = take<TSL>(p, per * D);
-    ll = take<TSL>(p, per * D);
-    lu = take<TSL>(p, per * D);
-    dza = take<TDA>(p, per * D);
-    dzw = take<TDZ>(p, per * D);
-    ew = take<TEG>(p, per * D);
-    gw = take<TEG>(p, per * D);
-    Kw = take<TGN>(p, per * NU * NX);
-    Sw = take<TGN>(p, per * NU * NU);
-    dw = take<TGN>(p, per * NU);
-    sc = take<TSL>(p, per * NC);
-    lc = take<TSL>(p, per * NC);
-    rc = take<TZ>(p, per * NC);
+  MPC_HD BoxQpIpm(const BoxQpArgs<TIO>& args, const T* shared, int64_t scenario, int64_t lane, int64_t /*lanes*/)
+      : a(args), sh(shared), b(scenario), bs(args.batch) {
+    static_assert(sizeof(TZ) == 8 || sizeof(TZ) == 4, "4- or 8-byte sections");
+    char* tile = static_cast<char*>(a.ws) + (lane / kTile) * ((int64_t)a.N * kStage);
+    const int l = (int)(lane % kTile);
+    t8 = tile + l * 8;
+    t4 = tile + l * 4;
     mu_scale = T(1);
     for (int i = 0; i < NX * NX; ++i) {
       const T v = sh[SH::oQ + i] < T(0) ? -sh[SH::oQ + i] : sh[SH::oQ + i];
@@ -224,7 +228,11 @@ struct BoxQpIpm {
   }
 
   MPC_HD int64_t ix(int k, int i, int per) const { return ((int64_t)k * per + i) * bs + b; }     // caller's arrays
-  MPC_HD int64_t wx(int k, int i, int per) const { return ((int64_t)k * per + i) * wbs + wb; }   // workspace
+  MPC_HD bool is_ltv() const {
+    if constexpr (MODEL == 2) return false;
+    else if constexpr (MODEL == 3) return true;
+    else return a.ltv != 0;
+  }
   MPC_HD bool hasl(int i) const { return sh[SH::oLo + i] > T(-kBigBound); }
   MPC_HD bool hasu(int i) const { return sh[SH::oHi + i] < T(kBigBound); }
   MPC_HD T lo(int i) const { return sh[SH::oLo + i]; }
@@ -240,23 +248,21 @@ struct BoxQpIpm {
   MPC_HD void load(int k, Stage& s) const {
 #pragma unroll
     for (int i = 0; i < D; ++i) {
-      const int64_t o = wx(k, i, D);
-      s.z[i] = (T)z[o];
-      s.sl[i] = (T)sl[o];
-      s.su[i] = (T)su[o];
-      s.ll[i] = (T)ll[o];
-      s.lu[i] = (T)lu[o];
+      s.z[i] = (T)*row<Zs>(k, i);
+      s.sl[i] = (T)*row<SLs>(k, i);
+      s.su[i] = (T)*row<SUs>(k, i);
+      s.ll[i] = (T)*row<LLs>(k, i);
+      s.lu[i] = (T)*row<LUs>(k, i);
     }
   }
   MPC_HD void store_stage(int k, const Stage& s) {
 #pragma unroll
     for (int i = 0; i < D; ++i) {
-      const int64_t o = wx(k, i, D);
-      z[o] = (TZ)s.z[i];
-      sl[o] = (TSL)s.sl[i];
-      su[o] = (TSL)s.su[i];
-      ll[o] = (TSL)s.ll[i];
-      lu[o] = (TSL)s.lu[i];
+      *row<Zs>(k, i) = (TZ)s.z[i];
+      *row<SLs>(k, i) = (TSL)s.sl[i];
+      *row<SUs>(k, i) = (TSL)s.su[i];
+      *row<LLs>(k, i) = (TSL)s.ll[i];
+      *row<LUs>(k, i) = (TSL)s.lu[i];
     }
   }
   // the values the next sweeps will read back (identity for float64 storage)
@@ -286,10 +292,10 @@ struct BoxQpIpm {
     (void)p;
 #endif
   }
-  template <int PER, typename S>
-  MPC_HD void pf_rows(const S* base, int k) const {
+  template <class SEC, int PER>
+  MPC_HD void pf_rows(int k) const {
 #pragma unroll
-    for (int i = 0; i < PER; ++i) pf(base + wx(k, i, PER));
+    for (int i = 0; i < PER; ++i) pf(row<SEC>(k, i));
   }
   template <int PER, typename S>
   MPC_HD void pf_rows_io(const S* base, int k) const {
@@ -297,16 +303,16 @@ struct BoxQpIpm {
     for (int i = 0; i < PER; ++i) pf(base + ix(k, i, PER));
   }
   MPC_HD void pf_iterate(int k) const {
-    pf_rows<D>(z, k);
-    pf_rows<D>(sl, k);
-    pf_rows<D>(su, k);
-    pf_rows<D>(ll, k);
-    pf_rows<D>(lu, k);
+    pf_rows<Zs, D>(k);
+    pf_rows<SLs, D>(k);
+    pf_rows<SUs, D>(k);
+    pf_rows<LLs, D>(k);
+    pf_rows<LUs, D>(k);
   }
   MPC_HD void pf_model(int k) const {
     if constexpr (MODEL == 1) {
       pf_rows_io<kBicyclePack>(a.A, k);
-    } else if (a.ltv) {
+    } else if (is_ltv()) {
       pf_rows_io<NX * NX>(a.A, k);
       pf_rows_io<NX * NU>(a.B, k);
     }
@@ -321,15 +327,15 @@ struct BoxQpIpm {
 #endif
   }
 
-  template <int PER, typename S>
-  MPC_HD void loadn(const S* base, int k, T* v) const {
+  template <class SEC, int PER>
+  MPC_HD void loadn(int k, T* v) const {
 #pragma unroll
-    for (int i = 0; i < PER; ++i) v[i] = (T)base[wx(k, i, PER)];
+    for (int i = 0; i < PER; ++i) v[i] = (T)*row<SEC>(k, i);
   }
-  template <int PER, typename S>
-  MPC_HD void storen(S* base, int k, const T* v) const {
+  template <class SEC, int PER>
+  MPC_HD void storen(int k, const T* v) const {
 #pragma unroll
-    for (int i = 0; i < PER; ++i) base[wx(k, i, PER)] = (S)v[i];
+    for (int i = 0; i < PER; ++i) *row<SEC>(k, i) = (typename SEC::type)v[i];
   }
   template <int PER>
   MPC_HD void loadn_io(const TIO* base, int k, T* v) const {
@@ -376,7 +382,7 @@ struct BoxQpIpm {
       for (int i = 0; i < NX; ++i) c[i] = v[10 + i];
       return;
     }
-    if (a.ltv) {
+    if (is_ltv()) {
       loadn_io<NX * NX>(a.A, k, A);
       loadn_io<NX * NU>(a.B, k, B);
       loadn_io<NX>(a.c, k, c);
@@ -463,11 +469,11 @@ struct BoxQpIpm {
               const T h = load_row_c(k, j, C);
               const T w = dotx(C, xn) - h;
               const T s = round_to<TSL>(w > T(1) ? w : T(1));
-              sc[wx(k, j, NC)] = (TSL)s;
-              lc[wx(k, j, NC)] = (TSL)(mu0 / s);
+              *row<SCs>(k, j) = (TSL)s;
+              *row<LCs>(k, j) = (TSL)(mu0 / s);
               // the row residual is carried, not recomputed: it decays exactly by (1 - alpha) per step, whereas
               // C x - h - s recomputed from a dot product keeps ~1e-16 of rounding noise that Sigma ~ 1e12 amplifies
-              rc[wx(k, j, NC)] = (TZ)(w - s);
+              *row<RCs>(k, j) = (TZ)(w - s);
             }
           }
         }
@@ -533,8 +539,8 @@ struct BoxQpIpm {
       for (int j = 0; j < NC; ++j) {
         T C[NX];
         (void)load_row_c(k, j, C);
-        const T s = (T)sc[wx(k, j, NC)], l = (T)lc[wx(k, j, NC)];
-        const T r = (T)rc[wx(k, j, NC)];
+        const T s = (T)*row<SCs>(k, j), l = (T)*row<LCs>(k, j);
+        const T r = (T)*row<RCs>(k, j);
         const T ds = dotx(C, dz + NU) + r;
         const T inv = rcp_(s), sgc = l * inv;
         const T cc = cc_of(dotx(C, da + NU), r, sgc, l);
@@ -547,9 +553,9 @@ struct BoxQpIpm {
         // the residual is carried: it must absorb the storage rounding of the slack, or C x - h = s + r drifts by an
         // ulp of s per iteration (2e-7 on the active rows after ~15 iterations with float32 slacks)
         const T sr = round_to<TSL>(sn);
-        sc[wx(k, j, NC)] = (TSL)sr;
-        lc[wx(k, j, NC)] = (TSL)ln;
-        rc[wx(k, j, NC)] = (TZ)((T(1) - alpha) * r + (sn - sr));
+        *row<SCs>(k, j) = (TSL)sr;
+        *row<LCs>(k, j) = (TSL)ln;
+        *row<RCs>(k, j) = (TZ)((T(1) - alpha) * r + (sn - sr));
       }
     }
   }
@@ -633,8 +639,8 @@ struct BoxQpIpm {
         pf_iterate(k - a.pf_dist);
         pf_model(k - a.pf_dist);
         if (have_step) {
-          pf_rows<D>(dza, k - a.pf_dist);
-          pf_rows<D>(dzw, k - a.pf_dist);
+          pf_rows<DAs, D>(k - a.pf_dist);
+          pf_rows<DZs, D>(k - a.pf_dist);
         }
       }
       T znew[D], sig[D], rhs[D];
@@ -647,8 +653,8 @@ struct BoxQpIpm {
         load_model(k, A, B, c);
         if (have_step) {
           T dz[D], da[D];
-          loadn<D>(dzw, k, dz);
-          loadn<D>(dza, k, da);
+          loadn<DZs, D>(k, dz);
+          loadn<DAs, D>(k, da);
           apply_step_rows(k, dz, da, tau, alpha);
           apply_step(cur, dz, da, tau, alpha);
           store_stage(k, cur);
@@ -680,24 +686,22 @@ struct BoxQpIpm {
         TSL slr[D], sur[D], llr[D], lur[D];
 #pragma unroll
         for (int i = 0; i < D; ++i) {
-          const int64_t o = wx(k, i, D);
-          zr[i] = z[o];
-          slr[i] = sl[o];
-          sur[i] = su[o];
-          llr[i] = ll[o];
-          lur[i] = lu[o];
+          zr[i] = *row<Zs>(k, i);
+          slr[i] = *row<SLs>(k, i);
+          sur[i] = *row<SUs>(k, i);
+          llr[i] = *row<LLs>(k, i);
+          lur[i] = *row<LUs>(k, i);
         }
         T dz[D], da[D];
         if (have_step) {
-          loadn<D>(dzw, k, dz);
-          loadn<D>(dza, k, da);
+          loadn<DZs, D>(k, dz);
+          loadn<DAs, D>(k, da);
         }
         load_model(k, A, B, c);
         if (have_step) apply_step_rows(k, dz, da, tau, alpha);
         // per element: (previous step applied,) Sigma and the bound part of the affine right-hand side
 #pragma unroll
         for (int i = 0; i < D; ++i) {
-          const int64_t o = wx(k, i, D);
           const T zi = (T)zr[i];
           const T zn = have_step ? round_to<TZ>(zi + alpha * dz[i]) : zi;
           T sg = T(0), r = T(0);
@@ -705,8 +709,8 @@ struct BoxQpIpm {
             T s = (T)slr[i], l = (T)llr[i];
             if (have_step) {
               step_bound(s, l, zi - lo(i) - s, dz[i], da[i], tau, alpha);
-              sl[o] = (TSL)s;
-              ll[o] = (TSL)l;
+              *row<SLs>(k, i) = (TSL)s;
+              *row<LLs>(k, i) = (TSL)l;
             }
             const T sgl = l * rcp_(s);
             sg += sgl;
@@ -716,14 +720,14 @@ struct BoxQpIpm {
             T s = (T)sur[i], l = (T)lur[i];
             if (have_step) {
               step_bound(s, l, hi(i) - zi - s, -dz[i], -da[i], tau, alpha);
-              su[o] = (TSL)s;
-              lu[o] = (TSL)l;
+              *row<SUs>(k, i) = (TSL)s;
+              *row<LUs>(k, i) = (TSL)l;
             }
             const T sgu = l * rcp_(s);
             sg += sgu;
             r = fma_<T>(sgu, hi(i) - zn - s, r);
           }
-          if (have_step) z[o] = (TZ)zn;
+          if (have_step) *row<Zs>(k, i) = (TZ)zn;
           znew[i] = zn;
           sig[i] = sg;
           rhs[i] = r;
@@ -753,9 +757,9 @@ struct BoxQpIpm {
         for (int j = 0; j < NC; ++j) {
           T C[NX];
           (void)load_row_c(k, j, C);
-          const T s = (T)sc[wx(k, j, NC)], l = (T)lc[wx(k, j, NC)];
+          const T s = (T)*row<SCs>(k, j), l = (T)*row<LCs>(k, j);
           const T sgc = l * rcp_(s);
-          const T r = (T)rc[wx(k, j, NC)];
+          const T r = (T)*row<RCs>(k, j);
           const T rhs_c = -sgc * r;
 #pragma unroll
           for (int i = 0; i < NX; ++i) rhs[NU + i] = fma_<T>(C[i], rhs_c, rhs[NU + i]);
@@ -820,12 +824,12 @@ struct BoxQpIpm {
             Pacc[i * NX + j] = acc;
             Pacc[j * NX + i] = acc;
           }
-        storen<NU * NX>(Kw, k, K);
-        storen<NU * NU>(Sw, k, Sinv);
+        storen<Ks, NU * NX>(k, K);
+        storen<Ss, NU * NU>(k, Sinv);
       }
       T dff[NU];
       ff_stage(A, B, K, Sinv, rhs, pacc, dff);
-      storen<NU>(dw, k, dff);
+      storen<Ds, NU>(k, dff);
     }
   }
 
@@ -848,14 +852,14 @@ struct BoxQpIpm {
       if (pf_on(k + a.pf_dist)) {
         pf_iterate(k + a.pf_dist);
         pf_model(k + a.pf_dist);
-        pf_rows<NU * NX>(Kw, k + a.pf_dist);
-        pf_rows<NU>(dw, k + a.pf_dist);
+        pf_rows<Ks, NU * NX>(k + a.pf_dist);
+        pf_rows<Ds, NU>(k + a.pf_dist);
       }
       Stage cur;
       load(k, cur);
       T K[NU * NX], dff[NU];
-      loadn<NU * NX>(Kw, k, K);
-      loadn<NU>(dw, k, dff);
+      loadn<Ks, NU * NX>(k, K);
+      loadn<Ds, NU>(k, dff);
       T A[NX * NX], B[NX * NU], c[NX];
       load_model(k, A, B, c);
 #pragma unroll
@@ -904,8 +908,8 @@ struct BoxQpIpm {
         for (int j = 0; j < NC; ++j) {
           T C[NX];
           (void)load_row_c(k, j, C);
-          const T s = (T)sc[wx(k, j, NC)], l = (T)lc[wx(k, j, NC)];
-          const T r = (T)rc[wx(k, j, NC)];
+          const T s = (T)*row<SCs>(k, j), l = (T)*row<LCs>(k, j);
+          const T r = (T)*row<RCs>(k, j);
           const T ds = dotx(C, dzv + NU) + r;
           const T inv = rcp_(s);
           const T t = ds * inv;
@@ -921,9 +925,9 @@ struct BoxQpIpm {
           }
         }
       }
-      storen<D>(dza, k, dzv);
-      storen<D>(ew, k, ev);
-      storen<D>(gw, k, gv);
+      storen<DAs, D>(k, dzv);
+      storen<Es, D>(k, ev);
+      storen<Gs, D>(k, gv);
       // the rollout continues with the UNROUNDED state direction (the stored copy is only used for cc)
 #pragma unroll
       for (int i = 0; i < NX; ++i) x[i] = xn[i];
@@ -938,29 +942,29 @@ struct BoxQpIpm {
     for (int i = 0; i < NX; ++i) pacc[i] = T(0);
     for (int k = a.N - 1; k >= 0; --k) {
       if (pf_on(k - a.pf_dist)) {
-        pf_rows<D>(ew, k - a.pf_dist);
-        pf_rows<D>(gw, k - a.pf_dist);
-        pf_rows<NU * NX>(Kw, k - a.pf_dist);
-        pf_rows<NU * NU>(Sw, k - a.pf_dist);
-        pf_rows<NU>(dw, k - a.pf_dist);
+        pf_rows<Es, D>(k - a.pf_dist);
+        pf_rows<Gs, D>(k - a.pf_dist);
+        pf_rows<Ks, NU * NX>(k - a.pf_dist);
+        pf_rows<Ss, NU * NU>(k - a.pf_dist);
+        pf_rows<Ds, NU>(k - a.pf_dist);
         pf_model(k - a.pf_dist);
       }
       T ev[D], gv[D], K[NU * NX], Sinv[NU * NU];
-      loadn<D>(ew, k, ev);
-      loadn<D>(gw, k, gv);
-      loadn<NU * NX>(Kw, k, K);
-      loadn<NU * NU>(Sw, k, Sinv);
+      loadn<Es, D>(k, ev);
+      loadn<Gs, D>(k, gv);
+      loadn<Ks, NU * NX>(k, K);
+      loadn<Ss, NU * NU>(k, Sinv);
       T A[NX * NX], B[NX * NU], c[NX];
       load_model(k, A, B, c);
       T rhs[D];
 #pragma unroll
       for (int i = 0; i < D; ++i) rhs[i] = fma_<T>(tau, ev[i], -gv[i]);
       T dff[NU], daff[NU];
-      loadn<NU>(dw, k, daff);
+      loadn<Ds, NU>(k, daff);
       ff_stage(A, B, K, Sinv, rhs, pacc, dff);
 #pragma unroll
       for (int j = 0; j < NU; ++j) dff[j] += daff[j];  // d_aff + d_cor: sweep D rolls the whole direction out at once
-      storen<NU>(dw, k, dff);
+      storen<Ds, NU>(k, dff);
     }
   }
 
@@ -977,16 +981,16 @@ struct BoxQpIpm {
       if (pf_on(k + a.pf_dist)) {
         pf_iterate(k + a.pf_dist);
         pf_model(k + a.pf_dist);
-        pf_rows<NU * NX>(Kw, k + a.pf_dist);
-        pf_rows<NU>(dw, k + a.pf_dist);
-        pf_rows<D>(dza, k + a.pf_dist);
+        pf_rows<Ks, NU * NX>(k + a.pf_dist);
+        pf_rows<Ds, NU>(k + a.pf_dist);
+        pf_rows<DAs, D>(k + a.pf_dist);
       }
       Stage cur;
       load(k, cur);
       T K[NU * NX], dff[NU], da[D];
-      loadn<NU * NX>(Kw, k, K);
-      loadn<NU>(dw, k, dff);
-      loadn<D>(dza, k, da);
+      loadn<Ks, NU * NX>(k, K);
+      loadn<Ds, NU>(k, dff);
+      loadn<DAs, D>(k, da);
       T A[NX * NX], B[NX * NU], c[NX];
       load_model(k, A, B, c);
 #pragma unroll
@@ -1036,8 +1040,8 @@ struct BoxQpIpm {
         for (int j = 0; j < NC; ++j) {
           T C[NX];
           (void)load_row_c(k, j, C);
-          const T s = (T)sc[wx(k, j, NC)], l = (T)lc[wx(k, j, NC)];
-          const T r = (T)rc[wx(k, j, NC)];
+          const T s = (T)*row<SCs>(k, j), l = (T)*row<LCs>(k, j);
+          const T r = (T)*row<RCs>(k, j);
           const T ds = dotx(C, dzv + NU) + r;
           const T rinv = rcp_(s * l), inv_s = rinv * l, inv_l = rinv * s;
           const T sgc = l * inv_s;
@@ -1050,7 +1054,7 @@ struct BoxQpIpm {
           acc.rp = max_(acc.rp, abs_(r));
         }
       }
-      storen<D>(dzw, k, dzv);
+      storen<DZs, D>(k, dzv);
 #pragma unroll
       for (int i = 0; i < NX; ++i) x[i] = xn[i];
     }
@@ -1072,8 +1076,8 @@ struct BoxQpIpm {
       load_model(k, A, B, c);
       if (have_step) {
         T dz[D], da[D];
-        loadn<D>(dzw, k, dz);
-        loadn<D>(dza, k, da);
+        loadn<DZs, D>(k, dz);
+        loadn<DAs, D>(k, da);
         apply_step_rows(k, dz, da, tau, alpha);
         apply_step(st, dz, da, tau, alpha);
       }
@@ -1095,7 +1099,7 @@ struct BoxQpIpm {
         if (a.sat_c) {
 #pragma unroll 1
           for (int j = 0; j < NC; ++j)
-            a.sat_c[ix(k, j, NC)] = (T)lc[wx(k, j, NC)] > (T)sc[wx(k, j, NC)] ? (int8_t)-1 : (int8_t)0;
+            a.sat_c[ix(k, j, NC)] = (T)*row<LCs>(k, j) > (T)*row<SCs>(k, j) ? (int8_t)-1 : (int8_t)0;
         }
       }
       cost += quad<T, NX>(sh + SH::oQ, x) + quad<T, NU>(sh + SH::oR, u);
