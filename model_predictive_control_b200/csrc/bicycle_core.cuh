@@ -220,7 +220,8 @@ struct ObstacleParams {
 // Linearisation at xbar of the kObsCircles^2 collision constraints: rows C x >= h with
 // C = grad g(xbar), h = r2 - g(xbar) + C xbar  (g_ij(x) = |p + a_i (cos psi, sin psi) - o_j|^2).
 template <typename T, typename TIO>
-MPC_HD void obstacle_rows(const ObstacleParams<T>& ob, const T* xbar, TIO* Cg, TIO* hg, int64_t stride) {
+MPC_HD void obstacle_rows(const ObstacleParams<T>& ob, const T* xbar, const StageRows<TIO>& Cg, const StageRows<TIO>& hg,
+                          int k) {
   T sp, cp;
   sincos(xbar[2], &sp, &cp);
 #pragma unroll
@@ -233,11 +234,11 @@ MPC_HD void obstacle_rows(const ObstacleParams<T>& ob, const T* xbar, TIO* Cg, T
       const T c0 = T(2) * dx, c1 = T(2) * dy;
       const T c2 = T(2) * dx * (-ob.a[i] * sp) + T(2) * dy * (ob.a[i] * cp);
       const int row = i * kObsCircles + j;
-      Cg[(int64_t)(row * 4 + 0) * stride] = (TIO)c0;
-      Cg[(int64_t)(row * 4 + 1) * stride] = (TIO)c1;
-      Cg[(int64_t)(row * 4 + 2) * stride] = (TIO)c2;
-      Cg[(int64_t)(row * 4 + 3) * stride] = TIO(0);
-      hg[(int64_t)row * stride] = (TIO)(ob.r2 - g + c0 * xbar[0] + c1 * xbar[1] + c2 * xbar[2]);
+      Cg.at(k, row * 4 + 0) = (TIO)c0;
+      Cg.at(k, row * 4 + 1) = (TIO)c1;
+      Cg.at(k, row * 4 + 2) = (TIO)c2;
+      Cg.at(k, row * 4 + 3) = TIO(0);
+      hg.at(k, row) = (TIO)(ob.r2 - g + c0 * xbar[0] + c1 * xbar[1] + c2 * xbar[2]);
     }
   }
 }
@@ -270,9 +271,9 @@ MPC_HD T obstacle_clearance(const ObstacleParams<T>& ob, const T* x) {
 // Optional: obstacle rows Cg [N][9*4][batch], hg [N][9][batch] linearised at xbar_{k+1} (ob != nullptr).
 // T = arithmetic type, TIO = element type of the arrays.
 template <typename T, typename TIO>
-MPC_HD void rti_prepare_body(const BicycleModel<T>& p, T friction, const TIO* y, const TIO* Uprev, int first, TIO* warm,
-                             TIO* A, TIO* B, TIO* c, int N, int64_t bs, int64_t b, const ObstacleParams<T>* ob = nullptr,
-                             TIO* Cg = nullptr, TIO* hg = nullptr, TIO* pack = nullptr) {
+MPC_HD void rti_prepare_views(const BicycleModel<T>& p, T friction, const TIO* y, const TIO* Uprev, int first, TIO* warm,
+                              TIO* A, TIO* B, TIO* c, int N, int64_t bs, int64_t b, const ObstacleParams<T>* ob,
+                              const StageRows<TIO>& Cg, const StageRows<TIO>& hg, const StageRows<TIO>& pack) {
   T x[4], xn[4], u[2], Ak[16], Bk[8];
 #pragma unroll
   for (int i = 0; i < 4; ++i) x[i] = (T)y[i * bs + b];
@@ -301,12 +302,12 @@ MPC_HD void rti_prepare_body(const BicycleModel<T>& p, T friction, const TIO* y,
       acc = fma_<T>(-Bk[i * 2 + 1], u[1], acc);
       ck[i] = acc;
     }
-    if (pack) {
+    if (pack.p) {
       // forward-Euler model only: the entries of A, B that are not structurally 0 or 1 (see BoxQpIpm, MODEL = 1)
       const T v[kBicyclePack] = {Ak[2], Ak[3], Ak[6], Ak[7], Ak[11], Ak[15], Bk[1], Bk[3], Bk[5], Bk[6],
                                  ck[0], ck[1], ck[2], ck[3]};
 #pragma unroll
-      for (int i = 0; i < kBicyclePack; ++i) pack[((int64_t)k * kBicyclePack + i) * bs + b] = (TIO)v[i];
+      for (int i = 0; i < kBicyclePack; ++i) pack.at(k, i) = (TIO)v[i];
     } else {
 #pragma unroll
       for (int i = 0; i < 16; ++i) A[((int64_t)k * 16 + i) * bs + b] = (TIO)Ak[i];
@@ -315,21 +316,29 @@ MPC_HD void rti_prepare_body(const BicycleModel<T>& p, T friction, const TIO* y,
 #pragma unroll
       for (int i = 0; i < 4; ++i) c[((int64_t)k * 4 + i) * bs + b] = (TIO)ck[i];
     }
-    if (ob) {
-      constexpr int R = kObsCircles * kObsCircles;
-      obstacle_rows<T, TIO>(*ob, xn, Cg + (int64_t)k * R * 4 * bs + b, hg + (int64_t)k * R * bs + b, bs);
-    }
+    if (ob) obstacle_rows<T, TIO>(*ob, xn, Cg, hg, k);
 #pragma unroll
     for (int i = 0; i < 4; ++i) x[i] = xn[i];
   }
 }
 
-// out-of-line copies for the fused loop (see MPC_HD_COLD)
+// the same on arrays in the caller's [N][rows][batch] layout
+template <typename T, typename TIO>
+MPC_HD void rti_prepare_body(const BicycleModel<T>& p, T friction, const TIO* y, const TIO* Uprev, int first, TIO* warm,
+                             TIO* A, TIO* B, TIO* c, int N, int64_t bs, int64_t b, const ObstacleParams<T>* ob = nullptr,
+                             TIO* Cg = nullptr, TIO* hg = nullptr, TIO* pack = nullptr) {
+  constexpr int R = kObsCircles * kObsCircles;
+  rti_prepare_views<T, TIO>(p, friction, y, Uprev, first, warm, A, B, c, N, bs, b, ob, batch_rows(Cg, R * 4, bs, b),
+                            batch_rows(hg, R, bs, b), batch_rows(pack, kBicyclePack, bs, b));
+}
+
+// out-of-line copy for the fused loop (see MPC_HD_COLD)
 template <typename T, typename TIO>
 MPC_HD_COLD void rti_prepare_cold(const BicycleModel<T>& p, T friction, const TIO* y, const TIO* Uprev, int first,
                                   TIO* warm, TIO* A, TIO* B, TIO* c, int N, int64_t bs, int64_t b,
-                                  const ObstacleParams<T>* ob, TIO* Cg, TIO* hg, TIO* pack) {
-  rti_prepare_body<T, TIO>(p, friction, y, Uprev, first, warm, A, B, c, N, bs, b, ob, Cg, hg, pack);
+                                  const ObstacleParams<T>* ob, StageRows<TIO> Cg, StageRows<TIO> hg,
+                                  StageRows<TIO> pack) {
+  rti_prepare_views<T, TIO>(p, friction, y, Uprev, first, warm, A, B, c, N, bs, b, ob, Cg, hg, pack);
 }
 template <typename T>
 MPC_HD_COLD void bicycle_plant_cold(const BicycleModel<T>& p, T friction, int substeps, T* x, const T* u) {
@@ -445,10 +454,21 @@ MPC_HD void rti_closed_loop_body(const RtiLoopArgs<T, TIO>& a, const T* sh, int6
 #pragma unroll
     for (int i = 0; i < 4; ++i) a.xcur[i * bs + b] = (TIO)x[i];
     for (int round = 0; round < a.sqp_iters; ++round) {
-      rti_prepare_cold<T, TIO>(a.model, a.friction_model, a.xcur, a.qp.U, (t == 0 || round > 0) ? 1 : 0, a.warm, a.Acur,
-                               a.Bcur, a.ccur, N, bs, b, NC > 0 ? &a.ob : nullptr, a.Cgcur, a.hgcur,
-                               PACKED ? a.Acur : nullptr);
-      BoxQpIpm<T, TIO, 4, 2, NC, PACKED ? 1 : 0, ST> ipm(a.qp, sh, b, b, bs);
+      // forward-Euler prediction model: the packed stage model and the collision rows live in the QP's workspace tile
+      // (MODEL = 4); RK4 prediction model: dense stage matrices in the side arrays (MODEL = 3)
+      using Ipm = BoxQpIpm<T, TIO, 4, 2, NC, PACKED ? 4 : 3, ST>;
+      Ipm ipm(a.qp, sh, b, b, bs);
+      if constexpr (PACKED) {
+        rti_prepare_cold<T, TIO>(a.model, a.friction_model, a.xcur, a.qp.U, (t == 0 || round > 0) ? 1 : 0, a.warm, a.Acur,
+                                 a.Bcur, a.ccur, N, bs, b, NC > 0 ? &a.ob : nullptr,
+                                 ipm.template view<typename Ipm::CGs>(), ipm.template view<typename Ipm::HGs>(),
+                                 ipm.template view<typename Ipm::MDs>());
+      } else {
+        constexpr int R = kObsCircles * kObsCircles;
+        rti_prepare_cold<T, TIO>(a.model, a.friction_model, a.xcur, a.qp.U, (t == 0 || round > 0) ? 1 : 0, a.warm, a.Acur,
+                                 a.Bcur, a.ccur, N, bs, b, NC > 0 ? &a.ob : nullptr, batch_rows(a.Cgcur, R * 4, bs, b),
+                                 batch_rows(a.hgcur, R, bs, b), StageRows<TIO>{nullptr, 0, 0});
+      }
       ipm.solve();
       const bool solved = a.qp.status[b] == MPC_SOLVED;
       if (!solved) ++nfail;

@@ -18,7 +18,9 @@ constexpr int64_t kWsHeader = 256;
 
 // MINB = resident CTAs per SM the register allocation must allow (latency hiding for the streamed
 // workspace matters more than a few spills).  NC > 0: general stage rows (polytopic constraints), same body.
-template <typename TIO, class ST, int NX, int NU, int NC, int MINB>
+// LTV = the stage model: false = shared (A, B), true = per-scenario (A_k, B_k, c_k) arrays; a compile-time choice, so
+// that the other case's loads and address arithmetic are not in the instruction stream
+template <typename TIO, class ST, int NX, int NU, int NC, int MINB, bool LTV>
 __global__ void __launch_bounds__(kQpThreads, MINB) boxqp_ipm_kernel(BoxQpArgs<TIO> a) {
   using SH = BoxQpShared<NX, NU>;
   __shared__ double sh[SH::total];
@@ -29,7 +31,7 @@ __global__ void __launch_bounds__(kQpThreads, MINB) boxqp_ipm_kernel(BoxQpArgs<T
   // lane b of the workspace solves scenario order[b] (or b): with scenarios ordered along a space-filling curve of
   // their initial states, the lanes of a warp see similar active sets and finish after similar iteration counts
   const int64_t scn = a.order ? (int64_t)a.order[b] : b;
-  BoxQpIpm<double, TIO, NX, NU, NC, 0, ST> ipm(a, sh, scn, b, a.batch);
+  BoxQpIpm<double, TIO, NX, NU, NC, LTV ? 3 : 2, ST> ipm(a, sh, scn, b, a.batch);
   ipm.solve();
 }
 
@@ -160,7 +162,8 @@ static int launch_boxqp_st(const BoxQpArgs<TIO>& a_in, cudaStream_t st) {
   if (const char* env = getenv("MPC_QP_REFILL")) refill = atoi(env);
   if constexpr (NC > 0) {
     a.ws = static_cast<char*>(a.ws) + kWsHeader;
-    boxqp_ipm_kernel<TIO, ST, NX, NU, NC, 2><<<grid, kQpThreadsRt, 0, st>>>(a);
+    if (a.ltv) boxqp_ipm_kernel<TIO, ST, NX, NU, NC, 2, true><<<grid, kQpThreadsRt, 0, st>>>(a);
+    else boxqp_ipm_kernel<TIO, ST, NX, NU, NC, 2, false><<<grid, kQpThreadsRt, 0, st>>>(a);
     return check_launch("boxqp_ipm_rows_kernel");
   } else if constexpr (NX + NU <= 3) {
     // (2,1): residency against registers, measured on B200 (tools/prof/exp_q3.sh); default 4 CTAs/SM
@@ -172,12 +175,16 @@ static int launch_boxqp_st(const BoxQpArgs<TIO>& a_in, cudaStream_t st) {
       return launch_refill<TIO, ST, NX, NU, 3>(a, refill, st);
     }
     a.ws = static_cast<char*>(a.ws) + kWsHeader;
-    if (minb >= 4) boxqp_ipm_kernel<TIO, ST, NX, NU, 0, 4><<<grid, kQpThreadsRt, 0, st>>>(a);
-    else boxqp_ipm_kernel<TIO, ST, NX, NU, 0, 3><<<grid, kQpThreadsRt, 0, st>>>(a);
+    if (a.ltv) boxqp_ipm_kernel<TIO, ST, NX, NU, 0, 4, true><<<grid, kQpThreadsRt, 0, st>>>(a);
+    else if (minb >= 6) boxqp_ipm_kernel<TIO, ST, NX, NU, 0, 6, false><<<grid, kQpThreadsRt, 0, st>>>(a);
+    else if (minb == 5) boxqp_ipm_kernel<TIO, ST, NX, NU, 0, 5, false><<<grid, kQpThreadsRt, 0, st>>>(a);
+    else if (minb == 4) boxqp_ipm_kernel<TIO, ST, NX, NU, 0, 4, false><<<grid, kQpThreadsRt, 0, st>>>(a);
+    else boxqp_ipm_kernel<TIO, ST, NX, NU, 0, 3, false><<<grid, kQpThreadsRt, 0, st>>>(a);
   } else {
     if (refill > 0 && a.batch > 4096) return launch_refill<TIO, ST, NX, NU, 2>(a, refill, st);
     a.ws = static_cast<char*>(a.ws) + kWsHeader;
-    boxqp_ipm_kernel<TIO, ST, NX, NU, 0, 2><<<grid, kQpThreadsRt, 0, st>>>(a);
+    if (a.ltv) boxqp_ipm_kernel<TIO, ST, NX, NU, 0, 2, true><<<grid, kQpThreadsRt, 0, st>>>(a);
+    else boxqp_ipm_kernel<TIO, ST, NX, NU, 0, 2, false><<<grid, kQpThreadsRt, 0, st>>>(a);
   }
   return check_launch("boxqp_ipm_kernel");
 }

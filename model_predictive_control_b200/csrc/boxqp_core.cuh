@@ -98,12 +98,13 @@ inline int64_t ws_round16(int64_t bytes) { return (bytes + 15) / 16 * 16; }
 // workspace bytes for `lanes` resident scenarios: tiles of 32 lanes, each [N stages][section rows][32 lanes]
 // (BoxQpIpm: kStage bytes per stage and tile)
 template <class ST>
-inline int64_t boxqp_ws_bytes(int n, int m, int N, int nc, int64_t lanes) {
+inline int64_t boxqp_ws_bytes(int n, int m, int N, int nc, int64_t lanes, int64_t extra_stage_bytes_per_lane = 0) {
   const int64_t d = n + m;
   int64_t per_lane = d * (int64_t)(sizeof(typename ST::Z) + 4 * sizeof(typename ST::SL) + sizeof(typename ST::DA) +
                                    sizeof(typename ST::DZ) + 2 * sizeof(typename ST::EG));
   per_lane += (int64_t)(m * n + m * m + m) * (int64_t)sizeof(typename ST::GN);
   per_lane += (int64_t)nc * (int64_t)(2 * sizeof(typename ST::SL) + sizeof(typename ST::Z));
+  per_lane += extra_stage_bytes_per_lane;  // stage model / rows kept in the tile (MODEL = 4, the fused RTI loop)
   const int64_t tiles = (lanes + 31) / 32;
   return tiles * N * per_lane * 32;
 }
@@ -144,7 +145,21 @@ MPC_HD T boxqp_shared_elem(const BoxQpArgs<TIO>& a, int i) {
 //            A = I + ts J_x and B = ts J_u that are not structurally 0 or 1, plus c: a.A -> [N][14][batch]
 //            {a02, a03, a12, a13, a23, a33, b01, b11, b21, b30, c0..c3}.  The structural zeros and ones are written
 //            as literals, so the unrolled register algebra drops the corresponding multiplications at compile time.
+// MODEL = 4: as 1, with the packed stage model (and the NC general rows) stored IN the workspace tile, written there by
+//            the fused RTI loop's preparation: the model loads of every sweep are immediate-offset accesses too.
 constexpr int kBicyclePack = 14;
+
+// a [stage][row] array of one scenario: element (k, i) at p[k * sk + i * si]
+template <typename S>
+struct StageRows {
+  S* p;
+  int64_t sk, si;
+  MPC_HD S& at(int k, int i) const { return p[(int64_t)k * sk + (int64_t)i * si]; }
+};
+template <typename S>
+MPC_HD StageRows<S> batch_rows(S* base, int rows, int64_t bs, int64_t b) {  // caller layout [N][rows][batch]
+  return StageRows<S>{base ? base + b : nullptr, (int64_t)rows * bs, bs};
+}
 
 template <typename S, typename T>
 MPC_HD T round_to(T v) {   // the value a later sweep will read back from a section stored as S
@@ -199,8 +214,19 @@ struct BoxQpIpm {
   using SCs = Sec<TSL, Ds::off + NU * Ds::rowb>;         // general rows: slack, multiplier
   using LCs = Sec<TSL, SCs::off + NC * SCs::rowb>;
   using RCs = Sec<TZ, LCs::off + NC * LCs::rowb>;        // general rows: residual C x - h - s (carried, see init)
-  static constexpr int kStage = RCs::off + NC * RCs::rowb;
+  static constexpr bool kPacked = MODEL == 1 || MODEL == 4;
+  static constexpr bool kTileModel = MODEL == 4;
+  static constexpr int kMdRows = kTileModel ? kBicyclePack : 0;
+  using MDs = Sec<TIO, RCs::off + NC * RCs::rowb>;       // MODEL = 4: packed stage model, general rows C, h
+  using CGs = Sec<TIO, MDs::off + kMdRows * MDs::rowb>;
+  using HGs = Sec<TIO, CGs::off + (kTileModel ? NC * NX : 0) * CGs::rowb>;
+  static constexpr int kStage = HGs::off + (kTileModel ? NC : 0) * HGs::rowb;
+  static constexpr int kModelBytesPerLane = kTileModel ? (kBicyclePack + NC * NX + NC) * (int)sizeof(TIO) : 0;
   char *t8, *t4;    // tile base + lane * 8 / lane * 4
+  template <class SEC>
+  MPC_HD StageRows<typename SEC::type> view() const {  // a section as a strided array (for code outside the sweeps)
+    return StageRows<typename SEC::type>{row<SEC>(0, 0), kStage / (int)sizeof(typename SEC::type), kTile};
+  }
 
   template <class SEC>
   MPC_HD typename SEC::type* row(int k, int i) const {
@@ -310,7 +336,9 @@ struct BoxQpIpm {
     pf_rows<LUs, D>(k);
   }
   MPC_HD void pf_model(int k) const {
-    if constexpr (MODEL == 1) {
+    if constexpr (kTileModel) {
+      pf_rows<MDs, kBicyclePack>(k);
+    } else if constexpr (MODEL == 1) {
       pf_rows_io<kBicyclePack>(a.A, k);
     } else if (is_ltv()) {
       pf_rows_io<NX * NX>(a.A, k);
@@ -345,9 +373,15 @@ struct BoxQpIpm {
 
   // general row j of stage k: coefficients C[NX] and right-hand side h
   MPC_HD T load_row_c(int k, int j, T* C) const {
+    if constexpr (kTileModel) {
 #pragma unroll
-    for (int i = 0; i < NX; ++i) C[i] = (T)a.Cg[ix(k, j * NX + i, NC * NX)];
-    return (T)a.hg[ix(k, j, NC)];
+      for (int i = 0; i < NX; ++i) C[i] = (T)*row<CGs>(k, j * NX + i);
+      return (T)*row<HGs>(k, j);
+    } else {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) C[i] = (T)a.Cg[ix(k, j * NX + i, NC * NX)];
+      return (T)a.hg[ix(k, j, NC)];
+    }
   }
   MPC_HD static T dotx(const T* C, const T* x) {
     T acc = T(0);
@@ -357,10 +391,11 @@ struct BoxQpIpm {
   }
 
   MPC_HD void load_model(int k, T* A, T* B, T* c) const {
-    if constexpr (MODEL == 1) {
-      static_assert(MODEL == 0 || (NX == 4 && NU == 2), "packed bicycle model is 4 x 2");
+    if constexpr (kPacked) {
+      static_assert(!kPacked || (NX == 4 && NU == 2), "packed bicycle model is 4 x 2");
       T v[kBicyclePack];
-      loadn_io<kBicyclePack>(a.A, k, v);
+      if constexpr (kTileModel) loadn<MDs, kBicyclePack>(k, v);
+      else loadn_io<kBicyclePack>(a.A, k, v);
 #pragma unroll
       for (int i = 0; i < NX * NX; ++i) A[i] = T(0);
 #pragma unroll

@@ -191,7 +191,10 @@ static int64_t rti_side_elems(int N, int nc) { return 6 + (int64_t)N * (16 + 8 +
 extern "C" int64_t mpc_rti_workspace_bytes(int64_t batch, int N, int nc, int dtype) {
   if (batch < 0 || N < 1 || nc < 0) return 0;
   const int64_t es = dtype == MPC_F32 ? 4 : 8;
-  const int64_t qp = dtype == MPC_F32 ? boxqp_ws_bytes<StoreF32>(4, 2, N, nc, batch) : boxqp_ws_bytes<StoreF64>(4, 2, N, nc, batch);
+  // the QP tile also holds the packed stage model and the collision rows of the forward-Euler prediction model
+  const int64_t extra = (kBicyclePack + nc * 5) * es;
+  const int64_t qp = dtype == MPC_F32 ? boxqp_ws_bytes<StoreF32>(4, 2, N, nc, batch, extra)
+                                      : boxqp_ws_bytes<StoreF64>(4, 2, N, nc, batch, extra);
   return qp + ws_round16(rti_side_elems(N, nc) * batch * es);
 }
 
@@ -205,7 +208,7 @@ static int rti_loop_impl(const BicycleModel<double>& model, double friction_mode
                          void* U_bundle, void* ws, int64_t batch, int N, int max_iter, double eps, cudaStream_t st) {
   char* p = static_cast<char*>(ws);
   void* qp_ws = p;
-  p += boxqp_ws_bytes<ST>(4, 2, N, nc, batch);
+  p += boxqp_ws_bytes<ST>(4, 2, N, nc, batch, (int64_t)(kBicyclePack + nc * 5) * (int64_t)sizeof(TIO));
   TIO* w = reinterpret_cast<TIO*>(p);
   TIO* xcur = w;
   w += 4 * batch;

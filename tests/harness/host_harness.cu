@@ -200,7 +200,7 @@ extern "C" int hh_plant_step(double lr, double lf, double accel, double ts, cons
 // the fused closed loop; nc = 0 (box) or 9 (obstacle rows, x_obs / length / width), store as in hh_boxqp_solve
 template <bool PACKED, int NC, class ST>
 static void rti_loop_st(RtiLoopArgs<double, double> a, int N, int64_t batch) {
-  std::vector<double> ws((size_t)(boxqp_ws_bytes<ST>(4, 2, N, NC, batch) / 8 + 2));
+  std::vector<double> ws((size_t)(boxqp_ws_bytes<ST>(4, 2, N, NC, batch, (kBicyclePack + NC * 5) * 8) / 8 + 2));
   a.qp.ws = ws.data();
   a.qp.ws_lanes = batch;
   const std::vector<double> sh = shared_block<double, 4, 2>(a.qp);
