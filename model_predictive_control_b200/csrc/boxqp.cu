@@ -35,6 +35,56 @@ __global__ void __launch_bounds__(kQpThreads, MINB) boxqp_ipm_kernel(BoxQpArgs<T
   ipm.solve();
 }
 
+// The same solve with the warp's workspace tile STREAMED THROUGH SHARED MEMORY (shared LTI model, no general rows):
+// the read set of every sweep is one contiguous byte range of a tile stage (boxqp_core.cuh, section order), which one
+// lane copies two stage visits ahead with cp.async.bulk (completion on the warp's mbarrier); the sweeps read shared
+// memory (29-cycle loads instead of L2 / HBM round trips on the critical path of every stage visit) and store to
+// global memory directly.  Dynamic shared memory: 2 buffers x kBufBytes per warp.
+template <typename TIO, class ST, int NX, int NU, int MINB>
+__global__ void __launch_bounds__(kQpThreads, MINB) boxqp_ipm_staged_kernel(BoxQpArgs<TIO> a) {
+  using SH = BoxQpShared<NX, NU>;
+  using Ipm = BoxQpIpm<double, TIO, NX, NU, 0, 2, ST, true>;
+  extern __shared__ __align__(128) char qp_stage_buffers[];
+  __shared__ double sh[SH::total];
+  __shared__ unsigned long long bars[2 * kQpThreads / 32];
+  for (int i = threadIdx.x; i < SH::total; i += blockDim.x) sh[i] = boxqp_shared_elem<double, TIO, NX, NU>(a, i);
+  const int warp = threadIdx.x / 32;
+  if (threadIdx.x % 32 == 0) {
+    for (int j = 0; j < 2; ++j)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(bars + 2 * warp + j)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned lanes = __ballot_sync(0xffffffffu, b < a.batch);
+  if (b >= a.batch) return;
+  const int64_t scn = a.order ? (int64_t)a.order[b] : b;
+  Ipm ipm(a, sh, scn, b, a.batch);
+  ipm.stage_setup(qp_stage_buffers + (size_t)warp * 2 * Ipm::kBufBytes, bars + 2 * warp, lanes);
+  ipm.solve();
+}
+
+template <typename TIO, class ST, int NX, int NU, int MINB>
+static int launch_staged(const BoxQpArgs<TIO>& a, unsigned grid, int threads, cudaStream_t st) {
+  using Ipm = BoxQpIpm<double, TIO, NX, NU, 0, 2, ST, true>;
+  auto kern = boxqp_ipm_staged_kernel<TIO, ST, NX, NU, MINB>;
+  const int smem = threads / 32 * 2 * Ipm::kBufBytes;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kQpThreads / 32 * 2 * Ipm::kBufBytes);
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    configured = true;
+  }
+  kern<<<grid, threads, smem, st>>>(a);
+  return check_launch("boxqp_ipm_staged_kernel");
+}
+
+// staged sweeps (shared LTI model, box constraints only): on unless MPC_QP_STAGED=0
+static bool staged_on() {
+  const char* env = getenv("MPC_QP_STAGED");
+  return !(env && atoi(env) == 0);
+}
+
 // Morton (Z-order) key of the initial state: 8 bits per coordinate, coordinates scaled by the batch's own range
 // (lohi = [min_0..min_{n-1}, max_0..max_{n-1}] on the device).  Sorting the scenarios by this key puts neighbouring
 // initial states -- similar active sets, similar interior-point iteration counts -- into the same warp.
@@ -72,7 +122,7 @@ __global__ void __launch_bounds__(kQpThreads, MINB) boxqp_ipm_refill_kernel(BoxQ
   __syncthreads();
   const int64_t lane = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool has_lane = lane < a.ws_lanes;
-  BoxQpIpm<double, TIO, NX, NU, 0, 0, ST, true> ipm(a, sh, 0, has_lane ? lane : 0, a.ws_lanes);
+  BoxQpIpm<double, TIO, NX, NU, 0, 0, ST> ipm(a, sh, 0, has_lane ? lane : 0, a.ws_lanes);
   auto fetch = [&]() -> int64_t {
     if (!has_lane) return -1;
     const unsigned long long t = atomicAdd(queue, 1ULL);
@@ -175,6 +225,11 @@ static int launch_boxqp_st(const BoxQpArgs<TIO>& a_in, cudaStream_t st) {
       return launch_refill<TIO, ST, NX, NU, 3>(a, refill, st);
     }
     a.ws = static_cast<char*>(a.ws) + kWsHeader;
+    if (!a.ltv && staged_on()) {
+      if (minb >= 6) return launch_staged<TIO, ST, NX, NU, 6>(a, grid, kQpThreadsRt, st);
+      if (minb == 5) return launch_staged<TIO, ST, NX, NU, 5>(a, grid, kQpThreadsRt, st);
+      return launch_staged<TIO, ST, NX, NU, 4>(a, grid, kQpThreadsRt, st);
+    }
     if (a.ltv) boxqp_ipm_kernel<TIO, ST, NX, NU, 0, 4, true><<<grid, kQpThreadsRt, 0, st>>>(a);
     else if (minb >= 6) boxqp_ipm_kernel<TIO, ST, NX, NU, 0, 6, false><<<grid, kQpThreadsRt, 0, st>>>(a);
     else if (minb == 5) boxqp_ipm_kernel<TIO, ST, NX, NU, 0, 5, false><<<grid, kQpThreadsRt, 0, st>>>(a);
@@ -183,6 +238,7 @@ static int launch_boxqp_st(const BoxQpArgs<TIO>& a_in, cudaStream_t st) {
   } else {
     if (refill > 0 && a.batch > 4096) return launch_refill<TIO, ST, NX, NU, 2>(a, refill, st);
     a.ws = static_cast<char*>(a.ws) + kWsHeader;
+    if (!a.ltv && staged_on()) return launch_staged<TIO, ST, NX, NU, 2>(a, grid, kQpThreadsRt, st);
     if (a.ltv) boxqp_ipm_kernel<TIO, ST, NX, NU, 0, 2, true><<<grid, kQpThreadsRt, 0, st>>>(a);
     else boxqp_ipm_kernel<TIO, ST, NX, NU, 0, 2, false><<<grid, kQpThreadsRt, 0, st>>>(a);
   }
