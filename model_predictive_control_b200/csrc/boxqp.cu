@@ -37,21 +37,21 @@ __global__ void __launch_bounds__(kQpThreads, MINB) boxqp_ipm_kernel(BoxQpArgs<T
 
 // The same solve with the warp's workspace tile STREAMED THROUGH SHARED MEMORY (shared LTI model, no general rows):
 // the read set of every sweep is one contiguous byte range of a tile stage (boxqp_core.cuh, section order), which one
-// lane copies two stage visits ahead with cp.async.bulk (completion on the warp's mbarrier); the sweeps read shared
+// lane copies kDepth stage visits ahead with cp.async.bulk (completion on the warp's mbarrier); the sweeps read shared
 // memory (29-cycle loads instead of L2 / HBM round trips on the critical path of every stage visit) and store to
-// global memory directly.  Dynamic shared memory: 2 buffers x kBufBytes per warp.
+// global memory directly.  Dynamic shared memory: kDepth buffers x kBufBytes per warp.
 template <typename TIO, class ST, int NX, int NU, int MINB>
 __global__ void __launch_bounds__(kQpThreads, MINB) boxqp_ipm_staged_kernel(BoxQpArgs<TIO> a) {
   using SH = BoxQpShared<NX, NU>;
   using Ipm = BoxQpIpm<double, TIO, NX, NU, 0, 2, ST, true>;
   extern __shared__ __align__(128) char qp_stage_buffers[];
   __shared__ double sh[SH::total];
-  __shared__ unsigned long long bars[2 * kQpThreads / 32];
+  __shared__ unsigned long long bars[Ipm::kDepth * kQpThreads / 32];
   for (int i = threadIdx.x; i < SH::total; i += blockDim.x) sh[i] = boxqp_shared_elem<double, TIO, NX, NU>(a, i);
   const int warp = threadIdx.x / 32;
   if (threadIdx.x % 32 == 0) {
-    for (int j = 0; j < 2; ++j)
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(bars + 2 * warp + j)));
+    for (int j = 0; j < Ipm::kDepth; ++j)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(bars + Ipm::kDepth * warp + j)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(kQpThreads, MINB) boxqp_ipm_staged_kernel(BoxQ
   if (b >= a.batch) return;
   const int64_t scn = a.order ? (int64_t)a.order[b] : b;
   Ipm ipm(a, sh, scn, b, a.batch);
-  ipm.stage_setup(qp_stage_buffers + (size_t)warp * 2 * Ipm::kBufBytes, bars + 2 * warp, lanes);
+  ipm.stage_setup(qp_stage_buffers + (size_t)warp * Ipm::kDepth * Ipm::kBufBytes, bars + Ipm::kDepth * warp, lanes);
   ipm.solve();
 }
 
@@ -68,10 +68,10 @@ template <typename TIO, class ST, int NX, int NU, int MINB>
 static int launch_staged(const BoxQpArgs<TIO>& a, unsigned grid, int threads, cudaStream_t st) {
   using Ipm = BoxQpIpm<double, TIO, NX, NU, 0, 2, ST, true>;
   auto kern = boxqp_ipm_staged_kernel<TIO, ST, NX, NU, MINB>;
-  const int smem = threads / 32 * 2 * Ipm::kBufBytes;
+  const int smem = threads / 32 * Ipm::kDepth * Ipm::kBufBytes;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kQpThreads / 32 * 2 * Ipm::kBufBytes);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kQpThreads / 32 * Ipm::kDepth * Ipm::kBufBytes);
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = true;
   }

@@ -90,7 +90,8 @@ struct BoxQpStore {
   using GN = TGN;  // gains K, S^-1, feed-forward d
 };
 using StoreF64 = BoxQpStore<double, double, double, double, double, double>;  // everything float64
-using StoreMix = BoxQpStore<double, float, float, double, double, double>;    // float64 product
+using StoreMix = BoxQpStore<double, float, float, double, float, double>;    // float64 product (float32 gains were
+// tried: the closed-loop rows A + B K must cancel to 1/Sigma ~ 1e-12 on active states, rounded gains stall hard solves)
 using StoreF32 = BoxQpStore<float, float, float, float, float, float>;        // float32 product
 
 inline int64_t ws_round16(int64_t bytes) { return (bytes + 15) / 16 * 16; }
@@ -258,10 +259,10 @@ struct BoxQpIpm {
     return *row<SEC>(k, i);
   }
 
-  // ---- staging pipeline (STAGED, device).  Two buffers + two mbarriers per warp.  pipe_begin: every lane makes its
+  // ---- staging pipeline (STAGED, device).  kDepth buffers + mbarriers per warp.  pipe_begin: every lane makes its
   // global stores of the previous sweep visible to the asynchronous proxy, then the leader starts the copies of the
-  // sweep's first two stages; visit_begin waits for the current stage; visit_end hands the buffer back (all lanes have
-  // read it) and the leader refills it with the stage two visits ahead.  The release sits at the END of the visit, when
+  // sweep's first kDepth stages; visit_begin waits for the current stage; visit_end hands the buffer back (all lanes have
+  // read it) and the leader refills it with the stage kDepth visits ahead.  The release sits at the END of the visit, when
   // every value read from the buffer has been consumed: a warp barrier does not wait for shared-memory loads in flight,
   // and a release right after the loads let the refill overwrite a buffer whose loads were still queued behind other
   // warps' scattered global accesses (measured: 0.6 % wrong solutions with permuted batches).  Per interior-point iteration each buffer is
@@ -271,7 +272,8 @@ struct BoxQpIpm {
   unsigned long long* sbar = nullptr;         // the warp's two mbarriers
   unsigned wmask = 0xffffffffu;               // lanes taking part in the current iteration
   unsigned par = 0;                           // bit j: parity the next wait on barrier j uses
-  int vis = 0;
+  int vis = 0;                                // buffer of the current visit
+  static constexpr int kDepth = 3;            // buffers per warp = stage visits a copy is issued ahead
   bool leader = false;
 #ifdef __CUDA_ARCH__
   __device__ __forceinline__ static unsigned sa(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -293,8 +295,9 @@ struct BoxQpIpm {
       __syncwarp(wmask);
       vis = 0;
       if (leader) {
-        issue_copy<LO, HI>(k0, 0);
-        if (a.N > 1) issue_copy<LO, HI>(k0 + dir, 1);
+#pragma unroll
+        for (int j = 0; j < kDepth; ++j)
+          if (j < a.N) issue_copy<LO, HI>(k0 + j * dir, j);
       }
     }
 #endif
@@ -303,7 +306,7 @@ struct BoxQpIpm {
   MPC_HD void visit_begin() {
 #ifdef __CUDA_ARCH__
     if constexpr (STAGED) {
-      const int j = vis & 1;
+      const int j = vis;
       const unsigned bar = sa(sbar + j), ph = (par >> j) & 1u;
       unsigned ok;
       do {
@@ -324,8 +327,8 @@ struct BoxQpIpm {
 #ifdef __CUDA_ARCH__
     if constexpr (STAGED) {
       __syncwarp(wmask);
-      if (leader && k_refill >= 0 && k_refill < a.N) issue_copy<LO, HI>(k_refill, vis & 1);
-      ++vis;
+      if (leader && k_refill >= 0 && k_refill < a.N) issue_copy<LO, HI>(k_refill, vis);
+      vis = vis + 1 == kDepth ? 0 : vis + 1;
     }
 #endif
   }
@@ -971,7 +974,7 @@ struct BoxQpIpm {
       T dff[NU];
       ff_stage(A, B, K, Sinv, rhs, pacc, dff);
       storen<Ds, NU>(k, dff);
-      visit_end<kLoA, kHiA>(k - 2);
+      visit_end<kLoA, kHiA>(k - kDepth);
     }
   }
 
@@ -1072,7 +1075,7 @@ struct BoxQpIpm {
       storen<DAs, D>(k, dzv);
       storen<Es, D>(k, ev);
       storen<Gs, D>(k, gv);
-      visit_end<kLoB, kHiB>(k + 2);
+      visit_end<kLoB, kHiB>(k + kDepth);
       // the rollout continues with the UNROUNDED state direction (the stored copy is only used for cc)
 #pragma unroll
       for (int i = 0; i < NX; ++i) x[i] = xn[i];
@@ -1112,7 +1115,7 @@ struct BoxQpIpm {
 #pragma unroll
       for (int j = 0; j < NU; ++j) dff[j] += daff[j];  // d_aff + d_cor: sweep D rolls the whole direction out at once
       storen<Ds, NU>(k, dff);
-      visit_end<kLoC, kHiC>(k - 2);
+      visit_end<kLoC, kHiC>(k - kDepth);
     }
   }
 
@@ -1205,7 +1208,7 @@ struct BoxQpIpm {
         }
       }
       storen<DZs, D>(k, dzv);
-      visit_end<kLoD, kHiD>(k + 2);
+      visit_end<kLoD, kHiD>(k + kDepth);
 #pragma unroll
       for (int i = 0; i < NX; ++i) x[i] = xn[i];
     }
@@ -1304,8 +1307,11 @@ struct BoxQpIpm {
     const T zn = acc.zn;
     const T mu_new = (acc.s0 + alpha * (acc.s1 + alpha * acc.s2)) * inv_nc;
     const T rp = (T(1) - alpha) * acc.rp;
-    const bool done = (ncons == 0) ||
-                      ((mu_new <= eps * mu_scale) && (rp <= eps * zn) && (alpha * acc.dzmax <= T(1e-6) * zn));
+    // no finite bound: one exact Newton step -- exact when the gains are stored in the arithmetic type; with narrower
+    // gains the step carries their rounding (1e-7 of the step), and one more iteration removes it
+    const bool small_step = alpha * acc.dzmax <= T(1e-6) * zn;
+    const bool done = (ncons == 0) ? (sizeof(TGN) == sizeof(T) || small_step)
+                                   : ((mu_new <= eps * mu_scale) && (rp <= eps * zn) && small_step);
     if (done) {
       status = MPC_SOLVED;
     } else {

@@ -108,7 +108,9 @@ def test_ltv_per_scenario_models(hh, n, m, store):
     np.testing.assert_array_equal(got["status"], port["status"])
     ok = got["status"] == bq.SOLVED
     assert ok.sum() >= batch // 2
-    np.testing.assert_allclose(got["U"][:, ok], port["U"][:, ok], rtol=1e-8, atol=1e-9)
+    # store 1 keeps the corrector data in float32: its iterates leave those of the all-float64 port at the level of the
+    # stopping tolerance (the bar against the exact solution below is the same 1e-6 for both)
+    np.testing.assert_allclose(got["U"][:, ok], port["U"][:, ok], rtol=1e-8, atol=1e-9 if store == 0 else 1e-7)
     for b in np.nonzero(ok)[0]:
         ex = bq.solve_exact(A[:, b], B[:, b], Q, R, Pf, N, x0[b], ulo, uhi, np.where(xlo < -1e19, -np.inf, xlo), xhi,
                             c=c[:, b])
@@ -124,12 +126,15 @@ def test_unconstrained_is_the_lq_solution(hh):
     prob = bq.Problem(N=12)
     big = 1e20
     x0 = np.array([[-3.0, 1.0], [2.0, -0.5]])
-    got = run_harness(hh, prob.A, prob.B, None, 0, prob.Q, prob.R, prob.Q, [-big], [big], [-big, -big], [big, big], x0, 12)
-    for b in range(2):
-        X, U, V, _, _ = lq.lq_open_loop(prob.A, prob.B, prob.Q.astype(float), prob.R.astype(float), prob.Q.astype(float), x0[b], 12)
-        np.testing.assert_allclose(got["U"][:, b], U, rtol=1e-9, atol=1e-10)
-        np.testing.assert_allclose(got["cost"][b], V, rtol=1e-10)
-    assert np.all(got["status"] == bq.SOLVED) and np.all(got["iters"] == 1)
+    for store in (0, 1):
+        got = run_harness(hh, prob.A, prob.B, None, 0, prob.Q, prob.R, prob.Q, [-big], [big], [-big, -big], [big, big], x0, 12,
+                          store=store)
+        for b in range(2):
+            X, U, V, _, _ = lq.lq_open_loop(prob.A, prob.B, prob.Q.astype(float), prob.R.astype(float), prob.Q.astype(float), x0[b], 12)
+            np.testing.assert_allclose(got["U"][:, b], U, rtol=1e-9, atol=1e-10)
+            np.testing.assert_allclose(got["cost"][b], V, rtol=1e-10)
+        # one exact Newton step (both workspaces keep the gains in float64)
+        assert np.all(got["status"] == bq.SOLVED) and np.all(got["iters"] == 1)
 
 
 def rows_problem(rng, batch, N, nc, n=4, m=2):

@@ -1,7 +1,7 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-T=${TAG:-b25}
+T=${TAG:-b26}
 timeout 900 python -m pytest tests/test_gpu_boxqp.py tests/test_gpu_round2.py -q -x > gpurun_out/pytest_$T.log 2>&1; tail -5 gpurun_out/pytest_$T.log
 run() { name=$1; wl=$2; shift; shift; e=$1; shift; env $e timeout 600 python bench.py "$@" --workload $wl --no-cpu > gpurun_out/${T}_$name.json 2> gpurun_out/${T}_$name.err; }
 run cfg3 cfg3 X=1 --steps 5 --warmup 3
