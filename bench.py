@@ -433,8 +433,13 @@ def k1_riccati_block(ctx, args, peak):
     batch = args.batch or (1 << 20)
     A, B, Q, R, Pf, _ = cfg2b_inputs_torch(batch, 1234 + 2 + 1000 * ctx.rank, ctx.dev, torch.float64)
 
+    # caller-owned result buffers: 3.4 GB of fresh torch allocations per call inside the timed loop made this block's
+    # number depend on the state of the caching allocator (0.85 - 1.86 ms per step between runs)
+    out = (torch.empty((N, batch, m, n), dtype=torch.float64, device=ctx.dev),
+           torch.empty((N + 1, batch, n, n), dtype=torch.float64, device=ctx.dev))
+
     def step():
-        return lq.riccati(A, B, Q, R, Pf, N, all_P=True)
+        return lq.riccati(A, B, Q, R, Pf, N, all_P=True, out=out)
 
     for _ in range(3):
         step()
@@ -451,7 +456,7 @@ def k1_riccati_block(ctx, args, peak):
     f_ric = 4 * n**3 + 6 * n * n * m + 4 * n * m * m + 2 * m**3 + 2 * n * n + m * m
     achieved = bytes_solve * batch / (ms * 1e-3) / 1e9
     fp_peak = lq.fma_peak(torch.float64)
-    del K, P
+    del K, P, out
     return {"value": ctx.world * batch / (ms * 1e-3), "unit": "recursions/s", "ms_per_step": ms, "steps": steps,
             "config": {"workload": f"k1: FHC.ricatti_recursion (FHC.py:51-61) with every K_k and P_k returned, nx=4 nu=1 N=20, "
                                    f"{batch} per-scenario models per GPU", "batch_per_gpu": batch,

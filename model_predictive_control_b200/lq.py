@@ -43,9 +43,10 @@ def _common_batch(bs, extra=None):
     return vals.pop() if vals else None
 
 
-def riccati(A, B, Q, R, Pf, N, all_P=True):
+def riccati(A, B, Q, R, Pf, N, all_P=True, out=None):
     """Backward Riccati recursion (K1).  Returns K [N, batch, m, n], P [N+1, batch, n, n]
     (or [batch, n, n] = P_0 when ``all_P`` is false).  batch = 1 when every matrix is shared.
+    ``out=(K, P)``: caller-owned result buffers of exactly those shapes (repeated solves without allocation).
     Replaces reference session_1/FHC.py:51-61."""
     _lib.require_cuda(A, B, Q, R, Pf)
     _same_kind(A, B=B, Q=Q, R=R, P_f=Pf)
@@ -59,8 +60,15 @@ def riccati(A, B, Q, R, Pf, N, all_P=True):
     N = int(N)
     if N < 0:
         raise ValueError("horizon must be non-negative")
-    K = torch.empty((N, batch, m, n), dtype=A.dtype, device=A.device)
-    P = torch.empty((N + 1, batch, n, n) if all_P else (batch, n, n), dtype=A.dtype, device=A.device)
+    k_shape, p_shape = (N, batch, m, n), ((N + 1, batch, n, n) if all_P else (batch, n, n))
+    if out is None:
+        K = torch.empty(k_shape, dtype=A.dtype, device=A.device)
+        P = torch.empty(p_shape, dtype=A.dtype, device=A.device)
+    else:
+        K, P = out
+        for name, t, shp in (("K", K, k_shape), ("P", P, p_shape)):
+            if tuple(t.shape) != shp or t.dtype != A.dtype or t.device != A.device or not t.is_contiguous():
+                raise ValueError(f"out {name} must be a contiguous {A.dtype} tensor of shape {shp} on {A.device}")
     with torch.cuda.device(A.device):
         _lib.check(_lib.lib().mpc_riccati(
             _lib.ptr(A), sA, _lib.ptr(B), sB, _lib.ptr(Q), sQ, _lib.ptr(R), sR, _lib.ptr(Pf), sP,

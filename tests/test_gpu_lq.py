@@ -178,6 +178,12 @@ def test_riccati_random_batched(mods, n, m, dtype):
     assert np.abs(P.cpu().numpy() - np.array(Po)).max() <= rtol * scaleP * 10
     K0, P0 = lq.riccati(dev(A), dev(B), dev(Q), dev(R), dev(Q), N, all_P=False)
     assert torch.equal(K0, K) and torch.equal(P0, P[0])
+    # caller-owned result buffers
+    out = (torch.empty_like(K), torch.empty_like(P))
+    K1, P1 = lq.riccati(dev(A), dev(B), dev(Q), dev(R), dev(Q), N, out=out)
+    assert K1 is out[0] and P1 is out[1] and torch.equal(K1, K) and torch.equal(P1, P)
+    with pytest.raises(ValueError):
+        lq.riccati(dev(A), dev(B), dev(Q), dev(R), dev(Q), N, out=(torch.empty_like(K), torch.empty_like(P)[1:]))
 
 
 @pytest.mark.parametrize("batch", [1, 2, 31, 33, 255, 1000, 4097])
