@@ -219,7 +219,7 @@ static int launch_boxqp_st(const BoxQpArgs<TIO>& a_in, cudaStream_t st) {
     // (2,1): residency against registers, measured on B200 (tools/prof/exp_q3.sh); default 4 CTAs/SM
     int minb = 4;
     if (const char* env = getenv("MPC_QP_MINB")) minb = atoi(env);
-    if (!getenv("MPC_QP_PREFETCH")) a.pf_dist = 1;
+    if (!getenv("MPC_QP_PREFETCH")) a.pf_dist = 2;  // kernels without staging (LTV, MPC_QP_STAGED=0): bulk L2 prefetch 2 visits ahead
     if (refill > 0 && a.batch > 4096) {
       if (minb >= 4) return launch_refill<TIO, ST, NX, NU, 4>(a, refill, st);
       return launch_refill<TIO, ST, NX, NU, 3>(a, refill, st);

@@ -429,12 +429,17 @@ struct BoxQpIpm {
 #pragma unroll
     for (int i = 0; i < PER; ++i) pf(base + ix(k, i, PER));
   }
-  MPC_HD void pf_iterate(int k) const {
-    pf_rows<Zs, D>(k);
-    pf_rows<SLs, D>(k);
-    pf_rows<SUs, D>(k);
-    pf_rows<LLs, D>(k);
-    pf_rows<LUs, D>(k);
+  // one bulk L2 prefetch of a contiguous byte range of the warp's tile stage (the read set of a sweep), issued by the
+  // lowest active lane: 2 instructions per stage visit instead of one prefetch per row and lane
+  template <int LO, int HI>
+  MPC_HD void pf_range(int k) const {
+#ifdef __CUDA_ARCH__
+    if ((threadIdx.x % kTile) == (unsigned)(__ffs(__activemask()) - 1))
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(tile_ + (int64_t)k * kStage + LO), "r"(HI - LO)
+                   : "memory");
+#else
+    (void)k;
+#endif
   }
   MPC_HD void pf_model(int k) const {
     if constexpr (kTileModel) {
@@ -448,7 +453,7 @@ struct BoxQpIpm {
   }
   MPC_HD bool pf_on(int k) const {
 #ifdef __CUDA_ARCH__
-    if constexpr (NC > 0 || STAGED) return false;
+    if constexpr (STAGED) return false;
     return a.pf_dist > 0 && k >= 0 && k < a.N;
 #else
     (void)k;
@@ -778,12 +783,8 @@ struct BoxQpIpm {
     for (int k = a.N - 1; k >= 0; --k) {
       visit_begin<kLoA>();
       if (pf_on(k - a.pf_dist)) {
-        pf_iterate(k - a.pf_dist);
-        pf_model(k - a.pf_dist);
-        if (have_step) {
-          pf_rows<DAs, D>(k - a.pf_dist);
-          pf_rows<DZs, D>(k - a.pf_dist);
-        }
+        pf_range<kLoA, kHiA>(k - a.pf_dist);
+        if constexpr (!kTileModel) pf_model(k - a.pf_dist);
       }
       T znew[D], sig[D], rhs[D];
       T A[NX * NX], B[NX * NU], c[NX];
@@ -997,10 +998,8 @@ struct BoxQpIpm {
     for (int k = 0; k < a.N; ++k) {
       visit_begin<kLoB>();
       if (pf_on(k + a.pf_dist)) {
-        pf_iterate(k + a.pf_dist);
-        pf_model(k + a.pf_dist);
-        pf_rows<Ks, NU * NX>(k + a.pf_dist);
-        pf_rows<Ds, NU>(k + a.pf_dist);
+        pf_range<kLoB, kHiB>(k + a.pf_dist);
+        if constexpr (!kTileModel) pf_model(k + a.pf_dist);
       }
       Stage cur;
       load<true>(k, cur);
@@ -1092,12 +1091,9 @@ struct BoxQpIpm {
     for (int k = a.N - 1; k >= 0; --k) {
       visit_begin<kLoC>();
       if (pf_on(k - a.pf_dist)) {
-        pf_rows<Es, D>(k - a.pf_dist);
-        pf_rows<Gs, D>(k - a.pf_dist);
-        pf_rows<Ks, NU * NX>(k - a.pf_dist);
-        pf_rows<Ss, NU * NU>(k - a.pf_dist);
-        pf_rows<Ds, NU>(k - a.pf_dist);
-        pf_model(k - a.pf_dist);
+        pf_range<kLoC, kHiC>(k - a.pf_dist);
+        if constexpr (kTileModel) pf_range<MDs::off, MDs::off + kMdRows * MDs::rowb>(k - a.pf_dist);
+        else pf_model(k - a.pf_dist);
       }
       T ev[D], gv[D], K[NU * NX], Sinv[NU * NU];
       loadn<Es, D, true>(k, ev);
@@ -1132,11 +1128,8 @@ struct BoxQpIpm {
     for (int k = 0; k < a.N; ++k) {
       visit_begin<kLoD>();
       if (pf_on(k + a.pf_dist)) {
-        pf_iterate(k + a.pf_dist);
-        pf_model(k + a.pf_dist);
-        pf_rows<Ks, NU * NX>(k + a.pf_dist);
-        pf_rows<Ds, NU>(k + a.pf_dist);
-        pf_rows<DAs, D>(k + a.pf_dist);
+        pf_range<kLoD, kHiD>(k + a.pf_dist);
+        if constexpr (!kTileModel) pf_model(k + a.pf_dist);
       }
       Stage cur;
       load<true>(k, cur);
