@@ -854,12 +854,12 @@ def cpu_baseline_secondary(workload, cores):
 
 def ipm_workspace_bytes_v2(n, m, N, model_elems, narrow=True, elem=8):
     """HBM bytes one interior-point iteration of the round-2 kernels moves BY DESIGN (csrc/boxqp_core.cuh, four sweeps;
-    `narrow` = the float64 product's mixed workspace: slacks, multipliers and dz_aff in float32):
+    `narrow` = the float64 product's mixed workspace: slacks, multipliers, dz_aff and the corrector data e, g in float32):
       A reads z, s, lam (4 d), dz, dz_aff (+ model) and writes z, s, lam, K, S^-1, d;  B reads z, s, lam, K, d (+ model) and
       writes dz_aff, e, g;  C reads e, g, K, S^-1, d (+ model) and writes d;  D reads z, s, lam, dz_aff, K, d (+ model), writes dz."""
     d = n + m
     z, sl, da = elem * d, (4 if narrow else elem) * 4 * d, (4 if narrow else elem) * d
-    dz, eg = elem * d, 2 * elem * d
+    dz, eg = elem * d, 2 * (4 if narrow else elem) * d
     K, S, ff, mod = elem * m * n, elem * m * m, elem * m, elem * model_elems
     a = (z + sl + dz + da + mod) + (z + sl + K + S + ff)
     b = (z + sl + K + ff + mod) + (da + eg)
@@ -899,7 +899,8 @@ def secondary_line(ctx, workload, steps, warmup, batch=0, horizon=0, cpu=False, 
         name = f"cfg3: session-2 Problem box-QP (input + state bounds), nx=2 nu=1 N={N}, {batch} scenarios per GPU"
         io_bytes = es * (n + N * m + (N + 1) * n + 1) + 8 + N * (n + m)
         host_in, host_out = [x0T], lambda r: [r.U, r.X, r.cost, r.status]
-        kname, model_elems = "boxqp_ipm_kernel", 0
+        # shared LTI model, box constraints: the staged kernel (tile stages copied into shared memory by cp.async.bulk)
+        kname, model_elems = ("boxqp_ipm_staged_kernel" if os.environ.get("MPC_QP_STAGED") != "0" else "boxqp_ipm_kernel"), 0
     elif workload == "cfg5":
         import numpy as np
         batch = batch or (1 << 20)
@@ -1049,7 +1050,8 @@ def secondary_line(ctx, workload, steps, warmup, batch=0, horizon=0, cpu=False, 
                                      "measured_fma_peak_tflops": fp_peak / 1e12, "frac": flops / (kern_ms * 1e-3) / fp_peak}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": sum(t_.numel() * t_.element_size() for t_ in pin_in),
                     "d2h_bytes_per_step": sum(t_.numel() * t_.element_size() for t_ in pin_out)},
-            "gpu_launches": steps, "clocks": clocks, "summary": merged,
+            # cfg 3: mpc_state_order_keys + the solve per step (the device sort between them is torch's)
+            "gpu_launches": steps * (2 if workload == "cfg3" else 1), "clocks": clocks, "summary": merged,
         }
         if solved_only is not None:
             line["solved_only"] = solved_only

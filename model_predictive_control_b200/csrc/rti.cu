@@ -283,7 +283,13 @@ static int rti_loop_impl(const BicycleModel<double>& model, double friction_mode
   } else if (model.rk4) {
     rti_closed_loop_kernel<TIO, false, 0, ST, 2><<<grid, threads, 0, st>>>(a);
   } else {  // forward-Euler prediction model: packed sparse stage matrices
-    rti_closed_loop_kernel<TIO, true, 0, ST, 2><<<grid, threads, 0, st>>>(a);
+    // MPC_RTI_PAD_SMEM=<bytes>: unused dynamic shared memory per CTA, an occupancy experiment (fewer resident CTAs with
+    // the same code): tells a latency-bound kernel from a bandwidth-bound one
+    int pad = 0;
+    if (const char* env = getenv("MPC_RTI_PAD_SMEM")) pad = atoi(env);
+    if (pad > 48 * 1024)
+      cudaFuncSetAttribute(rti_closed_loop_kernel<TIO, true, 0, ST, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+    rti_closed_loop_kernel<TIO, true, 0, ST, 2><<<grid, threads, pad, st>>>(a);
   }
   return check_launch("rti_closed_loop_kernel");
 }

@@ -119,6 +119,51 @@ def test_ltv_per_scenario(mods, n, m):
     assert nchk >= batch // 2
 
 
+@pytest.mark.parametrize("n,m", [(4, 1), (4, 2)])
+def test_lti_4x_staged_kernel_against_exact_and_unstaged(mods, n, m):
+    """Shared LTI models of the (4,1) / (4,2) shapes run on the staged kernel (tile stages copied into shared memory by
+    cp.async.bulk): against the exact oracle on a subsample, and bitwise against the same solve without staging
+    (MPC_QP_STAGED=0), ragged batch, caller's order and a permuted one."""
+    import os
+    boxqp, problem, log, torch = mods
+    rng = np.random.default_rng(400 + n * 10 + m)
+    batch, N = 9000 + 13, 25
+    A = np.eye(n) + 0.1 * np.diag(np.ones(n - 1), 1) + 0.01 * rng.standard_normal((n, n))
+    B = np.zeros((n, m)); B[-1, 0] = 0.1
+    if m > 1:
+        B[-2, 1] = 0.1
+    Q = np.diag(rng.uniform(0.5, 2.0, n)); R = np.diag(rng.uniform(0.05, 0.2, m)); Pf = 5 * Q
+    ulo, uhi = -np.ones(m), 0.5 * np.ones(m)
+    xlo, xhi = -2.0 * np.ones(n), 2.0 * np.ones(n)
+    xlo[0] = -np.inf
+    x0 = rng.uniform(-1.4, 1.4, (batch, n))
+    dev = lambda a: torch.tensor(np.ascontiguousarray(a), dtype=torch.float64, device="cuda")
+    args = (dev(A), dev(B), dev(Q), dev(R), dev(Pf), N, dev(x0.T), ulo, uhi, xlo, xhi)
+    res = boxqp.solve(*args, order=None)
+    keep = [t.clone() for t in (res.U, res.X, res.cost, res.status, res.iters, res.sat_u, res.sat_x)]
+    sub = rng.choice(batch, 48, replace=False)
+    ex = [bq.solve_exact(A, B, Q, R, Pf, N, x0[b], ulo, uhi, xlo, xhi) for b in sub]
+    idx = torch.tensor(sub, device="cuda")
+    nchk = check_against_exact(res.input_prediction[idx].cpu().numpy(), res.state_prediction[idx].cpu().numpy(),
+                               res.cost[idx].cpu().numpy(), res.status[idx].cpu().numpy(),
+                               res.sat_u.permute(2, 0, 1)[idx].cpu().numpy(), res.sat_x.permute(2, 0, 1)[idx].cpu().numpy(),
+                               ex, ulo, uhi)
+    assert nchk >= 16   # solved and certified by the oracle (the rest: infeasible starts, flagged by both)
+    perm = torch.randperm(batch, device="cuda").to(torch.int32)
+    old = os.environ.get("MPC_QP_STAGED")
+    try:
+        for staged, order in (("1", perm), ("0", None), ("0", perm)):
+            os.environ["MPC_QP_STAGED"] = staged
+            r2 = boxqp.solve(*args, order=order)
+            for a_, b_ in zip(keep, (r2.U, r2.X, r2.cost, r2.status, r2.iters, r2.sat_u, r2.sat_x)):
+                assert torch.equal(a_, b_)
+    finally:
+        if old is None:
+            os.environ.pop("MPC_QP_STAGED", None)
+        else:
+            os.environ["MPC_QP_STAGED"] = old
+
+
 def test_unconstrained_equals_session1_lq(mods):
     """With every bound at infinity the QP is the finite-horizon LQ problem of session 1."""
     boxqp, problem, log, torch = mods
