@@ -68,12 +68,18 @@ template <typename TIO, class ST, int NX, int NU, int MINB>
 static int launch_staged(const BoxQpArgs<TIO>& a, unsigned grid, int threads, cudaStream_t st) {
   using Ipm = BoxQpIpm<double, TIO, NX, NU, 0, 2, ST, true>;
   auto kern = boxqp_ipm_staged_kernel<TIO, ST, NX, NU, MINB>;
-  const int smem = threads / 32 * Ipm::kDepth * Ipm::kBufBytes;
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kQpThreads / 32 * Ipm::kDepth * Ipm::kBufBytes);
+  int smem = threads / 32 * Ipm::kDepth * Ipm::kBufBytes;
+  // MPC_QP_PAD_SMEM=<bytes>: unused shared memory per CTA, an occupancy experiment (fewer resident CTAs, same code):
+  // fewer resident warps = a smaller streamed working set against the 126 MB L2
+  int pad = 0;
+  if (const char* env = getenv("MPC_QP_PAD_SMEM")) pad = atoi(env);
+  if (pad < 0 || pad > 180 * 1024) pad = 0;
+  smem += pad;
+  static int configured = -1;
+  if (configured != pad) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kQpThreads / 32 * Ipm::kDepth * Ipm::kBufBytes + pad);
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    configured = true;
+    configured = pad;
   }
   kern<<<grid, threads, smem, st>>>(a);
   return check_launch("boxqp_ipm_staged_kernel");
