@@ -50,8 +50,13 @@ struct CoopLayout {
   static constexpr int wXn = wX + NX;
   static constexpr int wU = wXn + NX;
   static constexpr int warp_total = wU + NU;
-  // workspace slot (global), elements
-  __host__ __device__ static int64_t slot_elems(int N) { return (int64_t)N * (7 * D + NU * NX + NU * NU + NU); }
+  // workspace slot (global), elements: STAGE-MAJOR -- one stage of the slot is kStage contiguous doubles with every
+  // section at a compile-time offset, so a stage visit addresses [slot + k * kStage + immediate + lane] from ONE pointer
+  // (round 1: ten section pointers = 20 of the kernel's 64 registers, a 64-bit multiply-add per access)
+  static constexpr int sZ = 0, sSl = D, sSu = 2 * D, sLl = 3 * D, sLu = 4 * D, sDa = 5 * D, sDz = 6 * D;
+  static constexpr int sK = 7 * D, sS = sK + NU * NX, sDw = sS + NU * NU;
+  static constexpr int kStage = sDw + NU;
+  __host__ __device__ static int64_t slot_elems(int N) { return (int64_t)N * kStage; }
 };
 
 __device__ __forceinline__ double warp_max(double v) {
@@ -132,25 +137,14 @@ struct CoopIpm {
   double* w;         // this warp's shared-memory slice
   int lane;
   int64_t b, bs;     // scenario, batch (I/O stride)
-  // workspace slot sections, each [N][per]
-  double *z, *sl, *su, *ll, *lu, *dza, *dzw, *Kw, *Sw, *dw;
+  double* slot;      // this warp's workspace slot, [N][kStage]
+  __device__ __forceinline__ double* st(int k) const { return slot + (int64_t)k * L::kStage; }
   double mu_scale, mu0;
   bool hl, hu;   // this lane's element has a finite lower / upper bound
   double lo, hi;
 
-  __device__ CoopIpm(const BoxQpArgs<double>& args, const double* shared, double* wsm, double* slot, int ln)
-      : a(args), sh(shared), w(wsm), lane(ln), b(0), bs(args.batch) {
-    const int64_t sec = (int64_t)a.N * D;
-    z = slot;
-    sl = z + sec;
-    su = sl + sec;
-    ll = su + sec;
-    lu = ll + sec;
-    dza = lu + sec;
-    dzw = dza + sec;
-    Kw = dzw + sec;
-    Sw = Kw + (int64_t)a.N * NU * NX;
-    dw = Sw + (int64_t)a.N * NU * NU;
+  __device__ CoopIpm(const BoxQpArgs<double>& args, const double* shared, double* wsm, double* slot_, int ln)
+      : a(args), sh(shared), w(wsm), lane(ln), b(0), bs(args.batch), slot(slot_) {
     mu_scale = 1.0;
     for (int i = 0; i < NX * NX; ++i) mu_scale = fmax(mu_scale, fabs(sh[L::oQ + i]));
     for (int i = 0; i < NU * NU; ++i) mu_scale = fmax(mu_scale, fabs(sh[L::oR + i]));
@@ -222,12 +216,12 @@ struct CoopIpm {
             s_u = fmax(hi - zi, 1.0);
             l_u = mu0 / s_u;
           }
-          const int64_t o = (int64_t)k * D + lane;
-          z[o] = zi;
-          sl[o] = s_l;
-          su[o] = s_u;
-          ll[o] = l_l;
-          lu[o] = l_u;
+          double* const sk = st(k);
+          sk[L::sZ + lane] = zi;
+          sk[L::sSl + lane] = s_l;
+          sk[L::sSu + lane] = s_u;
+          sk[L::sLl + lane] = l_l;
+          sk[L::sLu + lane] = l_u;
         }
         if (lane < NX) w[L::wX + lane] = w[L::wXn + lane];
         __syncwarp();
@@ -250,20 +244,20 @@ struct CoopIpm {
     if (lane < NX) w[L::wPacc + lane] = 0.0;
     __syncwarp();
     for (int k = a.N - 1; k >= 0; --k) {
-      const int64_t o = (int64_t)k * D + lane;
+      double* const sk = st(k);
       double zi = 0.0, s_l = 1.0, s_u = 1.0, l_l = 0.0, l_u = 0.0, da = 0.0;
       if (lane < D) {
-        zi = z[o];
-        s_l = sl[o];
-        s_u = su[o];
-        l_l = ll[o];
-        l_u = lu[o];
-        if (!FACTOR) da = dza[o];
+        zi = sk[L::sZ + lane];
+        s_l = sk[L::sSl + lane];
+        s_u = sk[L::sSu + lane];
+        l_l = sk[L::sLl + lane];
+        l_u = sk[L::sLu + lane];
+        if (!FACTOR) da = sk[L::sDa + lane];
         w[L::wZ + lane] = zi;
       }
       if (!FACTOR) {
-        for (int e = lane; e < NU * NX; e += 32) w[L::wK + e] = Kw[(int64_t)k * NU * NX + e];
-        for (int e = lane; e < NU * NU; e += 32) w[L::wSi + e] = Sw[(int64_t)k * NU * NU + e];
+        for (int e = lane; e < NU * NX; e += 32) w[L::wK + e] = sk[L::sK + e];
+        for (int e = lane; e < NU * NU; e += 32) w[L::wSi + e] = sk[L::sS + e];
       }
       __syncwarp();
       double r = -hz(k), sg = 0.0;
@@ -381,8 +375,8 @@ struct CoopIpm {
           w[L::wP + i * NX + j] = acc;
           w[L::wP + j * NX + i] = acc;
         }
-        for (int e = lane; e < NU * NX; e += 32) Kw[(int64_t)k * NU * NX + e] = w[L::wK + e];
-        for (int e = lane; e < NU * NU; e += 32) Sw[(int64_t)k * NU * NU + e] = w[L::wSi + e];
+        for (int e = lane; e < NU * NX; e += 32) sk[L::sK + e] = w[L::wK + e];
+        for (int e = lane; e < NU * NU; e += 32) sk[L::sS + e] = w[L::wSi + e];
         __syncwarp();
       }
       // h = -(rhs_x + pacc);  gu = rhs_u - B'h;  dff = Sinv gu;  pacc <- -A'h + K'gu
@@ -399,7 +393,7 @@ struct CoopIpm {
         double acc = 0.0;
 #pragma unroll
         for (int j = 0; j < NU; ++j) acc = fma(w[L::wSi + lane * NU + j], w[L::wGu + j], acc);
-        dw[(int64_t)k * NU + lane] = acc;
+        sk[L::sDw + lane] = acc;
       }
       if (lane < NX) {
         double acc = 0.0;
@@ -424,18 +418,18 @@ struct CoopIpm {
     if (lane < NX) w[L::wX + lane] = 0.0;  // dx_0 = 0
     __syncwarp();
     for (int k = 0; k < a.N; ++k) {
-      const int64_t o = (int64_t)k * D + lane;
+      double* const sk = st(k);
       double zi = 0.0, s_l = 1.0, s_u = 1.0, l_l = 0.0, l_u = 0.0, da = 0.0;
       if (lane < D) {
-        zi = z[o];
-        s_l = sl[o];
-        s_u = su[o];
-        l_l = ll[o];
-        l_u = lu[o];
-        if (!AFFINE) da = dza[o];
+        zi = sk[L::sZ + lane];
+        s_l = sk[L::sSl + lane];
+        s_u = sk[L::sSu + lane];
+        l_l = sk[L::sLl + lane];
+        l_u = sk[L::sLu + lane];
+        if (!AFFINE) da = sk[L::sDa + lane];
       }
-      for (int e = lane; e < NU * NX; e += 32) w[L::wK + e] = Kw[(int64_t)k * NU * NX + e];
-      if (lane < NU) w[L::wDff + lane] = dw[(int64_t)k * NU + lane];
+      for (int e = lane; e < NU * NX; e += 32) w[L::wK + e] = sk[L::sK + e];
+      if (lane < NU) w[L::wDff + lane] = sk[L::sDw + lane];
       __syncwarp();
       if (lane < NU) {
         double u = w[L::wDff + lane];
@@ -448,7 +442,7 @@ struct CoopIpm {
       __syncwarp();
       const double dz = lane < NU ? w[L::wU + lane] : (lane < D ? w[L::wXn + lane - NU] : 0.0);
       if (lane < D) {
-        (AFFINE ? dza : dzw)[o] = dz;
+        sk[(AFFINE ? L::sDa : L::sDz) + lane] = dz;
         if (!AFFINE) dzmax = fmax(dzmax, fabs(dz));
       }
       if (hl) {
@@ -488,26 +482,26 @@ struct CoopIpm {
     double zn = 1.0;
     if (lane < D) {
       for (int k = 0; k < a.N; ++k) {
-        const int64_t o = (int64_t)k * D + lane;
-        const double zi = z[o], dz = dzw[o], da = second_order ? dza[o] : 0.0;
+        double* const sk = st(k);
+        const double zi = sk[L::sZ + lane], dz = sk[L::sDz + lane], da = second_order ? sk[L::sDa + lane] : 0.0;
         if (hl) {
-          const double s = sl[o], l = ll[o], r = zi - lo - s, ds = dz + r;
+          const double s = sk[L::sSl + lane], l = sk[L::sLl + lane], r = zi - lo - s, ds = dz + r;
           const double inv = rcp_(s), sgl = l * inv;
           const double cc = second_order ? cc_of(da, r, sgl, l) : 0.0;
           const double dl = (sig_mu - cc) * inv - l - sgl * ds;
-          sl[o] = s + alpha * ds;
-          ll[o] = l + alpha * dl;
+          sk[L::sSl + lane] = s + alpha * ds;
+          sk[L::sLl + lane] = l + alpha * dl;
         }
         if (hu) {
-          const double s = su[o], l = lu[o], r = hi - zi - s, ds = -dz + r;
+          const double s = sk[L::sSu + lane], l = sk[L::sLu + lane], r = hi - zi - s, ds = -dz + r;
           const double inv = rcp_(s), sgu = l * inv;
           const double cc = second_order ? cc_of(-da, r, sgu, l) : 0.0;
           const double dl = (sig_mu - cc) * inv - l - sgu * ds;
-          su[o] = s + alpha * ds;
-          lu[o] = l + alpha * dl;
+          sk[L::sSu + lane] = s + alpha * ds;
+          sk[L::sLu + lane] = l + alpha * dl;
         }
         const double zn_i = zi + alpha * dz;
-        z[o] = zn_i;
+        sk[L::sZ + lane] = zn_i;
         zn = fmax(zn, fabs(zn_i));
       }
     }
@@ -523,13 +517,13 @@ struct CoopIpm {
     }
     __syncwarp();
     for (int k = 0; k < a.N; ++k) {
-      const int64_t o = (int64_t)k * D + lane;
+      double* const sk = st(k);
       int sat = 0;
       double zi = 0.0;
       if (lane < D) {
-        zi = z[o];
-        if (hl && ll[o] > sl[o]) sat = -1;
-        if (hu && lu[o] > su[o]) sat = 1;
+        zi = sk[L::sZ + lane];
+        if (hl && sk[L::sLl + lane] > sk[L::sSl + lane]) sat = -1;
+        if (hu && sk[L::sLu + lane] > sk[L::sSu + lane]) sat = 1;
       }
       if (lane < NU) {
         const double u = sat < 0 ? lo : (sat > 0 ? hi : zi);
