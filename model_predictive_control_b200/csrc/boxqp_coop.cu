@@ -139,6 +139,11 @@ struct CoopIpm {
   int64_t b, bs;     // scenario, batch (I/O stride)
   double* slot;      // this warp's workspace slot, [N][kStage]
   __device__ __forceinline__ double* st(int k) const { return slot + (int64_t)k * L::kStage; }
+  // one bulk L2 prefetch of a whole stage of the slot (contiguous kStage doubles), a.pf_dist stage visits ahead
+  __device__ __forceinline__ void pf(int k) const {
+    if (a.pf_dist > 0 && k >= 0 && k < a.N && lane == 0)
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(st(k)), "r"(L::kStage * 8) : "memory");
+  }
   double mu_scale, mu0;
   bool hl, hu;   // this lane's element has a finite lower / upper bound
   double lo, hi;
@@ -156,9 +161,9 @@ struct CoopIpm {
     hu = lane < D && hi < kBigBound;
   }
 
-  // (An L2 prefetch of the next stage's workspace rows -- one lane per section, `prefetch.global.L2` -- was measured
-  // here in round 2: 4.23 s instead of 3.53 s per 2^20 cfg-5 solves.  The long-scoreboard stalls of this kernel are not
-  // DRAM latency that a prefetch could hide cheaply; not kept.)
+  // (With the section-major slot of the first half of round 2 an L2 prefetch of the next stage's rows -- one lane per
+  // section, `prefetch.global.L2` -- cost more than it brought: 4.23 s instead of 3.53 s per 2^20 cfg-5 solves.  With the
+  // stage-major slot it is ONE bulk prefetch of a contiguous 1 440-byte stage: pf() above.)
   // x+ = A x + B u (lanes < NX), from / to the warp's vectors
   __device__ void step_vec(const double* x, const double* u, double* xn) {
     if (lane < NX) {
@@ -244,6 +249,7 @@ struct CoopIpm {
     if (lane < NX) w[L::wPacc + lane] = 0.0;
     __syncwarp();
     for (int k = a.N - 1; k >= 0; --k) {
+      pf(k - a.pf_dist);
       double* const sk = st(k);
       double zi = 0.0, s_l = 1.0, s_u = 1.0, l_l = 0.0, l_u = 0.0, da = 0.0;
       if (lane < D) {
@@ -418,6 +424,7 @@ struct CoopIpm {
     if (lane < NX) w[L::wX + lane] = 0.0;  // dx_0 = 0
     __syncwarp();
     for (int k = 0; k < a.N; ++k) {
+      pf(k + a.pf_dist);
       double* const sk = st(k);
       double zi = 0.0, s_l = 1.0, s_u = 1.0, l_l = 0.0, l_u = 0.0, da = 0.0;
       if (lane < D) {
@@ -482,6 +489,7 @@ struct CoopIpm {
     double zn = 1.0;
     if (lane < D) {
       for (int k = 0; k < a.N; ++k) {
+        pf(k + a.pf_dist);
         double* const sk = st(k);
         const double zi = sk[L::sZ + lane], dz = sk[L::sDz + lane], da = second_order ? sk[L::sDa + lane] : 0.0;
         if (hl) {
@@ -517,6 +525,7 @@ struct CoopIpm {
     }
     __syncwarp();
     for (int k = 0; k < a.N; ++k) {
+      pf(k + a.pf_dist);
       double* const sk = st(k);
       int sat = 0;
       double zi = 0.0;
@@ -678,7 +687,11 @@ static int launch_coop_variant(const BoxQpArgs<double>& a, cudaStream_t st) {
   return check_launch("boxqp_ipm_coop_kernel");
 }
 
-int launch_boxqp_coop(const BoxQpArgs<double>& a, int n, int m, cudaStream_t st) {
+int launch_boxqp_coop(const BoxQpArgs<double>& a_in, int n, int m, cudaStream_t st) {
+  BoxQpArgs<double> a = a_in;
+  a.pf_dist = 1;  // stage visits of bulk L2 prefetch ahead of each pass (env MPC_COOP_PREFETCH; 0 / 1 / 2: 1.578 / 1.514 /
+                  // 1.518 s per 2^19 cfg-5 solves)
+  if (const char* env = getenv("MPC_COOP_PREFETCH")) a.pf_dist = atoi(env);
   if (n == 12 && m == 4) {
     int minb = 4;  // measured on B200: 4 CTAs/SM (64 registers) is marginally the fastest
     if (const char* env = getenv("MPC_COOP_MINB")) minb = atoi(env);
