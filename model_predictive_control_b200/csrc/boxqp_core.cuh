@@ -453,7 +453,9 @@ struct BoxQpIpm {
   }
   MPC_HD bool pf_on(int k) const {
 #ifdef __CUDA_ARCH__
-    if constexpr (STAGED) return false;
+    // compiled out with general rows: the prefetch does not pay there (obstacle loop 3.34 -> 3.90 s at distance 2), and
+    // even switched off at run time its code in the four sweeps cost that register-starved kernel 13 % (3.38 -> 3.81 s)
+    if constexpr (STAGED || NC > 0) return false;
     return a.pf_dist > 0 && k >= 0 && k < a.N;
 #else
     (void)k;
