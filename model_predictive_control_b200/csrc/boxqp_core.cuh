@@ -35,10 +35,11 @@
 //   D  forward   dz by rollout with d_aff + d_cor; per bound ds, dlam, the step ratio and the sums that give the new
 //                barrier parameter; stores dz.  The step itself is applied by the next iteration's sweep A (or by
 //                the output pass after the last iteration).
-// Storage precision is a template policy (BoxQpStore): the float64 product keeps z, the gains and the corrector data
-// and the step dz in float64 and the slacks, multipliers and dz_aff in float32 (relative quantities: they enter through
-// ratios/products only, and every sweep reads the SAME rounded value, so the Newton system stays consistent); the
-// float32 product stores everything in float32.  All arithmetic is float64 in both.
+// Storage precision is a template policy (BoxQpStore): the float64 product keeps z, the gains and the step dz in
+// float64 and the slacks, multipliers, dz_aff and the corrector data e, g in float32 (relative quantities: they enter
+// through ratios/products only, every sweep reads the SAME rounded value, and e, g only perturb the direction, so the
+// Newton system stays consistent and its fixed point does not move); the float32 product stores everything in float32.
+// All arithmetic is float64 in both.
 // The body is __host__ __device__: tests/harness runs it on the CPU against oracle/boxqp.py.
 #pragma once
 
@@ -168,7 +169,7 @@ MPC_HD T round_to(T v) {   // the value a later sweep will read back from a sect
 }
 
 // STAGED (device only): the warp streams its tile through shared memory -- every sweep's read set is ONE contiguous
-// byte range of a stage, copied two stage visits ahead by a bulk asynchronous copy (cp.async.bulk + mbarrier, issued
+// byte range of a stage, copied kDepth stage visits ahead by a bulk asynchronous copy (cp.async.bulk + mbarrier, issued
 // by one lane); the sweeps read shared memory, their stores go to global memory directly.
 template <typename T, typename TIO, int NX, int NU, int NC = 0, int MODEL = 0, class ST = StoreMix, bool STAGED = false>
 struct BoxQpIpm {
@@ -268,8 +269,8 @@ struct BoxQpIpm {
   // warps' scattered global accesses (measured: 0.6 % wrong solutions with permuted batches).  Per interior-point iteration each buffer is
   // used an even number of times (4 sweeps), so lanes that sit an iteration out keep the right barrier parities.
   const char *rb8 = nullptr, *rb4 = nullptr;  // staged copy of the current stage: buffer - range lo + lane * 8 / 4
-  char* sbuf = nullptr;                       // the warp's two buffers (shared memory), kBufBytes each
-  unsigned long long* sbar = nullptr;         // the warp's two mbarriers
+  char* sbuf = nullptr;                       // the warp's kDepth buffers (shared memory), kBufBytes each
+  unsigned long long* sbar = nullptr;         // the warp's kDepth mbarriers
   unsigned wmask = 0xffffffffu;               // lanes taking part in the current iteration
   unsigned par = 0;                           // bit j: parity the next wait on barrier j uses
   int vis = 0;                                // buffer of the current visit
@@ -1357,7 +1358,7 @@ struct BoxQpIpm {
     }
     output(status, it, have_step, tau, alpha);
   }
-  // STAGED: the warp's staging buffers (2 x kBufBytes, 128-byte aligned), its two mbarriers (initialised to one
+  // STAGED: the warp's staging buffers (kDepth x kBufBytes, 128-byte aligned), its kDepth mbarriers (initialised to one
   // arrival each by the caller) and the lanes of the warp that own a scenario
   MPC_HD void stage_setup(char* buffers, unsigned long long* barriers, unsigned lanes_mask) {
     sbuf = buffers;
