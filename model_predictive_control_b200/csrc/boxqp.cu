@@ -75,11 +75,23 @@ static int launch_staged(const BoxQpArgs<TIO>& a, unsigned grid, int threads, cu
   if (const char* env = getenv("MPC_QP_PAD_SMEM")) pad = atoi(env);
   if (pad < 0 || pad > 180 * 1024) pad = 0;
   smem += pad;
-  static int configured = -1;
-  if (configured != pad) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kQpThreads / 32 * Ipm::kDepth * Ipm::kBufBytes + pad);
+  // function attributes are per device: one flag per device of the process (not thread-safe beyond a repeated,
+  // idempotent attribute call)
+  static int configured[64];
+  static bool init_done = false;
+  if (!init_done) {
+    for (int& c : configured) c = -1;
+    init_done = true;
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || configured[dev] != pad) {
+    const int want = kQpThreads / 32 * Ipm::kDepth * Ipm::kBufBytes + pad;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+    if (e != cudaSuccess)
+      return fail((int)e, "mpc_boxqp_solve: %d bytes of shared memory per CTA for the staged kernel: %s", want, cudaGetErrorString(e));
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    configured = pad;
+    if (dev >= 0 && dev < 64) configured[dev] = pad;
   }
   kern<<<grid, threads, smem, st>>>(a);
   return check_launch("boxqp_ipm_staged_kernel");
