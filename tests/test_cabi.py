@@ -89,3 +89,37 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f"{f} imports the oracle"
+
+
+def test_workspace_sizes_are_whole_tiles(built_lib):
+    """The box-QP / RTI workspaces are laid out in tiles of 32 lanes (csrc/boxqp_core.cuh): their size depends on the
+    batch only through the number of tiles, grows linearly in tiles and in the horizon, and the float32 product needs
+    no more than the float64 one (no GPU needed: pure host arithmetic of the library)."""
+    I64 = ctypes.c_int64
+    f = built_lib.mpc_boxqp_workspace_bytes
+    f.restype = I64
+    f.argtypes = [I64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    g = built_lib.mpc_boxqp_rows_workspace_bytes
+    g.restype = I64
+    g.argtypes = [I64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    r = built_lib.mpc_rti_workspace_bytes
+    r.restype = I64
+    r.argtypes = [I64, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    header = 256
+    from model_predictive_control_b200 import _lib
+    F64, F32 = _lib.MPC_F64, _lib.MPC_F32
+    for n, m in ((2, 1), (4, 1), (4, 2)):
+        for N in (5, 30):
+            one = f(1, n, m, N, F64) - header
+            assert one > 0 and f(32, n, m, N, F64) - header == one and f(33, n, m, N, F64) - header == 2 * one
+            assert f(64 * 1000, n, m, N, F64) - header == 2000 * one
+            assert f(32, n, m, 2 * N, F64) - header == 2 * one
+            assert f(32, n, m, N, F32) <= f(32, n, m, N, F64)
+            # all-float64 layout: 9 (n+m) + m*n + m*m + m doubles per stage and lane (z, 4 slack/multiplier rows, dz_aff,
+            # dz, e, g; gains K, S^-1, d)
+            d = n + m
+            assert one == N * 32 * 8 * (9 * d + m * n + m * m + m)
+    assert g(32, 4, 2, 10, 9, F64) - header == 10 * 32 * 8 * (9 * 6 + 8 + 4 + 2 + 3 * 9)
+    assert g(1, 4, 2, 10, 9, F64) == g(32, 4, 2, 10, 9, F64) < g(33, 4, 2, 10, 9, F64)
+    assert r(64, 20, 0, F64) > r(32, 20, 0, F64) > 0 and r(32, 20, 9, F64) > r(32, 20, 0, F64)
+    assert f(0, 2, 1, 30, F64) == header   # empty batch: the header only
