@@ -1,3 +1,6 @@
+"""Staged vs unstaged box-QP kernel on a full-machine cfg-3 batch: bitwise comparison in the caller's order, with an
+identity / random / Morton permutation and sorted by iteration count (the check that found the early-release race of the
+staging pipeline; every line must print `differ: 0`)."""
 import os, sys, torch
 sys.path.insert(0, ".")
 from model_predictive_control_b200 import boxqp, problem
