@@ -161,10 +161,13 @@ int mpc_summary(const void* cost, const void* viol, const int32_t* n_sat, const 
  *   U [N][m][batch], X [N+1][n][batch], cost [batch], status [batch], iters [batch],
  *   sat_u [N][m][batch] / sat_x [N][n][batch] optional int8: -1 at lower bound, +1 at upper, 0 free.
  *   Inputs at an active bound are returned exactly equal to the bound.
- *   ws: caller-owned workspace of mpc_boxqp_workspace_bytes(...) bytes.
+ *   ws: caller-owned workspace of mpc_boxqp_workspace_bytes(...) bytes; opaque (tiles of 32 scenarios,
+ *   [tile][stage][section row][lane]: the size depends on the batch through ceil(batch / 32) only).
  * Method: Mehrotra predictor-corrector interior point, Newton systems solved by Riccati sweeps; arithmetic is float64
  * for both dtypes.  MPC_F64: float64 arrays; the workspace keeps the iterate, gains and steps in float64 and slacks /
- * multipliers in float32 (env MPC_QP_STORE=f64: everything float64).  MPC_F32: float32 arrays and workspace
+ * multipliers / affine direction / corrector data in float32 (env MPC_QP_STORE=f64: everything float64).  A shared
+ * model (ltv = 0) without general rows runs on the staged kernel (tile stages copied into shared memory by
+ * cp.async.bulk; env MPC_QP_STAGED=0: the kernel without staging; results are bitwise the same).  MPC_F32: float32 arrays and workspace
  * (north-star tolerance 1e-4).  Supported (n, m): (2,1), (4,1), (4,2) with one thread per
  * scenario (register-resident matrices); (12,4), MPC_F64, with a shared model (ltv = 0) on a persistent
  * warp-per-scenario kernel whose workspace is one slot per resident warp, independent of the batch.
