@@ -166,14 +166,19 @@ struct CoopIpm {
   // stage-major slot it is ONE bulk prefetch of a contiguous 1 440-byte stage: pf() above.)
   // x+ = A x + B u (lanes < NX), from / to the warp's vectors
   __device__ void step_vec(const double* x, const double* u, double* xn) {
-    if (lane < NX) {
-      double acc = 0.0;
+    // 2 NX lanes: lane = 2 i + h does half of row i (NX / 2 columns of A, NU / 2 of B), the halves meet by one shuffle
+    // (half the dependent FMA chain of the row-per-lane form; every lane of the warp executes the shuffle)
+    static_assert(2 * NX <= 32 && NX % 2 == 0 && NU % 2 == 0, "split rows over lane pairs");
+    const int i = lane >> 1, h = lane & 1;
+    double acc = 0.0;
+    if (lane < 2 * NX) {
 #pragma unroll
-      for (int j = 0; j < NX; ++j) acc = fma(sh[L::oA + lane * NX + j], x[j], acc);
+      for (int j = 0; j < NX / 2; ++j) acc = fma(sh[L::oA + i * NX + h * (NX / 2) + j], x[h * (NX / 2) + j], acc);
 #pragma unroll
-      for (int j = 0; j < NU; ++j) acc = fma(sh[L::oB + lane * NU + j], u[j], acc);
-      xn[lane] = acc;
+      for (int j = 0; j < NU / 2; ++j) acc = fma(sh[L::oB + i * NU + h * (NU / 2) + j], u[h * (NU / 2) + j], acc);
     }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (lane < 2 * NX && h == 0) xn[i] = acc;
   }
 
   // (H z)_lane for the stage vector in w[wZ]: R u for inputs, Q x (Pf x at the last stage) for states
@@ -435,14 +440,21 @@ struct CoopIpm {
         l_u = sk[L::sLu + lane];
         if (!AFFINE) da = sk[L::sDa + lane];
       }
-      for (int e = lane; e < NU * NX; e += 32) w[L::wK + e] = sk[L::sK + e];
-      if (lane < NU) w[L::wDff + lane] = sk[L::sDw + lane];
-      __syncwarp();
-      if (lane < NU) {
-        double u = w[L::wDff + lane];
+      // u = d + K x on 4 NU lanes: lane = 4 i + q multiplies NX / 4 entries of row i of K, read straight from the slot
+      // (no shared-memory copy of the gains in this pass), two shuffles add the quarters
+      static_assert(4 * NU <= 32 && NX % 4 == 0, "quarter rows of K over the lanes");
+      {
+        const int i = lane >> 2, q = lane & 3;
+        double kx = 0.0;
+        if (lane < 4 * NU) {
+          const double* kr = sk + L::sK + i * NX + q * (NX / 4);
 #pragma unroll
-        for (int j = 0; j < NX; ++j) u = fma(w[L::wK + lane * NX + j], w[L::wX + j], u);
-        w[L::wU + lane] = u;
+          for (int j = 0; j < NX / 4; ++j) kx = fma(kr[j], w[L::wX + q * (NX / 4) + j], kx);
+          if (q == 0) kx += sk[L::sDw + i];
+        }
+        kx += __shfl_xor_sync(0xffffffffu, kx, 1);
+        kx += __shfl_xor_sync(0xffffffffu, kx, 2);
+        if (lane < 4 * NU && q == 0) w[L::wU + i] = kx;
       }
       __syncwarp();
       step_vec(w + L::wX, w + L::wU, w + L::wXn);
